@@ -1,0 +1,151 @@
+/* kc_b200.h — C ABI of the B200-native k-mer clustering engine.
+ *
+ * Drop-in boundary for the hot path of Isabella136/uniprot_kmer_based_clustering.
+ * The reference is a single Rust binary with no FFI of its own; the functions below are
+ * what an FFI crate for that path binds, one entry point per reference stage.  Citations
+ * (file:line) are relative to the reference root.  INTEGRATION.md shows the Rust
+ * `extern "C"` block and the safe wrappers that keep the reference's module API.
+ *
+ * Conventions
+ *   - One opaque engine per GPU (one process per GPU; the engine owns all device memory).
+ *   - Every call returns 0 (KC_OK) or a KC_E* code; the message is kc_last_error(engine).
+ *     Nothing panics or throws across the boundary (the reference panics, e.g.
+ *     src/main.rs:55-63; the wrappers turn codes back into panics where parity wants it).
+ *   - Host output goes into caller-allocated buffers sized from the stats structs.
+ *   - Calls on one engine come from one host thread at a time.
+ *   - There is no CPU fallback: without a CUDA device kc_create fails with KC_ENODEVICE.
+ *   - Protein indices are 0-based in the order given to kc_set_proteins (FASTA order,
+ *     SURVEY C1).  k-mer ids are canonical: rank of the k-mer among the repeated k-mers
+ *     in ascending k-mer order (replaces boomphf ids).
+ */
+#ifndef KC_B200_H_
+#define KC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KC_ABI_VERSION 1
+
+enum {
+  KC_OK = 0,
+  KC_EINVAL = 1,    /* bad argument / call order */
+  KC_ENODEVICE = 2, /* no usable CUDA device */
+  KC_ECUDA = 3,     /* CUDA runtime error, see kc_last_error */
+  KC_ENOMEM = 4,    /* device or host allocation failed */
+  KC_ETOOLARGE = 5  /* input exceeds a documented limit (2^32-1 residues, 2^32-1 nnz) */
+};
+
+typedef struct kc_engine kc_engine;
+
+typedef struct kc_config {
+  int32_t k;                /* 5 (reference, src/protein.rs:29-37) or 7 (src/tree.rs:96-101) */
+  int32_t device;           /* CUDA device ordinal */
+  uint32_t threshold;       /* emit pairs with count > threshold; reference 10, src/graph/mod.rs:242 */
+  int32_t cross_class_only; /* 1 = reference (remove_uninteresting_edges, src/graph/mod.rs:580-587) */
+  int32_t want_blosum;      /* 1 = fill kc_edge.blosum (src/blosum.rs table, framework-defined score) */
+  uint32_t reserved0;
+  uint64_t max_edges;       /* device edge-buffer capacity; 0 = automatic (grows and retries) */
+} kc_config;
+
+/* src/main.rs:84-147 census + split; nnz = sum over proteins of |get_five_hash()| */
+typedef struct kc_index_stats {
+  uint64_t n_positions;  /* sum of max(0, len-k+1): |get_five_mers()| over all proteins */
+  uint64_t n_incidences; /* sum of per-protein distinct k-mers (src/main.rs:100-102) */
+  uint64_t n_distinct;   /* census length (src/main.rs:138) */
+  uint64_t n_singleton;  /* five_mer_unique (src/main.rs:131-133) */
+  uint64_t n_repeated;   /* five_mer_repeat, printed at src/graph/mod.rs:50 */
+  uint64_t nnz;          /* sum of kmer_freq (src/main.rs:187-193) */
+} kc_index_stats;
+
+typedef struct kc_pair_stats {
+  uint64_t n_multi_edges;      /* "Number of total edges", src/graph/mod.rs:51 (whole set) */
+  uint64_t n_multi_edges_kept; /* "Number of edges now" after the class filter, :695 */
+  uint64_t n_pairs_kept;       /* "Number of edges now" after combine_edges, :545 */
+  uint64_t n_edges_out;        /* pairs with count > threshold, :242 */
+  uint64_t sum_count_out;      /* sum of their counts */
+  uint64_t n_rows;             /* proteins (rows of the pair triangle) this call scored */
+  uint64_t n_retries;          /* edge-buffer growth retries (0 in steady state) */
+} kc_pair_stats;
+
+/* One surviving pair = KmerEdgeGroup {vertices_key, kmers.len()} (src/graph/edge.rs:48-52),
+ * a < b in input order, list sorted by (a, b). */
+typedef struct kc_edge {
+  uint32_t a, b, count;
+  int32_t blosum;
+} kc_edge;
+
+/* CUDA-event timings of the last calls (milliseconds, on the engine's stream) */
+typedef struct kc_timings {
+  float h2d_ms, extract_ms, index_ms, pairs_ms, edges_ms, d2h_ms;
+  uint32_t kernel_launches; /* launches of this library's kernels since kc_reset_timings */
+  uint32_t reserved;
+  float pair_kernel_ms;     /* accumulation kernels only (the roofline kernel family) */
+  float census_kernel_ms;   /* extract+dedup+census kernel only */
+} kc_timings;
+
+int kc_abi_version(void);
+int kc_device_count(void);
+
+int kc_create(const kc_config* cfg, kc_engine** out);
+void kc_destroy(kc_engine* e);
+const char* kc_last_error(const kc_engine* e);
+/* run the engine's work on an existing CUDA stream (cudaStream_t); NULL = engine-owned stream */
+int kc_set_stream(kc_engine* e, void* cuda_stream);
+
+/* Stage the residue stream: replaces the Vec<Protein> built at src/main.rs:62-72.
+ * residues = ASCII bytes of all sequences back to back (no separators, no line breaks),
+ * offsets[n+1] delimit proteins, class_id[n] = dictionary id of the AMR class string
+ * (Protein::get_amr_class, src/protein.rs:135-138).  Host pointers; copied to HBM. */
+int kc_set_proteins(kc_engine* e, const uint8_t* residues, const uint64_t* offsets,
+                    const uint32_t* class_id, uint64_t n_proteins);
+/* Same, inputs already resident in HBM on the engine's device (borrowed until the next
+ * kc_set_proteins* / kc_destroy; the engine does not modify them). */
+int kc_set_proteins_device(kc_engine* e, const uint8_t* d_residues, const uint64_t* d_offsets,
+                           const uint32_t* d_class_id, uint64_t n_proteins);
+
+/* Protein::new + get_five_mers (src/protein.rs:107-132,141): one packed k-mer per start
+ * position, proteins back to back, duplicates kept.  kmers_out may be NULL (compute only);
+ * otherwise it receives n_positions u32 values (capacity checked). */
+int kc_extract_kmers(kc_engine* e, uint32_t* kmers_out, uint64_t capacity, uint64_t* n_positions);
+
+/* Census, unique/repeated split, perfect k-mer index, per-protein id lists, kmer_freq
+ * (src/main.rs:84-199; replaces boomphf Mphf::new at :139-140). */
+int kc_build_index(kc_engine* e, kc_index_stats* stats);
+/* all distinct k-mers, ascending (the census keys, src/main.rs:138) */
+int kc_get_distinct_kmers(kc_engine* e, uint32_t* kmers_out, uint64_t capacity);
+/* repeated k-mers ascending (= id order) and kmer_freq[id] (src/main.rs:135,187-193) */
+int kc_get_vocab(kc_engine* e, uint32_t* kmers_out, uint32_t* freq_out, uint64_t capacity);
+/* Protein::get_five_hash for every protein as CSR: row_offsets[n+1], ids[nnz] ascending
+ * within a row (src/protein.rs:146-148; vertex.rs:82-85 sorts them before use) */
+int kc_get_protein_ids(kc_engine* e, uint64_t* row_offsets, uint32_t* ids_out, uint64_t capacity);
+/* Mphf::hash (src/main.rs:145,192): id of each k-mer, 0xFFFFFFFF if not a repeated k-mer */
+int kc_lookup_kmers(kc_engine* e, const uint32_t* kmers, uint64_t n, uint32_t* ids_out);
+
+/* Graph::new + remove_uninteresting_edges + combine_edges + the threshold of
+ * align_and_output_pairs (src/graph/mod.rs:39-193, 549-697, 322-546, 242) in one pass;
+ * the multigraph is never materialised. */
+int kc_score_pairs(kc_engine* e, kc_pair_stats* stats);
+/* Same for shard `shard` of `n_shards` work-balanced row blocks of the pair triangle
+ * (multi-GPU: every rank holds the same index and scores its own shard). */
+int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pair_stats* stats);
+/* the surviving pairs of the last kc_score_pairs*, sorted by (a, b) */
+int kc_get_edges(kc_engine* e, kc_edge* edges_out, uint64_t capacity);
+/* KmerEdgeGroup.kmers (src/graph/edge.rs:49,74) for edge i of the last result, as k-mer
+ * VALUES ascending; kmers_out holds edges[i].count entries */
+int kc_get_edge_kmers(kc_engine* e, uint64_t edge_index, uint32_t* kmers_out, uint64_t capacity);
+
+int kc_get_timings(kc_engine* e, kc_timings* out);
+int kc_reset_timings(kc_engine* e);
+
+/* Dense presence-bitset path (north star item 3; used by the host tree, src/tree.rs:185-216):
+ * counts[i*n_rows+j] = |K_rows[i] ∩ K_rows[j]| over the repeated-k-mer vocabulary, computed
+ * with AND+popcount on per-protein bitsets.  rows = protein indices (host), counts = host. */
+int kc_bitset_pair_counts(kc_engine* e, const uint32_t* rows, uint32_t n_rows, uint32_t* counts_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KC_B200_H_ */

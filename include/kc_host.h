@@ -1,0 +1,53 @@
+/* kc_host.h — host-side helpers around the engine: FASTA staging and the synthetic
+ * protein-set generator used by the benchmarks.  Plain C ABI, no CUDA types.
+ *
+ * kc_fasta_* restates what the reference gets from seq_io (src/main.rs:62-72) and from
+ * Protein::new / get_amr_class (src/protein.rs:107-110,135-138):
+ *   id       = header text after '>' up to the first space or tab
+ *   sequence = the record's residue bytes with line breaks removed
+ *   class    = 4th '|'-separated field of the id (split_terminator semantics); records whose
+ *              id has fewer than 4 fields get the empty class name (the reference would
+ *              panic on them at src/protein.rs:137) and are counted in n_missing_class
+ * ALL records are read regardless of file size, in file order.
+ */
+#ifndef KC_HOST_H_
+#define KC_HOST_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kc_fasta kc_fasta;
+
+/* threads = worker threads for parsing (the CLI's second argument, src/main.rs:59-60) */
+int kc_fasta_parse_file(const char* path, int threads, kc_fasta** out);
+int kc_fasta_parse_buffer(const char* data, uint64_t len, int threads, kc_fasta** out);
+void kc_fasta_free(kc_fasta* f);
+uint64_t kc_fasta_n_proteins(const kc_fasta* f);
+uint64_t kc_fasta_n_residues(const kc_fasta* f);
+const uint8_t* kc_fasta_residues(const kc_fasta* f);  /* page-locked when CUDA is present */
+const uint64_t* kc_fasta_offsets(const kc_fasta* f);  /* n_proteins + 1 */
+const uint32_t* kc_fasta_class_ids(const kc_fasta* f);
+uint32_t kc_fasta_n_classes(const kc_fasta* f);
+uint64_t kc_fasta_n_missing_class(const kc_fasta* f);
+const char* kc_fasta_class_name(const kc_fasta* f, uint32_t class_id);
+const char* kc_fasta_id(const kc_fasta* f, uint64_t protein);
+
+/* Synthetic generator "G1" (frozen; BASELINE.md / DESIGN.md give the law).  All-integer and
+ * counter-based, so any subset of proteins can be generated independently and in parallel.
+ *   length_law 0 ("A"): 50 + sum of four uniform ints in [0,150]   (mean 350)
+ *   length_law 1 ("B"): 50 + 1950 * (t / 2^16)^4, t uniform in [0, 65535] (50..2000, skewed)
+ * Families of 16 consecutive proteins share a base sequence; member j re-draws each residue
+ * with probability j * 1311 / 65536.  class = family % 15, except every 8th family where
+ * class = (family + j) % 15.
+ * Step 1 fills offsets[n+1] and class_id[n]; step 2 fills residues[offsets[n]]. */
+int kc_synth_layout(uint64_t n, int length_law, uint64_t seed, uint64_t* offsets, uint32_t* class_id);
+int kc_synth_residues(uint64_t n, int length_law, uint64_t seed, int threads, const uint64_t* offsets,
+                      uint8_t* residues);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KC_HOST_H_ */

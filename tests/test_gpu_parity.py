@@ -1,0 +1,368 @@
+"""GPU parity suite: the CUDA engine, called through the C ABI, against the CPU oracle and the
+committed golden vectors.  Integer work: every comparison is bit-exact."""
+import numpy as np
+import pytest
+
+import uniprot_kmer_based_clustering_b200 as kc
+from conftest import edges_abc, random_protein_set, sha16
+from oracle.oracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def run_oracle(ps, k, thr, cross, blosum=True, threads=8):
+    o = Oracle(k, threads)
+    o.set_proteins(ps.residues, ps.offsets, ps.class_id)
+    km = o.extract_kmers()
+    ix = o.build_index()
+    pr = o.score_pairs(thr, cross, blosum, mode=1)
+    return km, ix, pr
+
+
+def check_index(e, ix):
+    st = e.index_stats
+    for name in ("n_positions", "n_incidences", "n_distinct", "n_singleton", "n_repeated", "nnz"):
+        assert st[name] == ix.stats[name], name
+    assert np.array_equal(e.get_distinct_kmers(), ix.distinct)
+    v, f = e.get_vocab()
+    assert np.array_equal(v, ix.vocab)
+    assert np.array_equal(f, ix.freq)
+    ro, ids = e.get_protein_ids()
+    assert np.array_equal(ro, ix.row_offsets)
+    assert np.array_equal(ids, ix.ids)
+
+
+def check_pairs(stats, edges, pr):
+    for name in ("n_multi_edges", "n_multi_edges_kept", "n_pairs_kept", "n_edges_out", "sum_count_out"):
+        assert stats[name] == pr.stats[name], name
+    assert np.array_equal(edges, pr.edges)
+
+
+# ---------------------------------------------------------------- ARG set vs golden + oracle
+@pytest.mark.parametrize("k", [5, 7])
+def test_arg_extract_kmers(k, arg_set, arg_oracle, golden):
+    g = golden[f"k{k}"]
+    with kc.Engine(k) as e:
+        e.set_protein_set(arg_set)
+        km = e.extract_kmers()
+    assert km.size == g["n_positions"]
+    assert int(km.astype(np.uint64).sum()) == g["sum_positions"]
+    assert int(np.bitwise_xor.reduce(km)) == g["xor_positions"]
+    assert km[:6].tolist() == g["first_kmers_protein0"]
+    assert np.array_equal(km, arg_oracle[k][1])
+
+
+@pytest.mark.parametrize("k", [5, 7])
+def test_arg_index(k, arg_set, arg_oracle, golden):
+    g = golden[f"k{k}"]
+    with kc.Engine(k) as e:
+        e.set_protein_set(arg_set)
+        e.build_index()
+        assert sha16(e.get_distinct_kmers().astype("<u4")) == g["sha_distinct"]
+        v, f = e.get_vocab()
+        assert sha16(v.astype("<u4")) == g["sha_repeated"]
+        top = np.argsort(-f.astype(np.int64), kind="stable")[:3]
+        assert [[int(v[i]), int(f[i])] for i in top] == g["top3"]
+        check_index(e, arg_oracle[k][2])
+        # Mphf::hash stand-in: ids of repeated k-mers are their ranks; others are rejected
+        probe = np.concatenate([v[:100], v[-100:], np.array([0, 1, 21 ** k - 1, 21 ** k, 2 ** 32 - 1], np.uint32)])
+        ids = e.lookup_kmers(probe)
+        assert np.array_equal(ids[:100], np.arange(100))
+        assert np.array_equal(ids[100:200], np.arange(v.size - 100, v.size))
+        exp_tail = [int(np.searchsorted(v, x)) if (x < 21 ** k and x in v) else 0xFFFFFFFF
+                    for x in probe[200:].tolist()]
+        assert ids[200:].tolist() == exp_tail
+
+
+@pytest.mark.parametrize("k", [5, 7])
+@pytest.mark.parametrize("name,cross,thr", [("cross_gt10", True, 10), ("cross_gt0", True, 0),
+                                            ("all_gt10", False, 10)])
+def test_arg_pairs(k, name, cross, thr, arg_set, arg_oracle, golden):
+    g = golden[f"k{k}"]
+    with kc.Engine(k, threshold=thr, cross_class_only=cross, want_blosum=True) as e:
+        e.set_protein_set(arg_set)
+        e.build_index()
+        st = e.score_pairs()
+        edges = e.get_edges()
+    assert st["n_multi_edges"] == g["n_multi_edges"]
+    assert edges.size == g[name]["n"]
+    assert sha16(edges_abc(edges)) == g[name]["sha"]
+    assert int(edges["count"].sum()) == g[name]["sum_count"] == st["sum_count_out"]
+    assert int(edges["blosum"].astype(np.int64).sum()) == g[name]["blosum_sum"]
+    assert edges["blosum"][:3].tolist() == g[name]["blosum_first3"]
+    if cross:
+        assert st["n_multi_edges_kept"] == g["n_multi_edges_cross"]
+        assert st["n_pairs_kept"] == g["n_pairs_cross"]
+    else:
+        assert st["n_multi_edges_kept"] == g["n_multi_edges"]
+        assert st["n_pairs_kept"] == g["n_pairs_all"]
+    pr = arg_oracle[k][0].score_pairs(thr, cross, True, mode=1)
+    check_pairs(st, edges, pr)
+
+
+def test_arg_reference_api_flow(arg_set, golden, capsys):
+    """The reference's call sequence (src/main.rs:216-232) through the module mirror."""
+    import io
+    from uniprot_kmer_based_clustering_b200.graph import Graph
+    from uniprot_kmer_based_clustering_b200.protein import Mphf, ProteinList
+    g = golden["k5"]
+    log = io.StringIO()
+    with kc.Engine(5) as e:
+        pl = ProteinList(e, arg_set)
+        pl.build_index()
+        p0 = pl[0]
+        assert p0.get_amr_class() == "beta_lactam"
+        assert p0.get_five_mers()[:6].tolist() == g["first_kmers_protein0"]
+        assert p0.get_id_and_seq()[0] == golden["protein0_id"]
+        phf = Mphf(e)
+        v, _ = e.get_vocab()
+        assert phf.hash(int(v[1234])) == 1234
+        assert np.array_equal(v[p0.get_five_hash()], np.intersect1d(np.unique(p0.get_five_mers()), v))
+        graph = Graph.new(pl.kmer_freq, 8, pl, log=log)
+        graph.remove_uninteresting_edges(8)
+        graph.combine_edges(8)
+        edges = graph.align_and_output_pairs(8)
+        text = log.getvalue()
+        assert "Number of 5mers found in at least two proteins: 231253" in text
+        assert "Number of total edges: 258621291" in text
+        assert "Number of edges now: 5300233" in text
+        assert "Number of edges now: 4350628" in text
+        assert text.count("Cross-checking:") == 465 == len(edges)
+        ke = graph.edges[0]
+        assert ke.get_vertices_key() == [26, 2838]
+        kms = ke.get_kmer_values()
+        assert kms.size == 167 and np.all(np.diff(kms.astype(np.int64)) > 0)
+        a, b = np.unique(pl[26].get_five_mers()), np.unique(pl[2838].get_five_mers())
+        assert np.array_equal(kms, np.intersect1d(np.intersect1d(a, b), v))
+        assert np.array_equal(ke.get_kmers(), np.searchsorted(v, kms))
+        assert ke.get_proteins_ids_and_sequences()[1][0] == arg_set.ids[2838]
+
+
+# ---------------------------------------------------------------- randomised + edge cases
+@pytest.mark.parametrize("k", [5, 7])
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+@pytest.mark.parametrize("cross", [True, False])
+def test_random_small_sets(k, seed, cross):
+    ps = random_protein_set(seed, 150 + 37 * seed, min_len=0, max_len=90, n_classes=1 + seed, family=5)
+    thr = [10, 0, 3, 1][seed]
+    km, ix, pr = run_oracle(ps, k, thr, cross)
+    with kc.Engine(k, threshold=thr, cross_class_only=cross, want_blosum=True) as e:
+        e.set_protein_set(ps)
+        assert np.array_equal(e.extract_kmers(), km)
+        e.build_index()
+        check_index(e, ix)
+        st = e.score_pairs()
+        check_pairs(st, e.get_edges(), pr)
+
+
+@pytest.mark.parametrize("k", [5, 7])
+def test_degenerate_inputs(k):
+    z = np.zeros(0, np.uint8)
+    with kc.Engine(k, threshold=0, cross_class_only=False, want_blosum=True) as e:
+        # empty set
+        e.set_proteins(z, np.zeros(1, np.uint64), np.zeros(0, np.uint32))
+        assert e.extract_kmers().size == 0
+        st = e.build_index()
+        assert st["n_repeated"] == 0 and st["n_positions"] == 0
+        assert e.score_pairs()["n_edges_out"] == 0 and e.get_edges().size == 0
+        # only proteins shorter than k, including empty ones
+        res = np.frombuffer(b"ACDACD" + b"MK", np.uint8)
+        e.set_proteins(res, np.array([0, 3, 3, 6, 8], np.uint64), np.array([0, 1, 0, 1], np.uint32))
+        assert e.extract_kmers().size == 0
+        assert e.build_index()["n_distinct"] == 0
+        assert e.score_pairs()["n_edges_out"] == 0
+        # one protein: every k-mer is a singleton
+        one = np.frombuffer(b"MKHKNQATHKEFSQLEKKFDARLGLYAIDTG", np.uint8)
+        e.set_proteins(one, np.array([0, one.size], np.uint64), np.array([0], np.uint32))
+        st = e.build_index()
+        assert st["n_repeated"] == 0 and st["n_singleton"] == st["n_distinct"] > 0
+        assert e.score_pairs()["n_edges_out"] == 0
+        # identical proteins: every pair shares every distinct k-mer
+        n = 9
+        e.set_proteins(np.tile(one, n), (np.arange(n + 1) * one.size).astype(np.uint64), np.zeros(n, np.uint32))
+        st = e.build_index()
+        nd = np.unique(np.lib.stride_tricks.sliding_window_view(one, k), axis=0).shape[0]
+        assert st["n_repeated"] == nd and st["n_singleton"] == 0 and st["nnz"] == n * nd
+        ps = e.score_pairs()
+        ed = e.get_edges()
+        assert ps["n_edges_out"] == n * (n - 1) // 2 and np.all(ed["count"] == nd)
+        assert ps["n_multi_edges"] == nd * n * (n - 1) // 2
+    # same set, one class, cross-class only: nothing survives
+    with kc.Engine(k, threshold=0, cross_class_only=True) as e:
+        e.set_proteins(np.tile(one, n), (np.arange(n + 1) * one.size).astype(np.uint64), np.zeros(n, np.uint32))
+        e.build_index()
+        ps = e.score_pairs()
+        assert ps["n_edges_out"] == 0 and ps["n_multi_edges_kept"] == 0 and ps["n_multi_edges"] > 0
+
+
+@pytest.mark.parametrize("k", [5, 7])
+def test_unknown_residues_and_case(k):
+    """bytes outside the 20 letters (X, Z, *, lower case, digits) all map to code 20"""
+    a = b"MKXKNQZTHK*FSQLEKKFDARLGLYAIDTGmkhknqathkefsqlekk1234567890"
+    b_ = b"MKBKNQJTHKOFSQLEKKFDARLGLYAIDTGUUUUUUUUUUUUUUUUUUU-.-.-.-.-."
+    ps = kc.ProteinSet(np.frombuffer(a + b_, np.uint8), np.array([0, len(a), len(a) + len(b_)], np.uint64),
+                       np.array([0, 1], np.uint32), ["p0|a|b|c0|g", "p1|a|b|c1|g"], ["c0", "c1"])
+    km, ix, pr = run_oracle(ps, k, 0, True)
+    with kc.Engine(k, threshold=0, want_blosum=True) as e:
+        e.set_protein_set(ps)
+        assert np.array_equal(e.extract_kmers(), km)
+        e.build_index()
+        check_index(e, ix)
+        v, _ = e.get_vocab()
+        assert (21 ** k - 1) in v  # the all-'*' k-mer is an ordinary repeated k-mer
+        st = e.score_pairs()
+        check_pairs(st, e.get_edges(), pr)
+        assert st["n_edges_out"] == 1
+
+
+@pytest.mark.parametrize("k", [5, 7])
+def test_long_proteins_cover_block_and_global_paths(k):
+    """positions > 1024 (one CTA, shared memory) and > 32768 (global scratch) per protein"""
+    rng = np.random.default_rng(7)
+    letters = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)
+    lens = [40000, 1500, 300, 36000, 5000, 1030, 1024 + k - 1, 1025 + k - 1, 20]
+    base = letters[rng.integers(0, 6, size=max(lens))]  # small alphabet: many repeats
+    seqs = []
+    for i, L in enumerate(lens):
+        s = base[:L].copy()
+        m = rng.random(L) < 0.02 * i
+        s[m] = letters[rng.integers(0, 20, size=int(m.sum()))]
+        seqs.append(s)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    ps = kc.ProteinSet(np.concatenate(seqs), off, (np.arange(len(lens)) % 2).astype(np.uint32))
+    km, ix, pr = run_oracle(ps, k, 10, False)
+    with kc.Engine(k, threshold=10, cross_class_only=False, want_blosum=True) as e:
+        e.set_protein_set(ps)
+        assert np.array_equal(e.extract_kmers(), km)
+        e.build_index()
+        check_index(e, ix)
+        check_pairs(e.score_pairs(), e.get_edges(), pr)
+
+
+@pytest.mark.parametrize("k,cross", [(5, False), (7, False), (5, True)])
+def test_synthetic_20k_against_oracle(k, cross):
+    ps = kc.ProteinSet.synthetic(20000, "A", 0xB2000003, threads=8)
+    km, ix, pr = run_oracle(ps, k, 10, cross)
+    with kc.Engine(k, threshold=10, cross_class_only=cross, want_blosum=True) as e:
+        e.set_protein_set(ps)
+        e.build_index()
+        check_index(e, ix)
+        st = e.score_pairs()
+        check_pairs(st, e.get_edges(), pr)
+        assert st["n_edges_out"] > 1000
+
+
+def test_skewed_lengths_against_oracle():
+    ps = kc.ProteinSet.synthetic(6000, "B", 0xB2000005, threads=8)
+    km, ix, pr = run_oracle(ps, 5, 10, False)
+    with kc.Engine(5, threshold=10, cross_class_only=False, want_blosum=False) as e:
+        e.set_protein_set(ps)
+        assert np.array_equal(e.extract_kmers(), km)
+        e.build_index()
+        check_index(e, ix)
+        st = e.score_pairs()
+        ed = e.get_edges()
+        assert np.array_equal(edges_abc(ed), edges_abc(pr.edges))
+        assert np.all(ed["blosum"] == 0)
+
+
+# ---------------------------------------------------------------- shards, device input, extras
+@pytest.mark.parametrize("n_shards", [2, 3, 8])
+def test_shards_partition_the_pair_triangle(n_shards, arg_set):
+    with kc.Engine(7, threshold=10, cross_class_only=False, want_blosum=True) as e:
+        e.set_protein_set(arg_set)
+        e.build_index()
+        full_st = e.score_pairs()
+        full = e.get_edges()
+        parts, tot = [], {"n_multi_edges_kept": 0, "n_pairs_kept": 0, "n_edges_out": 0, "n_rows": 0}
+        for s in range(n_shards):
+            st = e.score_pairs(s, n_shards)
+            parts.append(e.get_edges())
+            for key in tot:
+                tot[key] += st[key]
+            assert st["n_multi_edges"] == full_st["n_multi_edges"]
+        for key in ("n_multi_edges_kept", "n_pairs_kept", "n_edges_out"):
+            assert tot[key] == full_st[key], key
+        assert tot["n_rows"] == arg_set.n
+        merged = np.concatenate(parts)
+        merged = merged[np.lexsort((merged["b"], merged["a"]))]
+        assert np.array_equal(merged, full)
+        # work balance: no shard should carry more than ~2x its share of the multi-edges
+        shares = [int(p["count"].sum()) for p in parts]
+        assert len(shares) == n_shards
+
+
+def test_device_resident_input_matches_host_input(arg_set):
+    torch = pytest.importorskip("torch")
+    res = torch.from_numpy(arg_set.residues).cuda()
+    off = torch.from_numpy(arg_set.offsets.astype(np.int64)).cuda()
+    cls = torch.from_numpy(arg_set.class_id.astype(np.int32)).cuda()
+    with kc.Engine(5, want_blosum=True) as e, kc.Engine(5, want_blosum=True) as h:
+        e.set_proteins_ptr(res.data_ptr(), off.data_ptr(), cls.data_ptr(), arg_set.n, on_device=True)
+        h.set_protein_set(arg_set)
+        assert e.build_index() == h.build_index()
+        assert e.score_pairs() == h.score_pairs()
+        assert np.array_equal(e.get_edges(), h.get_edges())
+
+
+def test_rerun_is_idempotent_and_edge_buffer_grows(arg_set):
+    with kc.Engine(5, threshold=10, cross_class_only=False, max_edges=1000) as e:
+        e.set_protein_set(arg_set)
+        e.build_index()
+        st1 = e.score_pairs()
+        e1 = e.get_edges()
+        assert st1["n_retries"] == 1 and st1["n_edges_out"] == 5969297
+        st2 = e.score_pairs()
+        assert st2["n_retries"] == 0
+        assert np.array_equal(e1, e.get_edges())
+        assert np.all((e1["a"][1:] > e1["a"][:-1]) | ((e1["a"][1:] == e1["a"][:-1]) & (e1["b"][1:] > e1["b"][:-1])))
+        e.build_index()
+        assert e.score_pairs()["n_edges_out"] == st1["n_edges_out"]
+
+
+def test_permuting_the_input_permutes_the_edges():
+    ps = kc.ProteinSet.synthetic(3000, "A", 99, threads=4)
+    perm = np.random.default_rng(5).permutation(ps.n)
+    lens = np.diff(ps.offsets.astype(np.int64))
+    res2 = np.concatenate([ps.residues[int(ps.offsets[p]):int(ps.offsets[p + 1])] for p in perm])
+    off2 = np.concatenate([[0], np.cumsum(lens[perm])]).astype(np.uint64)
+    with kc.Engine(5, cross_class_only=True, want_blosum=True) as e:
+        e.set_protein_set(ps)
+        e.build_index()
+        s1 = e.score_pairs()
+        e1 = e.get_edges()
+        e.set_proteins(res2, off2, ps.class_id[perm])
+        e.build_index()
+        s2 = e.score_pairs()
+        e2 = e.get_edges()
+    for key in ("n_multi_edges", "n_multi_edges_kept", "n_pairs_kept", "n_edges_out", "sum_count_out"):
+        assert s1[key] == s2[key]
+    a, b = perm[e2["a"]], perm[e2["b"]]
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    order = np.lexsort((hi, lo))
+    assert np.array_equal(lo[order], e1["a"]) and np.array_equal(hi[order], e1["b"])
+    assert np.array_equal(e2["count"][order], e1["count"])
+    assert np.array_equal(e2["blosum"][order], e1["blosum"])
+
+
+def test_bitset_pair_counts_match_sparse_counts(arg_set, arg_oracle):
+    rows = np.array([26, 39, 67, 2838, 0, 3, 61, 75, 10618, 5000, 5001], dtype=np.uint32)
+    ix = arg_oracle[5][2]
+    sets = [set(ix.ids[int(ix.row_offsets[r]):int(ix.row_offsets[r + 1])].tolist()) for r in rows]
+    exp = np.array([[len(a & b) for b in sets] for a in sets], dtype=np.uint32)
+    with kc.Engine(5) as e:
+        e.set_protein_set(arg_set)
+        e.build_index()
+        got = e.bitset_pair_counts(rows)
+    assert np.array_equal(got, exp)
+    assert got[0, 3] == 167 and got[1, 3] == 217 and got[2, 3] == 258
+
+
+def test_call_order_errors():
+    with kc.Engine(5) as e:
+        with pytest.raises(kc.KcError):
+            e.build_index()
+        with pytest.raises(kc.KcError):
+            e.score_pairs()
+        with pytest.raises(kc.KcError):
+            e.set_proteins(np.zeros(4, np.uint8), np.array([0, 3, 2], np.uint64), np.zeros(2, np.uint32))

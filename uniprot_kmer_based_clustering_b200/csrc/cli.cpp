@@ -1,0 +1,115 @@
+// cli.cpp — `kmer_cluster <fasta> <threads>`: the reference's command line
+// (`cargo run --release -- <fasta> <threads>`, src/main.rs:50-239) over the B200 engine.
+// Progress lines and the five parity counters are printed on stderr with the reference's
+// wording (src/main.rs:51,74,124,151,201,214; src/graph/mod.rs:50-51,545,550,695,250-251).
+// The DIAMOND hand-off (src/graph/mod.rs:253-317) is out of scope; the surviving pairs are
+// written to stdout as TSV instead of the Debug dump.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/kc_b200.h"
+#include "../../include/kc_host.h"
+
+static void die(const char* what, kc_engine* e, int rc) {
+  std::fprintf(stderr, "%s failed (%d): %s\n", what, rc, e ? kc_last_error(e) : "");
+  std::exit(101);  // the reference panics (exit status 101)
+}
+
+int main(int argc, char** argv) {
+  std::fprintf(stderr, "We start main\n");
+  // Arguments required: input, threads (src/main.rs:54-60); options may follow
+  if (argc < 3) {
+    std::fprintf(stderr, "Requires two command line arguments: input and thread\n");
+    return 101;
+  }
+  const char* input = argv[1];
+  char* endp = nullptr;
+  const long threads = std::strtol(argv[2], &endp, 10);
+  if (!endp || *endp || threads < 0) {
+    std::fprintf(stderr, "threads argument should be of type int\n");
+    return 101;
+  }
+  kc_config cfg{};
+  cfg.k = 5;
+  cfg.device = 0;
+  cfg.threshold = 10;
+  cfg.cross_class_only = 1;
+  cfg.want_blosum = 0;
+  bool list_kmers = false;
+  for (int i = 3; i < argc; ++i) {
+    const std::string a = argv[i];
+    if (a == "--k" && i + 1 < argc) cfg.k = std::atoi(argv[++i]);
+    else if (a == "--threshold" && i + 1 < argc) cfg.threshold = (uint32_t)std::atoi(argv[++i]);
+    else if (a == "--device" && i + 1 < argc) cfg.device = std::atoi(argv[++i]);
+    else if (a == "--all-classes") cfg.cross_class_only = 0;
+    else if (a == "--blosum") cfg.want_blosum = 1;
+    else if (a == "--kmers") list_kmers = true;
+    else {
+      std::fprintf(stderr, "unknown option %s\n", a.c_str());
+      return 101;
+    }
+  }
+  kc_fasta* fa = nullptr;
+  int rc = kc_fasta_parse_file(input, (int)threads, &fa);
+  if (rc != KC_OK) {
+    std::fprintf(stderr, "input argument should refer to an existing fasta file\n");
+    return 101;
+  }
+  std::fprintf(stderr, "We created Protein structs\n");
+  kc_engine* e = nullptr;
+  rc = kc_create(&cfg, &e);
+  if (rc != KC_OK) {
+    std::fprintf(stderr, "kc_create failed (%d): no usable CUDA device or bad option\n", rc);
+    return 101;
+  }
+  const uint64_t n = kc_fasta_n_proteins(fa);
+  rc = kc_set_proteins(e, kc_fasta_residues(fa), kc_fasta_offsets(fa), kc_fasta_class_ids(fa), n);
+  if (rc) die("kc_set_proteins", e, rc);
+  kc_index_stats is{};
+  rc = kc_build_index(e, &is);
+  if (rc) die("kc_build_index", e, rc);
+  std::fprintf(stderr, "We combined k-mers\nWe found unique k-mers\nWe made unique hash\nWe can make a graph\n");
+  std::fprintf(stderr, "Number of %dmers found in at least two proteins: %llu\n", cfg.k,
+               (unsigned long long)is.n_repeated);
+  auto t0 = std::chrono::steady_clock::now();
+  kc_pair_stats ps{};
+  rc = kc_score_pairs(e, &ps);
+  if (rc) die("kc_score_pairs", e, rc);
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  std::fprintf(stderr, "Number of total edges: %llu\n", (unsigned long long)ps.n_multi_edges);
+  if (cfg.cross_class_only) {
+    std::fprintf(stderr, "Remove edges without diverging AMR labels\n");
+    std::fprintf(stderr, "Number of edges now: %llu\n", (unsigned long long)ps.n_multi_edges_kept);
+  }
+  std::fprintf(stderr, "Combine edges with the same two vertices\n");
+  std::fprintf(stderr, "Number of edges now: %llu\n", (unsigned long long)ps.n_pairs_kept);
+  std::fprintf(stderr, "Graph construction and refinement time: %g seconds\n", secs);
+  std::vector<kc_edge> edges(ps.n_edges_out);
+  rc = kc_get_edges(e, edges.data(), edges.size());
+  if (rc) die("kc_get_edges", e, rc);
+  std::printf("a\tb\tid_a\tid_b\tkmers_in_common%s%s\n", cfg.want_blosum ? "\tblosum" : "",
+              list_kmers ? "\tkmers" : "");
+  std::vector<uint32_t> kms;
+  for (size_t i = 0; i < edges.size(); ++i) {
+    const kc_edge& ed = edges[i];
+    std::fprintf(stderr, "Cross-checking:\n\treference protein:%s\n\tquery protein:%s\n\tkmers in common:%u\n",
+                 kc_fasta_id(fa, ed.a), kc_fasta_id(fa, ed.b), ed.count);
+    std::printf("%u\t%u\t%s\t%s\t%u", ed.a, ed.b, kc_fasta_id(fa, ed.a), kc_fasta_id(fa, ed.b), ed.count);
+    if (cfg.want_blosum) std::printf("\t%d", ed.blosum);
+    if (list_kmers) {
+      kms.resize(ed.count);
+      rc = kc_get_edge_kmers(e, i, kms.data(), kms.size());
+      if (rc) die("kc_get_edge_kmers", e, rc);
+      std::printf("\t");
+      for (size_t j = 0; j < kms.size(); ++j) std::printf(j ? ",%u" : "%u", kms[j]);
+    }
+    std::printf("\n");
+  }
+  kc_destroy(e);
+  kc_fasta_free(fa);
+  return 0;
+}

@@ -1,0 +1,962 @@
+// engine.cu — C ABI (include/kc_b200.h) over the sm_100a kernels.  One engine per GPU.
+// No CPU fallback: every compute entry point launches CUDA kernels or fails.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/kc_b200.h"
+#include "common.cuh"
+#include "extract.cuh"
+#include "index.cuh"
+#include "pairs.cuh"
+#include "primitives.cuh"
+
+using namespace kc;
+
+namespace {
+
+struct DBuf {  // grow-only device buffer
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t want) {
+    if (want <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    want = (want + 255) & ~size_t(255);
+    cudaError_t rc = cudaMalloc(&p, want);
+    if (rc == cudaSuccess) bytes = want;
+    return rc;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+struct DeviceScalars {  // one small block of u64 counters, zeroed per stage
+  unsigned long long n_incid, n_distinct, n_repeated, nnz, work_total, multi_total, scan_total;
+  unsigned long long edge_cursor;
+  PairCounters pc;
+  uint32_t list_counts[4];
+  uint32_t row_cursor[8];
+  uint32_t bin_counts[8];
+  uint32_t shard_rows[2];
+  uint32_t n_shared;
+  uint32_t pad;
+};
+
+enum Ev { EV_H2D0, EV_H2D1, EV_X0, EV_X1, EV_I0, EV_IC0, EV_IC1, EV_I1, EV_P0, EV_PK0, EV_PK1, EV_P1, EV_E1, EV_D0, EV_D1, EV_COUNT };
+
+}  // namespace
+
+struct kc_engine {
+  kc_config cfg{};
+  int dev = 0;
+  int num_sm = kNumSM;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  uint32_t launches = 0;
+  cudaEvent_t ev[EV_COUNT]{};
+  bool ev_set[EV_COUNT]{};
+
+  // proteins
+  uint64_t n = 0, R = 0;
+  bool have_proteins = false, have_index = false, have_pairs = false;
+  std::vector<uint64_t> h_off;
+  std::vector<uint32_t> h_cls, h_orig, h_rank, h_first_after, h_pstart, h_plen;
+  std::vector<uint32_t> h_long, h_huge;
+  std::vector<unsigned long long> h_huge_off;
+  uint32_t max_block_np2 = 0, max_block_len = 0;
+  DBuf d_res, d_off, d_kpos, d_pstart, d_plen, d_orig, d_rank, d_first_after, d_long, d_huge, d_huge_off,
+      d_huge_scratch;
+  // index
+  uint32_t universe = 0;
+  uint64_t n_words = 0;
+  kc_index_stats istats{};
+  uint64_t multi_total = 0, work_total = 0;
+  DBuf d_pk, d_ndist, d_rowlen, d_seen1, d_seen2, d_dict, d_vocab, d_freq, d_self, d_colptr, d_cursor, d_col,
+      d_suf, d_rowwork, d_lists, d_colscratch, d_workprefix;
+  // pairs
+  DBuf d_rowbin, d_edges, d_keys_a, d_keys_b, d_vals_a, d_vals_b, d_hist, d_edges_sorted;
+  uint64_t edge_cap = 0, n_edges = 0;
+  kc_pair_stats pstats{};
+  // misc
+  DBuf d_scalars, d_scan_tiles, d_tmp;
+  ScanScratch scan;
+  DeviceScalars* ds = nullptr;
+};
+
+namespace {
+
+#define KC_CUDA(e, call)                                                                      \
+  do {                                                                                        \
+    cudaError_t rc__ = (call);                                                                \
+    if (rc__ != cudaSuccess) {                                                                \
+      (e)->err = std::string(#call) + ": " + cudaGetErrorString(rc__);                        \
+      return rc__ == cudaErrorMemoryAllocation ? KC_ENOMEM : KC_ECUDA;                        \
+    }                                                                                         \
+  } while (0)
+
+#define KC_LAUNCH(e, kernel, grid, block, smem, ...)                \
+  do {                                                              \
+    ++(e)->launches;                                                \
+    kernel<<<(grid), (block), (smem), (e)->stream>>>(__VA_ARGS__);  \
+  } while (0)
+
+int fail(kc_engine* e, int code, const std::string& msg) {
+  e->err = msg;
+  return code;
+}
+
+void mark(kc_engine* e, Ev which) {
+  cudaEventRecord(e->ev[which], e->stream);
+  e->ev_set[which] = true;
+}
+
+float elapsed(kc_engine* e, Ev a, Ev b) {
+  if (!e->ev_set[a] || !e->ev_set[b]) return 0.f;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, e->ev[a], e->ev[b]) != cudaSuccess) {
+    cudaGetLastError();
+    return 0.f;
+  }
+  return ms;
+}
+
+int ensure_scan(kc_engine* e, uint64_t n_items) {
+  const uint64_t tiles = (n_items + kScanTile - 1) / kScanTile + 1;
+  if (tiles > e->scan.cap_tiles) {
+    KC_CUDA(e, e->d_scan_tiles.ensure(tiles * 8));
+    e->scan.tile_sums = e->d_scan_tiles.as<unsigned long long>();
+    e->scan.cap_tiles = tiles;
+  }
+  e->scan.total = &e->ds->scan_total;
+  return KC_OK;
+}
+
+uint32_t blocks_for(uint64_t items, uint32_t per_block, uint32_t cap) {
+  uint64_t b = (items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  return (uint32_t)std::min<uint64_t>(b, cap);
+}
+
+// ---- host-side staging shared by both kc_set_proteins flavours ---------------------------
+int stage_layout(kc_engine* e) {
+  const uint64_t n = e->n;
+  const int k = e->cfg.k;
+  const auto& off = e->h_off;
+  for (uint64_t p = 0; p < n; ++p)
+    if (off[p + 1] < off[p]) return fail(e, KC_EINVAL, "offsets must be non-decreasing");
+  if (off[0] != 0) return fail(e, KC_EINVAL, "offsets[0] must be 0");
+  e->R = off[n];
+  if (e->R >= 0xFFFF0000ull) return fail(e, KC_ETOOLARGE, "more than 2^32-65536 residues");
+  if (n >= 0xFFFFFFF0ull) return fail(e, KC_ETOOLARGE, "too many proteins");
+  // pair order: input order, or class-major (stable) when only cross-class pairs are wanted,
+  // so that the same-class holders a row must skip are one contiguous run of every posting
+  e->h_orig.resize(n);
+  e->h_rank.resize(n);
+  std::iota(e->h_orig.begin(), e->h_orig.end(), 0u);
+  e->h_first_after.clear();
+  if (e->cfg.cross_class_only) {
+    std::stable_sort(e->h_orig.begin(), e->h_orig.end(),
+                     [&](uint32_t a, uint32_t b) { return e->h_cls[a] < e->h_cls[b]; });
+    e->h_first_after.resize(n);
+    uint64_t i = 0;
+    while (i < n) {
+      uint64_t j = i;
+      while (j < n && e->h_cls[e->h_orig[j]] == e->h_cls[e->h_orig[i]]) ++j;
+      for (uint64_t r = i; r < j; ++r) e->h_first_after[r] = (uint32_t)j;
+      i = j;
+    }
+  }
+  for (uint64_t r = 0; r < n; ++r) e->h_rank[e->h_orig[r]] = (uint32_t)r;
+  e->h_pstart.resize(n);
+  e->h_plen.resize(n);
+  e->h_long.clear();
+  e->h_huge.clear();
+  e->h_huge_off.clear();
+  e->max_block_np2 = 0;
+  e->max_block_len = 0;
+  unsigned long long huge_total = 0;
+  for (uint64_t r = 0; r < n; ++r) {
+    const uint32_t p = e->h_orig[r];
+    const uint64_t len = off[p + 1] - off[p];
+    e->h_pstart[r] = (uint32_t)off[p];
+    e->h_plen[r] = (uint32_t)len;
+    if (len >= (uint64_t)k) {
+      const uint32_t npos = (uint32_t)(len - k + 1);
+      if (npos > kBlockMaxPos) {
+        e->h_huge.push_back((uint32_t)r);
+        e->h_huge_off.push_back(huge_total);
+        huge_total += next_pow2_u32(npos);
+      } else if (npos > kWarpMaxPos) {
+        e->h_long.push_back((uint32_t)r);
+        e->max_block_np2 = std::max(e->max_block_np2, next_pow2_u32(npos));
+        e->max_block_len = std::max(e->max_block_len, (uint32_t)len);
+      }
+    }
+  }
+  auto up = [&](DBuf& b, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t rc = b.ensure(std::max<size_t>(bytes, 16));
+    if (rc != cudaSuccess) return rc;
+    if (bytes == 0) return cudaSuccess;
+    return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, e->stream);
+  };
+  KC_CUDA(e, up(e->d_pstart, e->h_pstart.data(), n * 4));
+  KC_CUDA(e, up(e->d_plen, e->h_plen.data(), n * 4));
+  KC_CUDA(e, up(e->d_orig, e->h_orig.data(), n * 4));
+  KC_CUDA(e, up(e->d_rank, e->h_rank.data(), n * 4));
+  if (e->cfg.cross_class_only) KC_CUDA(e, up(e->d_first_after, e->h_first_after.data(), n * 4));
+  KC_CUDA(e, up(e->d_long, e->h_long.data(), e->h_long.size() * 4));
+  KC_CUDA(e, up(e->d_huge, e->h_huge.data(), e->h_huge.size() * 4));
+  KC_CUDA(e, up(e->d_huge_off, e->h_huge_off.data(), e->h_huge_off.size() * 8));
+  if (huge_total) KC_CUDA(e, e->d_huge_scratch.ensure(huge_total * 4));
+  e->have_proteins = true;
+  e->have_index = e->have_pairs = false;
+  return KC_OK;
+}
+
+size_t padded_res_bytes(uint64_t R) { return (size_t)((R + kTileRes - 1) / kTileRes + 1) * kTileRes; }
+
+template <int K>
+int run_extract_census(kc_engine* e) {
+  const uint32_t n = (uint32_t)e->n;
+  DeviceScalars* ds = e->ds;
+  const uint8_t* res = e->d_res.as<uint8_t>();
+  uint32_t* pk = e->d_pk.as<uint32_t>();
+  uint32_t* ndist = e->d_ndist.as<uint32_t>();
+  uint32_t* s1 = e->d_seen1.as<uint32_t>();
+  uint32_t* s2 = e->d_seen2.as<uint32_t>();
+  if (n) {
+    const uint32_t grid = blocks_for(n, kExtractWarps, e->num_sm * 5);
+    KC_LAUNCH(e, extract_dedup_warp_kernel<K>, grid, kExtractWarps * 32, 0, res, e->d_pstart.as<uint32_t>(),
+              e->d_plen.as<uint32_t>(), n, pk, ndist, s1, s2, &ds->n_incid);
+  }
+  if (!e->h_long.empty()) {
+    const size_t smem = (size_t)e->max_block_np2 * 4 + e->max_block_len + 16;
+    KC_CUDA(e, cudaFuncSetAttribute(extract_dedup_block_kernel<K, false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KC_LAUNCH(e, (extract_dedup_block_kernel<K, false>), (uint32_t)e->h_long.size(), 512, smem, res,
+              e->d_pstart.as<uint32_t>(), e->d_plen.as<uint32_t>(), e->d_long.as<uint32_t>(), nullptr, nullptr,
+              pk, ndist, s1, s2, &ds->n_incid);
+  }
+  if (!e->h_huge.empty()) {
+    KC_LAUNCH(e, (extract_dedup_block_kernel<K, true>), (uint32_t)e->h_huge.size(), 512, 0, res,
+              e->d_pstart.as<uint32_t>(), e->d_plen.as<uint32_t>(), e->d_huge.as<uint32_t>(),
+              e->d_huge_off.as<unsigned long long>(), e->d_huge_scratch.as<uint32_t>(), pk, ndist, s1, s2,
+              &ds->n_incid);
+  }
+  return KC_OK;
+}
+
+template <int K>
+int run_positions(kc_engine* e, uint32_t* out) {
+  const uint32_t grid = (uint32_t)((e->R + kTileRes - 1) / kTileRes);
+  if (grid)
+    KC_LAUNCH(e, kmers_per_position_kernel<K>, grid, 256, 0, e->d_res.as<uint8_t>(), e->R,
+              e->d_off.as<unsigned long long>(), e->d_kpos.as<unsigned long long>(), (uint32_t)e->n, out);
+  return KC_OK;
+}
+
+template <int LOG_H, int GROUP_WARPS, int CTA_WARPS>
+int launch_hash(kc_engine* e, uint8_t bin, const EdgeSink& sink) {
+  constexpr size_t smem = (size_t)(CTA_WARPS / GROUP_WARPS) * 2 * (1u << LOG_H) * 4;
+  auto kern = pairs_hash_kernel<LOG_H, GROUP_WARPS, CTA_WARPS>;
+  KC_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CTA_WARPS * 32, smem));
+  if (per_sm < 1) per_sm = 1;
+  const uint32_t grid = (uint32_t)(e->num_sm * per_sm);
+  KC_LAUNCH(e, kern, grid, CTA_WARPS * 32, smem, e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(),
+            e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), e->d_rowbin.as<uint8_t>(), bin, (uint32_t)e->n,
+            &e->ds->row_cursor[bin], sink, &e->ds->pc);
+  return KC_OK;
+}
+
+__global__ void shard_bounds_kernel(const unsigned long long* __restrict__ prefix, uint32_t n, uint32_t shard,
+                                    uint32_t n_shards, uint32_t* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const unsigned long long total = prefix[n];
+  for (int side = 0; side < 2; ++side) {
+    const uint32_t s = shard + side;
+    uint32_t row;
+    if (s == 0) row = 0;
+    else if (s >= n_shards) row = n;
+    else {
+      // first row whose prefix reaches total * s / n_shards
+      const unsigned long long target = total / n_shards * s + (total % n_shards) * s / n_shards;
+      uint32_t lo = 0, hi = n;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (prefix[mid] < target) lo = mid + 1; else hi = mid;
+      }
+      row = lo;
+    }
+    out[side] = row;
+  }
+}
+
+struct WorkIn {
+  const uint32_t* rowwork;
+  const uint32_t* rowlen;
+  __device__ unsigned long long operator()(uint64_t i) const {
+    return (unsigned long long)rowwork[i] + 2ull * rowlen[i] + (rowwork[i] ? 64ull : 0ull);
+  }
+};
+struct U64ExclOut {
+  unsigned long long* p;
+  __device__ void operator()(uint64_t i, unsigned long long excl, unsigned long long v) const {
+    p[i] = excl;
+    (void)v;
+  }
+};
+struct U64ExclOutWithTail {
+  unsigned long long* p;
+  uint64_t n;
+  __device__ void operator()(uint64_t i, unsigned long long excl, unsigned long long v) const {
+    p[i] = excl;
+    if (i + 1 == n) p[n] = excl + v;
+  }
+};
+struct ColptrOut {
+  uint32_t* p;
+  __device__ void operator()(uint64_t i, unsigned long long excl, unsigned long long) const {
+    p[i] = (uint32_t)excl;
+  }
+};
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+int kc_abi_version(void) { return KC_ABI_VERSION; }
+
+int kc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int kc_create(const kc_config* cfg, kc_engine** out) {
+  if (!cfg || !out) return KC_EINVAL;
+  *out = nullptr;
+  if (cfg->k != 5 && cfg->k != 7) return KC_EINVAL;  // src/tree.rs:104 panics on anything else
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return KC_ENODEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return KC_ENODEVICE;
+  kc_engine* e = new kc_engine();
+  e->cfg = *cfg;
+  e->dev = cfg->device;
+  if (cudaSetDevice(e->dev) != cudaSuccess) {
+    delete e;
+    return KC_ENODEVICE;
+  }
+  cudaDeviceProp prop{};
+  cudaGetDeviceProperties(&prop, e->dev);
+  e->num_sm = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : kNumSM;
+  e->smem_optin = prop.sharedMemPerBlockOptin;
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete e;
+    return KC_ECUDA;
+  }
+  e->own_stream = true;
+  for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&e->ev[i]);
+  // residue LUT: src/protein.rs:9-13 order, everything else -> 20 (src/protein.rs:49-54)
+  uint8_t lut[256];
+  std::memset(lut, 20, sizeof(lut));
+  const char* alphabet = "CSTAGPDEQNHRKMILVWYF*";
+  for (int i = 0; i < 21; ++i) lut[(unsigned char)alphabet[i]] = (uint8_t)i;
+  if (cudaMemcpyToSymbol(c_residue_lut, lut, 256) != cudaSuccess ||
+      e->d_scalars.ensure(sizeof(DeviceScalars)) != cudaSuccess) {
+    kc_destroy(e);
+    return KC_ECUDA;
+  }
+  e->ds = e->d_scalars.as<DeviceScalars>();
+  cudaMemset(e->ds, 0, sizeof(DeviceScalars));
+  e->universe = pow21(cfg->k);
+  e->n_words = ((uint64_t)e->universe + 31) / 32;
+  *out = e;
+  return KC_OK;
+}
+
+void kc_destroy(kc_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->dev);
+  cudaDeviceSynchronize();
+  DBuf* all[] = {&e->d_res, &e->d_off, &e->d_kpos, &e->d_pstart, &e->d_plen, &e->d_orig, &e->d_rank,
+                 &e->d_first_after, &e->d_long, &e->d_huge, &e->d_huge_off, &e->d_huge_scratch, &e->d_pk,
+                 &e->d_ndist, &e->d_rowlen, &e->d_seen1, &e->d_seen2, &e->d_dict, &e->d_vocab, &e->d_freq,
+                 &e->d_self, &e->d_colptr, &e->d_cursor, &e->d_col, &e->d_suf, &e->d_rowwork, &e->d_lists,
+                 &e->d_colscratch, &e->d_workprefix, &e->d_rowbin, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
+                 &e->d_vals_a, &e->d_vals_b, &e->d_hist, &e->d_edges_sorted, &e->d_scalars, &e->d_scan_tiles,
+                 &e->d_tmp};
+  for (DBuf* b : all) b->release();
+  for (int i = 0; i < EV_COUNT; ++i)
+    if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+const char* kc_last_error(const kc_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+int kc_set_stream(kc_engine* e, void* cuda_stream) {
+  if (!e) return KC_EINVAL;
+  cudaSetDevice(e->dev);
+  cudaStreamSynchronize(e->stream);
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  e->own_stream = false;
+  if (cuda_stream) {
+    e->stream = (cudaStream_t)cuda_stream;
+  } else {
+    KC_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->own_stream = true;
+  }
+  return KC_OK;
+}
+
+int kc_set_proteins(kc_engine* e, const uint8_t* residues, const uint64_t* offsets, const uint32_t* class_id,
+                    uint64_t n) {
+  if (!e || !offsets || (n && !class_id)) return KC_EINVAL;
+  KC_CUDA(e, cudaSetDevice(e->dev));
+  e->n = n;
+  e->h_off.assign(offsets, offsets + n + 1);
+  e->h_cls.assign(class_id, class_id + n);
+  const uint64_t R = offsets[n];
+  if (R && !residues) return fail(e, KC_EINVAL, "null residues");
+  if (R >= 0xFFFF0000ull) return fail(e, KC_ETOOLARGE, "more than 2^32-65536 residues");
+  mark(e, EV_H2D0);
+  const size_t padded = padded_res_bytes(R);
+  KC_CUDA(e, e->d_res.ensure(padded));
+  if (R) KC_CUDA(e, cudaMemcpyAsync(e->d_res.p, residues, R, cudaMemcpyHostToDevice, e->stream));
+  KC_CUDA(e, cudaMemsetAsync(e->d_res.as<uint8_t>() + R, 0, padded - R, e->stream));
+  KC_CUDA(e, e->d_off.ensure((n + 1) * 8));
+  KC_CUDA(e, cudaMemcpyAsync(e->d_off.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+  int rc = stage_layout(e);
+  mark(e, EV_H2D1);
+  return rc;
+}
+
+int kc_set_proteins_device(kc_engine* e, const uint8_t* d_residues, const uint64_t* d_offsets,
+                           const uint32_t* d_class_id, uint64_t n) {
+  if (!e || !d_offsets || (n && !d_class_id)) return KC_EINVAL;
+  KC_CUDA(e, cudaSetDevice(e->dev));
+  e->n = n;
+  e->h_off.resize(n + 1);
+  e->h_cls.resize(n);
+  // the layout tables (pair order, length classes) are derived on the host from the offsets
+  // and classes: 12 bytes per protein come back, the residues stay in HBM
+  KC_CUDA(e, cudaMemcpyAsync(e->h_off.data(), d_offsets, (n + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (n) KC_CUDA(e, cudaMemcpyAsync(e->h_cls.data(), d_class_id, n * 4, cudaMemcpyDeviceToHost, e->stream));
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  const uint64_t R = e->h_off[n];
+  if (R >= 0xFFFF0000ull) return fail(e, KC_ETOOLARGE, "more than 2^32-65536 residues");
+  mark(e, EV_H2D0);
+  const size_t padded = padded_res_bytes(R);
+  KC_CUDA(e, e->d_res.ensure(padded));
+  if (R) KC_CUDA(e, cudaMemcpyAsync(e->d_res.p, d_residues, R, cudaMemcpyDeviceToDevice, e->stream));
+  KC_CUDA(e, cudaMemsetAsync(e->d_res.as<uint8_t>() + R, 0, padded - R, e->stream));
+  KC_CUDA(e, e->d_off.ensure((n + 1) * 8));
+  KC_CUDA(e, cudaMemcpyAsync(e->d_off.p, d_offsets, (n + 1) * 8, cudaMemcpyDeviceToDevice, e->stream));
+  int rc = stage_layout(e);
+  mark(e, EV_H2D1);
+  return rc;
+}
+
+int kc_extract_kmers(kc_engine* e, uint32_t* kmers_out, uint64_t capacity, uint64_t* n_positions) {
+  if (!e) return KC_EINVAL;
+  if (!e->have_proteins) return fail(e, KC_EINVAL, "kc_set_proteins first");
+  KC_CUDA(e, cudaSetDevice(e->dev));
+  const uint64_t n = e->n;
+  const int k = e->cfg.k;
+  std::vector<unsigned long long> kpos(n + 1, 0);
+  for (uint64_t p = 0; p < n; ++p) {
+    const uint64_t len = e->h_off[p + 1] - e->h_off[p];
+    kpos[p + 1] = kpos[p] + (len >= (uint64_t)k ? len - k + 1 : 0);
+  }
+  const uint64_t npos = kpos[n];
+  if (n_positions) *n_positions = npos;
+  if (kmers_out && capacity < npos) return fail(e, KC_EINVAL, "kmers_out capacity too small");
+  KC_CUDA(e, e->d_kpos.ensure((n + 1) * 8));
+  KC_CUDA(e, cudaMemcpyAsync(e->d_kpos.p, kpos.data(), (n + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+  KC_CUDA(e, e->d_tmp.ensure(std::max<uint64_t>(npos, 4) * 4));
+  mark(e, EV_X0);
+  int rc = k == 5 ? run_positions<5>(e, e->d_tmp.as<uint32_t>()) : run_positions<7>(e, e->d_tmp.as<uint32_t>());
+  mark(e, EV_X1);
+  if (rc) return rc;
+  KC_CUDA(e, cudaGetLastError());
+  if (kmers_out && npos)
+    KC_CUDA(e, cudaMemcpyAsync(kmers_out, e->d_tmp.p, npos * 4, cudaMemcpyDeviceToHost, e->stream));
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  return KC_OK;
+}
+
+int kc_build_index(kc_engine* e, kc_index_stats* stats) {
+  if (!e) return KC_EINVAL;
+  if (!e->have_proteins) return fail(e, KC_EINVAL, "kc_set_proteins first");
+  KC_CUDA(e, cudaSetDevice(e->dev));
+  const uint32_t n = (uint32_t)e->n;
+  const uint64_t R = e->R, W = e->n_words;
+  DeviceScalars* ds = e->ds;
+  e->have_index = e->have_pairs = false;
+  KC_CUDA(e, e->d_pk.ensure((R + 64) * 4));
+  KC_CUDA(e, e->d_ndist.ensure(((uint64_t)n + 1) * 4));
+  KC_CUDA(e, e->d_rowlen.ensure(((uint64_t)n + 1) * 4));
+  KC_CUDA(e, e->d_seen1.ensure(W * 4));
+  KC_CUDA(e, e->d_seen2.ensure(W * 4));
+  KC_CUDA(e, e->d_dict.ensure(W * 8));
+  int rc = ensure_scan(e, std::max<uint64_t>(W, (uint64_t)n + 1));
+  if (rc) return rc;
+
+  mark(e, EV_I0);
+  KC_CUDA(e, cudaMemsetAsync(e->d_seen1.p, 0, W * 4, e->stream));
+  KC_CUDA(e, cudaMemsetAsync(e->d_seen2.p, 0, W * 4, e->stream));
+  KC_CUDA(e, cudaMemsetAsync(ds, 0, sizeof(DeviceScalars), e->stream));
+  // positions are known on the host
+  unsigned long long n_positions = 0;
+  for (uint32_t r = 0; r < n; ++r)
+    if (e->h_plen[r] >= (uint32_t)e->cfg.k) n_positions += e->h_plen[r] - e->cfg.k + 1;
+
+  // K1-K3: extract, per-protein dedup, census bitmaps
+  mark(e, EV_IC0);
+  rc = e->cfg.k == 5 ? run_extract_census<5>(e) : run_extract_census<7>(e);
+  mark(e, EV_IC1);
+  if (rc) return rc;
+  // K4: rank dictionary over "held by >= 2 proteins"
+  e->launches += exclusive_scan(PopcIn{e->d_seen2.as<uint32_t>()},
+                                DictOut{e->d_seen2.as<uint32_t>(), e->d_dict.as<uint2>()}, W, e->scan, e->stream);
+  KC_CUDA(e, cudaMemcpyAsync(&ds->n_repeated, &ds->scan_total, 8, cudaMemcpyDeviceToDevice, e->stream));
+  KC_LAUNCH(e, popc_reduce_kernel, blocks_for(W, 256 * 8, e->num_sm * 8), 256, 0, e->d_seen1.as<uint32_t>(), W,
+            &ds->n_distinct);
+  DeviceScalars hs{};
+  KC_CUDA(e, cudaMemcpyAsync(&hs, ds, sizeof(hs), cudaMemcpyDeviceToHost, e->stream));
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  KC_CUDA(e, cudaGetLastError());
+  const uint64_t V = hs.n_repeated, n_incid = hs.n_incid;
+  if (V >= 0xFFFFFFF0ull || n_incid >= 0xFFFFFFF0ull) return fail(e, KC_ETOOLARGE, "index too large");
+
+  KC_CUDA(e, e->d_vocab.ensure((V + 1) * 4));
+  KC_CUDA(e, e->d_freq.ensure((V + 1) * 4));
+  KC_CUDA(e, e->d_self.ensure(V + 16));
+  KC_CUDA(e, e->d_colptr.ensure((V + 2) * 4));
+  KC_CUDA(e, e->d_cursor.ensure((V + 2) * 4));
+  KC_CUDA(e, e->d_col.ensure((n_incid + 64) * 4));
+  KC_CUDA(e, e->d_suf.ensure((R + 64) * 8));
+  KC_CUDA(e, e->d_rowwork.ensure(((uint64_t)n + 1) * 4));
+  KC_CUDA(e, e->d_workprefix.ensure(((uint64_t)n + 2) * 8));
+  const uint64_t list_cap = n_incid / 33 + 16;
+  KC_CUDA(e, e->d_lists.ensure(list_cap * 3 * 4));
+  rc = ensure_scan(e, std::max<uint64_t>(V + 1, (uint64_t)n + 1));
+  if (rc) return rc;
+  KC_CUDA(e, cudaMemsetAsync(e->d_freq.p, 0, (V + 1) * 4, e->stream));
+
+  if (V) {
+    KC_LAUNCH(e, expand_bitmap_kernel, blocks_for(W, 256, e->num_sm * 16), 256, 0, e->d_dict.as<uint2>(), W,
+              e->d_vocab.as<uint32_t>(), e->d_self.as<uint8_t>(), e->cfg.k);
+  }
+  // K5: ids (in place over the distinct k-mers), row lengths, kmer_freq
+  const uint32_t warp_grid = blocks_for(n, 8, e->num_sm * 8);
+  if (n)
+    KC_LAUNCH(e, ids_freq_kernel, warp_grid, 256, 0, e->d_dict.as<uint2>(), e->d_pstart.as<uint32_t>(),
+              e->d_ndist.as<uint32_t>(), n, e->d_pk.as<uint32_t>(), e->d_rowlen.as<uint32_t>(),
+              e->d_freq.as<uint32_t>(), &ds->nnz);
+  // postings: colptr = exclusive scan of freq, fill, sort every column by protein rank
+  e->launches += exclusive_scan(U32In{e->d_freq.as<uint32_t>()}, ColptrOut{e->d_colptr.as<uint32_t>()}, V + 1,
+                                e->scan, e->stream);
+  KC_CUDA(e, cudaMemcpyAsync(e->d_cursor.p, e->d_colptr.p, (V + 1) * 4, cudaMemcpyDeviceToDevice, e->stream));
+  if (n && V) {
+    KC_LAUNCH(e, postings_fill_kernel, warp_grid, 256, 0, e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(),
+              n, e->d_pk.as<uint32_t>(), e->d_cursor.as<uint32_t>(), e->d_col.as<uint32_t>());
+    uint32_t* lists = e->d_lists.as<uint32_t>();
+    KC_LAUNCH(e, postings_sort_small_kernel, blocks_for(V, 256, e->num_sm * 8), 256, 0,
+              e->d_colptr.as<uint32_t>(), (uint32_t)V, e->d_col.as<uint32_t>(), lists, lists + list_cap,
+              lists + 2 * list_cap, ds->list_counts);
+    if (n > 32) {
+      KC_LAUNCH(e, postings_sort_mid_kernel, e->num_sm * 8, 128, 0, e->d_colptr.as<uint32_t>(), lists,
+                ds->list_counts, e->d_col.as<uint32_t>());
+    }
+    if (n > kColWarpMax) {
+      const uint32_t np2 = std::min<uint32_t>(next_pow2_u32(n), kColBlockMax);
+      const size_t smem = (size_t)np2 * 4;
+      KC_CUDA(e, cudaFuncSetAttribute(postings_sort_big_kernel<false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      KC_LAUNCH(e, postings_sort_big_kernel<false>, e->num_sm, 512, smem, e->d_colptr.as<uint32_t>(),
+                lists + list_cap, ds->list_counts, 1, e->d_col.as<uint32_t>(), nullptr, 0u);
+    }
+    if (n > kColBlockMax) {
+      const uint32_t stride = next_pow2_u32(n);
+      const uint32_t ctas = 32;
+      KC_CUDA(e, e->d_colscratch.ensure((size_t)stride * ctas * 4));
+      KC_LAUNCH(e, postings_sort_big_kernel<true>, ctas, 512, 0, e->d_colptr.as<uint32_t>(), lists + 2 * list_cap,
+                ds->list_counts, 2, e->d_col.as<uint32_t>(), e->d_colscratch.as<uint32_t>(), stride);
+    }
+    KC_LAUNCH(e, multi_edge_total_kernel, blocks_for(V, 256 * 4, e->num_sm * 4), 256, 0, e->d_freq.as<uint32_t>(),
+              (uint32_t)V, &ds->multi_total);
+    KC_LAUNCH(e, suffix_ranges_kernel, warp_grid, 256, 0, e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(), n,
+              e->d_pk.as<uint32_t>(), e->d_colptr.as<uint32_t>(), e->d_col.as<uint32_t>(),
+              e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr, e->d_suf.as<uint2>(),
+              e->d_rowwork.as<uint32_t>(), &ds->work_total);
+  } else if (n) {
+    KC_CUDA(e, cudaMemsetAsync(e->d_rowwork.p, 0, (uint64_t)n * 4, e->stream));
+  }
+  // work prefix for the shard partition
+  if (n) {
+    e->launches += exclusive_scan(WorkIn{e->d_rowwork.as<uint32_t>(), e->d_rowlen.as<uint32_t>()},
+                                  U64ExclOutWithTail{e->d_workprefix.as<unsigned long long>(), n}, n, e->scan,
+                                  e->stream);
+  }
+  mark(e, EV_I1);
+  KC_CUDA(e, cudaMemcpyAsync(&hs, ds, sizeof(hs), cudaMemcpyDeviceToHost, e->stream));
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  KC_CUDA(e, cudaGetLastError());
+  e->istats.n_positions = n_positions;
+  e->istats.n_incidences = n_incid;
+  e->istats.n_distinct = hs.n_distinct;
+  e->istats.n_repeated = V;
+  e->istats.n_singleton = hs.n_distinct - V;
+  e->istats.nnz = hs.nnz;
+  e->multi_total = hs.multi_total;
+  e->work_total = hs.work_total;
+  if (stats) *stats = e->istats;
+  e->have_index = true;
+  return KC_OK;
+}
+
+int kc_get_distinct_kmers(kc_engine* e, uint32_t* out, uint64_t capacity) {
+  if (!e || !out) return KC_EINVAL;
+  if (!e->have_index) return fail(e, KC_EINVAL, "kc_build_index first");
+  if (capacity < e->istats.n_distinct) return fail(e, KC_EINVAL, "capacity too small");
+  KC_CUDA(e, cudaSetDevice(e->dev));
+  const uint64_t W = e->n_words, D = e->istats.n_distinct;
+  DBuf dict1, list;
+  cudaError_t a = dict1.ensure(W * 8), b = list.ensure((D + 1) * 4);
+  if (a != cudaSuccess || b != cudaSuccess) {
+    dict1.release();
+    list.release();
+    return fail(e, KC_ENOMEM, "out of device memory");
+  }
+  e->launches += exclusive_scan(PopcIn{e->d_seen1.as<uint32_t>()},
+                                DictOut{e->d_seen1.as<uint32_t>(), dict1.as<uint2>()}, W, e->scan, e->stream);
+  KC_LAUNCH(e, expand_bitmap_kernel, blocks_for(W, 256, e->num_sm * 16), 256, 0, dict1.as<uint2>(), W,
+            list.as<uint32_t>(), nullptr, e->cfg.k);
+  cudaError_t rc = cudaMemcpyAsync(out, list.p, D * 4, cudaMemcpyDeviceToHost, e->stream);
+  if (rc == cudaSuccess) rc = cudaStreamSynchronize(e->stream);
+  dict1.release();
+  list.release();
+  KC_CUDA(e, rc);
+  return KC_OK;
+}
+
+int kc_get_vocab(kc_engine* e, uint32_t* kmers_out, uint32_t* freq_out, uint64_t capacity) {
+  if (!e) return KC_EINVAL;
+  if (!e->have_index) return fail(e, KC_EINVAL, "kc_build_index first");
+  const uint64_t V = e->istats.n_repeated;
+  if (capacity < V) return fail(e, KC_EINVAL, "capacity too small");
+  KC_CUDA(e, cudaSetDevice(e->dev));
+  if (kmers_out && V) KC_CUDA(e, cudaMemcpyAsync(kmers_out, e->d_vocab.p, V * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (freq_out && V) KC_CUDA(e, cudaMemcpyAsync(freq_out, e->d_freq.p, V * 4, cudaMemcpyDeviceToHost, e->stream));
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  return KC_OK;
+}
+
+int kc_get_protein_ids(kc_engine* e, uint64_t* row_offsets, uint32_t* ids_out, uint64_t capacity) {
+  if (!e || !row_offsets) return KC_EINVAL;
+  if (!e->have_index) return fail(e, KC_EINVAL, "kc_build_index first");
+  KC_CUDA(e, cudaSetDevice(e->dev));
+  const uint32_t n = (uint32_t)e->n;
+  std::vector<uint32_t> rowlen(n);
+  if (n) KC_CUDA(e, cudaMemcpyAsync(rowlen.data(), e->d_rowlen.p, (uint64_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  row_offsets[0] = 0;
+  for (uint32_t p = 0; p < n; ++p) row_offsets[p + 1] = row_offsets[p] + rowlen[e->h_rank[p]];
+  const uint64_t nnz = row_offsets[n];
+  if (!ids_out) return KC_OK;
+  if (capacity < nnz) return fail(e, KC_EINVAL, "capacity too small");
+  if (!nnz) return KC_OK;
+  DBuf d_ro, d_out;
+  cudaError_t a = d_ro.ensure(((uint64_t)n + 1) * 8), b = d_out.ensure(nnz * 4);
+  if (a != cudaSuccess || b != cudaSuccess) {
+    d_ro.release();
+    d_out.release();
+    return fail(e, KC_ENOMEM, "out of device memory");
+  }
+  cudaMemcpyAsync(d_ro.p, row_offsets, ((uint64_t)n + 1) * 8, cudaMemcpyHostToDevice, e->stream);
+  KC_LAUNCH(e, compact_rows_kernel, blocks_for(n, 8, e->num_sm * 8), 256, 0, e->d_pstart.as<uint32_t>(),
+            e->d_rowlen.as<uint32_t>(), d_ro.as<unsigned long long>(), e->d_rank.as<uint32_t>(), n,
+            e->d_pk.as<uint32_t>(), d_out.as<uint32_t>());
+  cudaError_t rc = cudaMemcpyAsync(ids_out, d_out.p, nnz * 4, cudaMemcpyDeviceToHost, e->stream);
+  if (rc == cudaSuccess) rc = cudaStreamSynchronize(e->stream);
+  d_ro.release();
+  d_out.release();
+  KC_CUDA(e, rc);
+  return KC_OK;
+}
+
+int kc_lookup_kmers(kc_engine* e, const uint32_t* kmers, uint64_t n, uint32_t* ids_out) {
+  if (!e || (n && (!kmers || !ids_out))) return KC_EINVAL;
+  if (!e->have_index) return fail(e, KC_EINVAL, "kc_build_index first");
+  if (!n) return KC_OK;
+  KC_CUDA(e, cudaSetDevice(e->dev));
+  KC_CUDA(e, e->d_tmp.ensure(n * 8));
+  uint32_t* d_in = e->d_tmp.as<uint32_t>();
+  uint32_t* d_out = d_in + n;
+  KC_CUDA(e, cudaMemcpyAsync(d_in, kmers, n * 4, cudaMemcpyHostToDevice, e->stream));
+  KC_LAUNCH(e, lookup_kernel, blocks_for(n, 256, e->num_sm * 8), 256, 0, e->d_dict.as<uint2>(), d_in, n,
+            e->universe, d_out);
+  KC_CUDA(e, cudaMemcpyAsync(ids_out, d_out, n * 4, cudaMemcpyDeviceToHost, e->stream));
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  return KC_OK;
+}
+
+int kc_score_pairs(kc_engine* e, kc_pair_stats* stats) { return kc_score_pairs_shard(e, 0, 1, stats); }
+
+int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pair_stats* stats) {
+  if (!e || n_shards == 0 || shard >= n_shards) return KC_EINVAL;
+  if (!e->have_index) return fail(e, KC_EINVAL, "kc_build_index first");
+  KC_CUDA(e, cudaSetDevice(e->dev));
+  const uint32_t n = (uint32_t)e->n;
+  DeviceScalars* ds = e->ds;
+  e->have_pairs = false;
+  e->n_edges = 0;
+  kc_pair_stats ps{};
+  ps.n_multi_edges = e->multi_total;
+  if (n == 0 || e->istats.n_repeated == 0) {
+    e->pstats = ps;
+    if (stats) *stats = ps;
+    e->have_pairs = true;
+    mark(e, EV_P0);
+    mark(e, EV_PK0);
+    mark(e, EV_PK1);
+    mark(e, EV_P1);
+    mark(e, EV_E1);
+    return KC_OK;
+  }
+  KC_CUDA(e, e->d_rowbin.ensure((uint64_t)n + 64));
+  if (e->edge_cap == 0) {
+    e->edge_cap = e->cfg.max_edges ? e->cfg.max_edges : (1ull << 22);
+    KC_CUDA(e, e->d_edges.ensure(e->edge_cap * 16));
+  }
+  // dense accumulators: u16 unless some row could exceed it
+  uint32_t max_rowlen = 0;
+  for (uint32_t r = 0; r < n; ++r) max_rowlen = std::max(max_rowlen, e->h_plen[r]);
+  const bool wide = max_rowlen >= 65535u;
+  const size_t dense_budget = std::min<size_t>(e->smem_optin ? e->smem_optin : 48 * 1024, 200 * 1024);
+  const uint32_t dense_cap_cols = (uint32_t)((dense_budget - 64) / (wide ? 4 : 2)) & ~7u;
+  const uint32_t dense_cols = std::min<uint32_t>(dense_cap_cols, (n + 7u) & ~7u);
+  const size_t dense_smem = (size_t)(wide ? dense_cols : (dense_cols + 1) / 2) * 4 + 16;
+
+  mark(e, EV_P0);
+  for (int attempt = 0;; ++attempt) {
+    KC_CUDA(e, cudaMemsetAsync(&ds->edge_cursor, 0,
+                               sizeof(DeviceScalars) - offsetof(DeviceScalars, edge_cursor), e->stream));
+    KC_LAUNCH(e, shard_bounds_kernel, 1, 32, 0, e->d_workprefix.as<unsigned long long>(), n, shard, n_shards,
+              ds->shard_rows);
+    KC_LAUNCH(e, classify_rows_kernel, (n + 255) / 256, 256, 0, e->d_rowwork.as<uint32_t>(),
+              e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr, n, ds->shard_rows, dense_cols,
+              e->d_rowbin.as<uint8_t>(), ds->bin_counts);
+    EdgeSink sink{e->d_edges.as<uint4>(), &ds->edge_cursor, e->edge_cap, e->cfg.threshold};
+    mark(e, EV_PK0);
+    int rc;
+    if ((rc = launch_hash<8, 1, 8>(e, kBinHash8, sink))) return rc;
+    if ((rc = launch_hash<9, 1, 8>(e, kBinHash9, sink))) return rc;
+    if ((rc = launch_hash<10, 1, 8>(e, kBinHash10, sink))) return rc;
+    if ((rc = launch_hash<11, 1, 4>(e, kBinHash11, sink))) return rc;
+    if ((rc = launch_hash<12, 1, 4>(e, kBinHash12, sink))) return rc;
+    if ((rc = launch_hash<14, 8, 8>(e, kBinHash14, sink))) return rc;
+    {
+      int per_sm = 1;
+      if (wide) {
+        KC_CUDA(e, cudaFuncSetAttribute(pairs_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)dense_smem));
+        KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairs_dense_kernel<true>, 256, dense_smem));
+      } else {
+        KC_CUDA(e, cudaFuncSetAttribute(pairs_dense_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)dense_smem));
+        KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairs_dense_kernel<false>, 256, dense_smem));
+      }
+      if (per_sm < 1) per_sm = 1;
+      const uint32_t grid = (uint32_t)(e->num_sm * per_sm);
+      const uint32_t* fa = e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr;
+      if (wide)
+        KC_LAUNCH(e, pairs_dense_kernel<true>, grid, 256, dense_smem, e->d_pstart.as<uint32_t>(),
+                  e->d_rowlen.as<uint32_t>(), e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), fa,
+                  e->d_rowbin.as<uint8_t>(), n, dense_cols, &ds->row_cursor[kBinDense], sink, &ds->pc);
+      else
+        KC_LAUNCH(e, pairs_dense_kernel<false>, grid, 256, dense_smem, e->d_pstart.as<uint32_t>(),
+                  e->d_rowlen.as<uint32_t>(), e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), fa,
+                  e->d_rowbin.as<uint8_t>(), n, dense_cols, &ds->row_cursor[kBinDense], sink, &ds->pc);
+    }
+    mark(e, EV_PK1);
+    DeviceScalars hs{};
+    KC_CUDA(e, cudaMemcpyAsync(&hs, ds, sizeof(hs), cudaMemcpyDeviceToHost, e->stream));
+    KC_CUDA(e, cudaStreamSynchronize(e->stream));
+    KC_CUDA(e, cudaGetLastError());
+    if (hs.edge_cursor > e->edge_cap) {  // grow to the exact need and score again
+      if (attempt >= 2) return fail(e, KC_ECUDA, "edge buffer did not converge");
+      e->edge_cap = hs.edge_cursor + (hs.edge_cursor >> 4) + 1024;
+      e->d_edges.release();
+      KC_CUDA(e, e->d_edges.ensure(e->edge_cap * 16));
+      ps.n_retries++;
+      continue;
+    }
+    ps.n_pairs_kept = hs.pc.n_pairs;
+    ps.n_edges_out = hs.pc.n_edges;
+    ps.sum_count_out = hs.pc.sum_count;
+    ps.n_rows = hs.shard_rows[1] - hs.shard_rows[0];
+    e->n_edges = hs.edge_cursor;
+    ps.n_multi_edges_kept = hs.pc.n_multi;
+    break;
+  }
+  mark(e, EV_P1);
+  const uint64_t ne = e->n_edges;
+  // K9 + canonical order
+  if (ne) {
+    if (e->cfg.want_blosum)
+      KC_LAUNCH(e, edge_blosum_kernel, blocks_for(ne, 8, e->num_sm * 8), 256, 0, e->d_edges.as<uint4>(), ne,
+                e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(), e->d_pk.as<uint32_t>(),
+                e->d_self.as<uint8_t>());
+    KC_CUDA(e, e->d_keys_a.ensure(ne * 8));
+    KC_CUDA(e, e->d_keys_b.ensure(ne * 8));
+    KC_CUDA(e, e->d_vals_a.ensure(ne * 8));
+    KC_CUDA(e, e->d_vals_b.ensure(ne * 8));
+    const uint32_t nb = (uint32_t)((ne + kRsTile - 1) / kRsTile);
+    KC_CUDA(e, e->d_hist.ensure((size_t)nb * 256 * 4));
+    int rc = ensure_scan(e, (uint64_t)nb * 256);
+    if (rc) return rc;
+    KC_CUDA(e, e->d_edges_sorted.ensure(ne * 16));
+    KC_LAUNCH(e, finalize_edges_kernel, blocks_for(ne, 256, e->num_sm * 8), 256, 0, e->d_edges.as<uint4>(), ne,
+              e->d_orig.as<uint32_t>(), e->d_keys_a.as<unsigned long long>(), e->d_vals_a.as<unsigned long long>());
+    int nbits = 1;
+    while ((1ull << nbits) < (uint64_t)n) ++nbits;
+    int passes[8], np = 0;
+    for (int s = 0; s < nbits; s += 8) passes[np++] = s;
+    for (int s = 0; s < nbits; s += 8) passes[np++] = 32 + s;
+    int in_b = 0;
+    e->launches += radix_sort_pairs(e->d_keys_a.as<unsigned long long>(), e->d_vals_a.as<unsigned long long>(),
+                                    e->d_keys_b.as<unsigned long long>(), e->d_vals_b.as<unsigned long long>(), ne,
+                                    passes, np, e->d_hist.as<uint32_t>(), e->scan, e->stream, &in_b);
+    KC_LAUNCH(e, assemble_edges_kernel, blocks_for(ne, 256, e->num_sm * 8), 256, 0,
+              (in_b ? e->d_keys_b : e->d_keys_a).as<unsigned long long>(),
+              (in_b ? e->d_vals_b : e->d_vals_a).as<unsigned long long>(), ne, e->d_edges_sorted.as<uint4>());
+  }
+  mark(e, EV_E1);
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  KC_CUDA(e, cudaGetLastError());
+  e->pstats = ps;
+  e->have_pairs = true;
+  if (stats) *stats = e->pstats;
+  return KC_OK;
+}
+
+int kc_get_edges(kc_engine* e, kc_edge* out, uint64_t capacity) {
+  if (!e) return KC_EINVAL;
+  if (!e->have_pairs) return fail(e, KC_EINVAL, "kc_score_pairs first");
+  if (capacity < e->n_edges) return fail(e, KC_EINVAL, "capacity too small");
+  if (!e->n_edges) return KC_OK;
+  if (!out) return KC_EINVAL;
+  KC_CUDA(e, cudaSetDevice(e->dev));
+  mark(e, EV_D0);
+  KC_CUDA(e, cudaMemcpyAsync(out, e->d_edges_sorted.p, e->n_edges * 16, cudaMemcpyDeviceToHost, e->stream));
+  mark(e, EV_D1);
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  return KC_OK;
+}
+
+int kc_get_edge_kmers(kc_engine* e, uint64_t edge_index, uint32_t* kmers_out, uint64_t capacity) {
+  if (!e || !kmers_out) return KC_EINVAL;
+  if (!e->have_pairs) return fail(e, KC_EINVAL, "kc_score_pairs first");
+  if (edge_index >= e->n_edges) return fail(e, KC_EINVAL, "edge index out of range");
+  KC_CUDA(e, cudaSetDevice(e->dev));
+  uint4 ed;
+  KC_CUDA(e, cudaMemcpyAsync(&ed, e->d_edges_sorted.as<uint4>() + edge_index, 16, cudaMemcpyDeviceToHost, e->stream));
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (capacity < ed.z) return fail(e, KC_EINVAL, "capacity too small");
+  KC_CUDA(e, e->d_tmp.ensure((uint64_t)ed.z * 4 + 16));
+  KC_LAUNCH(e, shared_kmers_kernel, 1, 32, 0, e->h_rank[ed.x], e->h_rank[ed.y], e->d_pstart.as<uint32_t>(),
+            e->d_rowlen.as<uint32_t>(), e->d_pk.as<uint32_t>(), e->d_vocab.as<uint32_t>(), e->d_tmp.as<uint32_t>(),
+            ed.z, &e->ds->n_shared);
+  KC_CUDA(e, cudaMemcpyAsync(kmers_out, e->d_tmp.p, (uint64_t)ed.z * 4, cudaMemcpyDeviceToHost, e->stream));
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  return KC_OK;
+}
+
+int kc_get_timings(kc_engine* e, kc_timings* out) {
+  if (!e || !out) return KC_EINVAL;
+  cudaSetDevice(e->dev);
+  cudaStreamSynchronize(e->stream);
+  std::memset(out, 0, sizeof(*out));
+  out->h2d_ms = elapsed(e, EV_H2D0, EV_H2D1);
+  out->extract_ms = elapsed(e, EV_X0, EV_X1);
+  out->index_ms = elapsed(e, EV_I0, EV_I1);
+  out->pairs_ms = elapsed(e, EV_P0, EV_P1);
+  out->edges_ms = elapsed(e, EV_P1, EV_E1);
+  out->d2h_ms = elapsed(e, EV_D0, EV_D1);
+  out->pair_kernel_ms = elapsed(e, EV_PK0, EV_PK1);
+  out->census_kernel_ms = elapsed(e, EV_IC0, EV_IC1);
+  out->kernel_launches = e->launches;
+  return KC_OK;
+}
+
+int kc_reset_timings(kc_engine* e) {
+  if (!e) return KC_EINVAL;
+  e->launches = 0;
+  for (int i = 0; i < EV_COUNT; ++i) e->ev_set[i] = false;
+  return KC_OK;
+}
+
+int kc_bitset_pair_counts(kc_engine* e, const uint32_t* rows, uint32_t n_rows, uint32_t* counts_out) {
+  if (!e || (n_rows && (!rows || !counts_out))) return KC_EINVAL;
+  if (!e->have_index) return fail(e, KC_EINVAL, "kc_build_index first");
+  if (!n_rows) return KC_OK;
+  for (uint32_t i = 0; i < n_rows; ++i)
+    if (rows[i] >= e->n) return fail(e, KC_EINVAL, "row out of range");
+  KC_CUDA(e, cudaSetDevice(e->dev));
+  const uint32_t words = (uint32_t)((e->istats.n_repeated + 31) / 32) + 1;
+  std::vector<uint32_t> ranks(n_rows);
+  for (uint32_t i = 0; i < n_rows; ++i) ranks[i] = e->h_rank[rows[i]];
+  DBuf d_rows, d_bits, d_counts;
+  cudaError_t a = d_rows.ensure((size_t)n_rows * 4), b = d_bits.ensure((size_t)n_rows * words * 4),
+              c = d_counts.ensure((size_t)n_rows * n_rows * 4);
+  if (a != cudaSuccess || b != cudaSuccess || c != cudaSuccess) {
+    d_rows.release();
+    d_bits.release();
+    d_counts.release();
+    return fail(e, KC_ENOMEM, "out of device memory");
+  }
+  cudaMemcpyAsync(d_rows.p, ranks.data(), (size_t)n_rows * 4, cudaMemcpyHostToDevice, e->stream);
+  cudaMemsetAsync(d_bits.p, 0, (size_t)n_rows * words * 4, e->stream);
+  KC_LAUNCH(e, bitset_fill_kernel, blocks_for(n_rows, 8, e->num_sm * 8), 256, 0, d_rows.as<uint32_t>(), n_rows,
+            e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(), e->d_pk.as<uint32_t>(), words,
+            d_bits.as<uint32_t>());
+  const uint32_t tiles = (n_rows + kBitTile - 1) / kBitTile;
+  KC_LAUNCH(e, bitset_pairs_kernel, dim3(tiles, tiles), kBitTile * 32, 0, d_bits.as<uint32_t>(), n_rows, words,
+            d_counts.as<uint32_t>());
+  cudaError_t rc = cudaMemcpyAsync(counts_out, d_counts.p, (size_t)n_rows * n_rows * 4, cudaMemcpyDeviceToHost,
+                                   e->stream);
+  if (rc == cudaSuccess) rc = cudaStreamSynchronize(e->stream);
+  d_rows.release();
+  d_bits.release();
+  d_counts.release();
+  KC_CUDA(e, rc);
+  return KC_OK;
+}
+
+}  // extern "C"
+

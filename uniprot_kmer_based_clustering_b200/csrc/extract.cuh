@@ -1,0 +1,309 @@
+// extract.cuh — K1/K2/K3: residue encode, k-mer extraction, per-protein dedup, census marks.
+//
+// Replaces (reference root relative):
+//   amino_acid_to_bits  src/protein.rs:49-54   -> 256-entry LUT in shared memory
+//   create_five_mer     src/protein.rs:29-37   -> base-21 pack, first residue most significant
+//   Protein::new        src/protein.rs:107-132 -> kmers_per_position_kernel (get_five_mers)
+//   sort(); dedup()     src/main.rs:100-102    -> bitonic sort + adjacent-diff in shared memory
+//   merge_sort census   src/main.rs:23-48,103-116 -> two presence bitmaps over the 21^k universe:
+//                       seen1 = "held by >= 1 protein", seen2 = "held by >= 2 proteins"
+#pragma once
+#include "common.cuh"
+
+namespace kc {
+
+__constant__ uint8_t c_residue_lut[256];
+
+// ---- census: first holder sets seen1, every later holder (a different protein, because the
+// caller has deduplicated within the protein) sets seen2.  The plain pre-read may be stale;
+// it only skips work that is idempotent.
+__device__ __forceinline__ void census_mark(uint32_t kmer, uint32_t* __restrict__ seen1,
+                                            uint32_t* __restrict__ seen2) {
+  const uint32_t w = kmer >> 5, bit = 1u << (kmer & 31u);
+  if (seen2[w] & bit) return;
+  const uint32_t old = atomicOr(&seen1[w], bit);
+  if (old & bit) atomicOr(&seen2[w], bit);
+}
+
+template <int K>
+__device__ __forceinline__ uint32_t pack_kmer(const uint8_t* codes) {
+  uint32_t v = 0;
+#pragma unroll
+  for (int j = 0; j < K; ++j) v = v * 21u + codes[j];
+  return v;
+}
+
+// stage `len` residues of one protein as codes into shared memory (word loads, any alignment)
+__device__ __forceinline__ void stage_codes(const uint8_t* __restrict__ res, uint32_t pstart, uint32_t len,
+                                            uint8_t* codes, const uint8_t* lut, uint32_t tid,
+                                            uint32_t nthreads) {
+  const uint32_t a0 = pstart & ~3u;
+  const uint32_t words = (pstart + len - a0 + 3u) >> 2;
+  const uint32_t* rw = reinterpret_cast<const uint32_t*>(res + a0);
+  for (uint32_t wi = tid; wi < words; wi += nthreads) {
+    const uint32_t x = ld_stream_u32(rw + wi);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int idx = (int)(a0 + 4u * wi + b) - (int)pstart;
+      if (idx >= 0 && (uint32_t)idx < len) codes[idx] = lut[(x >> (8 * b)) & 255u];
+    }
+  }
+}
+
+// warp-synchronous bitonic sort of np2 (power of two) keys in shared memory
+__device__ __forceinline__ void warp_bitonic(uint32_t* keys, uint32_t np2, uint32_t lane) {
+  for (uint32_t size = 2; size <= np2; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t t = lane; t < (np2 >> 1); t += 32) {
+        const uint32_t i = ((t & ~(stride - 1u)) << 1) | (t & (stride - 1u));
+        const uint32_t j = i | stride;
+        const bool up = (i & size) == 0;
+        const uint32_t a = keys[i], b = keys[j];
+        if ((a > b) == up) {
+          keys[i] = b;
+          keys[j] = a;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// block-wide bitonic sort (keys may live in shared or global memory)
+__device__ __forceinline__ void block_bitonic(uint32_t* keys, uint32_t np2) {
+  for (uint32_t size = 2; size <= np2; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
+        const uint32_t i = ((t & ~(stride - 1u)) << 1) | (t & (stride - 1u));
+        const uint32_t j = i | stride;
+        const bool up = (i & size) == 0;
+        const uint32_t a = keys[i], b = keys[j];
+        if ((a > b) == up) {
+          keys[i] = b;
+          keys[j] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+constexpr uint32_t kWarpMaxPos = 1024;    // proteins with <= this many positions: one warp
+constexpr uint32_t kBlockMaxPos = 32768;  // <= this many: one CTA, keys in shared memory
+constexpr int kExtractWarps = 8;
+
+// ---------------------------------------------------------------------------------------
+// K2 (short proteins): one warp per protein.  Writes the protein's sorted distinct k-mers to
+// pk[pstart .. pstart+ndist) and marks the census bitmaps.
+// ---------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kExtractWarps * 32)
+    extract_dedup_warp_kernel(const uint8_t* __restrict__ res, const uint32_t* __restrict__ pstart,
+                              const uint32_t* __restrict__ plen, uint32_t n, uint32_t* __restrict__ pk,
+                              uint32_t* __restrict__ ndist, uint32_t* __restrict__ seen1,
+                              uint32_t* __restrict__ seen2, unsigned long long* __restrict__ n_incid) {
+  __shared__ uint8_t s_lut[256];
+  __shared__ uint32_t s_keys[kExtractWarps][kWarpMaxPos];
+  __shared__ __align__(4) uint8_t s_codes[kExtractWarps][kWarpMaxPos + 8];
+  const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
+  s_lut[threadIdx.x] = c_residue_lut[threadIdx.x];
+  __syncthreads();
+  uint32_t* keys = s_keys[w];
+  uint8_t* codes = s_codes[w];
+  unsigned long long incid = 0;
+  const uint32_t nwarps = gridDim.x * kExtractWarps;
+  for (uint32_t r = blockIdx.x * kExtractWarps + w; r < n; r += nwarps) {
+    const uint32_t len = plen[r];
+    if (len < (uint32_t)K) {
+      if (lane == 0) ndist[r] = 0;
+      continue;
+    }
+    const uint32_t npos = len - K + 1;
+    if (npos > kWarpMaxPos) continue;  // handled by the block kernels
+    const uint32_t ps = pstart[r];
+    stage_codes(res, ps, len, codes, s_lut, lane, 32);
+    __syncwarp();
+    const uint32_t np2 = next_pow2_u32(npos);
+    for (uint32_t i = lane; i < np2; i += 32) keys[i] = i < npos ? pack_kmer<K>(codes + i) : kSentinel;
+    __syncwarp();
+    warp_bitonic(keys, np2, lane);
+    uint32_t base = 0;
+    for (uint32_t c = 0; c < npos; c += 32) {
+      const uint32_t i = c + lane;
+      const uint32_t v = i < npos ? keys[i] : kSentinel;
+      const bool first = i < npos && (i == 0 || v != keys[i - 1]);
+      const uint32_t m = __ballot_sync(kFullMask, first);
+      if (first) {
+        pk[ps + base + __popc(m & lanemask_lt())] = v;
+        census_mark(v, seen1, seen2);
+      }
+      base += __popc(m);
+    }
+    if (lane == 0) ndist[r] = base;
+    incid += base;
+    __syncwarp();
+  }
+  if (lane == 0 && incid) atomicAdd(n_incid, incid);
+}
+
+// ---------------------------------------------------------------------------------------
+// K2 (long proteins): one CTA per listed protein.  GLOBAL_KEYS = keys in a global scratch
+// slice (proteins beyond the shared-memory capacity), else in dynamic shared memory.
+// ---------------------------------------------------------------------------------------
+template <int K, bool GLOBAL_KEYS>
+__global__ void __launch_bounds__(512)
+    extract_dedup_block_kernel(const uint8_t* __restrict__ res, const uint32_t* __restrict__ pstart,
+                               const uint32_t* __restrict__ plen, const uint32_t* __restrict__ list,
+                               const unsigned long long* __restrict__ scratch_off,
+                               uint32_t* __restrict__ scratch, uint32_t* __restrict__ pk,
+                               uint32_t* __restrict__ ndist, uint32_t* __restrict__ seen1,
+                               uint32_t* __restrict__ seen2, unsigned long long* __restrict__ n_incid) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  __shared__ uint8_t s_lut[256];
+  __shared__ uint32_t s_wcnt[32];
+  if (threadIdx.x < 256) s_lut[threadIdx.x] = c_residue_lut[threadIdx.x];
+  const uint32_t r = list[blockIdx.x];
+  const uint32_t len = plen[r], ps = pstart[r];
+  const uint32_t npos = len - K + 1;
+  const uint32_t np2 = next_pow2_u32(npos);
+  uint32_t* keys;
+  __syncthreads();
+  if (GLOBAL_KEYS) {
+    keys = scratch + scratch_off[blockIdx.x];
+    for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x) {
+      uint32_t v = kSentinel;
+      if (i < npos) {
+        v = 0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) v = v * 21u + s_lut[res[ps + i + j]];
+      }
+      keys[i] = v;
+    }
+  } else {
+    keys = reinterpret_cast<uint32_t*>(dyn_smem);
+    uint8_t* codes = dyn_smem + (size_t)np2 * 4;
+    stage_codes(res, ps, len, codes, s_lut, threadIdx.x, blockDim.x);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x)
+      keys[i] = i < npos ? pack_kmer<K>(codes + i) : kSentinel;
+  }
+  __syncthreads();
+  block_bitonic(keys, np2);
+  // two-pass compaction: every warp owns a contiguous slice
+  const uint32_t lane = lane_id(), w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const uint32_t slice = (((npos + nw - 1) / nw) + 31u) & ~31u;
+  const uint32_t lo = min(npos, w * slice), hi = min(npos, lo + slice);
+  uint32_t cnt = 0;
+  for (uint32_t c = lo; c < hi; c += 32) {
+    const uint32_t i = c + lane;
+    const bool first = i < hi && (i == 0 || keys[i] != keys[i - 1]);
+    cnt += __popc(__ballot_sync(kFullMask, first));
+  }
+  if (lane == 0) s_wcnt[w] = cnt;
+  __syncthreads();
+  uint32_t base = 0, total = 0;
+  for (uint32_t i = 0; i < nw; ++i) {
+    if (i < w) base += s_wcnt[i];
+    total += s_wcnt[i];
+  }
+  for (uint32_t c = lo; c < hi; c += 32) {
+    const uint32_t i = c + lane;
+    const uint32_t v = i < hi ? keys[i] : kSentinel;
+    const bool first = i < hi && (i == 0 || v != keys[i - 1]);
+    const uint32_t m = __ballot_sync(kFullMask, first);
+    if (first) {
+      pk[ps + base + __popc(m & lanemask_lt())] = v;
+      census_mark(v, seen1, seen2);
+    }
+    base += __popc(m);
+  }
+  if (threadIdx.x == 0) {
+    ndist[r] = total;
+    atomicAdd(n_incid, (unsigned long long)total);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K1: Protein::new / get_five_mers — one packed k-mer per start position, proteins back to
+// back in INPUT order.  A CTA stages a 4096-residue tile plus a (K-1)-residue halo in shared
+// memory with 16-byte loads; the tile's protein boundaries are staged next to it.
+// ---------------------------------------------------------------------------------------
+constexpr int kTileRes = 4096;
+constexpr int kTileMaxProt = 1024;
+
+template <int K>
+__global__ void __launch_bounds__(256)
+    kmers_per_position_kernel(const uint8_t* __restrict__ res, uint64_t n_res,
+                              const unsigned long long* __restrict__ off,
+                              const unsigned long long* __restrict__ kpos_off, uint32_t n_prot,
+                              uint32_t* __restrict__ out) {
+  __shared__ uint8_t s_lut[256];
+  __shared__ __align__(16) uint8_t s_codes[kTileRes + 16];
+  __shared__ unsigned long long s_off[kTileMaxProt + 1];
+  __shared__ uint32_t s_p0, s_np;
+  const uint32_t t = threadIdx.x;
+  s_lut[t] = c_residue_lut[t];
+  const uint64_t tile0 = (uint64_t)blockIdx.x * kTileRes;
+  if (t == 0) {
+    // first protein whose end is beyond tile0: upper_bound(off, tile0) - 1
+    uint32_t lo = 0, hi = n_prot;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (off[mid + 1] <= tile0) lo = mid + 1; else hi = mid;
+    }
+    s_p0 = lo;
+    // number of proteins starting before the tile end
+    const uint64_t tend = tile0 + kTileRes;
+    uint32_t lo2 = lo, hi2 = n_prot;
+    while (lo2 < hi2) {
+      const uint32_t mid = (lo2 + hi2) >> 1;
+      if (off[mid] < tend) lo2 = mid + 1; else hi2 = mid;
+    }
+    s_np = lo2 - lo;
+  }
+  __syncthreads();
+  {
+    const uint4 x = ld_stream_u32x4(reinterpret_cast<const uint4*>(res + tile0) + t);  // buffer is padded
+    const uint32_t wv[4] = {x.x, x.y, x.z, x.w};
+    uint32_t packed[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      packed[q] = (uint32_t)s_lut[wv[q] & 255u] | ((uint32_t)s_lut[(wv[q] >> 8) & 255u] << 8) |
+                  ((uint32_t)s_lut[(wv[q] >> 16) & 255u] << 16) | ((uint32_t)s_lut[wv[q] >> 24] << 24);
+    }
+    reinterpret_cast<uint4*>(s_codes)[t] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    if (t < K - 1) {
+      const uint64_t g = tile0 + kTileRes + t;
+      s_codes[kTileRes + t] = g < n_res ? s_lut[res[g]] : (uint8_t)20;
+    }
+  }
+  const uint32_t p0 = s_p0, np = s_np;
+  const bool local = np <= (uint32_t)kTileMaxProt;
+  if (local)
+    for (uint32_t i = t; i <= np; i += 256) s_off[i] = off[p0 + i];
+  __syncthreads();
+#pragma unroll 4
+  for (int j = 0; j < kTileRes / 256; ++j) {
+    const uint32_t li = j * 256 + t;
+    const uint64_t g = tile0 + li;
+    if (g >= n_res) break;
+    // protein holding residue g
+    uint32_t lo = 0, hi = np;
+    if (local) {
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (s_off[mid + 1] <= g) lo = mid + 1; else hi = mid;
+      }
+    } else {
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (off[p0 + mid + 1] <= g) lo = mid + 1; else hi = mid;
+      }
+    }
+    const uint64_t pbeg = local ? s_off[lo] : off[p0 + lo];
+    const uint64_t pend = local ? s_off[lo + 1] : off[p0 + lo + 1];
+    if (g + K <= pend) out[kpos_off[p0 + lo] + (g - pbeg)] = pack_kmer<K>(s_codes + li);
+  }
+}
+
+}  // namespace kc

@@ -1,0 +1,316 @@
+// host.cpp — FASTA staging and the synthetic protein-set generator (include/kc_host.h).
+// Host code only; compiled with the engine into libkc_b200.so.
+#include <cuda_runtime_api.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/kc_b200.h"
+#include "../../include/kc_host.h"
+
+struct kc_fasta {
+  uint64_t n = 0, n_res = 0, n_missing = 0;
+  uint8_t* residues = nullptr;
+  bool pinned = false;
+  std::vector<uint64_t> offsets;
+  std::vector<uint32_t> class_ids;
+  std::vector<std::string> class_names;
+  std::vector<std::string> ids;
+};
+
+namespace {
+
+template <class F>
+void parallel_chunks(int threads, uint64_t n, uint64_t grain, F f) {
+  if (threads <= 1 || n <= grain) {
+    f(0, n);
+    return;
+  }
+  std::atomic<uint64_t> cursor{0};
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([&] {
+      for (;;) {
+        const uint64_t lo = cursor.fetch_add(grain);
+        if (lo >= n) break;
+        f(lo, std::min(n, lo + grain));
+      }
+    });
+  for (auto& th : pool) th.join();
+}
+
+uint8_t* alloc_residues(uint64_t bytes, bool* pinned) {
+  void* p = nullptr;
+  *pinned = false;
+  if (bytes == 0) bytes = 1;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 && cudaMallocHost(&p, bytes) == cudaSuccess) {
+    *pinned = true;
+    return static_cast<uint8_t*>(p);
+  }
+  cudaGetLastError();
+  return static_cast<uint8_t*>(std::malloc(bytes));
+}
+
+int parse(const char* data, uint64_t len, int threads, kc_fasta** out) {
+  if (threads < 1) threads = 1;
+  kc_fasta* f = new kc_fasta();
+  // record starts: '>' at the beginning of a line
+  std::vector<uint64_t> starts;
+  {
+    const int T = threads;
+    std::vector<std::vector<uint64_t>> local(T);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < T; ++t)
+      pool.emplace_back([&, t] {
+        const uint64_t lo = len * t / T, hi = len * (t + 1) / T;
+        const char* p = data + lo;
+        const char* end = data + hi;
+        while (p < end) {
+          const char* q = static_cast<const char*>(std::memchr(p, '>', end - p));
+          if (!q) break;
+          const uint64_t i = q - data;
+          if (i == 0 || data[i - 1] == '\n') local[t].push_back(i);
+          p = q + 1;
+        }
+      });
+    for (auto& th : pool) th.join();
+    for (auto& v : local) starts.insert(starts.end(), v.begin(), v.end());
+  }
+  const uint64_t n = starts.size();
+  f->n = n;
+  f->offsets.assign(n + 1, 0);
+  f->ids.resize(n);
+  std::vector<uint64_t> seq_begin(n), rec_end(n);
+  parallel_chunks(threads, n, 1024, [&](uint64_t lo, uint64_t hi) {
+    for (uint64_t r = lo; r < hi; ++r) {
+      const uint64_t s = starts[r], e = r + 1 < n ? starts[r + 1] : len;
+      const char* nl = static_cast<const char*>(std::memchr(data + s, '\n', e - s));
+      const uint64_t hdr_end = nl ? (uint64_t)(nl - data) : e;
+      uint64_t id_end = s + 1;
+      while (id_end < hdr_end && data[id_end] != ' ' && data[id_end] != '\t' && data[id_end] != '\r') ++id_end;
+      f->ids[r].assign(data + s + 1, id_end - s - 1);
+      seq_begin[r] = nl ? hdr_end + 1 : e;
+      rec_end[r] = e;
+      uint64_t cnt = 0;
+      for (uint64_t i = seq_begin[r]; i < e; ++i) cnt += data[i] != '\n' && data[i] != '\r';
+      f->offsets[r + 1] = cnt;
+    }
+  });
+  for (uint64_t r = 0; r < n; ++r) f->offsets[r + 1] += f->offsets[r];
+  f->n_res = f->offsets[n];
+  f->residues = alloc_residues(f->n_res + 64, &f->pinned);
+  if (!f->residues) {
+    delete f;
+    return KC_ENOMEM;
+  }
+  parallel_chunks(threads, n, 1024, [&](uint64_t lo, uint64_t hi) {
+    for (uint64_t r = lo; r < hi; ++r) {
+      uint8_t* dst = f->residues + f->offsets[r];
+      for (uint64_t i = seq_begin[r]; i < rec_end[r]; ++i) {
+        const char c = data[i];
+        if (c != '\n' && c != '\r') *dst++ = (uint8_t)c;
+      }
+    }
+  });
+  // class dictionary in first-occurrence order (Protein::get_amr_class, src/protein.rs:135-138)
+  f->class_ids.resize(n);
+  std::unordered_map<std::string, uint32_t> table;
+  for (uint64_t r = 0; r < n; ++r) {
+    const std::string& id = f->ids[r];
+    std::string name;
+    bool found = false;
+    {
+      // Rust split_terminator('|'): split on '|', drop one trailing empty piece
+      std::vector<std::pair<size_t, size_t>> pieces;
+      size_t pos = 0;
+      for (;;) {
+        const size_t bar = id.find('|', pos);
+        if (bar == std::string::npos) {
+          pieces.emplace_back(pos, id.size());
+          break;
+        }
+        pieces.emplace_back(pos, bar);
+        pos = bar + 1;
+      }
+      if (!pieces.empty() && pieces.back().first == pieces.back().second) pieces.pop_back();
+      if (pieces.size() > 3) {
+        name = id.substr(pieces[3].first, pieces[3].second - pieces[3].first);
+        found = true;
+      }
+    }
+    if (!found) f->n_missing++;
+    auto it = table.find(name);
+    if (it == table.end()) {
+      it = table.emplace(name, (uint32_t)f->class_names.size()).first;
+      f->class_names.push_back(name);
+    }
+    f->class_ids[r] = it->second;
+  }
+  *out = f;
+  return KC_OK;
+}
+
+// ---- generator G1 ------------------------------------------------------------------------
+struct SplitMix {
+  uint64_t s;
+  uint64_t next() {
+    s += 0x9E3779B97F4A7C15ull;
+    uint64_t z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  }
+};
+
+SplitMix stream(uint64_t seed, uint64_t index, uint64_t tag) {
+  SplitMix g{seed ^ ((index + 1) * 0x9E3779B97F4A7C15ull) ^ (tag * 0xC2B2AE3D27D4EB4Full)};
+  g.next();
+  return g;
+}
+
+// residue frequencies of the ARG protein set, total 3 436 746
+const char kLetters[21] = "LAGVISTFREKDPQNYMHWC";
+const uint32_t kCounts[20] = {377380, 336508, 269059, 258845, 257326, 206108, 194902, 176903, 163437, 158642,
+                              158511, 153089, 143715, 124590, 118853, 101563, 92047,  64642,  54450,  26176};
+const uint32_t kTotal = 3436746;
+
+struct Cumulative {
+  uint32_t c[20];
+  Cumulative() {
+    uint32_t s = 0;
+    for (int i = 0; i < 20; ++i) {
+      s += kCounts[i];
+      c[i] = s;
+    }
+  }
+  char pick(uint32_t u) const {  // u uniform in [0, kTotal)
+    int lo = 0, hi = 19;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (u < c[mid]) hi = mid; else lo = mid + 1;
+    }
+    return kLetters[lo];
+  }
+};
+const Cumulative kCum;
+
+uint32_t family_length(uint64_t seed, uint64_t fam, int law) {
+  SplitMix g = stream(seed, fam, 1);
+  if (law == 0) {
+    uint32_t len = 50;
+    for (int i = 0; i < 4; ++i) len += (uint32_t)(((g.next() >> 32) * 151ull) >> 32);
+    return len;
+  }
+  const uint64_t t = ((g.next() >> 32) * 65536ull) >> 32;
+  const uint64_t t4 = t * t * t * t;
+  return 50u + (uint32_t)(((t4 >> 32) * 1950ull) >> 32);
+}
+
+}  // namespace
+
+extern "C" {
+
+int kc_fasta_parse_buffer(const char* data, uint64_t len, int threads, kc_fasta** out) {
+  if (!out || (len && !data)) return KC_EINVAL;
+  return parse(data, len, threads, out);
+}
+
+int kc_fasta_parse_file(const char* path, int threads, kc_fasta** out) {
+  if (!path || !out) return KC_EINVAL;
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return KC_EINVAL;
+  struct stat st;
+  if (fstat(fd, &st) != 0) {
+    close(fd);
+    return KC_EINVAL;
+  }
+  const uint64_t len = (uint64_t)st.st_size;
+  if (len == 0) {
+    close(fd);
+    return parse("", 0, threads, out);
+  }
+  void* m = mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (m == MAP_FAILED) return KC_ENOMEM;
+  madvise(m, len, MADV_SEQUENTIAL);
+  const int rc = parse(static_cast<const char*>(m), len, threads, out);
+  munmap(m, len);
+  return rc;
+}
+
+void kc_fasta_free(kc_fasta* f) {
+  if (!f) return;
+  if (f->residues) {
+    if (f->pinned) cudaFreeHost(f->residues); else std::free(f->residues);
+  }
+  delete f;
+}
+uint64_t kc_fasta_n_proteins(const kc_fasta* f) { return f->n; }
+uint64_t kc_fasta_n_residues(const kc_fasta* f) { return f->n_res; }
+const uint8_t* kc_fasta_residues(const kc_fasta* f) { return f->residues; }
+const uint64_t* kc_fasta_offsets(const kc_fasta* f) { return f->offsets.data(); }
+const uint32_t* kc_fasta_class_ids(const kc_fasta* f) { return f->class_ids.data(); }
+uint32_t kc_fasta_n_classes(const kc_fasta* f) { return (uint32_t)f->class_names.size(); }
+uint64_t kc_fasta_n_missing_class(const kc_fasta* f) { return f->n_missing; }
+const char* kc_fasta_class_name(const kc_fasta* f, uint32_t c) {
+  return c < f->class_names.size() ? f->class_names[c].c_str() : "";
+}
+const char* kc_fasta_id(const kc_fasta* f, uint64_t p) { return p < f->n ? f->ids[p].c_str() : ""; }
+
+int kc_synth_layout(uint64_t n, int law, uint64_t seed, uint64_t* offsets, uint32_t* class_id) {
+  if (!offsets || (n && !class_id) || (law != 0 && law != 1)) return KC_EINVAL;
+  offsets[0] = 0;
+  uint32_t len = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint64_t fam = i / 16, j = i % 16;
+    if (j == 0 || i == 0) len = family_length(seed, fam, law);
+    offsets[i + 1] = offsets[i] + len;
+    class_id[i] = (uint32_t)((fam % 8 == 7) ? (fam + j) % 15 : fam % 15);
+  }
+  return KC_OK;
+}
+
+int kc_synth_residues(uint64_t n, int law, uint64_t seed, int threads, const uint64_t* offsets,
+                      uint8_t* residues) {
+  if (!offsets || (n && !residues) || (law != 0 && law != 1)) return KC_EINVAL;
+  (void)law;
+  const uint64_t n_fam = (n + 15) / 16;
+  parallel_chunks(threads < 1 ? 1 : threads, n_fam, 64, [&](uint64_t lo, uint64_t hi) {
+    std::vector<uint8_t> base;
+    for (uint64_t fam = lo; fam < hi; ++fam) {
+      const uint64_t first = fam * 16;
+      const uint64_t len = offsets[first + 1] - offsets[first];
+      base.resize(len);
+      SplitMix g = stream(seed, fam, 2);
+      for (uint64_t p = 0; p < len; ++p) {
+        const uint64_t r = g.next();
+        base[p] = (r & 8191u) == 0 ? (uint8_t)'X' : (uint8_t)kCum.pick((uint32_t)(((r >> 32) * kTotal) >> 32));
+      }
+      for (uint64_t j = 0; j < 16 && first + j < n; ++j) {
+        uint8_t* dst = residues + offsets[first + j];
+        SplitMix m = stream(seed, first + j, 3);
+        const uint32_t thr = (uint32_t)j * 1311u;
+        for (uint64_t p = 0; p < len; ++p) {
+          const uint64_t r = m.next();
+          dst[p] = (uint32_t)(r & 0xFFFFu) < thr
+                       ? (uint8_t)kCum.pick((uint32_t)((((r >> 16) & 0xFFFFFFFFull) * kTotal) >> 32))
+                       : base[p];
+        }
+      }
+    }
+  });
+  return KC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,305 @@
+// index.cuh — K4/K5: the perfect k-mer index, per-protein id lists, kmer_freq, postings.
+//
+// Replaces (reference root relative):
+//   split unique/repeated + Mphf::new x2 + unique bool table   src/main.rs:127-147
+//       -> rank dictionary over the seen2 bitmap: dict[w] = {bits, #set bits before word w};
+//          id(kmer) = dict[kmer>>5].y + popc(dict[kmer>>5].x & ((1<<(kmer&31))-1)).
+//          A minimal perfect, order-preserving hash of the repeated k-mers (one 8-byte load).
+//   remove_unique_five_mers + modify_hash_five_mer + kmer_freq  src/protein.rs:151-174,
+//       src/main.rs:182-193 -> ids_freq_kernel
+//   times_kmer_visited / triangular edge layout                 src/graph/vertex.rs:92-136
+//       -> postings (holders of every id, sorted by protein rank) + per-entry suffix ranges
+#pragma once
+#include "common.cuh"
+
+namespace kc {
+
+struct PopcIn {
+  const uint32_t* bits;
+  __device__ unsigned long long operator()(uint64_t i) const { return __popc(bits[i]); }
+};
+struct DictOut {
+  const uint32_t* bits;
+  uint2* dict;
+  __device__ void operator()(uint64_t i, unsigned long long excl, unsigned long long) const {
+    dict[i] = make_uint2(bits[i], (uint32_t)excl);
+  }
+};
+
+__global__ void popc_reduce_kernel(const uint32_t* __restrict__ bits, uint64_t n_words,
+                                   unsigned long long* __restrict__ total) {
+  unsigned long long s = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    s += __popc(bits[i]);
+  s = warp_sum64(s);
+  if (lane_id() == 0 && s) atomicAdd(total, s);
+}
+
+__device__ __forceinline__ int kmer_self_score(uint32_t kmer, int k) {
+  // B62[r][r] in the reference's residue order (src/blosum.rs:8-30 diagonal); code 20 -> 0
+  const int diag[21] = {9, 4, 5, 4, 6, 7, 6, 5, 5, 6, 8, 5, 5, 5, 4, 4, 4, 11, 7, 6, 0};
+  int s = 0;
+  for (int i = 0; i < k; ++i) {
+    s += diag[kmer % 21u];
+    kmer /= 21u;
+  }
+  return s;
+}
+
+// expand a bitmap into the ascending list of set positions (vocab[id] = kmer); optional
+// BLOSUM self-score per id.  `dict` supplies the rank of each word.
+__global__ void expand_bitmap_kernel(const uint2* __restrict__ dict, uint64_t n_words,
+                                     uint32_t* __restrict__ vocab, uint8_t* __restrict__ selfscore, int k) {
+  for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words;
+       w += (uint64_t)gridDim.x * blockDim.x) {
+    uint2 d = dict[w];
+    uint32_t bits = d.x, id = d.y;
+    while (bits) {
+      const uint32_t b = __ffs(bits) - 1;
+      const uint32_t kmer = (uint32_t)(w << 5) + b;
+      vocab[id] = kmer;
+      if (selfscore) selfscore[id] = (uint8_t)kmer_self_score(kmer, k);
+      ++id;
+      bits &= bits - 1;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t dict_lookup(const uint2* __restrict__ dict, uint32_t kmer) {
+  const uint2 d = dict[kmer >> 5];
+  const uint32_t bit = 1u << (kmer & 31u);
+  return (d.x & bit) ? d.y + __popc(d.x & (bit - 1u)) : kSentinel;
+}
+
+__global__ void lookup_kernel(const uint2* __restrict__ dict, const uint32_t* __restrict__ kmers, uint64_t n,
+                              uint32_t universe, uint32_t* __restrict__ ids) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t km = kmers[i];
+    ids[i] = km < universe ? dict_lookup(dict, km) : kSentinel;
+  }
+}
+
+// K5: one warp per protein.  Sorted distinct k-mers -> sorted repeated-k-mer ids, compacted in
+// place (pk[pstart .. pstart+rowlen)); freq[id] += 1.
+__global__ void __launch_bounds__(256)
+    ids_freq_kernel(const uint2* __restrict__ dict, const uint32_t* __restrict__ pstart,
+                    const uint32_t* __restrict__ ndist, uint32_t n, uint32_t* __restrict__ pk,
+                    uint32_t* __restrict__ rowlen, uint32_t* __restrict__ freq,
+                    unsigned long long* __restrict__ nnz_total) {
+  const uint32_t lane = lane_id();
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long tot = 0;
+  for (uint32_t r = gw; r < n; r += nw) {
+    const uint32_t nd = ndist[r], ps = pstart[r];
+    uint32_t base = 0;
+    for (uint32_t c = 0; c < nd; c += 32) {
+      const uint32_t i = c + lane;
+      uint32_t id = kSentinel;
+      if (i < nd) id = dict_lookup(dict, pk[ps + i]);
+      const uint32_t m = __ballot_sync(kFullMask, id != kSentinel);
+      if (id != kSentinel) {
+        pk[ps + base + __popc(m & lanemask_lt())] = id;
+        atomicAdd(&freq[id], 1u);
+      }
+      base += __popc(m);
+    }
+    if (lane == 0) rowlen[r] = base;
+    tot += base;
+  }
+  if (lane == 0 && tot) atomicAdd(nnz_total, tot);
+}
+
+// postings fill: col[cursor[id]++] = r  (cursor starts as a copy of colptr)
+__global__ void __launch_bounds__(256)
+    postings_fill_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen, uint32_t n,
+                         const uint32_t* __restrict__ ids, uint32_t* __restrict__ cursor,
+                         uint32_t* __restrict__ col) {
+  const uint32_t lane = lane_id();
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t r = gw; r < n; r += nw) {
+    const uint32_t nl = rowlen[r], ps = pstart[r];
+    for (uint32_t i = lane; i < nl; i += 32) {
+      const uint32_t slot = atomicAdd(&cursor[ids[ps + i]], 1u);
+      col[slot] = r;
+    }
+  }
+}
+
+// ---- postings sort: the atomic fill leaves every column in arrival order; the pair stage
+// needs ascending protein rank.  Columns of <= 8 holders are sorted by one lane in registers,
+// 9..32 by one warp (shuffle bitonic), longer ones are appended to work lists.
+__device__ __forceinline__ void cswap(uint32_t& a, uint32_t& b) {
+  const uint32_t lo = min(a, b), hi = max(a, b);
+  a = lo;
+  b = hi;
+}
+
+__device__ __forceinline__ uint32_t warp_bitonic_reg(uint32_t v, uint32_t lane) {
+#pragma unroll
+  for (uint32_t size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      const uint32_t o = __shfl_xor_sync(kFullMask, v, stride);
+      const bool up = (lane & size) == 0;
+      const bool lower = (lane & stride) == 0;
+      v = (lower == up) ? min(v, o) : max(v, o);
+    }
+  }
+  return v;
+}
+
+constexpr uint32_t kColWarpMax = 1024;   // columns up to this length: one warp, shared memory
+constexpr uint32_t kColBlockMax = 32768; // up to this: one CTA, shared memory; beyond: global
+
+__global__ void __launch_bounds__(256)
+    postings_sort_small_kernel(const uint32_t* __restrict__ colptr, uint32_t n_cols, uint32_t* __restrict__ col,
+                               uint32_t* __restrict__ list_mid, uint32_t* __restrict__ list_big,
+                               uint32_t* __restrict__ list_huge, uint32_t* __restrict__ list_counts) {
+  const uint32_t lane = lane_id();
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t c0 = gw * 32; c0 < n_cols; c0 += nw * 32) {
+    const uint32_t c = c0 + lane;
+    uint32_t lo = 0, f = 0;
+    if (c < n_cols) {
+      lo = colptr[c];
+      f = colptr[c + 1] - lo;
+    }
+    if (f >= 2 && f <= 8) {
+      uint32_t v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (uint32_t)i < f ? col[lo + i] : kSentinel;
+      // 19-comparator network for 8 keys
+      cswap(v[0], v[1]); cswap(v[2], v[3]); cswap(v[4], v[5]); cswap(v[6], v[7]);
+      cswap(v[0], v[2]); cswap(v[1], v[3]); cswap(v[4], v[6]); cswap(v[5], v[7]);
+      cswap(v[1], v[2]); cswap(v[5], v[6]); cswap(v[0], v[4]); cswap(v[3], v[7]);
+      cswap(v[1], v[5]); cswap(v[2], v[6]);
+      cswap(v[1], v[4]); cswap(v[3], v[6]);
+      cswap(v[2], v[4]); cswap(v[3], v[5]);
+      cswap(v[3], v[4]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if ((uint32_t)i < f) col[lo + i] = v[i];
+    } else if (f > 32) {
+      uint32_t* lst = f <= kColWarpMax ? list_mid : (f <= kColBlockMax ? list_big : list_huge);
+      const uint32_t which = f <= kColWarpMax ? 0 : (f <= kColBlockMax ? 1 : 2);
+      lst[atomicAdd(&list_counts[which], 1u)] = c;
+    }
+    uint32_t m = __ballot_sync(kFullMask, f > 8 && f <= 32);
+    while (m) {
+      const uint32_t src = __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t slo = __shfl_sync(kFullMask, lo, src), sf = __shfl_sync(kFullMask, f, src);
+      uint32_t v = lane < sf ? col[slo + lane] : kSentinel;
+      v = warp_bitonic_reg(v, lane);
+      if (lane < sf) col[slo + lane] = v;
+    }
+  }
+}
+
+// mid columns: one warp each, bitonic in shared memory
+__global__ void __launch_bounds__(128)
+    postings_sort_mid_kernel(const uint32_t* __restrict__ colptr, const uint32_t* __restrict__ list,
+                             const uint32_t* __restrict__ list_counts, uint32_t* __restrict__ col) {
+  __shared__ uint32_t s_keys[4][kColWarpMax];
+  const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
+  const uint32_t n_list = list_counts[0];
+  uint32_t* keys = s_keys[w];
+  for (uint32_t li = blockIdx.x * 4 + w; li < n_list; li += gridDim.x * 4) {
+    const uint32_t c = list[li];
+    const uint32_t lo = colptr[c], f = colptr[c + 1] - lo;
+    const uint32_t np2 = next_pow2_u32(f);
+    for (uint32_t i = lane; i < np2; i += 32) keys[i] = i < f ? col[lo + i] : kSentinel;
+    __syncwarp();
+    warp_bitonic(keys, np2, lane);
+    for (uint32_t i = lane; i < f; i += 32) col[lo + i] = keys[i];
+    __syncwarp();
+  }
+}
+
+// big columns: one CTA each; keys in dynamic shared memory, or in place in global memory
+template <bool GLOBAL_KEYS>
+__global__ void __launch_bounds__(512)
+    postings_sort_big_kernel(const uint32_t* __restrict__ colptr, const uint32_t* __restrict__ list,
+                             const uint32_t* __restrict__ list_counts, int which, uint32_t* __restrict__ col,
+                             uint32_t* __restrict__ scratch, uint32_t scratch_stride) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  const uint32_t n_list = list_counts[which];
+  for (uint32_t li = blockIdx.x; li < n_list; li += gridDim.x) {
+    const uint32_t c = list[li];
+    const uint32_t lo = colptr[c], f = colptr[c + 1] - lo;
+    const uint32_t np2 = next_pow2_u32(f);
+    uint32_t* keys = GLOBAL_KEYS ? scratch + (size_t)blockIdx.x * scratch_stride
+                                 : reinterpret_cast<uint32_t*>(dyn_smem);
+    for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x) keys[i] = i < f ? col[lo + i] : kSentinel;
+    __syncthreads();
+    block_bitonic(keys, np2);
+    for (uint32_t i = threadIdx.x; i < f; i += blockDim.x) col[lo + i] = keys[i];
+    __syncthreads();
+  }
+}
+
+// per-entry suffix ranges: for row r and each of its ids, the holders that come after r in the
+// pair order (and, when only cross-class pairs are wanted, after r's whole class block) are
+// col[suf.x .. suf.y).  rowwork[r] = sum of the range lengths = multi-edges row r accumulates.
+__global__ void __launch_bounds__(256)
+    suffix_ranges_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen, uint32_t n,
+                         const uint32_t* __restrict__ ids, const uint32_t* __restrict__ colptr,
+                         const uint32_t* __restrict__ col, const uint32_t* __restrict__ first_after,
+                         uint2* __restrict__ suf, uint32_t* __restrict__ rowwork,
+                         unsigned long long* __restrict__ work_total) {
+  const uint32_t lane = lane_id();
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long tot = 0;
+  for (uint32_t r = gw; r < n; r += nw) {
+    const uint32_t nl = rowlen[r], ps = pstart[r];
+    const uint32_t target = first_after ? first_after[r] : r + 1;  // first rank that pairs with r
+    unsigned long long work = 0;
+    for (uint32_t i = lane; i < nl; i += 32) {
+      const uint32_t id = ids[ps + i];
+      uint32_t lo = colptr[id];
+      const uint32_t end = colptr[id + 1];
+      uint32_t hi = end;
+      while (lo < hi) {  // lower_bound(col[lo..hi), target)
+        const uint32_t mid = (lo + hi) >> 1;
+        if (col[mid] < target) lo = mid + 1; else hi = mid;
+      }
+      suf[ps + i] = make_uint2(lo, end);
+      work += end - lo;
+    }
+    work = warp_sum64(work);
+    if (lane == 0) rowwork[r] = work > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)work;
+    tot += work;
+  }
+  if (lane == 0 && tot) atomicAdd(work_total, tot);
+}
+
+// Sum over ids of f(f-1)/2: "Number of total edges", src/graph/mod.rs:44-51
+__global__ void multi_edge_total_kernel(const uint32_t* __restrict__ freq, uint32_t n,
+                                        unsigned long long* __restrict__ total) {
+  unsigned long long s = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long f = freq[i];
+    s += f * (f - 1) / 2;
+  }
+  s = warp_sum64(s);
+  if (lane_id() == 0 && s) atomicAdd(total, s);
+}
+
+// compact the gapped id rows into a dense CSR for host readback
+__global__ void __launch_bounds__(256)
+    compact_rows_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen,
+                        const unsigned long long* __restrict__ row_off, const uint32_t* __restrict__ rank_of,
+                        uint32_t n, const uint32_t* __restrict__ ids, uint32_t* __restrict__ out) {
+  const uint32_t lane = lane_id();
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t p = gw; p < n; p += nw) {  // p = protein in input order
+    const uint32_t r = rank_of ? rank_of[p] : p;
+    const uint32_t nl = rowlen[r], ps = pstart[r];
+    const unsigned long long o = row_off[p];
+    for (uint32_t i = lane; i < nl; i += 32) out[o + i] = ids[ps + i];
+  }
+}
+
+}  // namespace kc

@@ -1,0 +1,474 @@
+// pairs.cuh — K7/K8/K9: all-pairs shared-k-mer counts, threshold, edge emission, BLOSUM.
+//
+// Replaces (reference root relative):
+//   Graph::new + update_graph_edges   src/graph/mod.rs:39-193, src/graph/vertex.rs:59-140
+//   remove_uninteresting_edges        src/graph/mod.rs:549-697
+//   combine_edges                     src/graph/mod.rs:322-546, src/graph/edge.rs:56-85
+//   threshold                         src/graph/mod.rs:242
+// The reference materialises one heap object per (k-mer, protein pair) and then filters and
+// groups them.  Here S = A*A^T (upper triangle in the pair order) is accumulated row by row
+// with ON-CHIP counters: row r walks, for each of its ids, the postings suffix
+// col[suf.x..suf.y) (holders that pair with r) and bumps one shared-memory counter per
+// holder.  Multi-edges are never written anywhere; only pairs over the threshold leave the SM.
+//
+// Three accumulator shapes, picked per row from its exact multi-edge count (rowwork) and
+// the number of candidate partners (span):
+//   hash  (one warp per row)  : open addressing, H = 256..4096 slots, for sparse rows
+//   hash  (one CTA per row)   : H = 16384 slots
+//   dense (one CTA per row)   : one u16/u32 counter per candidate partner, column-blocked
+//                               passes when the span exceeds the shared-memory block
+#pragma once
+#include "common.cuh"
+
+namespace kc {
+
+struct EdgeSink {
+  uint4* buf;                   // {rank_a, rank_b, count, blosum}
+  unsigned long long* cursor;   // edges wanted so far (may exceed cap: caller grows + retries)
+  unsigned long long cap;
+  uint32_t threshold;
+};
+
+struct PairCounters {            // device-side totals (u64 each)
+  unsigned long long n_pairs;    // distinct (row, partner) pairs with count >= 1
+  unsigned long long n_edges;    // pairs over the threshold
+  unsigned long long sum_count;  // sum of their counts
+  unsigned long long n_multi;    // sum of all counts = multi-edges accumulated
+};
+
+__device__ __forceinline__ void emit_edge(bool pred, uint32_t ra, uint32_t rb, uint32_t count,
+                                          const EdgeSink& sink) {
+  const uint32_t m = __ballot_sync(kFullMask, pred);
+  if (!m) return;
+  unsigned long long base = 0;
+  const uint32_t leader = __ffs(m) - 1;
+  if (lane_id() == leader) base = atomicAdd(sink.cursor, (unsigned long long)__popc(m));
+  base = __shfl_sync(kFullMask, base, leader);
+  const unsigned long long idx = base + __popc(m & lanemask_lt());
+  if (pred && idx < sink.cap) sink.buf[idx] = make_uint4(ra, rb, count, 0u);
+}
+
+// row classes
+enum : uint8_t {
+  kBinSkip = 0,
+  kBinHash8 = 1,   // warp, 256 slots
+  kBinHash9 = 2,   // warp, 512
+  kBinHash10 = 3,  // warp, 1024
+  kBinHash11 = 4,  // warp, 2048
+  kBinHash12 = 5,  // warp, 4096
+  kBinHash14 = 6,  // CTA, 16384
+  kBinDense = 7
+};
+
+// bounds[0..1] = the shard's row range (device memory: no host round trip)
+__global__ void __launch_bounds__(256)
+    classify_rows_kernel(const uint32_t* __restrict__ rowwork, const uint32_t* __restrict__ first_after,
+                         uint32_t n, const uint32_t* __restrict__ bounds, uint32_t dense_single_pass_cols,
+                         uint8_t* __restrict__ rowbin, uint32_t* __restrict__ bin_counts) {
+  __shared__ uint32_t s_cnt[8];
+  if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t row_lo = bounds[0], row_hi = bounds[1];
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) {
+    uint8_t bin = kBinSkip;
+    const uint32_t P = rowwork[r];
+    if (P != 0 && r >= row_lo && r < row_hi) {
+      const uint32_t target = first_after ? first_after[r] : r + 1;
+      const uint32_t span = n - target;
+      const uint32_t U = min(P, span);  // upper bound on distinct partners
+      if (span <= dense_single_pass_cols && span <= 8u * U) bin = kBinDense;
+      else if (U <= 128) bin = kBinHash8;
+      else if (U <= 256) bin = kBinHash9;
+      else if (U <= 512) bin = kBinHash10;
+      else if (U <= 1024) bin = kBinHash11;
+      else if (U <= 2048) bin = kBinHash12;
+      else if (U <= 8192) bin = kBinHash14;
+      else bin = kBinDense;
+      atomicAdd(&s_cnt[bin], 1u);
+    }
+    rowbin[r] = bin;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && s_cnt[threadIdx.x]) atomicAdd(&bin_counts[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+template <int LOG_H>
+__device__ __forceinline__ void hash_bump(uint32_t* keys, uint32_t* cnt, uint32_t b) {
+  constexpr uint32_t H = 1u << LOG_H;
+  uint32_t h = (b * 2654435761u) >> (32 - LOG_H);
+  for (;;) {
+    const uint32_t k = keys[h];
+    if (k == b) break;
+    if (k == kSentinel) {
+      const uint32_t old = atomicCAS(&keys[h], kSentinel, b);
+      if (old == kSentinel || old == b) break;
+    }
+    h = (h + 1u) & (H - 1u);
+  }
+  atomicAdd(&cnt[h], 1u);
+}
+
+// walk one 32-entry chunk of a row: long postings suffixes are read by the whole warp
+// (coalesced), short ones by the lane that owns the entry
+template <class Bump>
+__device__ __forceinline__ void walk_chunk(const uint32_t* __restrict__ col, uint2 e, Bump bump) {
+  const uint32_t lane = lane_id();
+  const uint32_t len = e.y - e.x;
+  uint32_t m = __ballot_sync(kFullMask, len >= 16u);
+  while (m) {
+    const uint32_t src = __ffs(m) - 1;
+    m &= m - 1;
+    const uint32_t s = __shfl_sync(kFullMask, e.x, src), t = __shfl_sync(kFullMask, e.y, src);
+    for (uint32_t j = s + lane; j < t; j += 32) bump(col[j]);
+  }
+  if (len < 16u)
+    for (uint32_t j = e.x; j < e.y; ++j) bump(col[j]);
+}
+
+// ---------------------------------------------------------------------------------------
+// hash accumulators.  GROUP_WARPS warps share one table and one row; a CTA holds
+// CTA_WARPS / GROUP_WARPS groups.  GROUP_WARPS is 1 (warp per row) or CTA_WARPS (CTA per row).
+// ---------------------------------------------------------------------------------------
+template <int LOG_H, int GROUP_WARPS, int CTA_WARPS>
+__global__ void __launch_bounds__(CTA_WARPS * 32)
+    pairs_hash_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen,
+                      const uint2* __restrict__ suf, const uint32_t* __restrict__ col,
+                      const uint8_t* __restrict__ rowbin, uint8_t my_bin, uint32_t n,
+                      uint32_t* __restrict__ row_cursor, EdgeSink sink, PairCounters* __restrict__ counters) {
+  static_assert(GROUP_WARPS == 1 || GROUP_WARPS == CTA_WARPS, "group = warp or CTA");
+  constexpr uint32_t H = 1u << LOG_H;
+  constexpr int GROUPS = CTA_WARPS / GROUP_WARPS;
+  constexpr uint32_t GSIZE = GROUP_WARPS * 32;
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  __shared__ uint32_t s_base;
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t group = warp / GROUP_WARPS, gwarp = warp % GROUP_WARPS;
+  const uint32_t gtid = gwarp * 32 + lane;
+  uint32_t* keys = reinterpret_cast<uint32_t*>(dyn_smem) + (size_t)group * 2 * H;
+  uint32_t* cnt = keys + H;
+  (void)GROUPS;
+  unsigned long long n_pairs = 0, n_edges = 0, sum_count = 0, n_multi = 0;
+
+  auto gsync = [&]() {
+    if (GROUP_WARPS == 1) __syncwarp(); else __syncthreads();
+  };
+
+  for (;;) {
+    uint32_t base;
+    if (GROUP_WARPS == 1) {
+      base = 0;
+      if (lane == 0) base = atomicAdd(row_cursor, 32u);
+      base = __shfl_sync(kFullMask, base, 0);
+    } else {
+      __syncthreads();
+      if (threadIdx.x == 0) s_base = atomicAdd(row_cursor, 32u);
+      __syncthreads();
+      base = s_base;
+    }
+    if (base >= n) break;
+    uint32_t todo = __ballot_sync(kFullMask, base + lane < n && rowbin[base + lane] == my_bin);
+    while (todo) {
+      const uint32_t r = base + __ffs(todo) - 1;
+      todo &= todo - 1;
+      // clear the table
+      for (uint32_t i = gtid * 4; i < H; i += GSIZE * 4) {
+        *reinterpret_cast<uint4*>(keys + i) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+        *reinterpret_cast<uint4*>(cnt + i) = make_uint4(0, 0, 0, 0);
+      }
+      gsync();
+      const uint32_t nl = rowlen[r], ps = pstart[r];
+      for (uint32_t c = gwarp * 32; c < nl; c += GSIZE) {
+        const uint2 e = c + lane < nl ? ld_stream_u32x2(suf + ps + c + lane) : make_uint2(0, 0);
+        walk_chunk(col, e, [&](uint32_t b) { hash_bump<LOG_H>(keys, cnt, b); });
+      }
+      gsync();
+      for (uint32_t i = gtid; i < H; i += GSIZE) {
+        const uint32_t b = keys[i];
+        const uint32_t c = b != kSentinel ? cnt[i] : 0u;
+        const bool out = c > sink.threshold;
+        n_pairs += c != 0;
+        n_multi += c;
+        n_edges += out;
+        sum_count += out ? c : 0u;
+        emit_edge(out, r, b, c, sink);
+      }
+      gsync();
+    }
+  }
+  n_pairs = warp_sum64(n_pairs);
+  n_edges = warp_sum64(n_edges);
+  sum_count = warp_sum64(sum_count);
+  n_multi = warp_sum64(n_multi);
+  if (lane == 0) {
+    if (n_multi) atomicAdd(&counters->n_multi, n_multi);
+    if (n_pairs) atomicAdd(&counters->n_pairs, n_pairs);
+    if (n_edges) atomicAdd(&counters->n_edges, n_edges);
+    if (sum_count) atomicAdd(&counters->sum_count, sum_count);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// dense accumulators: one CTA per row, one counter per candidate partner, in column blocks of
+// `block_cols` partners.  WIDE = u32 counters (rows with >= 65535 ids), else two u16 per word.
+// ---------------------------------------------------------------------------------------
+template <bool WIDE>
+__global__ void __launch_bounds__(256)
+    pairs_dense_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen,
+                       const uint2* __restrict__ suf, const uint32_t* __restrict__ col,
+                       const uint32_t* __restrict__ first_after, const uint8_t* __restrict__ rowbin, uint32_t n,
+                       uint32_t block_cols, uint32_t* __restrict__ row_cursor, EdgeSink sink,
+                       PairCounters* __restrict__ counters) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  __shared__ uint32_t s_base;
+  uint32_t* acc = reinterpret_cast<uint32_t*>(dyn_smem);
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t words = WIDE ? block_cols : (block_cols + 1) / 2;
+  const uint32_t words4 = (words + 3u) & ~3u;
+  unsigned long long n_pairs = 0, n_edges = 0, sum_count = 0, n_multi = 0;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = atomicAdd(row_cursor, 32u);
+    __syncthreads();
+    const uint32_t base = s_base;
+    if (base >= n) break;
+    uint32_t todo = __ballot_sync(kFullMask, base + lane < n && rowbin[base + lane] == kBinDense);
+    while (todo) {
+      const uint32_t r = base + __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t nl = rowlen[r], ps = pstart[r];
+      const uint32_t first = first_after ? first_after[r] : r + 1;
+      const bool multipass = n - first > block_cols;
+      for (uint32_t blk_lo = first; blk_lo < n; blk_lo += block_cols) {
+        const uint32_t blk_hi = min(n, blk_lo + block_cols);
+        for (uint32_t i = threadIdx.x * 4; i < words4; i += 256 * 4)
+          *reinterpret_cast<uint4*>(acc + i) = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        for (uint32_t c = warp * 32; c < nl; c += 256) {
+          uint2 e = c + lane < nl ? ld_stream_u32x2(suf + ps + c + lane) : make_uint2(0, 0);
+          if (multipass) {  // clip the suffix to holders in [blk_lo, blk_hi)
+            uint32_t lo = e.x, hi = e.y;
+            while (lo < hi) {
+              const uint32_t mid = (lo + hi) >> 1;
+              if (col[mid] < blk_lo) lo = mid + 1; else hi = mid;
+            }
+            e.x = lo;
+            hi = e.y;
+            while (lo < hi) {
+              const uint32_t mid = (lo + hi) >> 1;
+              if (col[mid] < blk_hi) lo = mid + 1; else hi = mid;
+            }
+            e.y = lo;
+          }
+          walk_chunk(col, e, [&](uint32_t b) {
+            const uint32_t idx = b - blk_lo;
+            if (WIDE) atomicAdd(&acc[idx], 1u);
+            else atomicAdd(&acc[idx >> 1], 1u << ((idx & 1u) * 16u));
+          });
+        }
+        __syncthreads();
+        const uint32_t ncols = blk_hi - blk_lo;
+        for (uint32_t i0 = warp * 32; i0 < words; i0 += 256) {  // warp-uniform trip count
+          const uint32_t i = i0 + lane;
+          const uint32_t x = i < words ? acc[i] : 0u;
+          if (WIDE) {
+            const bool out = x > sink.threshold;
+            n_pairs += x != 0;
+            n_multi += x;
+            n_edges += out;
+            sum_count += out ? x : 0u;
+            emit_edge(out, r, blk_lo + i, x, sink);
+          } else {
+            const uint32_t c0 = x & 0xFFFFu, c1 = x >> 16;
+            const bool o0 = c0 > sink.threshold, o1 = c1 > sink.threshold && 2 * i + 1 < ncols;
+            n_pairs += (c0 != 0) + (c1 != 0);
+            n_multi += c0 + c1;
+            n_edges += (uint32_t)o0 + (uint32_t)o1;
+            sum_count += (o0 ? c0 : 0u) + (o1 ? c1 : 0u);
+            emit_edge(o0, r, blk_lo + 2 * i, c0, sink);
+            emit_edge(o1, r, blk_lo + 2 * i + 1, c1, sink);
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+  n_pairs = warp_sum64(n_pairs);
+  n_edges = warp_sum64(n_edges);
+  sum_count = warp_sum64(sum_count);
+  n_multi = warp_sum64(n_multi);
+  if (lane == 0) {
+    if (n_multi) atomicAdd(&counters->n_multi, n_multi);
+    if (n_pairs) atomicAdd(&counters->n_pairs, n_pairs);
+    if (n_edges) atomicAdd(&counters->n_edges, n_edges);
+    if (sum_count) atomicAdd(&counters->sum_count, sum_count);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K9: per-edge sorted-list intersection of the two id rows.  One warp per edge: lanes take the
+// shorter row's ids and binary-search the longer row.  MODE 0: sum of BLOSUM62 self-scores of
+// the shared k-mers -> edge.w.  (The list itself is produced by shared_kmers_kernel.)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    edge_blosum_kernel(uint4* __restrict__ edges, unsigned long long n_edges, const uint32_t* __restrict__ pstart,
+                       const uint32_t* __restrict__ rowlen, const uint32_t* __restrict__ ids,
+                       const uint8_t* __restrict__ selfscore) {
+  const uint32_t lane = lane_id();
+  const unsigned long long gw = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  for (unsigned long long ei = gw; ei < n_edges; ei += nw) {
+    uint4 e = edges[ei];
+    uint32_t ra = e.x, rb = e.y;
+    if (rowlen[ra] > rowlen[rb]) {
+      const uint32_t t = ra;
+      ra = rb;
+      rb = t;
+    }
+    const uint32_t* A = ids + pstart[ra];
+    const uint32_t na = rowlen[ra];
+    const uint32_t* B = ids + pstart[rb];
+    const uint32_t nb = rowlen[rb];
+    int s = 0;
+    for (uint32_t i = lane; i < na; i += 32) {
+      const uint32_t x = A[i];
+      uint32_t lo = 0, hi = nb;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (B[mid] < x) lo = mid + 1; else hi = mid;
+      }
+      if (lo < nb && B[lo] == x) s += selfscore[x];
+    }
+    s = warp_sum_i(s);
+    if (lane == 0) {
+      e.w = (uint32_t)s;
+      edges[ei] = e;
+    }
+  }
+}
+
+// single-warp listing of the shared ids of two rows as k-mer values (ascending)
+__global__ void shared_kmers_kernel(uint32_t ra, uint32_t rb, const uint32_t* __restrict__ pstart,
+                                    const uint32_t* __restrict__ rowlen, const uint32_t* __restrict__ ids,
+                                    const uint32_t* __restrict__ vocab, uint32_t* __restrict__ out,
+                                    uint32_t cap, uint32_t* __restrict__ n_out) {
+  const uint32_t lane = lane_id();
+  const uint32_t* A = ids + pstart[ra];
+  const uint32_t na = rowlen[ra];
+  const uint32_t* B = ids + pstart[rb];
+  const uint32_t nb = rowlen[rb];
+  uint32_t base = 0;
+  for (uint32_t c = 0; c < na; c += 32) {
+    const uint32_t i = c + lane;
+    bool hit = false;
+    uint32_t x = 0;
+    if (i < na) {
+      x = A[i];
+      uint32_t lo = 0, hi = nb;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (B[mid] < x) lo = mid + 1; else hi = mid;
+      }
+      hit = lo < nb && B[lo] == x;
+    }
+    const uint32_t m = __ballot_sync(kFullMask, hit);
+    const uint32_t pos = base + __popc(m & lanemask_lt());
+    if (hit && pos < cap) out[pos] = vocab[x];
+    base += __popc(m);
+  }
+  if (lane == 0) *n_out = base;
+}
+
+// rank space -> input order, a < b, packed for the final sort:
+//   key = a << 32 | b, val = count | blosum << 32
+__global__ void finalize_edges_kernel(const uint4* __restrict__ edges, unsigned long long n_edges,
+                                      const uint32_t* __restrict__ orig_of, unsigned long long* __restrict__ keys,
+                                      unsigned long long* __restrict__ vals) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_edges;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint4 e = edges[i];
+    uint32_t a = orig_of ? orig_of[e.x] : e.x, b = orig_of ? orig_of[e.y] : e.y;
+    if (a > b) {
+      const uint32_t t = a;
+      a = b;
+      b = t;
+    }
+    keys[i] = ((unsigned long long)a << 32) | b;
+    vals[i] = (unsigned long long)e.z | ((unsigned long long)e.w << 32);
+  }
+}
+
+__global__ void assemble_edges_kernel(const unsigned long long* __restrict__ keys,
+                                      const unsigned long long* __restrict__ vals, unsigned long long n_edges,
+                                      uint4* __restrict__ out) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_edges;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long k = keys[i], v = vals[i];
+    out[i] = make_uint4((uint32_t)(k >> 32), (uint32_t)k, (uint32_t)v, (uint32_t)(v >> 32));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Dense presence-bitset path: per-protein bitsets over the repeated-k-mer vocabulary and
+// AND+popcount pair counts (one warp per pair, shuffle reduction).
+// ---------------------------------------------------------------------------------------
+__global__ void bitset_fill_kernel(const uint32_t* __restrict__ rows, uint32_t n_rows,
+                                   const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen,
+                                   const uint32_t* __restrict__ ids, uint32_t words, uint32_t* __restrict__ bits) {
+  const uint32_t lane = lane_id();
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t i = gw; i < n_rows; i += nw) {
+    const uint32_t r = rows[i];
+    const uint32_t* A = ids + pstart[r];
+    for (uint32_t j = lane; j < rowlen[r]; j += 32) {
+      const uint32_t id = A[j];
+      atomicOr(&bits[(size_t)i * words + (id >> 5)], 1u << (id & 31u));
+    }
+  }
+}
+
+constexpr int kBitTile = 8;  // 8x8 pairs per CTA, one warp per row of the tile
+__global__ void __launch_bounds__(kBitTile * 32)
+    bitset_pairs_kernel(const uint32_t* __restrict__ bits, uint32_t n_rows, uint32_t words,
+                        uint32_t* __restrict__ counts) {
+  // tile (ti, tj): warp w owns row ti*8+w and accumulates against the 8 rows of tj, the
+  // 8 column bitsets being staged chunk by chunk in shared memory
+  __shared__ uint32_t s_col[kBitTile][256];
+  const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
+  const uint32_t ti = blockIdx.y, tj = blockIdx.x;
+  if (tj < ti) return;
+  const uint32_t i = ti * kBitTile + w;
+  uint32_t acc[kBitTile];
+#pragma unroll
+  for (int q = 0; q < kBitTile; ++q) acc[q] = 0;
+  for (uint32_t w0 = 0; w0 < words; w0 += 256) {
+    __syncthreads();
+    for (uint32_t x = threadIdx.x; x < kBitTile * 256; x += kBitTile * 32) {
+      const uint32_t q = x >> 8, ww = w0 + (x & 255u), j = tj * kBitTile + q;
+      s_col[q][x & 255u] = (j < n_rows && ww < words) ? bits[(size_t)j * words + ww] : 0u;
+    }
+    __syncthreads();
+    if (i < n_rows) {
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        const uint32_t ww = w0 + s * 32 + lane;
+        const uint32_t a = ww < words ? bits[(size_t)i * words + ww] : 0u;
+#pragma unroll
+        for (int q = 0; q < kBitTile; ++q) acc[q] += __popc(a & s_col[q][s * 32 + lane]);
+      }
+    }
+  }
+  if (i < n_rows) {
+#pragma unroll
+    for (int q = 0; q < kBitTile; ++q) {
+      const uint32_t v = warp_sum(acc[q]);
+      const uint32_t j = tj * kBitTile + q;
+      if (lane == 0 && j < n_rows) {
+        counts[(size_t)i * n_rows + j] = v;
+        counts[(size_t)j * n_rows + i] = v;
+      }
+    }
+  }
+}
+
+}  // namespace kc
