@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the k-mer clustering hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+Metric (BASELINE.json): protein pairs scored per second (plus k-mers indexed per second),
+on the synthetic 1 M-protein, mean-350-aa, k=7, all-pairs configuration (config 4), which fits
+one GPU.  One "step" = one pass of the hot path over the whole protein set:
+    build_index (K1-K5: extract, per-protein dedup, census, perfect index, postings)
+  + score_pairs (K7-K9: all-pairs shared-k-mer counts, threshold 10, BLOSUM, sorted edges).
+`value` is measured with the residue stream already resident in HBM, CUDA events on the
+launching stream; `e2e` is the same step through the C ABI from pinned HOST buffers with the
+H2D staging and the D2H edge readback inside the timed region (wall clock around a sync).
+At N > 1 every rank holds the full index (replicated build) and scores its own work-balanced
+shard of the pair triangle; the sorted edge lists are gathered to rank 0 over NCCL inside the
+timed region.  Total work is fixed, so "scaling" is "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (n_proteins, length law, k, seed, cross_class_only)
+    "synth_1m_k7": (1_000_000, "A", 7, 0xB2000004, False),    # BASELINE.json configs[3]
+    "synth_100k_k5": (100_000, "A", 5, 0xB2000003, False),    # configs[2]
+    "synth_20k_k5": (20_000, "A", 5, 0xB2000003, False),      # quick check
+}
+THRESHOLD = 10
+CPU_SAMPLE = {"synth_1m_k7": 250_000, "synth_100k_k5": 50_000, "synth_20k_k5": 20_000}
+REF_SAMPLE = {"synth_1m_k7": 250_000, "synth_100k_k5": 50_000, "synth_20k_k5": 20_000}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_set(workload: str, n_override: int | None):
+    import uniprot_kmer_based_clustering_b200 as kc
+    n, law, k, seed, cross = WORKLOADS[workload]
+    if n_override:
+        n = n_override
+    threads = min(32, os.cpu_count() or 8)
+    return kc.ProteinSet.synthetic(n, law, seed, threads=threads), k, cross
+
+
+def oracle_run(ps, k, cross, n_sample, threads):
+    """CPU restatement (oracle/) on the first n_sample proteins; returns metric dict."""
+    from oracle.oracle import Oracle
+    n = min(n_sample, ps.n)
+    o = Oracle(k, threads)
+    o.set_proteins(ps.residues[:int(ps.offsets[n])], ps.offsets[:n + 1], ps.class_id[:n])
+    t0 = time.perf_counter()
+    o.extract_kmers()
+    ix = o.build_index()
+    t1 = time.perf_counter()
+    pr = o.score_pairs(THRESHOLD, cross, True, mode=1)
+    t2 = time.perf_counter()
+    pairs = n * (n - 1) // 2
+    return {"n": n, "pairs": pairs, "total_s": t2 - t0, "index_s": t1 - t0, "pairs_s": t2 - t1,
+            "positions": ix.stats["n_positions"], "multi_edges": pr.stats["n_multi_edges"],
+            "edges": pr.stats["n_edges_out"]}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (the oracle port; the Rust crate needs a
+    nightly toolchain + crates.io and cannot be built here) on all host threads, each step a
+    bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    ps, k, cross = make_set(args.workload, args.n_proteins)
+    n_sample = min(REF_SAMPLE[args.workload], ps.n)
+    for _ in range(args.warmup):
+        oracle_run(ps, k, cross, max(2000, n_sample // 20), threads)
+    runs = [oracle_run(ps, k, cross, n_sample, threads) for _ in range(args.steps)]
+    t = sum(r["total_s"] for r in runs) / len(runs)
+    r = runs[-1]
+    value = r["pairs"] / t
+    sample = (f"first {r['n']} of {ps.n} proteins of {args.workload} (k={k}), whole hot path per step; "
+              f"oracle port, {threads} threads")
+    line = {
+        "impl": "reference", "metric": "protein_pairs_scored_per_s", "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": args.workload, "k": k, "threshold": THRESHOLD, "cross_class_only": cross,
+                   "n_proteins": ps.n, "sample_proteins": r["n"]},
+        "kmers_indexed_per_s": r["positions"] / (sum(x["index_s"] for x in runs) / len(runs)),
+        "multi_edges_per_s": r["multi_edges"] / (sum(x["pairs_s"] for x in runs) / len(runs)),
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="synth_1m_k7", choices=sorted(WORKLOADS))
+    ap.add_argument("--n-proteins", type=int, default=None, help="override the workload's protein count")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import uniprot_kmer_based_clustering_b200 as kc
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W = max(args.warmup, 3)
+
+    ps, k, cross = make_set(args.workload, args.n_proteins)
+    n = ps.n
+    pairs_total = n * (n - 1) // 2
+    # pinned host staging buffers (e2e) and device-resident copies (value)
+    h_res = torch.from_numpy(ps.residues).pin_memory()
+    h_off = torch.from_numpy(ps.offsets.view(np.int64)).pin_memory()
+    h_cls = torch.from_numpy(ps.class_id.view(np.int32)).pin_memory()
+    d_res, d_off, d_cls = h_res.cuda(), h_off.cuda(), h_cls.cuda()
+    stream = torch.cuda.current_stream()
+
+    eng = kc.Engine(k, device=local_rank, threshold=THRESHOLD, cross_class_only=cross, want_blosum=True)
+    eng.set_stream(stream.cuda_stream)
+
+    def gather_edges(edges_np):
+        """edge lists -> rank 0 over NCCL (variable length: sizes first, then padded gather)"""
+        if world == 1:
+            return edges_np
+        cnt = torch.tensor([edges_np.size], dtype=torch.int64, device="cuda")
+        counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(counts, cnt)
+        mx = int(max(c.item() for c in counts))
+        buf = torch.zeros(max(mx, 1) * 4, dtype=torch.int32, device="cuda")
+        if edges_np.size:
+            buf[:edges_np.size * 4] = torch.from_numpy(edges_np.view(np.int32).reshape(-1)).cuda()
+        out = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+        dist.gather(buf, out, dst=0)
+        if rank != 0:
+            return None
+        parts = [o[:int(c.item()) * 4].cpu().numpy().view(kc.EDGE_DTYPE) for o, c in zip(out, counts)]
+        return np.concatenate(parts)
+
+    def step_resident():
+        ist = eng.build_index()
+        pst = eng.score_pairs(rank, world)
+        return ist, pst
+
+    def step_e2e():
+        eng.set_proteins_ptr(h_res.data_ptr(), h_off.data_ptr(), h_cls.data_ptr(), n, on_device=False)
+        ist = eng.build_index()
+        pst = eng.score_pairs(rank, world)
+        edges = eng.get_edges()
+        return ist, pst, gather_edges(edges)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM, CUDA events on the launching stream -------------------
+    eng.set_proteins_ptr(d_res.data_ptr(), d_off.data_ptr(), d_cls.data_ptr(), n, on_device=True)
+    for _ in range(W):
+        ist, pst = step_resident()
+    eng.reset_timings()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms = {"index_ms": 0.0, "pairs_ms": 0.0, "edges_ms": 0.0, "pair_kernel_ms": 0.0, "census_kernel_ms": 0.0}
+    ev0.record(stream)
+    for _ in range(args.steps):
+        ist, pst = step_resident()
+        t = eng.timings()
+        for key in stage_ms:
+            stage_ms[key] += t[key]
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = ev0.elapsed_time(ev1) / args.steps
+    launches = eng.timings()["kernel_launches"]
+    for key in stage_ms:
+        stage_ms[key] /= args.steps
+
+    # ---- e2e: host buffers, H2D + D2H (+ NCCL gather) inside the timed region, wall clock ------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ist_e, pst_e, edges = step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+
+    # max over ranks; sums over ranks for the sharded quantities
+    red = torch.tensor([dev_ms, e2e_s, stage_ms["index_ms"], stage_ms["pairs_ms"], stage_ms["pair_kernel_ms"],
+                        stage_ms["census_kernel_ms"], stage_ms["edges_ms"]], dtype=torch.float64, device="cuda")
+    sums = torch.tensor([pst["n_multi_edges_kept"], pst["n_edges_out"], pst["n_pairs_kept"], launches],
+                        dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_s, index_ms, pairs_ms, pair_kernel_ms, census_ms, edges_ms = red.tolist()
+    m_kept, e_out, p_kept, launches_all = (int(x) for x in sums.tolist())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        nnz = ist["nnz"]
+        # 4 B per multi-edge + 4 B per CSR nonzero + 16 B per emitted edge; at N > 1 every
+        # rank streams its own rows' suffixes, so the per-rank figure uses the rank-0 share
+        algo_bytes = 4 * pst["n_multi_edges_kept"] + 4 * nnz // world + 16 * pst["n_edges_out"]
+        achieved = algo_bytes / (stage_ms["pair_kernel_ms"] * 1e-3) / 1e9 if stage_ms["pair_kernel_ms"] > 0 else 0.0
+        idx_bytes = 9 * ist["n_positions"]
+        idx_achieved = idx_bytes / (stage_ms["index_ms"] * 1e-3) / 1e9 if stage_ms["index_ms"] > 0 else 0.0
+        h2d = int(h_res.numel() + h_off.numel() * 8 + h_cls.numel() * 4 + 16 * n)
+        d2h = int(pst_e["n_edges_out"] * 16 + 12 * n + 512)
+        line = {
+            "metric": "protein_pairs_scored_per_s", "value": pairs_total / (dev_ms * 1e-3), "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": dev_ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "n_proteins": n, "mean_len": round(ps.residues.size / n, 1),
+                       "k": k, "threshold": THRESHOLD, "cross_class_only": cross, "blosum": True,
+                       "generator": "G1 (include/kc_host.h)", "seed": hex(WORKLOADS[args.workload][3]),
+                       "l2_policy": f"inputs larger than L2 ({ps.residues.size / 1e6:.0f} MB residues, "
+                                    f"{4 * nnz / 1e6:.0f} MB postings); no flush needed",
+                       "parallelism": "replicated index, row-block sharded pair triangle" if world > 1 else "1 GPU"},
+            "kmers_indexed_per_s": ist["n_positions"] / (index_ms * 1e-3),
+            "pair_stage_pairs_per_s": pairs_total / (pairs_ms * 1e-3) if pairs_ms > 0 else None,
+            "multi_edges_per_s": m_kept / (pair_kernel_ms * 1e-3) if pair_kernel_ms > 0 else None,
+            "stage_ms": {"index": index_ms, "census_kernel": census_ms, "pairs": pairs_ms,
+                         "pair_kernels": pair_kernel_ms, "edges_sort_blosum": edges_ms},
+            "counts": {"n_positions": ist["n_positions"], "n_repeated": ist["n_repeated"], "nnz": nnz,
+                       "n_multi_edges": pst["n_multi_edges"], "n_pairs_nonzero": p_kept, "n_edges_out": e_out},
+            "roofline": {"bound": "hbm", "kernel": "pairs_hash_kernel/pairs_dense_kernel (K7-K8)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": algo_bytes},
+            "roofline_index": {"bound": "hbm", "kernel": "K1-K5 (extract, dedup, census, index, postings)",
+                               "achieved": idx_achieved, "peak": peak, "unit": "GB/s", "frac": idx_achieved / peak,
+                               "algorithmic_bytes": idx_bytes},
+            "e2e": {"value": pairs_total / e2e_s, "unit": "pairs/s", "ms_per_step": e2e_s * 1e3,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches_all,
+            "clocks": clocks,
+        }
+        if world == 1:
+            assert edges.size == pst_e["n_edges_out"]
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            r = oracle_run(ps, k, cross, CPU_SAMPLE[args.workload], threads)
+            line["cpu_baseline"] = {
+                "value": r["pairs"] / r["total_s"], "unit": "pairs/s", "cores": threads, "kind": "port",
+                "sample": f"first {r['n']} of {n} proteins, whole hot path once ({r['total_s']:.1f} s); "
+                          f"oracle port (CPU restatement), not the Rust binary",
+                "kmers_indexed_per_s": r["positions"] / r["index_s"],
+                "multi_edges_per_s": r["multi_edges"] / r["pairs_s"] if r["pairs_s"] > 0 else None}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
