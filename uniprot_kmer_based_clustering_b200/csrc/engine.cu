@@ -47,8 +47,8 @@ struct DeviceScalars {  // one small block of u64 counters, zeroed per stage
   unsigned long long edge_cursor;
   PairCounters pc;
   uint32_t list_counts[4];
-  uint32_t row_cursor[8];
-  uint32_t bin_counts[8];
+  uint32_t row_cursor[16];
+  uint32_t bin_counts[16];
   uint32_t shard_rows[2];
   uint32_t n_shared;
   uint32_t pad;
@@ -281,6 +281,22 @@ int launch_hash(kc_engine* e, uint8_t bin, const EdgeSink& sink) {
   KC_LAUNCH(e, kern, grid, CTA_WARPS * 32, smem, e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(),
             e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), e->d_rowbin.as<uint8_t>(), bin, (uint32_t)e->n,
             &e->ds->row_cursor[bin], sink, &e->ds->pc);
+  return KC_OK;
+}
+
+template <int LOG_H, int GROUP_WARPS, int CTA_WARPS>
+int launch_packed(kc_engine* e, uint8_t bin, uint32_t count_bits, const EdgeSink& sink) {
+  constexpr size_t smem =
+      ((size_t)(CTA_WARPS / GROUP_WARPS) * (1u << LOG_H) + (size_t)CTA_WARPS * kIdxPerWarp) * 4;
+  auto kern = pairs_packed_kernel<LOG_H, GROUP_WARPS, CTA_WARPS>;
+  KC_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CTA_WARPS * 32, smem));
+  if (per_sm < 1) per_sm = 1;
+  const uint32_t grid = (uint32_t)(e->num_sm * per_sm);
+  KC_LAUNCH(e, kern, grid, CTA_WARPS * 32, smem, e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(),
+            e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), e->d_rowbin.as<uint8_t>(), bin, (uint32_t)e->n,
+            count_bits, &e->ds->row_cursor[bin], sink, &e->ds->pc);
   return KC_OK;
 }
 
@@ -761,6 +777,10 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
   const uint32_t dense_cap_cols = (uint32_t)((dense_budget - 64) / (wide ? 4 : 2)) & ~7u;
   const uint32_t dense_cols = std::min<uint32_t>(dense_cap_cols, (n + 7u) & ~7u);
   const size_t dense_smem = (size_t)(wide ? dense_cols : (dense_cols + 1) / 2) * 4 + 16;
+  // packed hash slots: protein rank in the high bits (2^key_bits > n so no key is all ones)
+  uint32_t key_bits = 1;
+  while ((1ull << key_bits) <= (uint64_t)n) ++key_bits;
+  const uint32_t count_bits = 32 - key_bits;
 
   mark(e, EV_P0);
   for (int attempt = 0;; ++attempt) {
@@ -769,17 +789,19 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
     KC_LAUNCH(e, shard_bounds_kernel, 1, 32, 0, e->d_workprefix.as<unsigned long long>(), n, shard, n_shards,
               ds->shard_rows);
     KC_LAUNCH(e, classify_rows_kernel, (n + 255) / 256, 256, 0, e->d_rowwork.as<uint32_t>(),
-              e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr, n, ds->shard_rows, dense_cols,
-              e->d_rowbin.as<uint8_t>(), ds->bin_counts);
+              e->d_rowlen.as<uint32_t>(), e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr, n,
+              ds->shard_rows, dense_cols, count_bits, e->d_rowbin.as<uint8_t>(), ds->bin_counts);
     EdgeSink sink{e->d_edges.as<uint4>(), &ds->edge_cursor, e->edge_cap, e->cfg.threshold};
     mark(e, EV_PK0);
     int rc;
-    if ((rc = launch_hash<8, 1, 8>(e, kBinHash8, sink))) return rc;
-    if ((rc = launch_hash<9, 1, 8>(e, kBinHash9, sink))) return rc;
-    if ((rc = launch_hash<10, 1, 8>(e, kBinHash10, sink))) return rc;
-    if ((rc = launch_hash<11, 1, 4>(e, kBinHash11, sink))) return rc;
-    if ((rc = launch_hash<12, 1, 4>(e, kBinHash12, sink))) return rc;
-    if ((rc = launch_hash<14, 8, 8>(e, kBinHash14, sink))) return rc;
+    if ((rc = launch_packed<8, 1, 4>(e, kBinPack8, count_bits, sink))) return rc;
+    if ((rc = launch_packed<9, 1, 4>(e, kBinPack9, count_bits, sink))) return rc;
+    if ((rc = launch_packed<10, 1, 4>(e, kBinPack10, count_bits, sink))) return rc;
+    if ((rc = launch_packed<11, 1, 4>(e, kBinPack11, count_bits, sink))) return rc;
+    if ((rc = launch_packed<12, 4, 4>(e, kBinPack12, count_bits, sink))) return rc;
+    if ((rc = launch_packed<13, 8, 8>(e, kBinPack13, count_bits, sink))) return rc;
+    if ((rc = launch_packed<14, 8, 8>(e, kBinPack14, count_bits, sink))) return rc;
+    if ((rc = launch_hash<14, 8, 8>(e, kBinWide, sink))) return rc;
     {
       int per_sm = 1;
       if (wide) {

@@ -51,22 +51,27 @@ __device__ __forceinline__ void emit_edge(bool pred, uint32_t ra, uint32_t rb, u
 // row classes
 enum : uint8_t {
   kBinSkip = 0,
-  kBinHash8 = 1,   // warp, 256 slots
-  kBinHash9 = 2,   // warp, 512
-  kBinHash10 = 3,  // warp, 1024
-  kBinHash11 = 4,  // warp, 2048
-  kBinHash12 = 5,  // warp, 4096
-  kBinHash14 = 6,  // CTA, 16384
-  kBinDense = 7
+  kBinPack8 = 1,    // packed hash, one warp per row, 256 slots   (U <= 128)
+  kBinPack9 = 2,    //                                512          (U <= 256)
+  kBinPack10 = 3,   //                                1024         (U <= 512)
+  kBinPack11 = 4,   //                                2048         (U <= 1024)
+  kBinPack12 = 5,   // packed hash, 4 warps per row,  4096         (U <= 2048)
+  kBinPack13 = 6,   // packed hash, 8 warps per row,  8192         (U <= 4096)
+  kBinPack14 = 7,   // packed hash, 8 warps per row,  16384        (U <= 8192)
+  kBinWide = 8,     // key/count in separate words (rows whose counts do not fit a packed slot)
+  kBinDense = 9,
+  kNumBins = 10
 };
 
-// bounds[0..1] = the shard's row range (device memory: no host round trip)
+// bounds[0..1] = the shard's row range (device memory: no host round trip).
+// count_bits = bits left for the counter in a packed slot (32 - bits of a protein rank).
 __global__ void __launch_bounds__(256)
-    classify_rows_kernel(const uint32_t* __restrict__ rowwork, const uint32_t* __restrict__ first_after,
-                         uint32_t n, const uint32_t* __restrict__ bounds, uint32_t dense_single_pass_cols,
-                         uint8_t* __restrict__ rowbin, uint32_t* __restrict__ bin_counts) {
-  __shared__ uint32_t s_cnt[8];
-  if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+    classify_rows_kernel(const uint32_t* __restrict__ rowwork, const uint32_t* __restrict__ rowlen,
+                         const uint32_t* __restrict__ first_after, uint32_t n, const uint32_t* __restrict__ bounds,
+                         uint32_t dense_single_pass_cols, uint32_t count_bits, uint8_t* __restrict__ rowbin,
+                         uint32_t* __restrict__ bin_counts) {
+  __shared__ uint32_t s_cnt[kNumBins];
+  if (threadIdx.x < kNumBins) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t row_lo = bounds[0], row_hi = bounds[1];
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -77,20 +82,23 @@ __global__ void __launch_bounds__(256)
       const uint32_t target = first_after ? first_after[r] : r + 1;
       const uint32_t span = n - target;
       const uint32_t U = min(P, span);  // upper bound on distinct partners
-      if (span <= dense_single_pass_cols && span <= 8u * U) bin = kBinDense;
-      else if (U <= 128) bin = kBinHash8;
-      else if (U <= 256) bin = kBinHash9;
-      else if (U <= 512) bin = kBinHash10;
-      else if (U <= 1024) bin = kBinHash11;
-      else if (U <= 2048) bin = kBinHash12;
-      else if (U <= 8192) bin = kBinHash14;
-      else bin = kBinDense;
+      const bool packable = (rowlen[r] >> count_bits) == 0;  // a count never exceeds the row length
+      if (span <= dense_single_pass_cols && span <= 4u * U) bin = kBinDense;
+      else if (U > 8192) bin = kBinDense;
+      else if (!packable) bin = kBinWide;
+      else if (U <= 128) bin = kBinPack8;
+      else if (U <= 256) bin = kBinPack9;
+      else if (U <= 512) bin = kBinPack10;
+      else if (U <= 1024) bin = kBinPack11;
+      else if (U <= 2048) bin = kBinPack12;
+      else if (U <= 4096) bin = kBinPack13;
+      else bin = kBinPack14;
       atomicAdd(&s_cnt[bin], 1u);
     }
     rowbin[r] = bin;
   }
   __syncthreads();
-  if (threadIdx.x < 8 && s_cnt[threadIdx.x]) atomicAdd(&bin_counts[threadIdx.x], s_cnt[threadIdx.x]);
+  if (threadIdx.x < kNumBins && s_cnt[threadIdx.x]) atomicAdd(&bin_counts[threadIdx.x], s_cnt[threadIdx.x]);
 }
 
 template <int LOG_H>
@@ -192,6 +200,173 @@ __global__ void __launch_bounds__(CTA_WARPS * 32)
         n_edges += out;
         sum_count += out ? c : 0u;
         emit_edge(out, r, b, c, sink);
+      }
+      gsync();
+    }
+  }
+  n_pairs = warp_sum64(n_pairs);
+  n_edges = warp_sum64(n_edges);
+  sum_count = warp_sum64(sum_count);
+  n_multi = warp_sum64(n_multi);
+  if (lane == 0) {
+    if (n_multi) atomicAdd(&counters->n_multi, n_multi);
+    if (n_pairs) atomicAdd(&counters->n_pairs, n_pairs);
+    if (n_edges) atomicAdd(&counters->n_edges, n_edges);
+    if (sum_count) atomicAdd(&counters->sum_count, sum_count);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// packed hash accumulators (the main path).  One 32-bit slot = protein rank << count_bits |
+// count, so a 2048-slot table is 8 KB and 20+ rows are resident per SM.  The walk over a
+// row's postings suffixes is flattened: every lane first writes the postings indices of its
+// short suffixes into a per-warp index list, then the warp strides over that list with four
+// independent loads in flight per lane (no lane-serial dependent loads, no idle lanes).
+// The read-out pass clears the table for the next row.
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t kIdxPerWarp = 512;  // >= 32 lanes x 15 postings
+
+__device__ __forceinline__ void packed_bump(uint32_t* tab, uint32_t mask, uint32_t log_h, uint32_t cb,
+                                            uint32_t b) {
+  uint32_t h = (b * 2654435761u) >> (32u - log_h);
+  for (;;) {
+    const uint32_t s = tab[h];
+    if ((s >> cb) == b && s != kSentinel) {
+      atomicAdd(&tab[h], 1u);
+      return;
+    }
+    if (s == kSentinel) {
+      const uint32_t old = atomicCAS(&tab[h], kSentinel, (b << cb) | 1u);
+      if (old == kSentinel) return;
+      if ((old >> cb) == b) {
+        atomicAdd(&tab[h], 1u);
+        return;
+      }
+    }
+    h = (h + 1u) & mask;
+  }
+}
+
+template <class Bump>
+__device__ __forceinline__ void walk_chunk_flat(const uint32_t* __restrict__ col, uint2 e, uint32_t* idx,
+                                                Bump bump) {
+  const uint32_t lane = lane_id();
+  const uint32_t len = e.y - e.x;
+  // long suffixes: the whole warp reads 32 consecutive postings at a time
+  uint32_t m = __ballot_sync(kFullMask, len >= 16u);
+  while (m) {
+    const uint32_t src = __ffs(m) - 1;
+    m &= m - 1;
+    const uint32_t s = __shfl_sync(kFullMask, e.x, src), t = __shfl_sync(kFullMask, e.y, src);
+    for (uint32_t j = s + lane; j < t; j += 128) {
+      const uint32_t b0 = col[j];
+      const uint32_t b1 = j + 32 < t ? col[j + 32] : kSentinel;
+      const uint32_t b2 = j + 64 < t ? col[j + 64] : kSentinel;
+      const uint32_t b3 = j + 96 < t ? col[j + 96] : kSentinel;
+      bump(b0);
+      if (b1 != kSentinel) bump(b1);
+      if (b2 != kSentinel) bump(b2);
+      if (b3 != kSentinel) bump(b3);
+    }
+  }
+  // short suffixes: flatten into the per-warp index list
+  const uint32_t slen = len < 16u ? len : 0u;
+  const uint32_t incl = warp_scan_incl(slen);
+  const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+  if (total == 0) return;
+  uint32_t w = incl - slen;
+  for (uint32_t j = e.x; j < e.x + slen; ++j) idx[w++] = j;
+  __syncwarp();
+  for (uint32_t t0 = lane; t0 < total; t0 += 128) {
+    const uint32_t b0 = col[idx[t0]];
+    const uint32_t b1 = t0 + 32 < total ? col[idx[t0 + 32]] : kSentinel;
+    const uint32_t b2 = t0 + 64 < total ? col[idx[t0 + 64]] : kSentinel;
+    const uint32_t b3 = t0 + 96 < total ? col[idx[t0 + 96]] : kSentinel;
+    bump(b0);
+    if (b1 != kSentinel) bump(b1);
+    if (b2 != kSentinel) bump(b2);
+    if (b3 != kSentinel) bump(b3);
+  }
+  __syncwarp();
+}
+
+template <int LOG_H, int GROUP_WARPS, int CTA_WARPS>
+__global__ void __launch_bounds__(CTA_WARPS * 32)
+    pairs_packed_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen,
+                        const uint2* __restrict__ suf, const uint32_t* __restrict__ col,
+                        const uint8_t* __restrict__ rowbin, uint8_t my_bin, uint32_t n, uint32_t count_bits,
+                        uint32_t* __restrict__ row_cursor, EdgeSink sink, PairCounters* __restrict__ counters) {
+  static_assert(GROUP_WARPS == 1 || GROUP_WARPS == CTA_WARPS, "group = warp or CTA");
+  constexpr uint32_t H = 1u << LOG_H;
+  constexpr uint32_t GROUPS = CTA_WARPS / GROUP_WARPS;
+  constexpr uint32_t GSIZE = GROUP_WARPS * 32;
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  __shared__ uint32_t s_base;
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t group = warp / GROUP_WARPS, gwarp = warp % GROUP_WARPS;
+  const uint32_t gtid = gwarp * 32 + lane;
+  uint32_t* tab = reinterpret_cast<uint32_t*>(dyn_smem) + (size_t)group * H;
+  uint32_t* idx = reinterpret_cast<uint32_t*>(dyn_smem) + (size_t)GROUPS * H + (size_t)warp * kIdxPerWarp;
+  const uint32_t cb = count_bits, cmask = (1u << count_bits) - 1u;
+  unsigned long long n_pairs = 0, n_edges = 0, sum_count = 0, n_multi = 0;
+
+  auto gsync = [&]() {
+    if (GROUP_WARPS == 1) __syncwarp(); else __syncthreads();
+  };
+  for (uint32_t i = gtid * 4; i < H; i += GSIZE * 4)
+    *reinterpret_cast<uint4*>(tab + i) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+  gsync();
+
+  for (;;) {
+    uint32_t base;
+    if (GROUP_WARPS == 1) {
+      base = 0;
+      if (lane == 0) base = atomicAdd(row_cursor, 32u);
+      base = __shfl_sync(kFullMask, base, 0);
+    } else {
+      __syncthreads();
+      if (threadIdx.x == 0) s_base = atomicAdd(row_cursor, 32u);
+      __syncthreads();
+      base = s_base;
+    }
+    if (base >= n) break;
+    uint32_t todo = __ballot_sync(kFullMask, base + lane < n && rowbin[base + lane] == my_bin);
+    while (todo) {
+      const uint32_t r = base + __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t nl = rowlen[r], ps = pstart[r];
+      uint32_t c = gwarp * 32;
+      uint2 e_next = c + lane < nl ? ld_stream_u32x2(suf + ps + c + lane) : make_uint2(0, 0);
+      for (; c < nl; c += GSIZE) {
+        const uint2 e = e_next;
+        const uint32_t cn = c + GSIZE;
+        e_next = cn + lane < nl ? ld_stream_u32x2(suf + ps + cn + lane) : make_uint2(0, 0);
+        walk_chunk_flat(col, e, idx, [&](uint32_t b) { packed_bump(tab, H - 1u, LOG_H, cb, b); });
+      }
+      gsync();
+      // read out and clear
+      for (uint32_t i = gtid * 4; i < H; i += GSIZE * 4) {
+        const uint4 v = *reinterpret_cast<uint4*>(tab + i);
+        *reinterpret_cast<uint4*>(tab + i) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+        const uint32_t sv[4] = {v.x, v.y, v.z, v.w};
+        bool any_out = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t cq = sv[q] != kSentinel ? (sv[q] & cmask) : 0u;
+          n_pairs += cq != 0;
+          n_multi += cq;
+          any_out |= cq > sink.threshold;
+        }
+        if (__any_sync(kFullMask, any_out)) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t cq = sv[q] != kSentinel ? (sv[q] & cmask) : 0u;
+            const bool out = cq > sink.threshold;
+            n_edges += out;
+            sum_count += out ? cq : 0u;
+            emit_edge(out, r, sv[q] >> cb, cq, sink);
+          }
+        }
       }
       gsync();
     }
