@@ -266,6 +266,27 @@ def test_skewed_lengths_against_oracle():
         assert np.all(ed["blosum"] == 0)
 
 
+@pytest.mark.parametrize("slices", ["1", "5", "64"])
+def test_l2_blocking_slices_do_not_change_results(slices, monkeypatch, arg_set, arg_oracle):
+    """the index is built slice by slice over the k-mer universe (L2 blocking); any slicing must
+    give the same index and edges"""
+    monkeypatch.setenv("KC_B200_SLICES", slices)
+    ps = random_protein_set(4, 300, min_len=0, max_len=400, n_classes=3, family=6)
+    for k in (5, 7):
+        km, ix, pr = run_oracle(ps, k, 2, True)
+        with kc.Engine(k, threshold=2, cross_class_only=True, want_blosum=True) as e:
+            e.set_protein_set(ps)
+            e.build_index()
+            check_index(e, ix)
+            check_pairs(e.score_pairs(), e.get_edges(), pr)
+    with kc.Engine(5, threshold=10, want_blosum=True) as e:
+        e.set_protein_set(arg_set)
+        e.build_index()
+        check_index(e, arg_oracle[5][2])
+        st = e.score_pairs()
+        check_pairs(st, e.get_edges(), arg_oracle[5][0].score_pairs(10, True, True, mode=1))
+
+
 # ---------------------------------------------------------------- shards, device input, extras
 @pytest.mark.parametrize("n_shards", [2, 3, 8])
 def test_shards_partition_the_pair_triangle(n_shards, arg_set):

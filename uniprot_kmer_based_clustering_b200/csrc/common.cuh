@@ -62,6 +62,38 @@ __device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v) {
   return v;
 }
 
+// first index i in [0, n) with a[i] >= key (a ascending); all 32 lanes call it, result uniform.
+// 32 samples per round: two dependent loads for n <= 1024.
+__device__ __forceinline__ uint32_t warp_lower_bound(const uint32_t* __restrict__ a, uint32_t n, uint32_t key) {
+  const uint32_t lane = lane_id();
+  uint32_t lo = 0, hi = n;
+  while (hi - lo > 32u) {
+    const uint32_t step = (hi - lo + 31u) >> 5;
+    const uint32_t i = lo + lane * step;
+    const bool lt = i < hi && a[i] < key;
+    const uint32_t c = __popc(__ballot_sync(kFullMask, lt));
+    const uint32_t nlo = c == 0 ? lo : lo + (c - 1u) * step + 1u;
+    const uint32_t nhi = min(hi, lo + c * step);
+    lo = nlo;
+    hi = nhi;
+  }
+  const uint32_t i = lo + lane;
+  const bool lt = i < hi && a[i] < key;
+  return lo + __popc(__ballot_sync(kFullMask, lt));
+}
+
+// sub-warp groups of G lanes (G = 8 or 32): one group works on one row of a sliced pass
+template <int G>
+__device__ __forceinline__ uint32_t group_mask() {
+  return G == 32 ? kFullMask : (((1u << (G & 31)) - 1u) << ((lane_id() / G) * G));
+}
+template <int G>
+__device__ __forceinline__ unsigned long long group_sum64(unsigned long long v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(group_mask<G>(), v, o);
+  return v;
+}
+
 __host__ __device__ __forceinline__ uint32_t next_pow2_u32(uint32_t v) {
   if (v <= 1) return 1;
   --v;

@@ -1,7 +1,9 @@
 // engine.cu — C ABI (include/kc_b200.h) over the sm_100a kernels.  One engine per GPU.
 // No CPU fallback: every compute entry point launches CUDA kernels or fails.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -85,8 +87,9 @@ struct kc_engine {
   uint64_t n_words = 0;
   kc_index_stats istats{};
   uint64_t multi_total = 0, work_total = 0;
-  DBuf d_pk, d_ndist, d_rowlen, d_seen1, d_seen2, d_dict, d_vocab, d_freq, d_self, d_colptr, d_cursor, d_col,
-      d_suf, d_rowwork, d_lists, d_colscratch, d_workprefix;
+  DBuf d_pk, d_ndist, d_rowlen, d_seen, d_dict, d_vocab, d_freq, d_self, d_colptr, d_cursor, d_col,
+      d_suf, d_rowwork, d_lists, d_colscratch, d_workprefix, d_ksplit, d_isplit, d_rowwork64;
+  uint32_t slice_shift = 31, n_slices = 1;
   // pairs
   DBuf d_rowbin, d_edges, d_keys_a, d_keys_b, d_vals_a, d_vals_b, d_hist, d_edges_sorted;
   uint64_t edge_cap = 0, n_edges = 0;
@@ -236,12 +239,11 @@ int run_extract_census(kc_engine* e) {
   const uint8_t* res = e->d_res.as<uint8_t>();
   uint32_t* pk = e->d_pk.as<uint32_t>();
   uint32_t* ndist = e->d_ndist.as<uint32_t>();
-  uint32_t* s1 = e->d_seen1.as<uint32_t>();
-  uint32_t* s2 = e->d_seen2.as<uint32_t>();
+  uint32_t* ksplit = e->d_ksplit.as<uint32_t>();
   if (n) {
     const uint32_t grid = blocks_for(n, kExtractWarps, e->num_sm * 5);
     KC_LAUNCH(e, extract_dedup_warp_kernel<K>, grid, kExtractWarps * 32, 0, res, e->d_pstart.as<uint32_t>(),
-              e->d_plen.as<uint32_t>(), n, pk, ndist, s1, s2, &ds->n_incid);
+              e->d_plen.as<uint32_t>(), n, pk, ndist, e->slice_shift, e->n_slices, ksplit, &ds->n_incid);
   }
   if (!e->h_long.empty()) {
     const size_t smem = (size_t)e->max_block_np2 * 4 + e->max_block_len + 16;
@@ -249,13 +251,13 @@ int run_extract_census(kc_engine* e) {
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KC_LAUNCH(e, (extract_dedup_block_kernel<K, false>), (uint32_t)e->h_long.size(), 512, smem, res,
               e->d_pstart.as<uint32_t>(), e->d_plen.as<uint32_t>(), e->d_long.as<uint32_t>(), nullptr, nullptr,
-              pk, ndist, s1, s2, &ds->n_incid);
+              pk, ndist, n, e->slice_shift, e->n_slices, ksplit, &ds->n_incid);
   }
   if (!e->h_huge.empty()) {
     KC_LAUNCH(e, (extract_dedup_block_kernel<K, true>), (uint32_t)e->h_huge.size(), 512, 0, res,
               e->d_pstart.as<uint32_t>(), e->d_plen.as<uint32_t>(), e->d_huge.as<uint32_t>(),
-              e->d_huge_off.as<unsigned long long>(), e->d_huge_scratch.as<uint32_t>(), pk, ndist, s1, s2,
-              &ds->n_incid);
+              e->d_huge_off.as<unsigned long long>(), e->d_huge_scratch.as<uint32_t>(), pk, ndist, n,
+              e->slice_shift, e->n_slices, ksplit, &ds->n_incid);
   }
   return KC_OK;
 }
@@ -419,9 +421,9 @@ void kc_destroy(kc_engine* e) {
   cudaDeviceSynchronize();
   DBuf* all[] = {&e->d_res, &e->d_off, &e->d_kpos, &e->d_pstart, &e->d_plen, &e->d_orig, &e->d_rank,
                  &e->d_first_after, &e->d_long, &e->d_huge, &e->d_huge_off, &e->d_huge_scratch, &e->d_pk,
-                 &e->d_ndist, &e->d_rowlen, &e->d_seen1, &e->d_seen2, &e->d_dict, &e->d_vocab, &e->d_freq,
+                 &e->d_ndist, &e->d_rowlen, &e->d_seen, &e->d_dict, &e->d_vocab, &e->d_freq,
                  &e->d_self, &e->d_colptr, &e->d_cursor, &e->d_col, &e->d_suf, &e->d_rowwork, &e->d_lists,
-                 &e->d_colscratch, &e->d_workprefix, &e->d_rowbin, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
+                 &e->d_colscratch, &e->d_workprefix, &e->d_ksplit, &e->d_isplit, &e->d_rowwork64, &e->d_rowbin, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
                  &e->d_vals_a, &e->d_vals_b, &e->d_hist, &e->d_edges_sorted, &e->d_scalars, &e->d_scan_tiles,
                  &e->d_tmp};
   for (DBuf* b : all) b->release();
@@ -535,15 +537,31 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
   KC_CUDA(e, e->d_pk.ensure((R + 64) * 4));
   KC_CUDA(e, e->d_ndist.ensure(((uint64_t)n + 1) * 4));
   KC_CUDA(e, e->d_rowlen.ensure(((uint64_t)n + 1) * 4));
-  KC_CUDA(e, e->d_seen1.ensure(W * 4));
-  KC_CUDA(e, e->d_seen2.ensure(W * 4));
+  KC_CUDA(e, e->d_seen.ensure(W * 8));  // 2 bits per k-mer
+  // L2 blocking plan: slices of 2^slice_shift k-mers such that the randomly accessed part of
+  // every sliced pass (census state / dictionary + freq / cursor + postings) is ~32 MB
+  {
+    unsigned long long n_positions_est = 0;
+    for (uint32_t r = 0; r < n; ++r)
+      if (e->h_plen[r] >= (uint32_t)e->cfg.k) n_positions_est += e->h_plen[r] - e->cfg.k + 1;
+    const double footprint = std::max((double)e->universe / 4.0 * 1.5, (double)n_positions_est * 5.0);
+    uint32_t want = (uint32_t)std::min(64.0, std::ceil(footprint / (32.0 * 1024 * 1024)));
+    if (const char* env = std::getenv("KC_B200_SLICES")) want = (uint32_t)std::max(1, std::atoi(env));  // tests
+    uint32_t shift = 31;
+    while (shift > 12 && ((((uint64_t)e->universe - 1) >> shift) + 1) < want) --shift;
+    e->slice_shift = shift;
+    e->n_slices = (uint32_t)((((uint64_t)e->universe - 1) >> shift) + 1);
+  }
+  const uint32_t P = e->n_slices;
+  KC_CUDA(e, e->d_ksplit.ensure(((uint64_t)P + 1) * std::max<uint64_t>(n, 1) * 4));
+  KC_CUDA(e, e->d_isplit.ensure(((uint64_t)P + 1) * std::max<uint64_t>(n, 1) * 4));
+  KC_CUDA(e, e->d_rowwork64.ensure(((uint64_t)n + 1) * 8));
   KC_CUDA(e, e->d_dict.ensure(W * 8));
   int rc = ensure_scan(e, std::max<uint64_t>(W, (uint64_t)n + 1));
   if (rc) return rc;
 
   mark(e, EV_I0);
-  KC_CUDA(e, cudaMemsetAsync(e->d_seen1.p, 0, W * 4, e->stream));
-  KC_CUDA(e, cudaMemsetAsync(e->d_seen2.p, 0, W * 4, e->stream));
+  KC_CUDA(e, cudaMemsetAsync(e->d_seen.p, 0, W * 8, e->stream));
   KC_CUDA(e, cudaMemsetAsync(ds, 0, sizeof(DeviceScalars), e->stream));
   // positions are known on the host
   unsigned long long n_positions = 0;
@@ -553,14 +571,25 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
   // K1-K3: extract, per-protein dedup, census bitmaps
   mark(e, EV_IC0);
   rc = e->cfg.k == 5 ? run_extract_census<5>(e) : run_extract_census<7>(e);
-  mark(e, EV_IC1);
   if (rc) return rc;
+  const bool narrow = P >= 4;  // few entries per (row, slice): 8 lanes per row instead of 32
+  const uint32_t pass_grid = blocks_for(n, narrow ? 32 : 8, e->num_sm * 8);
+  auto split = [&](DBuf& b, uint32_t q) { return b.as<uint32_t>() + (size_t)q * n; };
+  for (uint32_t q = 0; q < P && n; ++q) {
+    if (narrow)
+      KC_LAUNCH(e, census_pass_kernel<8>, pass_grid, 256, 0, e->d_pk.as<uint32_t>(), e->d_pstart.as<uint32_t>(),
+                split(e->d_ksplit, q), split(e->d_ksplit, q + 1), n, e->d_seen.as<uint32_t>());
+    else
+      KC_LAUNCH(e, census_pass_kernel<32>, pass_grid, 256, 0, e->d_pk.as<uint32_t>(), e->d_pstart.as<uint32_t>(),
+                split(e->d_ksplit, q), split(e->d_ksplit, q + 1), n, e->d_seen.as<uint32_t>());
+  }
+  mark(e, EV_IC1);
   // K4: rank dictionary over "held by >= 2 proteins"
-  e->launches += exclusive_scan(PopcIn{e->d_seen2.as<uint32_t>()},
-                                DictOut{e->d_seen2.as<uint32_t>(), e->d_dict.as<uint2>()}, W, e->scan, e->stream);
+  e->launches += exclusive_scan(PopcIn<1>{e->d_seen.as<uint32_t>()},
+                                DictOut<1>{e->d_seen.as<uint32_t>(), e->d_dict.as<uint2>()}, W, e->scan, e->stream);
   KC_CUDA(e, cudaMemcpyAsync(&ds->n_repeated, &ds->scan_total, 8, cudaMemcpyDeviceToDevice, e->stream));
-  KC_LAUNCH(e, popc_reduce_kernel, blocks_for(W, 256 * 8, e->num_sm * 8), 256, 0, e->d_seen1.as<uint32_t>(), W,
-            &ds->n_distinct);
+  KC_LAUNCH(e, popc_reduce_kernel, blocks_for(2 * W, 256 * 8, e->num_sm * 8), 256, 0, e->d_seen.as<uint32_t>(),
+            2 * W, &ds->n_distinct);
   DeviceScalars hs{};
   KC_CUDA(e, cudaMemcpyAsync(&hs, ds, sizeof(hs), cudaMemcpyDeviceToHost, e->stream));
   KC_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -587,19 +616,34 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
     KC_LAUNCH(e, expand_bitmap_kernel, blocks_for(W, 256, e->num_sm * 16), 256, 0, e->d_dict.as<uint2>(), W,
               e->d_vocab.as<uint32_t>(), e->d_self.as<uint8_t>(), e->cfg.k);
   }
-  // K5: ids (in place over the distinct k-mers), row lengths, kmer_freq
-  const uint32_t warp_grid = blocks_for(n, 8, e->num_sm * 8);
-  if (n)
-    KC_LAUNCH(e, ids_freq_kernel, warp_grid, 256, 0, e->d_dict.as<uint2>(), e->d_pstart.as<uint32_t>(),
-              e->d_ndist.as<uint32_t>(), n, e->d_pk.as<uint32_t>(), e->d_rowlen.as<uint32_t>(),
-              e->d_freq.as<uint32_t>(), &ds->nnz);
+  // K5: ids (in place over the distinct k-mers), row lengths, kmer_freq — one launch per slice
+  if (n) KC_CUDA(e, cudaMemsetAsync(e->d_rowlen.p, 0, (uint64_t)n * 4, e->stream));
+  for (uint32_t q = 0; q < P && n; ++q) {
+    uint32_t* last = q + 1 == P ? split(e->d_isplit, P) : nullptr;
+    if (narrow)
+      KC_LAUNCH(e, ids_freq_kernel<8>, pass_grid, 256, 0, e->d_dict.as<uint2>(), e->d_pstart.as<uint32_t>(),
+                split(e->d_ksplit, q), split(e->d_ksplit, q + 1), n, e->d_pk.as<uint32_t>(),
+                e->d_rowlen.as<uint32_t>(), split(e->d_isplit, q), last, e->d_freq.as<uint32_t>(), &ds->nnz);
+    else
+      KC_LAUNCH(e, ids_freq_kernel<32>, pass_grid, 256, 0, e->d_dict.as<uint2>(), e->d_pstart.as<uint32_t>(),
+                split(e->d_ksplit, q), split(e->d_ksplit, q + 1), n, e->d_pk.as<uint32_t>(),
+                e->d_rowlen.as<uint32_t>(), split(e->d_isplit, q), last, e->d_freq.as<uint32_t>(), &ds->nnz);
+  }
   // postings: colptr = exclusive scan of freq, fill, sort every column by protein rank
   e->launches += exclusive_scan(U32In{e->d_freq.as<uint32_t>()}, ColptrOut{e->d_colptr.as<uint32_t>()}, V + 1,
                                 e->scan, e->stream);
   KC_CUDA(e, cudaMemcpyAsync(e->d_cursor.p, e->d_colptr.p, (V + 1) * 4, cudaMemcpyDeviceToDevice, e->stream));
   if (n && V) {
-    KC_LAUNCH(e, postings_fill_kernel, warp_grid, 256, 0, e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(),
-              n, e->d_pk.as<uint32_t>(), e->d_cursor.as<uint32_t>(), e->d_col.as<uint32_t>());
+    for (uint32_t q = 0; q < P; ++q) {
+      if (narrow)
+        KC_LAUNCH(e, postings_fill_kernel<8>, pass_grid, 256, 0, e->d_pstart.as<uint32_t>(), split(e->d_isplit, q),
+                  split(e->d_isplit, q + 1), n, e->d_pk.as<uint32_t>(), e->d_cursor.as<uint32_t>(),
+                  e->d_col.as<uint32_t>());
+      else
+        KC_LAUNCH(e, postings_fill_kernel<32>, pass_grid, 256, 0, e->d_pstart.as<uint32_t>(), split(e->d_isplit, q),
+                  split(e->d_isplit, q + 1), n, e->d_pk.as<uint32_t>(), e->d_cursor.as<uint32_t>(),
+                  e->d_col.as<uint32_t>());
+    }
     uint32_t* lists = e->d_lists.as<uint32_t>();
     KC_LAUNCH(e, postings_sort_small_kernel, blocks_for(V, 256, e->num_sm * 8), 256, 0,
               e->d_colptr.as<uint32_t>(), (uint32_t)V, e->d_col.as<uint32_t>(), lists, lists + list_cap,
@@ -625,10 +669,22 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
     }
     KC_LAUNCH(e, multi_edge_total_kernel, blocks_for(V, 256 * 4, e->num_sm * 4), 256, 0, e->d_freq.as<uint32_t>(),
               (uint32_t)V, &ds->multi_total);
-    KC_LAUNCH(e, suffix_ranges_kernel, warp_grid, 256, 0, e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(), n,
-              e->d_pk.as<uint32_t>(), e->d_colptr.as<uint32_t>(), e->d_col.as<uint32_t>(),
-              e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr, e->d_suf.as<uint2>(),
-              e->d_rowwork.as<uint32_t>(), &ds->work_total);
+    KC_CUDA(e, cudaMemsetAsync(e->d_rowwork64.p, 0, (uint64_t)n * 8, e->stream));
+    const uint32_t* fa = e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr;
+    for (uint32_t q = 0; q < P; ++q) {
+      if (narrow)
+        KC_LAUNCH(e, suffix_ranges_kernel<8>, pass_grid, 256, 0, e->d_pstart.as<uint32_t>(), split(e->d_isplit, q),
+                  split(e->d_isplit, q + 1), n, e->d_pk.as<uint32_t>(), e->d_colptr.as<uint32_t>(),
+                  e->d_col.as<uint32_t>(), fa, e->d_suf.as<uint2>(), e->d_rowwork64.as<unsigned long long>(),
+                  &ds->work_total);
+      else
+        KC_LAUNCH(e, suffix_ranges_kernel<32>, pass_grid, 256, 0, e->d_pstart.as<uint32_t>(), split(e->d_isplit, q),
+                  split(e->d_isplit, q + 1), n, e->d_pk.as<uint32_t>(), e->d_colptr.as<uint32_t>(),
+                  e->d_col.as<uint32_t>(), fa, e->d_suf.as<uint2>(), e->d_rowwork64.as<unsigned long long>(),
+                  &ds->work_total);
+    }
+    KC_LAUNCH(e, clamp_rowwork_kernel, (n + 255) / 256, 256, 0, e->d_rowwork64.as<unsigned long long>(), n,
+              e->d_rowwork.as<uint32_t>());
   } else if (n) {
     KC_CUDA(e, cudaMemsetAsync(e->d_rowwork.p, 0, (uint64_t)n * 4, e->stream));
   }
@@ -668,8 +724,8 @@ int kc_get_distinct_kmers(kc_engine* e, uint32_t* out, uint64_t capacity) {
     list.release();
     return fail(e, KC_ENOMEM, "out of device memory");
   }
-  e->launches += exclusive_scan(PopcIn{e->d_seen1.as<uint32_t>()},
-                                DictOut{e->d_seen1.as<uint32_t>(), dict1.as<uint2>()}, W, e->scan, e->stream);
+  e->launches += exclusive_scan(PopcIn<0>{e->d_seen.as<uint32_t>()},
+                                DictOut<0>{e->d_seen.as<uint32_t>(), dict1.as<uint2>()}, W, e->scan, e->stream);
   KC_LAUNCH(e, expand_bitmap_kernel, blocks_for(W, 256, e->num_sm * 16), 256, 0, dict1.as<uint2>(), W,
             list.as<uint32_t>(), nullptr, e->cfg.k);
   cudaError_t rc = cudaMemcpyAsync(out, list.p, D * 4, cudaMemcpyDeviceToHost, e->stream);

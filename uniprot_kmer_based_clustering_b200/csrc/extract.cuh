@@ -6,7 +6,7 @@
 //   Protein::new        src/protein.rs:107-132 -> kmers_per_position_kernel (get_five_mers)
 //   sort(); dedup()     src/main.rs:100-102    -> bitonic sort + adjacent-diff in shared memory
 //   merge_sort census   src/main.rs:23-48,103-116 -> two presence bitmaps over the 21^k universe:
-//                       seen1 = "held by >= 1 protein", seen2 = "held by >= 2 proteins"
+//                       2 bits of state per k-mer (see census_mark)
 #pragma once
 #include "common.cuh"
 
@@ -14,15 +14,27 @@ namespace kc {
 
 __constant__ uint8_t c_residue_lut[256];
 
-// ---- census: first holder sets seen1, every later holder (a different protein, because the
-// caller has deduplicated within the protein) sets seen2.  The plain pre-read may be stale;
-// it only skips work that is idempotent.
-__device__ __forceinline__ void census_mark(uint32_t kmer, uint32_t* __restrict__ seen1,
-                                            uint32_t* __restrict__ seen2) {
-  const uint32_t w = kmer >> 5, bit = 1u << (kmer & 31u);
-  if (seen2[w] & bit) return;
-  const uint32_t old = atomicOr(&seen1[w], bit);
-  if (old & bit) atomicOr(&seen2[w], bit);
+// ---- census: two bits of state per k-mer, interleaved in one word (16 k-mers per u32):
+// bit 2j = "held by >= 1 protein", bit 2j+1 = "held by >= 2 proteins".  The first holder sets
+// the low bit; every later holder (a different protein, because the caller has deduplicated
+// within the protein) finds it set and sets the high bit.  Both bits live in the same 32-byte
+// sector, so one incidence costs one random sector.  The plain pre-read may be stale; it only
+// skips work that is idempotent.
+__device__ __forceinline__ void census_mark(uint32_t kmer, uint32_t* __restrict__ seen) {
+  const uint32_t w = kmer >> 4, sh = (kmer & 15u) * 2u;
+  const uint32_t lo = 1u << sh, hi = 2u << sh;
+  if (seen[w] & hi) return;
+  const uint32_t old = atomicOr(&seen[w], lo);
+  if ((old & lo) && !(old & hi)) atomicOr(&seen[w], hi);
+}
+
+// L2 blocking: the k-mer universe is cut into n_slices slices of 2^slice_shift k-mers.  While a
+// row's sorted distinct k-mers are written out, ksplit[q * n + r] records where slice q starts
+// in row r (ksplit[n_slices * n + r] = number of distinct k-mers), so that every later pass
+// over one slice reads one contiguous run of each row without searching.
+__device__ __forceinline__ void record_slice_starts(uint32_t* __restrict__ ksplit, uint32_t n, uint32_t r,
+                                                    uint32_t q_from, uint32_t q_to, uint32_t j) {
+  for (uint32_t q = q_from; q <= q_to; ++q) ksplit[(size_t)q * n + r] = j;
 }
 
 template <int K>
@@ -94,14 +106,14 @@ constexpr int kExtractWarps = 8;
 
 // ---------------------------------------------------------------------------------------
 // K2 (short proteins): one warp per protein.  Writes the protein's sorted distinct k-mers to
-// pk[pstart .. pstart+ndist) and marks the census bitmaps.
+// pk[pstart .. pstart+ndist).
 // ---------------------------------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(kExtractWarps * 32)
     extract_dedup_warp_kernel(const uint8_t* __restrict__ res, const uint32_t* __restrict__ pstart,
                               const uint32_t* __restrict__ plen, uint32_t n, uint32_t* __restrict__ pk,
-                              uint32_t* __restrict__ ndist, uint32_t* __restrict__ seen1,
-                              uint32_t* __restrict__ seen2, unsigned long long* __restrict__ n_incid) {
+                              uint32_t* __restrict__ ndist, uint32_t slice_shift, uint32_t n_slices,
+                              uint32_t* __restrict__ ksplit, unsigned long long* __restrict__ n_incid) {
   __shared__ uint8_t s_lut[256];
   __shared__ uint32_t s_keys[kExtractWarps][kWarpMaxPos];
   __shared__ __align__(4) uint8_t s_codes[kExtractWarps][kWarpMaxPos + 8];
@@ -116,6 +128,7 @@ __global__ void __launch_bounds__(kExtractWarps * 32)
     const uint32_t len = plen[r];
     if (len < (uint32_t)K) {
       if (lane == 0) ndist[r] = 0;
+      for (uint32_t q = lane; q <= n_slices; q += 32) ksplit[(size_t)q * n + r] = 0;
       continue;
     }
     const uint32_t npos = len - K + 1;
@@ -134,12 +147,15 @@ __global__ void __launch_bounds__(kExtractWarps * 32)
       const bool first = i < npos && (i == 0 || v != keys[i - 1]);
       const uint32_t m = __ballot_sync(kFullMask, first);
       if (first) {
-        pk[ps + base + __popc(m & lanemask_lt())] = v;
-        census_mark(v, seen1, seen2);
+        const uint32_t j = base + __popc(m & lanemask_lt());
+        pk[ps + j] = v;
+        record_slice_starts(ksplit, n, r, i == 0 ? 0u : (keys[i - 1] >> slice_shift) + 1u, v >> slice_shift, j);
       }
       base += __popc(m);
     }
     if (lane == 0) ndist[r] = base;
+    for (uint32_t q = (keys[npos - 1] >> slice_shift) + 1u + lane; q <= n_slices; q += 32)
+      ksplit[(size_t)q * n + r] = base;
     incid += base;
     __syncwarp();
   }
@@ -156,8 +172,8 @@ __global__ void __launch_bounds__(512)
                                const uint32_t* __restrict__ plen, const uint32_t* __restrict__ list,
                                const unsigned long long* __restrict__ scratch_off,
                                uint32_t* __restrict__ scratch, uint32_t* __restrict__ pk,
-                               uint32_t* __restrict__ ndist, uint32_t* __restrict__ seen1,
-                               uint32_t* __restrict__ seen2, unsigned long long* __restrict__ n_incid) {
+                               uint32_t* __restrict__ ndist, uint32_t n, uint32_t slice_shift, uint32_t n_slices,
+                               uint32_t* __restrict__ ksplit, unsigned long long* __restrict__ n_incid) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ uint8_t s_lut[256];
   __shared__ uint32_t s_wcnt[32];
@@ -212,14 +228,36 @@ __global__ void __launch_bounds__(512)
     const bool first = i < hi && (i == 0 || v != keys[i - 1]);
     const uint32_t m = __ballot_sync(kFullMask, first);
     if (first) {
-      pk[ps + base + __popc(m & lanemask_lt())] = v;
-      census_mark(v, seen1, seen2);
+      const uint32_t j = base + __popc(m & lanemask_lt());
+      pk[ps + j] = v;
+      record_slice_starts(ksplit, n, r, i == 0 ? 0u : (keys[i - 1] >> slice_shift) + 1u, v >> slice_shift, j);
     }
     base += __popc(m);
   }
+  for (uint32_t q = (keys[npos - 1] >> slice_shift) + 1u + threadIdx.x; q <= n_slices; q += blockDim.x)
+    ksplit[(size_t)q * n + r] = total;
   if (threadIdx.x == 0) {
     ndist[r] = total;
     atomicAdd(n_incid, (unsigned long long)total);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: census pass over one k-mer slice.  L2 blocking: the census state of the whole 21^k
+// universe (450 MB at k=7) does not fit the 126 MB L2, so the random read-modify-writes are
+// done slice by slice; lo[r]..hi[r] is the run of row r that falls into the slice.
+// G lanes work on one row.
+// ---------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256)
+    census_pass_kernel(const uint32_t* __restrict__ pk, const uint32_t* __restrict__ pstart,
+                       const uint32_t* __restrict__ lo, const uint32_t* __restrict__ hi, uint32_t n,
+                       uint32_t* __restrict__ seen) {
+  const uint32_t gl = lane_id() % G;
+  const uint32_t gg = (blockIdx.x * blockDim.x + threadIdx.x) / G, ng = (gridDim.x * blockDim.x) / G;
+  for (uint32_t r = gg; r < n; r += ng) {
+    const uint32_t i0 = lo[r], i1 = hi[r], ps = pstart[r];
+    for (uint32_t i = i0 + gl; i < i1; i += G) census_mark(pk[ps + i], seen);
   }
 }
 

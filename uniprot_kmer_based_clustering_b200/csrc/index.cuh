@@ -2,7 +2,7 @@
 //
 // Replaces (reference root relative):
 //   split unique/repeated + Mphf::new x2 + unique bool table   src/main.rs:127-147
-//       -> rank dictionary over the seen2 bitmap: dict[w] = {bits, #set bits before word w};
+//       -> rank dictionary over the census "held by >= 2" bits: dict[w] = {bits, #set bits before word w};
 //          id(kmer) = dict[kmer>>5].y + popc(dict[kmer>>5].x & ((1<<(kmer&31))-1)).
 //          A minimal perfect, order-preserving hash of the repeated k-mers (one 8-byte load).
 //   remove_unique_five_mers + modify_hash_five_mer + kmer_freq  src/protein.rs:151-174,
@@ -14,24 +14,43 @@
 
 namespace kc {
 
+// gather the odd (ODD=1) or even (ODD=0) bits of a census word into its low 16 bits
+template <int ODD>
+__device__ __forceinline__ uint32_t gather_bits(uint32_t s) {
+  uint32_t x = (s >> ODD) & 0x55555555u;
+  x = (x | (x >> 1)) & 0x33333333u;
+  x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+  x = (x | (x >> 4)) & 0x00FF00FFu;
+  x = (x | (x >> 8)) & 0x0000FFFFu;
+  return x;
+}
+// presence bits of dictionary word i (32 consecutive k-mers) from census words 2i, 2i+1
+template <int ODD>
+__device__ __forceinline__ uint32_t dict_bits(const uint32_t* __restrict__ seen, uint64_t i) {
+  const uint2 s = *reinterpret_cast<const uint2*>(seen + 2 * i);
+  return gather_bits<ODD>(s.x) | (gather_bits<ODD>(s.y) << 16);
+}
+template <int ODD>
 struct PopcIn {
-  const uint32_t* bits;
-  __device__ unsigned long long operator()(uint64_t i) const { return __popc(bits[i]); }
+  const uint32_t* seen;
+  __device__ unsigned long long operator()(uint64_t i) const { return __popc(dict_bits<ODD>(seen, i)); }
 };
+template <int ODD>
 struct DictOut {
-  const uint32_t* bits;
+  const uint32_t* seen;
   uint2* dict;
   __device__ void operator()(uint64_t i, unsigned long long excl, unsigned long long) const {
-    dict[i] = make_uint2(bits[i], (uint32_t)excl);
+    dict[i] = make_uint2(dict_bits<ODD>(seen, i), (uint32_t)excl);
   }
 };
 
+// number of k-mers held by >= 1 protein (even bits of the census words)
 __global__ void popc_reduce_kernel(const uint32_t* __restrict__ bits, uint64_t n_words,
                                    unsigned long long* __restrict__ total) {
   unsigned long long s = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words;
        i += (uint64_t)gridDim.x * blockDim.x)
-    s += __popc(bits[i]);
+    s += __popc(bits[i] & 0x55555555u);
   s = warp_sum64(s);
   if (lane_id() == 0 && s) atomicAdd(total, s);
 }
@@ -81,46 +100,61 @@ __global__ void lookup_kernel(const uint2* __restrict__ dict, const uint32_t* __
   }
 }
 
-// K5: one warp per protein.  Sorted distinct k-mers -> sorted repeated-k-mer ids, compacted in
-// place (pk[pstart .. pstart+rowlen)); freq[id] += 1.
+// K5, one k-mer slice per launch, G lanes per protein.  Sorted distinct k-mers of the slice
+// (pk[ps+klo[r] .. ps+khi[r])) -> sorted repeated-k-mer ids appended in place behind what the
+// earlier slices wrote (rowlen[r]); freq[id] += 1.  islo[r] records where this slice's ids
+// start in the row (ishi on the last slice: the final row length), which is what the id-sliced
+// passes below read.  The dictionary and freq slices of one launch stay L2-resident.
+template <int G>
 __global__ void __launch_bounds__(256)
     ids_freq_kernel(const uint2* __restrict__ dict, const uint32_t* __restrict__ pstart,
-                    const uint32_t* __restrict__ ndist, uint32_t n, uint32_t* __restrict__ pk,
-                    uint32_t* __restrict__ rowlen, uint32_t* __restrict__ freq,
+                    const uint32_t* __restrict__ klo, const uint32_t* __restrict__ khi, uint32_t n,
+                    uint32_t* __restrict__ pk, uint32_t* __restrict__ rowlen, uint32_t* __restrict__ islo,
+                    uint32_t* __restrict__ ishi_last, uint32_t* __restrict__ freq,
                     unsigned long long* __restrict__ nnz_total) {
-  const uint32_t lane = lane_id();
-  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = lane_id(), gl = lane % G, gshift = (lane / G) * G;
+  const uint32_t gmask = group_mask<G>();
+  const uint32_t gg = (blockIdx.x * blockDim.x + threadIdx.x) / G, ng = (gridDim.x * blockDim.x) / G;
   unsigned long long tot = 0;
-  for (uint32_t r = gw; r < n; r += nw) {
-    const uint32_t nd = ndist[r], ps = pstart[r];
-    uint32_t base = 0;
-    for (uint32_t c = 0; c < nd; c += 32) {
-      const uint32_t i = c + lane;
+  for (uint32_t r = gg; r < n; r += ng) {
+    const uint32_t i0 = klo[r], i1 = khi[r], ps = pstart[r];
+    uint32_t base = rowlen[r];
+    const uint32_t base0 = base;
+    for (uint32_t c = i0; c < i1; c += G) {
+      const uint32_t i = c + gl;
       uint32_t id = kSentinel;
-      if (i < nd) id = dict_lookup(dict, pk[ps + i]);
-      const uint32_t m = __ballot_sync(kFullMask, id != kSentinel);
+      if (i < i1) id = dict_lookup(dict, pk[ps + i]);
+      const uint32_t m = (__ballot_sync(gmask, id != kSentinel) >> gshift) & (G == 32 ? kFullMask : ((1u << (G & 31)) - 1u));
       if (id != kSentinel) {
-        pk[ps + base + __popc(m & lanemask_lt())] = id;
+        pk[ps + base + __popc(m & ((1u << gl) - 1u))] = id;
         atomicAdd(&freq[id], 1u);
       }
       base += __popc(m);
     }
-    if (lane == 0) rowlen[r] = base;
-    tot += base;
+    if (gl == 0) {
+      islo[r] = base0;
+      if (ishi_last) ishi_last[r] = base;
+      if (base != base0) rowlen[r] = base;
+      tot += base - base0;
+    }
   }
+  tot = warp_sum64(tot);
   if (lane == 0 && tot) atomicAdd(nnz_total, tot);
 }
 
-// postings fill: col[cursor[id]++] = r  (cursor starts as a copy of colptr)
+// postings fill, one id slice per launch: col[cursor[id]++] = r (cursor starts as a copy of
+// colptr).  The cursor and postings slices of one launch stay L2-resident, so the scattered
+// 4-byte writes merge into full lines before they go to HBM.
+template <int G>
 __global__ void __launch_bounds__(256)
-    postings_fill_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen, uint32_t n,
-                         const uint32_t* __restrict__ ids, uint32_t* __restrict__ cursor,
-                         uint32_t* __restrict__ col) {
-  const uint32_t lane = lane_id();
-  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t r = gw; r < n; r += nw) {
-    const uint32_t nl = rowlen[r], ps = pstart[r];
-    for (uint32_t i = lane; i < nl; i += 32) {
+    postings_fill_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ lo,
+                         const uint32_t* __restrict__ hi, uint32_t n, const uint32_t* __restrict__ ids,
+                         uint32_t* __restrict__ cursor, uint32_t* __restrict__ col) {
+  const uint32_t gl = lane_id() % G;
+  const uint32_t gg = (blockIdx.x * blockDim.x + threadIdx.x) / G, ng = (gridDim.x * blockDim.x) / G;
+  for (uint32_t r = gg; r < n; r += ng) {
+    const uint32_t i0 = lo[r], i1 = hi[r], ps = pstart[r];
+    for (uint32_t i = i0 + gl; i < i1; i += G) {
       const uint32_t slot = atomicAdd(&cursor[ids[ps + i]], 1u);
       col[slot] = r;
     }
@@ -242,37 +276,50 @@ __global__ void __launch_bounds__(512)
 
 // per-entry suffix ranges: for row r and each of its ids, the holders that come after r in the
 // pair order (and, when only cross-class pairs are wanted, after r's whole class block) are
-// col[suf.x .. suf.y).  rowwork[r] = sum of the range lengths = multi-edges row r accumulates.
+// col[suf.x .. suf.y).  rowwork64[r] = sum of the range lengths = multi-edges row r accumulates.
+// One id slice per launch like the fill (colptr and postings slices stay L2-resident).
+template <int G>
 __global__ void __launch_bounds__(256)
-    suffix_ranges_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen, uint32_t n,
-                         const uint32_t* __restrict__ ids, const uint32_t* __restrict__ colptr,
-                         const uint32_t* __restrict__ col, const uint32_t* __restrict__ first_after,
-                         uint2* __restrict__ suf, uint32_t* __restrict__ rowwork,
-                         unsigned long long* __restrict__ work_total) {
-  const uint32_t lane = lane_id();
-  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    suffix_ranges_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ lo,
+                         const uint32_t* __restrict__ hi, uint32_t n, const uint32_t* __restrict__ ids,
+                         const uint32_t* __restrict__ colptr, const uint32_t* __restrict__ col,
+                         const uint32_t* __restrict__ first_after, uint2* __restrict__ suf,
+                         unsigned long long* __restrict__ rowwork64, unsigned long long* __restrict__ work_total) {
+  const uint32_t lane = lane_id(), gl = lane % G;
+  const uint32_t gg = (blockIdx.x * blockDim.x + threadIdx.x) / G, ng = (gridDim.x * blockDim.x) / G;
   unsigned long long tot = 0;
-  for (uint32_t r = gw; r < n; r += nw) {
-    const uint32_t nl = rowlen[r], ps = pstart[r];
+  for (uint32_t r = gg; r < n; r += ng) {
+    const uint32_t i0 = lo[r], i1 = hi[r], ps = pstart[r];
+    if (i0 >= i1) continue;
     const uint32_t target = first_after ? first_after[r] : r + 1;  // first rank that pairs with r
     unsigned long long work = 0;
-    for (uint32_t i = lane; i < nl; i += 32) {
+    for (uint32_t i = i0 + gl; i < i1; i += G) {
       const uint32_t id = ids[ps + i];
-      uint32_t lo = colptr[id];
+      uint32_t a = colptr[id];
       const uint32_t end = colptr[id + 1];
-      uint32_t hi = end;
-      while (lo < hi) {  // lower_bound(col[lo..hi), target)
-        const uint32_t mid = (lo + hi) >> 1;
-        if (col[mid] < target) lo = mid + 1; else hi = mid;
+      uint32_t b = end;
+      while (a < b) {  // lower_bound(col[a..b), target)
+        const uint32_t mid = (a + b) >> 1;
+        if (col[mid] < target) a = mid + 1; else b = mid;
       }
-      suf[ps + i] = make_uint2(lo, end);
-      work += end - lo;
+      suf[ps + i] = make_uint2(a, end);
+      work += end - a;
     }
-    work = warp_sum64(work);
-    if (lane == 0) rowwork[r] = work > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)work;
-    tot += work;
+    work = group_sum64<G>(work);
+    if (gl == 0) {
+      rowwork64[r] += work;
+      tot += work;
+    }
   }
+  tot = warp_sum64(tot);
   if (lane == 0 && tot) atomicAdd(work_total, tot);
+}
+
+// clamp the 64-bit per-row work to the 32-bit value the row classifier uses
+__global__ void clamp_rowwork_kernel(const unsigned long long* __restrict__ w64, uint32_t n,
+                                     uint32_t* __restrict__ w32) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) w32[r] = w64[r] > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)w64[r];
 }
 
 // Sum over ids of f(f-1)/2: "Number of total edges", src/graph/mod.rs:44-51

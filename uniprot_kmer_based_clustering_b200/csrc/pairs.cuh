@@ -485,13 +485,16 @@ __global__ void __launch_bounds__(256)
 // shorter row's ids and binary-search the longer row.  MODE 0: sum of BLOSUM62 self-scores of
 // the shared k-mers -> edge.w.  (The list itself is produced by shared_kmers_kernel.)
 // ---------------------------------------------------------------------------------------
+constexpr uint32_t kBlosumStage = 1024;  // ids of the shorter row staged per warp
 __global__ void __launch_bounds__(256)
     edge_blosum_kernel(uint4* __restrict__ edges, unsigned long long n_edges, const uint32_t* __restrict__ pstart,
                        const uint32_t* __restrict__ rowlen, const uint32_t* __restrict__ ids,
                        const uint8_t* __restrict__ selfscore) {
-  const uint32_t lane = lane_id();
+  __shared__ uint32_t s_row[8][kBlosumStage];
+  const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
   const unsigned long long gw = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  uint32_t* sa = s_row[w];
   for (unsigned long long ei = gw; ei < n_edges; ei += nw) {
     uint4 e = edges[ei];
     uint32_t ra = e.x, rb = e.y;
@@ -505,14 +508,30 @@ __global__ void __launch_bounds__(256)
     const uint32_t* B = ids + pstart[rb];
     const uint32_t nb = rowlen[rb];
     int s = 0;
-    for (uint32_t i = lane; i < na; i += 32) {
-      const uint32_t x = A[i];
-      uint32_t lo = 0, hi = nb;
-      while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (B[mid] < x) lo = mid + 1; else hi = mid;
+    if (na <= kBlosumStage) {
+      // stage the shorter row; lanes stream the longer row (coalesced) and search on chip
+      for (uint32_t i = lane; i < na; i += 32) sa[i] = A[i];
+      __syncwarp();
+      for (uint32_t i = lane; i < nb; i += 32) {
+        const uint32_t x = B[i];
+        uint32_t lo = 0, hi = na;
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (sa[mid] < x) lo = mid + 1; else hi = mid;
+        }
+        if (lo < na && sa[lo] == x) s += selfscore[x];
       }
-      if (lo < nb && B[lo] == x) s += selfscore[x];
+      __syncwarp();
+    } else {
+      for (uint32_t i = lane; i < na; i += 32) {
+        const uint32_t x = A[i];
+        uint32_t lo = 0, hi = nb;
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (B[mid] < x) lo = mid + 1; else hi = mid;
+        }
+        if (lo < nb && B[lo] == x) s += selfscore[x];
+      }
     }
     s = warp_sum_i(s);
     if (lane == 0) {
