@@ -387,3 +387,32 @@ def test_call_order_errors():
             e.score_pairs()
         with pytest.raises(kc.KcError):
             e.set_proteins(np.zeros(4, np.uint8), np.array([0, 3, 2], np.uint64), np.zeros(2, np.uint32))
+
+
+def test_cli_prints_the_reference_counters(tmp_path, arg_fasta_bytes, golden):
+    """`kmer_cluster <fasta> <threads>` = `cargo run --release -- <fasta> <threads>` (src/main.rs:50-60)"""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "uniprot_kmer_based_clustering_b200", "bin", "kmer_cluster")
+    fa = tmp_path / "arg.fasta"
+    fa.write_bytes(arg_fasta_bytes)
+    r = subprocess.run([exe, str(fa), "4", "--blosum"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-500:]
+    err = r.stderr
+    assert err.startswith("We start main\n")
+    for line in ("Number of 5mers found in at least two proteins: 231253", "Number of total edges: 258621291",
+                 "Remove edges without diverging AMR labels", "Number of edges now: 5300233",
+                 "Combine edges with the same two vertices", "Number of edges now: 4350628"):
+        assert line in err, line
+    assert err.count("Cross-checking:") == 465
+    assert "kmers in common:567" in err
+    rows = [ln.split("\t") for ln in r.stdout.strip().splitlines()[1:]]
+    assert len(rows) == 465 and rows[0][:2] == ["26", "2838"] and rows[0][4] == "167"
+    assert sum(int(x[5]) for x in rows) == golden["k5"]["cross_gt10"]["blosum_sum"]
+    # wrong usage panics like the reference (exit status 101)
+    assert subprocess.run([exe, str(fa)], capture_output=True).returncode == 101
+    assert subprocess.run([exe, "/nonexistent.fasta", "2"], capture_output=True).returncode == 101
+    r7 = subprocess.run([exe, str(fa), "2", "--k", "7"], capture_output=True, text=True, timeout=120)
+    assert "Number of 7mers found in at least two proteins: 288551" in r7.stderr
+    assert r7.stderr.count("Cross-checking:") == 463

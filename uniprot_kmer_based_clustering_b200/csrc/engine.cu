@@ -539,13 +539,13 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
   KC_CUDA(e, e->d_rowlen.ensure(((uint64_t)n + 1) * 4));
   KC_CUDA(e, e->d_seen.ensure(W * 8));  // 2 bits per k-mer
   // L2 blocking plan: slices of 2^slice_shift k-mers such that the randomly accessed part of
-  // every sliced pass (census state / dictionary + freq / cursor + postings) is ~32 MB
+  // every sliced pass (census state / dictionary + freq / cursor + postings) is <= ~64 MB
   {
     unsigned long long n_positions_est = 0;
     for (uint32_t r = 0; r < n; ++r)
       if (e->h_plen[r] >= (uint32_t)e->cfg.k) n_positions_est += e->h_plen[r] - e->cfg.k + 1;
     const double footprint = std::max((double)e->universe / 4.0 * 1.5, (double)n_positions_est * 5.0);
-    uint32_t want = (uint32_t)std::min(64.0, std::ceil(footprint / (32.0 * 1024 * 1024)));
+    uint32_t want = (uint32_t)std::min(64.0, std::ceil(footprint / (64.0 * 1024 * 1024)));
     if (const char* env = std::getenv("KC_B200_SLICES")) want = (uint32_t)std::max(1, std::atoi(env));  // tests
     uint32_t shift = 31;
     while (shift > 12 && ((((uint64_t)e->universe - 1) >> shift) + 1) < want) --shift;
@@ -906,10 +906,6 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
   const uint64_t ne = e->n_edges;
   // K9 + canonical order
   if (ne) {
-    if (e->cfg.want_blosum)
-      KC_LAUNCH(e, edge_blosum_kernel, blocks_for(ne, 8, e->num_sm * 8), 256, 0, e->d_edges.as<uint4>(), ne,
-                e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(), e->d_pk.as<uint32_t>(),
-                e->d_self.as<uint8_t>());
     KC_CUDA(e, e->d_keys_a.ensure(ne * 8));
     KC_CUDA(e, e->d_keys_b.ensure(ne * 8));
     KC_CUDA(e, e->d_vals_a.ensure(ne * 8));
@@ -930,6 +926,12 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
     e->launches += radix_sort_pairs(e->d_keys_a.as<unsigned long long>(), e->d_vals_a.as<unsigned long long>(),
                                     e->d_keys_b.as<unsigned long long>(), e->d_vals_b.as<unsigned long long>(), ne,
                                     passes, np, e->d_hist.as<uint32_t>(), e->scan, e->stream, &in_b);
+    if (e->cfg.want_blosum)
+      KC_LAUNCH(e, edge_blosum_kernel, blocks_for((ne + 31) / 32, 4, e->num_sm * 5), 128, 0,
+                (in_b ? e->d_keys_b : e->d_keys_a).as<unsigned long long>(),
+                (in_b ? e->d_vals_b : e->d_vals_a).as<unsigned long long>(), ne, e->d_rank.as<uint32_t>(),
+                e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(), e->d_pk.as<uint32_t>(),
+                e->d_self.as<uint8_t>());
     KC_LAUNCH(e, assemble_edges_kernel, blocks_for(ne, 256, e->num_sm * 8), 256, 0,
               (in_b ? e->d_keys_b : e->d_keys_a).as<unsigned long long>(),
               (in_b ? e->d_vals_b : e->d_vals_a).as<unsigned long long>(), ne, e->d_edges_sorted.as<uint4>());

@@ -485,59 +485,135 @@ __global__ void __launch_bounds__(256)
 // shorter row's ids and binary-search the longer row.  MODE 0: sum of BLOSUM62 self-scores of
 // the shared k-mers -> edge.w.  (The list itself is produced by shared_kmers_kernel.)
 // ---------------------------------------------------------------------------------------
-constexpr uint32_t kBlosumStage = 1024;  // ids of the shorter row staged per warp
-__global__ void __launch_bounds__(256)
-    edge_blosum_kernel(uint4* __restrict__ edges, unsigned long long n_edges, const uint32_t* __restrict__ pstart,
-                       const uint32_t* __restrict__ rowlen, const uint32_t* __restrict__ ids,
-                       const uint8_t* __restrict__ selfscore) {
-  __shared__ uint32_t s_row[8][kBlosumStage];
+constexpr uint32_t kBlosumSlots = 2048;  // per-warp id hash: rows of up to 1024 ids
+// Runs over the SORTED edge list (keys = a << 32 | b in input order).  A warp takes a window of
+// 32 consecutive edges; while `a` stays the same it keeps row a's ids in a shared-memory hash
+// set (id -> BLOSUM62 self-score), streams row b's ids with coalesced loads and probes.
+// vals = count | blosum << 32 (blosum filled in here).
+__global__ void __launch_bounds__(128)
+    edge_blosum_kernel(const unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals,
+                       unsigned long long n_edges, const uint32_t* __restrict__ rank_of,
+                       const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen,
+                       const uint32_t* __restrict__ ids, const uint8_t* __restrict__ selfscore) {
+  __shared__ uint32_t s_key[4][kBlosumSlots];
+  __shared__ uint8_t s_val[4][kBlosumSlots];
   const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
+  uint32_t* hk = s_key[w];
+  uint8_t* hv = s_val[w];
+  const unsigned long long n_win = (n_edges + 31) / 32;
   const unsigned long long gw = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
-  uint32_t* sa = s_row[w];
-  for (unsigned long long ei = gw; ei < n_edges; ei += nw) {
-    uint4 e = edges[ei];
-    uint32_t ra = e.x, rb = e.y;
-    if (rowlen[ra] > rowlen[rb]) {
-      const uint32_t t = ra;
-      ra = rb;
-      rb = t;
+  for (unsigned long long win = gw; win < n_win; win += nw) {
+    // lane l fetches the metadata of edge win*32+l: all dependent loads of the window overlap
+    const unsigned long long my_e = win * 32 + lane;
+    uint32_t m_a = kSentinel, m_pa = 0, m_na = 0, m_pb = 0, m_nb = 0, m_score = 0;
+    unsigned long long m_val = 0;
+    if (my_e < n_edges) {
+      const unsigned long long key = keys[my_e];
+      m_val = vals[my_e];
+      m_a = (uint32_t)(key >> 32);
+      const uint32_t b = (uint32_t)key;
+      const uint32_t ra = rank_of ? rank_of[m_a] : m_a, rb = rank_of ? rank_of[b] : b;
+      m_pa = pstart[ra];
+      m_na = rowlen[ra];
+      m_pb = pstart[rb];
+      m_nb = rowlen[rb];
     }
-    const uint32_t* A = ids + pstart[ra];
-    const uint32_t na = rowlen[ra];
-    const uint32_t* B = ids + pstart[rb];
-    const uint32_t nb = rowlen[rb];
-    int s = 0;
-    if (na <= kBlosumStage) {
-      // stage the shorter row; lanes stream the longer row (coalesced) and search on chip
-      for (uint32_t i = lane; i < na; i += 32) sa[i] = A[i];
-      __syncwarp();
-      for (uint32_t i = lane; i < nb; i += 32) {
-        const uint32_t x = B[i];
-        uint32_t lo = 0, hi = na;
-        while (lo < hi) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (sa[mid] < x) lo = mid + 1; else hi = mid;
-        }
-        if (lo < na && sa[lo] == x) s += selfscore[x];
+    const uint32_t n_in_win = (uint32_t)min(32ull, n_edges - win * 32);
+    uint32_t cur_a = kSentinel;
+    bool hashed = false;
+    const uint32_t* A = nullptr;
+    uint32_t na = 0;
+    // software pipeline: the first 256 ids of the next edge's row b are loaded while the
+    // current edge is probed
+    uint32_t nxt[8];
+    {
+      const uint32_t* B0 = ids + __shfl_sync(kFullMask, m_pb, 0);
+      const uint32_t nb0 = __shfl_sync(kFullMask, m_nb, 0);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) nxt[u] = lane + 32 * u < nb0 ? B0[lane + 32 * u] : kSentinel;
+    }
+    for (uint32_t l = 0; l < n_in_win; ++l) {
+      uint32_t xs[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) xs[u] = nxt[u];
+      if (l + 1 < n_in_win) {
+        const uint32_t* B1 = ids + __shfl_sync(kFullMask, m_pb, l + 1);
+        const uint32_t nb1 = __shfl_sync(kFullMask, m_nb, l + 1);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) nxt[u] = lane + 32 * u < nb1 ? B1[lane + 32 * u] : kSentinel;
       }
-      __syncwarp();
-    } else {
-      for (uint32_t i = lane; i < na; i += 32) {
-        const uint32_t x = A[i];
-        uint32_t lo = 0, hi = nb;
-        while (lo < hi) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (B[mid] < x) lo = mid + 1; else hi = mid;
+      const uint32_t a = __shfl_sync(kFullMask, m_a, l);
+      const uint32_t pa = __shfl_sync(kFullMask, m_pa, l), na_l = __shfl_sync(kFullMask, m_na, l);
+      if (a != cur_a) {
+        cur_a = a;
+        A = ids + pa;
+        na = na_l;
+        hashed = na <= kBlosumSlots / 2;
+        __syncwarp();
+        if (hashed) {
+          for (uint32_t i = lane * 4; i < kBlosumSlots; i += 128)
+            *reinterpret_cast<uint4*>(hk + i) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+          __syncwarp();
+          for (uint32_t i0 = lane; i0 < na; i0 += 256) {
+            uint32_t as[8];
+            uint8_t sc[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) as[u] = i0 + 32 * u < na ? A[i0 + 32 * u] : kSentinel;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) sc[u] = as[u] != kSentinel ? selfscore[as[u]] : (uint8_t)0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const uint32_t x = as[u];
+              if (x == kSentinel) continue;
+              uint32_t h = (x * 2654435761u) >> 21;
+              while (atomicCAS(&hk[h], kSentinel, x) != kSentinel) h = (h + 1u) & (kBlosumSlots - 1u);
+              hv[h] = sc[u];
+            }
+          }
+          __syncwarp();
         }
-        if (lo < nb && B[lo] == x) s += selfscore[x];
       }
+      const uint32_t* B = ids + __shfl_sync(kFullMask, m_pb, l);
+      const uint32_t nb = __shfl_sync(kFullMask, m_nb, l);
+      int s = 0;
+      if (hashed) {
+        for (uint32_t i0 = lane; i0 < nb; i0 += 256) {
+          if (i0 >= 256) {  // rows longer than the prefetched 256 ids
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xs[u] = i0 + 32 * u < nb ? B[i0 + 32 * u] : kSentinel;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t x = xs[u];
+            if (x == kSentinel) continue;
+            uint32_t h = (x * 2654435761u) >> 21;
+            for (;;) {
+              const uint32_t k = hk[h];
+              if (k == x) {
+                s += hv[h];
+                break;
+              }
+              if (k == kSentinel) break;
+              h = (h + 1u) & (kBlosumSlots - 1u);
+            }
+          }
+        }
+      } else {
+        for (uint32_t i = lane; i < nb; i += 32) {
+          const uint32_t x = B[i];
+          uint32_t lo = 0, hi = na;
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (A[mid] < x) lo = mid + 1; else hi = mid;
+          }
+          if (lo < na && A[lo] == x) s += selfscore[x];
+        }
+      }
+      s = warp_sum_i(s);
+      if (lane == l) m_score = (uint32_t)s;
     }
-    s = warp_sum_i(s);
-    if (lane == 0) {
-      e.w = (uint32_t)s;
-      edges[ei] = e;
-    }
+    if (my_e < n_edges) vals[my_e] = (m_val & 0xFFFFFFFFull) | ((unsigned long long)m_score << 32);
   }
 }
 
