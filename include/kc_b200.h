@@ -68,6 +68,7 @@ typedef struct kc_pair_stats {
   uint64_t sum_count_out;      /* sum of their counts */
   uint64_t n_rows;             /* proteins (rows of the pair triangle) this call scored */
   uint64_t n_retries;          /* edge-buffer growth retries (0 in steady state) */
+  uint64_t n_rows_rescored;    /* rows whose optimistic on-chip table overflowed and were scored again */
 } kc_pair_stats;
 
 /* One surviving pair = KmerEdgeGroup {vertices_key, kmers.len()} (src/graph/edge.rs:48-52),

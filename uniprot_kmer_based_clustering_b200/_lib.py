@@ -38,7 +38,7 @@ class IndexStats(C.Structure):
 class PairStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("n_multi_edges", "n_multi_edges_kept", "n_pairs_kept", "n_edges_out", "sum_count_out",
-                 "n_rows", "n_retries")]
+                 "n_rows", "n_retries", "n_rows_rescored")]
 
 
 class Timings(C.Structure):

@@ -49,8 +49,10 @@ struct DeviceScalars {  // one small block of u64 counters, zeroed per stage
   unsigned long long edge_cursor;
   PairCounters pc;
   uint32_t list_counts[4];
-  uint32_t row_cursor[16];
+  uint32_t row_cursor[32];
   uint32_t bin_counts[16];
+  uint32_t n_overflow;
+  uint32_t pad2;
   uint32_t shard_rows[2];
   uint32_t n_shared;
   uint32_t pad;
@@ -91,7 +93,7 @@ struct kc_engine {
       d_suf, d_rowwork, d_lists, d_colscratch, d_workprefix, d_ksplit, d_isplit, d_rowwork64;
   uint32_t slice_shift = 31, n_slices = 1;
   // pairs
-  DBuf d_rowbin, d_edges, d_keys_a, d_keys_b, d_vals_a, d_vals_b, d_hist, d_edges_sorted;
+  DBuf d_rowbin, d_rowsafe, d_rowlogh, d_edges, d_keys_a, d_keys_b, d_vals_a, d_vals_b, d_hist, d_edges_sorted;
   uint64_t edge_cap = 0, n_edges = 0;
   kc_pair_stats pstats{};
   // misc
@@ -289,7 +291,7 @@ int launch_hash(kc_engine* e, uint8_t bin, const EdgeSink& sink) {
 template <int LOG_H, int GROUP_WARPS, int CTA_WARPS>
 int launch_packed(kc_engine* e, uint8_t bin, uint32_t count_bits, const EdgeSink& sink) {
   constexpr size_t smem =
-      ((size_t)(CTA_WARPS / GROUP_WARPS) * (1u << LOG_H) + (size_t)CTA_WARPS * kIdxPerWarp) * 4;
+      ((size_t)(CTA_WARPS / GROUP_WARPS) * (1u << LOG_H) + (size_t)CTA_WARPS * (kIdxPerWarp + kStageWords)) * 4;
   auto kern = pairs_packed_kernel<LOG_H, GROUP_WARPS, CTA_WARPS>;
   KC_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
@@ -821,6 +823,8 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
     return KC_OK;
   }
   KC_CUDA(e, e->d_rowbin.ensure((uint64_t)n + 64));
+  KC_CUDA(e, e->d_rowsafe.ensure((uint64_t)n + 64));
+  KC_CUDA(e, e->d_rowlogh.ensure((uint64_t)n + 64));
   if (e->edge_cap == 0) {
     e->edge_cap = e->cfg.max_edges ? e->cfg.max_edges : (1ull << 22);
     KC_CUDA(e, e->d_edges.ensure(e->edge_cap * 16));
@@ -846,10 +850,23 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
               ds->shard_rows);
     KC_LAUNCH(e, classify_rows_kernel, (n + 255) / 256, 256, 0, e->d_rowwork.as<uint32_t>(),
               e->d_rowlen.as<uint32_t>(), e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr, n,
-              ds->shard_rows, dense_cols, count_bits, e->d_rowbin.as<uint8_t>(), ds->bin_counts);
+              ds->shard_rows, dense_cols, count_bits, e->d_rowbin.as<uint8_t>(), e->d_rowsafe.as<uint8_t>(),
+              e->d_rowlogh.as<uint8_t>(), ds->bin_counts);
     EdgeSink sink{e->d_edges.as<uint4>(), &ds->edge_cursor, e->edge_cap, e->cfg.threshold};
     mark(e, EV_PK0);
     int rc;
+    {
+      constexpr size_t smem = (size_t)kMainWarps * ((1u << kMainLogHMax) + kIdxPerWarp + kStageWords) * 4;
+      KC_CUDA(e, cudaFuncSetAttribute(pairs_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 1;
+      KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairs_main_kernel, kMainWarps * 32, smem));
+      if (per_sm < 1) per_sm = 1;
+      KC_LAUNCH(e, pairs_main_kernel, (uint32_t)(e->num_sm * per_sm), kMainWarps * 32, smem,
+                e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(), e->d_suf.as<uint2>(),
+                e->d_col.as<uint32_t>(), e->d_rowbin.as<uint8_t>(), e->d_rowsafe.as<uint8_t>(),
+                e->d_rowlogh.as<uint8_t>(), n, count_bits, &ds->row_cursor[kBinMain], &ds->n_overflow, sink,
+                &ds->pc);
+    }
     if ((rc = launch_packed<8, 1, 4>(e, kBinPack8, count_bits, sink))) return rc;
     if ((rc = launch_packed<9, 1, 4>(e, kBinPack9, count_bits, sink))) return rc;
     if ((rc = launch_packed<10, 1, 4>(e, kBinPack10, count_bits, sink))) return rc;
@@ -886,6 +903,19 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
     KC_CUDA(e, cudaMemcpyAsync(&hs, ds, sizeof(hs), cudaMemcpyDeviceToHost, e->stream));
     KC_CUDA(e, cudaStreamSynchronize(e->stream));
     KC_CUDA(e, cudaGetLastError());
+    if (hs.n_overflow) {  // rows whose optimistic table overflowed: score them with safely sized tables
+      if ((rc = launch_packed<8, 1, 4>(e, kBinRetry + kBinPack8, count_bits, sink))) return rc;
+      if ((rc = launch_packed<9, 1, 4>(e, kBinRetry + kBinPack9, count_bits, sink))) return rc;
+      if ((rc = launch_packed<10, 1, 4>(e, kBinRetry + kBinPack10, count_bits, sink))) return rc;
+      if ((rc = launch_packed<11, 1, 4>(e, kBinRetry + kBinPack11, count_bits, sink))) return rc;
+      if ((rc = launch_packed<12, 4, 4>(e, kBinRetry + kBinPack12, count_bits, sink))) return rc;
+      if ((rc = launch_packed<13, 8, 8>(e, kBinRetry + kBinPack13, count_bits, sink))) return rc;
+      if ((rc = launch_packed<14, 8, 8>(e, kBinRetry + kBinPack14, count_bits, sink))) return rc;
+      mark(e, EV_PK1);
+      KC_CUDA(e, cudaMemcpyAsync(&hs, ds, sizeof(hs), cudaMemcpyDeviceToHost, e->stream));
+      KC_CUDA(e, cudaStreamSynchronize(e->stream));
+      KC_CUDA(e, cudaGetLastError());
+    }
     if (hs.edge_cursor > e->edge_cap) {  // grow to the exact need and score again
       if (attempt >= 2) return fail(e, KC_ECUDA, "edge buffer did not converge");
       e->edge_cap = hs.edge_cursor + (hs.edge_cursor >> 4) + 1024;
@@ -898,6 +928,7 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
     ps.n_edges_out = hs.pc.n_edges;
     ps.sum_count_out = hs.pc.sum_count;
     ps.n_rows = hs.shard_rows[1] - hs.shard_rows[0];
+    ps.n_rows_rescored = hs.n_overflow;
     e->n_edges = hs.edge_cursor;
     ps.n_multi_edges_kept = hs.pc.n_multi;
     break;

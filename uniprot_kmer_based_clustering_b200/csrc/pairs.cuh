@@ -48,6 +48,40 @@ __device__ __forceinline__ void emit_edge(bool pred, uint32_t ra, uint32_t rb, u
   if (pred && idx < sink.cap) sink.buf[idx] = make_uint4(ra, rb, count, 0u);
 }
 
+// Per-warp staging of emitted edges in shared memory: one global atomic per flush instead of
+// one per emitting instruction (ncu: the atomic's return latency was 30 % of all stall samples).
+constexpr uint32_t kStageEdges = 170;              // 170 x {row, partner, count} = 2040 B
+constexpr uint32_t kStageWords = 512;
+struct EdgeStage {
+  uint32_t* buf;
+  uint32_t cnt;  // warp-uniform
+};
+__device__ __forceinline__ void stage_flush(EdgeStage& st, const EdgeSink& sink) {
+  if (st.cnt == 0) return;
+  __syncwarp();
+  unsigned long long base = 0;
+  if (lane_id() == 0) base = atomicAdd(sink.cursor, (unsigned long long)st.cnt);
+  base = __shfl_sync(kFullMask, base, 0);
+  for (uint32_t i = lane_id(); i < st.cnt; i += 32) {
+    const unsigned long long idx = base + i;
+    if (idx < sink.cap) sink.buf[idx] = make_uint4(st.buf[3 * i], st.buf[3 * i + 1], st.buf[3 * i + 2], 0u);
+  }
+  __syncwarp();
+  st.cnt = 0;
+}
+// all 32 lanes call it; the caller guarantees room for 32 more edges
+__device__ __forceinline__ void stage_push(EdgeStage& st, bool pred, uint32_t r, uint32_t b, uint32_t c) {
+  const uint32_t m = __ballot_sync(kFullMask, pred);
+  if (!m) return;
+  if (pred) {
+    const uint32_t pos = st.cnt + __popc(m & lanemask_lt());
+    st.buf[3 * pos] = r;
+    st.buf[3 * pos + 1] = b;
+    st.buf[3 * pos + 2] = c;
+  }
+  st.cnt += __popc(m);
+}
+
 // row classes
 enum : uint8_t {
   kBinSkip = 0,
@@ -60,8 +94,11 @@ enum : uint8_t {
   kBinPack14 = 7,   // packed hash, 8 warps per row,  16384        (U <= 8192)
   kBinWide = 8,     // key/count in separate words (rows whose counts do not fit a packed slot)
   kBinDense = 9,
-  kNumBins = 10
+  kBinMain = 10,    // packed hash, one warp per row, table sized per row from an optimistic estimate
+  kNumBins = 11,
+  kBinRetry = 16    // added to a safe bin: the optimistic table of the main kernel overflowed
 };
+constexpr uint32_t kMainLogHMax = 11;  // 2048 slots = 8 KB per warp
 
 // bounds[0..1] = the shard's row range (device memory: no host round trip).
 // count_bits = bits left for the counter in a packed slot (32 - bits of a protein rank).
@@ -69,6 +106,7 @@ __global__ void __launch_bounds__(256)
     classify_rows_kernel(const uint32_t* __restrict__ rowwork, const uint32_t* __restrict__ rowlen,
                          const uint32_t* __restrict__ first_after, uint32_t n, const uint32_t* __restrict__ bounds,
                          uint32_t dense_single_pass_cols, uint32_t count_bits, uint8_t* __restrict__ rowbin,
+                         uint8_t* __restrict__ rowsafe, uint8_t* __restrict__ rowlogh,
                          uint32_t* __restrict__ bin_counts) {
   __shared__ uint32_t s_cnt[kNumBins];
   if (threadIdx.x < kNumBins) s_cnt[threadIdx.x] = 0;
@@ -93,6 +131,20 @@ __global__ void __launch_bounds__(256)
       else if (U <= 2048) bin = kBinPack12;
       else if (U <= 4096) bin = kBinPack13;
       else bin = kBinPack14;
+      uint8_t safe = bin;
+      if (bin >= kBinPack8 && bin <= kBinPack14) {
+        // U counts every multi-edge as a new partner.  Rows of related proteins meet the same
+        // partners again and again, so size the table for min(U, 2 * row length) partners
+        // instead and let the main kernel detect the (rare) overflow exactly.
+        const uint32_t est = min(U, max(128u, 2u * rowlen[r]));
+        uint32_t lh = 8;
+        while ((1u << lh) < 2u * est) ++lh;
+        if (lh <= kMainLogHMax && (est == U || P <= 6u * est)) {
+          bin = kBinMain;
+          rowlogh[r] = (uint8_t)lh;
+        }
+      }
+      rowsafe[r] = safe;
       atomicAdd(&s_cnt[bin], 1u);
     }
     rowbin[r] = bin;
@@ -226,6 +278,33 @@ __global__ void __launch_bounds__(CTA_WARPS * 32)
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t kIdxPerWarp = 512;  // >= 32 lanes x 15 postings
 
+// bounded variant for optimistically sized tables: counts new keys, gives up when the table is full
+__device__ __forceinline__ void packed_bump_checked(uint32_t* tab, uint32_t mask, uint32_t log_h, uint32_t cb,
+                                                    uint32_t b, uint32_t& inserted, bool& full) {
+  if (full) return;
+  uint32_t h = (b * 2654435761u) >> (32u - log_h);
+  for (uint32_t probe = 0; probe < 32u && probe <= mask; ++probe) {
+    const uint32_t s = tab[h];
+    if ((s >> cb) == b && s != kSentinel) {
+      atomicAdd(&tab[h], 1u);
+      return;
+    }
+    if (s == kSentinel) {
+      const uint32_t old = atomicCAS(&tab[h], kSentinel, (b << cb) | 1u);
+      if (old == kSentinel) {
+        ++inserted;
+        return;
+      }
+      if ((old >> cb) == b) {
+        atomicAdd(&tab[h], 1u);
+        return;
+      }
+    }
+    h = (h + 1u) & mask;
+  }
+  full = true;
+}
+
 __device__ __forceinline__ void packed_bump(uint32_t* tab, uint32_t mask, uint32_t log_h, uint32_t cb,
                                             uint32_t b) {
   uint32_t h = (b * 2654435761u) >> (32u - log_h);
@@ -247,9 +326,11 @@ __device__ __forceinline__ void packed_bump(uint32_t* tab, uint32_t mask, uint32
   }
 }
 
+// `stop` (optional): lane-local "give up" flag of an optimistically sized table; the loops have
+// warp-uniform trip counts so that the whole warp can leave as soon as any lane raises it.
 template <class Bump>
 __device__ __forceinline__ void walk_chunk_flat(const uint32_t* __restrict__ col, uint2 e, uint32_t* idx,
-                                                Bump bump) {
+                                                Bump bump, const bool* stop = nullptr) {
   const uint32_t lane = lane_id();
   const uint32_t len = e.y - e.x;
   // long suffixes: the whole warp reads 32 consecutive postings at a time
@@ -258,15 +339,17 @@ __device__ __forceinline__ void walk_chunk_flat(const uint32_t* __restrict__ col
     const uint32_t src = __ffs(m) - 1;
     m &= m - 1;
     const uint32_t s = __shfl_sync(kFullMask, e.x, src), t = __shfl_sync(kFullMask, e.y, src);
-    for (uint32_t j = s + lane; j < t; j += 128) {
-      const uint32_t b0 = col[j];
+    for (uint32_t j0 = s; j0 < t; j0 += 128) {
+      const uint32_t j = j0 + lane;
+      const uint32_t b0 = j < t ? col[j] : kSentinel;
       const uint32_t b1 = j + 32 < t ? col[j + 32] : kSentinel;
       const uint32_t b2 = j + 64 < t ? col[j + 64] : kSentinel;
       const uint32_t b3 = j + 96 < t ? col[j + 96] : kSentinel;
-      bump(b0);
+      if (b0 != kSentinel) bump(b0);
       if (b1 != kSentinel) bump(b1);
       if (b2 != kSentinel) bump(b2);
       if (b3 != kSentinel) bump(b3);
+      if (stop && __any_sync(kFullMask, *stop)) return;
     }
   }
   // short suffixes: flatten into the per-warp index list
@@ -277,15 +360,17 @@ __device__ __forceinline__ void walk_chunk_flat(const uint32_t* __restrict__ col
   uint32_t w = incl - slen;
   for (uint32_t j = e.x; j < e.x + slen; ++j) idx[w++] = j;
   __syncwarp();
-  for (uint32_t t0 = lane; t0 < total; t0 += 128) {
-    const uint32_t b0 = col[idx[t0]];
+  for (uint32_t t00 = 0; t00 < total; t00 += 128) {
+    const uint32_t t0 = t00 + lane;
+    const uint32_t b0 = t0 < total ? col[idx[t0]] : kSentinel;
     const uint32_t b1 = t0 + 32 < total ? col[idx[t0 + 32]] : kSentinel;
     const uint32_t b2 = t0 + 64 < total ? col[idx[t0 + 64]] : kSentinel;
     const uint32_t b3 = t0 + 96 < total ? col[idx[t0 + 96]] : kSentinel;
-    bump(b0);
+    if (b0 != kSentinel) bump(b0);
     if (b1 != kSentinel) bump(b1);
     if (b2 != kSentinel) bump(b2);
     if (b3 != kSentinel) bump(b3);
+    if (stop && __any_sync(kFullMask, *stop)) break;
   }
   __syncwarp();
 }
@@ -307,6 +392,9 @@ __global__ void __launch_bounds__(CTA_WARPS * 32)
   const uint32_t gtid = gwarp * 32 + lane;
   uint32_t* tab = reinterpret_cast<uint32_t*>(dyn_smem) + (size_t)group * H;
   uint32_t* idx = reinterpret_cast<uint32_t*>(dyn_smem) + (size_t)GROUPS * H + (size_t)warp * kIdxPerWarp;
+  EdgeStage stage{reinterpret_cast<uint32_t*>(dyn_smem) + (size_t)GROUPS * H + (size_t)CTA_WARPS * kIdxPerWarp +
+                      (size_t)warp * kStageWords,
+                  0u};
   const uint32_t cb = count_bits, cmask = (1u << count_bits) - 1u;
   unsigned long long n_pairs = 0, n_edges = 0, sum_count = 0, n_multi = 0;
 
@@ -358,19 +446,125 @@ __global__ void __launch_bounds__(CTA_WARPS * 32)
           any_out |= cq > sink.threshold;
         }
         if (__any_sync(kFullMask, any_out)) {
+          if (stage.cnt + 128u > kStageEdges) stage_flush(stage, sink);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint32_t cq = sv[q] != kSentinel ? (sv[q] & cmask) : 0u;
             const bool out = cq > sink.threshold;
             n_edges += out;
             sum_count += out ? cq : 0u;
-            emit_edge(out, r, sv[q] >> cb, cq, sink);
+            stage_push(stage, out, r, sv[q] >> cb, cq);
           }
         }
       }
       gsync();
     }
   }
+  stage_flush(stage, sink);
+  n_pairs = warp_sum64(n_pairs);
+  n_edges = warp_sum64(n_edges);
+  sum_count = warp_sum64(sum_count);
+  n_multi = warp_sum64(n_multi);
+  if (lane == 0) {
+    if (n_multi) atomicAdd(&counters->n_multi, n_multi);
+    if (n_pairs) atomicAdd(&counters->n_pairs, n_pairs);
+    if (n_edges) atomicAdd(&counters->n_edges, n_edges);
+    if (sum_count) atomicAdd(&counters->sum_count, sum_count);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Main pair kernel: one warp per row, rows handed out two at a time IN ORDER, so that related
+// proteins (neighbours in the input, which read the same postings) are scored by different
+// warps at the same moment and their postings reads hit L2.  The table size of a row comes from
+// an optimistic estimate of its distinct partners (rowlogh); new keys are counted exactly and a
+// row whose table passes 3/4 full is abandoned, its table cleared, and the row is flagged for
+// the safely sized kernels (rowbin = kBinRetry + safe bin).
+// ---------------------------------------------------------------------------------------
+constexpr int kMainWarps = 4;
+__global__ void __launch_bounds__(kMainWarps * 32)
+    pairs_main_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen,
+                      const uint2* __restrict__ suf, const uint32_t* __restrict__ col, uint8_t* __restrict__ rowbin,
+                      const uint8_t* __restrict__ rowsafe, const uint8_t* __restrict__ rowlogh, uint32_t n,
+                      uint32_t count_bits, uint32_t* __restrict__ row_cursor, uint32_t* __restrict__ n_overflow,
+                      EdgeSink sink, PairCounters* __restrict__ counters) {
+  constexpr uint32_t HMAX = 1u << kMainLogHMax;
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  uint32_t* tab = reinterpret_cast<uint32_t*>(dyn_smem) + (size_t)warp * HMAX;
+  uint32_t* idx = reinterpret_cast<uint32_t*>(dyn_smem) + (size_t)kMainWarps * HMAX + (size_t)warp * kIdxPerWarp;
+  EdgeStage stage{reinterpret_cast<uint32_t*>(dyn_smem) + (size_t)kMainWarps * (HMAX + kIdxPerWarp) +
+                      (size_t)warp * kStageWords,
+                  0u};
+  const uint32_t cb = count_bits, cmask = (1u << count_bits) - 1u;
+  unsigned long long n_pairs = 0, n_edges = 0, sum_count = 0, n_multi = 0;
+  for (uint32_t i = lane * 4; i < HMAX; i += 128)
+    *reinterpret_cast<uint4*>(tab + i) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+  __syncwarp();
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(row_cursor, 2u);
+    base = __shfl_sync(kFullMask, base, 0);
+    if (base >= n) break;
+    uint32_t todo = __ballot_sync(kFullMask, lane < 2 && base + lane < n && rowbin[base + lane] == kBinMain);
+    while (todo) {
+      const uint32_t r = base + __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t log_h = rowlogh[r], H = 1u << log_h;
+      const uint32_t nl = rowlen[r], ps = pstart[r];
+      uint32_t inserted = 0;
+      bool full = false, overflow = false;
+      uint2 e_next = lane < nl ? ld_stream_u32x2(suf + ps + lane) : make_uint2(0, 0);
+      for (uint32_t c = 0; c < nl; c += 32) {
+        const uint2 e = e_next;
+        e_next = c + 32 + lane < nl ? ld_stream_u32x2(suf + ps + c + 32 + lane) : make_uint2(0, 0);
+        walk_chunk_flat(col, e, idx,
+                        [&](uint32_t b) { packed_bump_checked(tab, H - 1u, log_h, cb, b, inserted, full); }, &full);
+        const uint32_t total_ins = warp_sum(inserted);
+        if (__any_sync(kFullMask, full) || 4u * total_ins > 3u * H) {
+          overflow = true;
+          break;
+        }
+      }
+      __syncwarp();
+      if (overflow) {
+        for (uint32_t i = lane * 4; i < H; i += 128)
+          *reinterpret_cast<uint4*>(tab + i) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+        if (lane == 0) {
+          rowbin[r] = (uint8_t)(kBinRetry + rowsafe[r]);
+          atomicAdd(n_overflow, 1u);
+        }
+        __syncwarp();
+        continue;
+      }
+      for (uint32_t i = lane * 4; i < H; i += 128) {
+        const uint4 v = *reinterpret_cast<uint4*>(tab + i);
+        *reinterpret_cast<uint4*>(tab + i) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+        const uint32_t sv[4] = {v.x, v.y, v.z, v.w};
+        bool any_out = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t cq = sv[q] != kSentinel ? (sv[q] & cmask) : 0u;
+          n_pairs += cq != 0;
+          n_multi += cq;
+          any_out |= cq > sink.threshold;
+        }
+        if (__any_sync(kFullMask, any_out)) {
+          if (stage.cnt + 128u > kStageEdges) stage_flush(stage, sink);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t cq = sv[q] != kSentinel ? (sv[q] & cmask) : 0u;
+            const bool out = cq > sink.threshold;
+            n_edges += out;
+            sum_count += out ? cq : 0u;
+            stage_push(stage, out, r, sv[q] >> cb, cq);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  stage_flush(stage, sink);
   n_pairs = warp_sum64(n_pairs);
   n_edges = warp_sum64(n_edges);
   sum_count = warp_sum64(sum_count);
@@ -396,11 +590,13 @@ __global__ void __launch_bounds__(256)
                        PairCounters* __restrict__ counters) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ uint32_t s_base;
+  __shared__ uint32_t s_stage[8][kStageWords];
   uint32_t* acc = reinterpret_cast<uint32_t*>(dyn_smem);
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   const uint32_t words = WIDE ? block_cols : (block_cols + 1) / 2;
   const uint32_t words4 = (words + 3u) & ~3u;
   unsigned long long n_pairs = 0, n_edges = 0, sum_count = 0, n_multi = 0;
+  EdgeStage stage{s_stage[warp], 0u};
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) s_base = atomicAdd(row_cursor, 32u);
@@ -446,13 +642,14 @@ __global__ void __launch_bounds__(256)
         for (uint32_t i0 = warp * 32; i0 < words; i0 += 256) {  // warp-uniform trip count
           const uint32_t i = i0 + lane;
           const uint32_t x = i < words ? acc[i] : 0u;
+          if (stage.cnt + 64u > kStageEdges) stage_flush(stage, sink);
           if (WIDE) {
             const bool out = x > sink.threshold;
             n_pairs += x != 0;
             n_multi += x;
             n_edges += out;
             sum_count += out ? x : 0u;
-            emit_edge(out, r, blk_lo + i, x, sink);
+            stage_push(stage, out, r, blk_lo + i, x);
           } else {
             const uint32_t c0 = x & 0xFFFFu, c1 = x >> 16;
             const bool o0 = c0 > sink.threshold, o1 = c1 > sink.threshold && 2 * i + 1 < ncols;
@@ -460,14 +657,15 @@ __global__ void __launch_bounds__(256)
             n_multi += c0 + c1;
             n_edges += (uint32_t)o0 + (uint32_t)o1;
             sum_count += (o0 ? c0 : 0u) + (o1 ? c1 : 0u);
-            emit_edge(o0, r, blk_lo + 2 * i, c0, sink);
-            emit_edge(o1, r, blk_lo + 2 * i + 1, c1, sink);
+            stage_push(stage, o0, r, blk_lo + 2 * i, c0);
+            stage_push(stage, o1, r, blk_lo + 2 * i + 1, c1);
           }
         }
         __syncthreads();
       }
     }
   }
+  stage_flush(stage, sink);
   n_pairs = warp_sum64(n_pairs);
   n_edges = warp_sum64(n_edges);
   sum_count = warp_sum64(sum_count);
