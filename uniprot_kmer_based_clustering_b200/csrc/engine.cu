@@ -90,7 +90,7 @@ struct kc_engine {
   kc_index_stats istats{};
   uint64_t multi_total = 0, work_total = 0;
   DBuf d_pk, d_ndist, d_rowlen, d_seen, d_dict, d_vocab, d_freq, d_self, d_colptr, d_cursor, d_col,
-      d_suf, d_rowwork, d_lists, d_colscratch, d_workprefix, d_ksplit, d_isplit, d_rowwork64;
+      d_suf, d_rowwork, d_lists, d_colscratch, d_workprefix, d_ksplit, d_isplit, d_rowwork64, d_rowinl, d_rowmaxlen;
   uint32_t slice_shift = 31, n_slices = 1;
   // pairs
   DBuf d_rowbin, d_rowsafe, d_rowlogh, d_edges, d_keys_a, d_keys_b, d_vals_a, d_vals_b, d_hist, d_edges_sorted;
@@ -425,7 +425,7 @@ void kc_destroy(kc_engine* e) {
                  &e->d_first_after, &e->d_long, &e->d_huge, &e->d_huge_off, &e->d_huge_scratch, &e->d_pk,
                  &e->d_ndist, &e->d_rowlen, &e->d_seen, &e->d_dict, &e->d_vocab, &e->d_freq,
                  &e->d_self, &e->d_colptr, &e->d_cursor, &e->d_col, &e->d_suf, &e->d_rowwork, &e->d_lists,
-                 &e->d_colscratch, &e->d_workprefix, &e->d_ksplit, &e->d_isplit, &e->d_rowwork64, &e->d_rowbin, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
+                 &e->d_colscratch, &e->d_workprefix, &e->d_ksplit, &e->d_isplit, &e->d_rowwork64, &e->d_rowinl, &e->d_rowmaxlen, &e->d_rowbin, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
                  &e->d_vals_a, &e->d_vals_b, &e->d_hist, &e->d_edges_sorted, &e->d_scalars, &e->d_scan_tiles,
                  &e->d_tmp};
   for (DBuf* b : all) b->release();
@@ -558,6 +558,12 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
   KC_CUDA(e, e->d_ksplit.ensure(((uint64_t)P + 1) * std::max<uint64_t>(n, 1) * 4));
   KC_CUDA(e, e->d_isplit.ensure(((uint64_t)P + 1) * std::max<uint64_t>(n, 1) * 4));
   KC_CUDA(e, e->d_rowwork64.ensure(((uint64_t)n + 1) * 8));
+  KC_CUDA(e, e->d_rowinl.ensure(((uint64_t)n + 1) * 4));
+  KC_CUDA(e, e->d_rowmaxlen.ensure(((uint64_t)n + 1) * 4));
+  if (n) {
+    KC_CUDA(e, cudaMemsetAsync(e->d_rowinl.p, 0, (uint64_t)n * 4, e->stream));
+    KC_CUDA(e, cudaMemsetAsync(e->d_rowmaxlen.p, 0, (uint64_t)n * 4, e->stream));
+  }
   KC_CUDA(e, e->d_dict.ensure(W * 8));
   int rc = ensure_scan(e, std::max<uint64_t>(W, (uint64_t)n + 1));
   if (rc) return rc;
@@ -678,12 +684,12 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
         KC_LAUNCH(e, suffix_ranges_kernel<8>, pass_grid, 256, 0, e->d_pstart.as<uint32_t>(), split(e->d_isplit, q),
                   split(e->d_isplit, q + 1), n, e->d_pk.as<uint32_t>(), e->d_colptr.as<uint32_t>(),
                   e->d_col.as<uint32_t>(), fa, e->d_suf.as<uint2>(), e->d_rowwork64.as<unsigned long long>(),
-                  &ds->work_total);
+                  e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>(), &ds->work_total);
       else
         KC_LAUNCH(e, suffix_ranges_kernel<32>, pass_grid, 256, 0, e->d_pstart.as<uint32_t>(), split(e->d_isplit, q),
                   split(e->d_isplit, q + 1), n, e->d_pk.as<uint32_t>(), e->d_colptr.as<uint32_t>(),
                   e->d_col.as<uint32_t>(), fa, e->d_suf.as<uint2>(), e->d_rowwork64.as<unsigned long long>(),
-                  &ds->work_total);
+                  e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>(), &ds->work_total);
     }
     KC_LAUNCH(e, clamp_rowwork_kernel, (n + 255) / 256, 256, 0, e->d_rowwork64.as<unsigned long long>(), n,
               e->d_rowwork.as<uint32_t>());
@@ -849,14 +855,15 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
     KC_LAUNCH(e, shard_bounds_kernel, 1, 32, 0, e->d_workprefix.as<unsigned long long>(), n, shard, n_shards,
               ds->shard_rows);
     KC_LAUNCH(e, classify_rows_kernel, (n + 255) / 256, 256, 0, e->d_rowwork.as<uint32_t>(),
-              e->d_rowlen.as<uint32_t>(), e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr, n,
+              e->d_rowlen.as<uint32_t>(), e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>(),
+              e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr, n,
               ds->shard_rows, dense_cols, count_bits, e->d_rowbin.as<uint8_t>(), e->d_rowsafe.as<uint8_t>(),
               e->d_rowlogh.as<uint8_t>(), ds->bin_counts);
     EdgeSink sink{e->d_edges.as<uint4>(), &ds->edge_cursor, e->edge_cap, e->cfg.threshold};
     mark(e, EV_PK0);
     int rc;
     {
-      constexpr size_t smem = (size_t)kMainWarps * ((1u << kMainLogHMax) + kIdxPerWarp + kStageWords) * 4;
+      constexpr size_t smem = (size_t)kMainWarps * ((1u << kMainLogHMax) + 2 * kIdxPerWarp + kMainCap / 2 + 4) * 4;
       KC_CUDA(e, cudaFuncSetAttribute(pairs_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 1;
       KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairs_main_kernel, kMainWarps * 32, smem));

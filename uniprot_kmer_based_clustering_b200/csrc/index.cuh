@@ -276,7 +276,8 @@ __global__ void __launch_bounds__(512)
 
 // per-entry suffix ranges: for row r and each of its ids, the holders that come after r in the
 // pair order (and, when only cross-class pairs are wanted, after r's whole class block) are
-// col[suf.x .. suf.y).  rowwork64[r] = sum of the range lengths = multi-edges row r accumulates.
+// col[suf.x .. suf.y) (or the single partner suf.x when suf.y is the sentinel).
+// rowwork64[r] = sum of the range lengths = multi-edges row r accumulates.
 // One id slice per launch like the fill (colptr and postings slices stay L2-resident).
 template <int G>
 __global__ void __launch_bounds__(256)
@@ -284,7 +285,8 @@ __global__ void __launch_bounds__(256)
                          const uint32_t* __restrict__ hi, uint32_t n, const uint32_t* __restrict__ ids,
                          const uint32_t* __restrict__ colptr, const uint32_t* __restrict__ col,
                          const uint32_t* __restrict__ first_after, uint2* __restrict__ suf,
-                         unsigned long long* __restrict__ rowwork64, unsigned long long* __restrict__ work_total) {
+                         unsigned long long* __restrict__ rowwork64, uint32_t* __restrict__ rowinl,
+                         uint32_t* __restrict__ rowmaxlen, unsigned long long* __restrict__ work_total) {
   const uint32_t lane = lane_id(), gl = lane % G;
   const uint32_t gg = (blockIdx.x * blockDim.x + threadIdx.x) / G, ng = (gridDim.x * blockDim.x) / G;
   unsigned long long tot = 0;
@@ -293,6 +295,7 @@ __global__ void __launch_bounds__(256)
     if (i0 >= i1) continue;
     const uint32_t target = first_after ? first_after[r] : r + 1;  // first rank that pairs with r
     unsigned long long work = 0;
+    uint32_t n_inl = 0, max_len = 0;
     for (uint32_t i = i0 + gl; i < i1; i += G) {
       const uint32_t id = ids[ps + i];
       uint32_t a = colptr[id];
@@ -302,12 +305,23 @@ __global__ void __launch_bounds__(256)
         const uint32_t mid = (a + b) >> 1;
         if (col[mid] < target) a = mid + 1; else b = mid;
       }
-      suf[ps + i] = make_uint2(a, end);
+      // a single partner is stored inline ({rank, sentinel}): the pair stage then needs no
+      // postings gather for it (a 4-byte read there costs a whole random 32-byte sector)
+      suf[ps + i] = end - a == 1u ? make_uint2(col[a], kSentinel) : make_uint2(a, end);
       work += end - a;
+      n_inl += end - a == 1u;
+      max_len = max(max_len, end - a == 1u ? 0u : end - a);
     }
     work = group_sum64<G>(work);
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      n_inl += __shfl_xor_sync(group_mask<G>(), n_inl, o);
+      max_len = max(max_len, __shfl_xor_sync(group_mask<G>(), max_len, o));
+    }
     if (gl == 0) {
       rowwork64[r] += work;
+      rowinl[r] += n_inl;
+      rowmaxlen[r] = max(rowmaxlen[r], max_len);
       tot += work;
     }
   }

@@ -98,12 +98,14 @@ enum : uint8_t {
   kNumBins = 11,
   kBinRetry = 16    // added to a safe bin: the optimistic table of the main kernel overflowed
 };
-constexpr uint32_t kMainLogHMax = 11;  // 2048 slots = 8 KB per warp
+constexpr uint32_t kMainLogHMax = 10;  // 1024 slots = 4 KB per warp
+constexpr uint32_t kMainCap = 640;     // distinct partners a row may collect in the main kernel (load 0.625)
 
 // bounds[0..1] = the shard's row range (device memory: no host round trip).
 // count_bits = bits left for the counter in a packed slot (32 - bits of a protein rank).
 __global__ void __launch_bounds__(256)
     classify_rows_kernel(const uint32_t* __restrict__ rowwork, const uint32_t* __restrict__ rowlen,
+                         const uint32_t* __restrict__ rowinl, const uint32_t* __restrict__ rowmaxlen,
                          const uint32_t* __restrict__ first_after, uint32_t n, const uint32_t* __restrict__ bounds,
                          uint32_t dense_single_pass_cols, uint32_t count_bits, uint8_t* __restrict__ rowbin,
                          uint8_t* __restrict__ rowsafe, uint8_t* __restrict__ rowlogh,
@@ -133,15 +135,15 @@ __global__ void __launch_bounds__(256)
       else bin = kBinPack14;
       uint8_t safe = bin;
       if (bin >= kBinPack8 && bin <= kBinPack14) {
-        // U counts every multi-edge as a new partner.  Rows of related proteins meet the same
-        // partners again and again, so size the table for min(U, 2 * row length) partners
-        // instead and let the main kernel detect the (rare) overflow exactly.
-        const uint32_t est = min(U, max(128u, 2u * rowlen[r]));
-        uint32_t lh = 8;
-        while ((1u << lh) < 2u * est) ++lh;
-        if (lh <= kMainLogHMax && (est == U || P <= 6u * est)) {
+        // U counts every multi-edge as a new partner, but related proteins meet the same partners
+        // again and again.  The main kernel counts distinct partners exactly as it goes and gives
+        // a row up when they pass kMainCap, so any row may be tried there; rows that certainly
+        // (inline partners are distinct) or very probably (far more multi-edges than any
+        // plausible duplication explains) exceed the cap go straight to their safe bin.
+        const uint32_t lower = max(rowinl[r], rowmaxlen[r]);
+        if (U <= kMainCap || (lower <= kMainCap && P <= 16u * max(lower, 16u))) {
           bin = kBinMain;
-          rowlogh[r] = (uint8_t)lh;
+          rowlogh[r] = (uint8_t)kMainLogHMax;
         }
       }
       rowsafe[r] = safe;
@@ -174,6 +176,10 @@ __device__ __forceinline__ void hash_bump(uint32_t* keys, uint32_t* cnt, uint32_
 template <class Bump>
 __device__ __forceinline__ void walk_chunk(const uint32_t* __restrict__ col, uint2 e, Bump bump) {
   const uint32_t lane = lane_id();
+  if (e.y == kSentinel) {  // single partner stored inline
+    bump(e.x);
+    e = make_uint2(0, 0);
+  }
   const uint32_t len = e.y - e.x;
   uint32_t m = __ballot_sync(kFullMask, len >= 16u);
   while (m) {
@@ -278,12 +284,49 @@ __global__ void __launch_bounds__(CTA_WARPS * 32)
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t kIdxPerWarp = 512;  // >= 32 lanes x 15 postings
 
+// main-kernel variant: every new key's slot is appended to the warp's dirty list (so the read-out
+// touches only occupied slots and the distinct-partner count is exact); gives up beyond `cap`
+__device__ __forceinline__ void packed_bump_dirty(uint32_t* tab, uint32_t mask, uint32_t log_h, uint32_t cb,
+                                                  uint32_t b, uint32_t* dirty_cnt, uint16_t* dirty, uint32_t cap,
+                                                  bool& full) {
+  if (full) return;
+  uint32_t h = (b * 2654435761u) >> (32u - log_h);
+  for (;;) {
+    const uint32_t s = tab[h];
+    if ((s >> cb) == b) {  // an empty slot never matches: its key bits are all ones
+      atomicAdd(&tab[h], 1u);
+      return;
+    }
+    if (s == kSentinel) {
+      const uint32_t old = atomicCAS(&tab[h], kSentinel, (b << cb) | 1u);
+      if (old == kSentinel) {
+        const uint32_t pos = atomicAdd(dirty_cnt, 1u);
+        if (pos < cap) dirty[pos] = (uint16_t)h;
+        else full = true;
+        return;
+      }
+      if ((old >> cb) == b) {
+        atomicAdd(&tab[h], 1u);
+        return;
+      }
+    }
+    h = (h + 1u) & mask;
+  }
+}
+
 // bounded variant for optimistically sized tables: counts new keys, gives up when the table is full
 __device__ __forceinline__ void packed_bump_checked(uint32_t* tab, uint32_t mask, uint32_t log_h, uint32_t cb,
                                                     uint32_t b, uint32_t& inserted, bool& full) {
   if (full) return;
   uint32_t h = (b * 2654435761u) >> (32u - log_h);
-  for (uint32_t probe = 0; probe < 32u && probe <= mask; ++probe) {
+  {  // fast path: the partner is already in its home slot (an empty slot never matches: its key bits are all ones)
+    const uint32_t s0 = tab[h];
+    if ((s0 >> cb) == b) {
+      atomicAdd(&tab[h], 1u);
+      return;
+    }
+  }
+  for (uint32_t probe = 0; probe < 128u && probe <= mask; ++probe) {  // long clusters happen at load 0.6
     const uint32_t s = tab[h];
     if ((s >> cb) == b && s != kSentinel) {
       atomicAdd(&tab[h], 1u);
@@ -332,6 +375,10 @@ template <class Bump>
 __device__ __forceinline__ void walk_chunk_flat(const uint32_t* __restrict__ col, uint2 e, uint32_t* idx,
                                                 Bump bump, const bool* stop = nullptr) {
   const uint32_t lane = lane_id();
+  if (e.y == kSentinel) {  // single partner stored inline
+    bump(e.x);
+    e = make_uint2(0, 0);
+  }
   const uint32_t len = e.y - e.x;
   // long suffixes: the whole warp reads 32 consecutive postings at a time
   uint32_t m = __ballot_sync(kFullMask, len >= 16u);
@@ -482,6 +529,24 @@ __global__ void __launch_bounds__(CTA_WARPS * 32)
 // the safely sized kernels (rowbin = kBinRetry + safe bin).
 // ---------------------------------------------------------------------------------------
 constexpr int kMainWarps = 4;
+
+// flatten the short postings suffixes (2..15 holders) of one 32-entry chunk into `idx` and start
+// the gathers of the first 128 flattened postings; returns the number of flattened postings
+__device__ __forceinline__ uint32_t chunk_prepare(const uint32_t* __restrict__ col, uint2 e, uint32_t* idx,
+                                                  uint32_t (&v)[4]) {
+  const uint32_t lane = lane_id();
+  const uint32_t len = e.y == kSentinel ? 0u : e.y - e.x;
+  const uint32_t slen = len < 16u ? len : 0u;
+  const uint32_t incl = warp_scan_incl(slen);
+  const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+  uint32_t w = incl - slen;
+  for (uint32_t j = e.x; j < e.x + slen; ++j) idx[w++] = j;
+  __syncwarp();
+#pragma unroll
+  for (int u = 0; u < 4; ++u) v[u] = lane + 32 * u < total ? col[idx[lane + 32 * u]] : kSentinel;
+  return total;
+}
+
 __global__ void __launch_bounds__(kMainWarps * 32)
     pairs_main_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen,
                       const uint2* __restrict__ suf, const uint32_t* __restrict__ col, uint8_t* __restrict__ rowbin,
@@ -491,11 +556,16 @@ __global__ void __launch_bounds__(kMainWarps * 32)
   constexpr uint32_t HMAX = 1u << kMainLogHMax;
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  uint32_t* tab = reinterpret_cast<uint32_t*>(dyn_smem) + (size_t)warp * HMAX;
-  uint32_t* idx = reinterpret_cast<uint32_t*>(dyn_smem) + (size_t)kMainWarps * HMAX + (size_t)warp * kIdxPerWarp;
-  EdgeStage stage{reinterpret_cast<uint32_t*>(dyn_smem) + (size_t)kMainWarps * (HMAX + kIdxPerWarp) +
-                      (size_t)warp * kStageWords,
-                  0u};
+  // per warp: table (HMAX words) | idx buffer 0 | idx buffer 1 (doubles as the edge stage) |
+  // dirty list (kMainCap u16 slot numbers) | dirty count
+  constexpr uint32_t kWarpWords = HMAX + 2 * kIdxPerWarp + kMainCap / 2 + 4;
+  uint32_t* wbase = reinterpret_cast<uint32_t*>(dyn_smem) + (size_t)warp * kWarpWords;
+  uint32_t* tab = wbase;
+  uint32_t* idxbuf[2] = {wbase + HMAX, wbase + HMAX + kIdxPerWarp};
+  uint16_t* dirty = reinterpret_cast<uint16_t*>(wbase + HMAX + 2 * kIdxPerWarp);
+  uint32_t* dirty_cnt = wbase + HMAX + 2 * kIdxPerWarp + kMainCap / 2;
+  if (lane == 0) *dirty_cnt = 0;
+  EdgeStage stage{idxbuf[1], 0u};
   const uint32_t cb = count_bits, cmask = (1u << count_bits) - 1u;
   unsigned long long n_pairs = 0, n_edges = 0, sum_count = 0, n_multi = 0;
   for (uint32_t i = lane * 4; i < HMAX; i += 128)
@@ -503,28 +573,83 @@ __global__ void __launch_bounds__(kMainWarps * 32)
   __syncwarp();
   for (;;) {
     uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(row_cursor, 2u);
+    if (lane == 0) base = atomicAdd(row_cursor, 4u);
     base = __shfl_sync(kFullMask, base, 0);
     if (base >= n) break;
-    uint32_t todo = __ballot_sync(kFullMask, lane < 2 && base + lane < n && rowbin[base + lane] == kBinMain);
+    // lane l < 4 fetches the metadata of row base + l (one round trip for the four rows)
+    uint32_t m_len = 0, m_ps = 0, m_lh = 0;
+    bool mine = false;
+    if (lane < 4 && base + lane < n && rowbin[base + lane] == kBinMain) {
+      mine = true;
+      m_len = rowlen[base + lane];
+      m_ps = pstart[base + lane];
+      m_lh = rowlogh[base + lane];
+    }
+    uint32_t todo = __ballot_sync(kFullMask, mine);
     while (todo) {
-      const uint32_t r = base + __ffs(todo) - 1;
+      const uint32_t l = __ffs(todo) - 1;
       todo &= todo - 1;
-      const uint32_t log_h = rowlogh[r], H = 1u << log_h;
-      const uint32_t nl = rowlen[r], ps = pstart[r];
-      uint32_t inserted = 0;
+      const uint32_t r = base + l;
+      const uint32_t nl = __shfl_sync(kFullMask, m_len, l), ps = __shfl_sync(kFullMask, m_ps, l);
+      constexpr uint32_t log_h = kMainLogHMax, H = HMAX;
       bool full = false, overflow = false;
-      uint2 e_next = lane < nl ? ld_stream_u32x2(suf + ps + lane) : make_uint2(0, 0);
-      for (uint32_t c = 0; c < nl; c += 32) {
-        const uint2 e = e_next;
-        e_next = c + 32 + lane < nl ? ld_stream_u32x2(suf + ps + c + 32 + lane) : make_uint2(0, 0);
-        walk_chunk_flat(col, e, idx,
-                        [&](uint32_t b) { packed_bump_checked(tab, H - 1u, log_h, cb, b, inserted, full); }, &full);
-        const uint32_t total_ins = warp_sum(inserted);
-        if (__any_sync(kFullMask, full) || 4u * total_ins > 3u * H) {
+      auto bump = [&](uint32_t b) { packed_bump_dirty(tab, H - 1u, log_h, cb, b, dirty_cnt, dirty, kMainCap, full); };
+      // software pipeline over 32-entry chunks: while chunk c is bumped into the table, the
+      // gathers of chunk c+1 and the entry load of chunk c+2 are in flight
+      uint2 e_cur = lane < nl ? ld_stream_u32x2(suf + ps + lane) : make_uint2(0, 0);
+      uint2 e_nxt = 32 + lane < nl ? ld_stream_u32x2(suf + ps + 32 + lane) : make_uint2(0, 0);
+      uint32_t v[4], w[4];
+      uint32_t tot_cur = chunk_prepare(col, e_cur, idxbuf[0], v), tot_nxt = 0;
+      uint32_t k = 0;
+      for (uint32_t c = 0; c < nl; c += 32, k ^= 1u) {
+        const bool more = c + 32 < nl;
+        uint2 e_nn = make_uint2(0, 0);
+        if (more) {
+          e_nn = c + 64 + lane < nl ? ld_stream_u32x2(suf + ps + c + 64 + lane) : make_uint2(0, 0);
+          tot_nxt = chunk_prepare(col, e_nxt, idxbuf[k ^ 1u], w);
+        }
+        // consume chunk c
+        if (e_cur.y == kSentinel) bump(e_cur.x);  // inline single partner
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (v[u] != kSentinel) bump(v[u]);
+        for (uint32_t t00 = 128; t00 < tot_cur; t00 += 128) {  // rare: more than 128 short postings
+          const uint32_t t0 = t00 + lane;
+          uint32_t x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) x[u] = t0 + 32 * u < tot_cur ? col[idxbuf[k][t0 + 32 * u]] : kSentinel;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (x[u] != kSentinel) bump(x[u]);
+        }
+        {  // long suffixes: the whole warp reads 32 consecutive postings at a time
+          const uint32_t len = e_cur.y == kSentinel ? 0u : e_cur.y - e_cur.x;
+          uint32_t m = __ballot_sync(kFullMask, len >= 16u);
+          while (m) {
+            const uint32_t src = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t s0 = __shfl_sync(kFullMask, e_cur.x, src), t1 = __shfl_sync(kFullMask, e_cur.y, src);
+            for (uint32_t j0 = s0; j0 < t1; j0 += 128) {
+              const uint32_t j = j0 + lane;
+              uint32_t x[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) x[u] = j + 32 * u < t1 ? col[j + 32 * u] : kSentinel;
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (x[u] != kSentinel) bump(x[u]);
+              if (__any_sync(kFullMask, full)) break;
+            }
+          }
+        }
+        if (__any_sync(kFullMask, full)) {
           overflow = true;
           break;
         }
+        e_cur = e_nxt;
+        e_nxt = e_nn;
+        tot_cur = tot_nxt;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = w[u];
       }
       __syncwarp();
       if (overflow) {
@@ -533,38 +658,36 @@ __global__ void __launch_bounds__(kMainWarps * 32)
         if (lane == 0) {
           rowbin[r] = (uint8_t)(kBinRetry + rowsafe[r]);
           atomicAdd(n_overflow, 1u);
+          *dirty_cnt = 0;
         }
         __syncwarp();
         continue;
       }
-      for (uint32_t i = lane * 4; i < H; i += 128) {
-        const uint4 v = *reinterpret_cast<uint4*>(tab + i);
-        *reinterpret_cast<uint4*>(tab + i) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
-        const uint32_t sv[4] = {v.x, v.y, v.z, v.w};
-        bool any_out = false;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t cq = sv[q] != kSentinel ? (sv[q] & cmask) : 0u;
-          n_pairs += cq != 0;
-          n_multi += cq;
-          any_out |= cq > sink.threshold;
+      // read out and clear exactly the occupied slots
+      const uint32_t n_dirty = *dirty_cnt;
+      __syncwarp();
+      for (uint32_t i0 = 0; i0 < n_dirty; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        uint32_t sv = kSentinel;
+        if (i < n_dirty) {
+          const uint32_t h = dirty[i];
+          sv = tab[h];
+          tab[h] = kSentinel;
         }
-        if (__any_sync(kFullMask, any_out)) {
-          if (stage.cnt + 128u > kStageEdges) stage_flush(stage, sink);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t cq = sv[q] != kSentinel ? (sv[q] & cmask) : 0u;
-            const bool out = cq > sink.threshold;
-            n_edges += out;
-            sum_count += out ? cq : 0u;
-            stage_push(stage, out, r, sv[q] >> cb, cq);
-          }
-        }
+        const uint32_t cq = sv != kSentinel ? (sv & cmask) : 0u;
+        const bool out = cq > sink.threshold;
+        n_pairs += cq != 0;
+        n_multi += cq;
+        n_edges += out;
+        sum_count += out ? cq : 0u;
+        if (stage.cnt + 32u > kStageEdges) stage_flush(stage, sink);
+        stage_push(stage, out, r, sv >> cb, cq);
       }
+      if (lane == 0) *dirty_cnt = 0;
+      stage_flush(stage, sink);  // the stage shares idx buffer 1 with the next row's walk
       __syncwarp();
     }
   }
-  stage_flush(stage, sink);
   n_pairs = warp_sum64(n_pairs);
   n_edges = warp_sum64(n_edges);
   sum_count = warp_sum64(sum_count);
@@ -617,7 +740,9 @@ __global__ void __launch_bounds__(256)
         __syncthreads();
         for (uint32_t c = warp * 32; c < nl; c += 256) {
           uint2 e = c + lane < nl ? ld_stream_u32x2(suf + ps + c + lane) : make_uint2(0, 0);
-          if (multipass) {  // clip the suffix to holders in [blk_lo, blk_hi)
+          if (multipass && e.y == kSentinel) {
+            if (e.x < blk_lo || e.x >= blk_hi) e = make_uint2(0, 0);
+          } else if (multipass) {  // clip the suffix to holders in [blk_lo, blk_hi)
             uint32_t lo = e.x, hi = e.y;
             while (lo < hi) {
               const uint32_t mid = (lo + hi) >> 1;
