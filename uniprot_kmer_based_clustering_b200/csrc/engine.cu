@@ -50,7 +50,7 @@ struct DeviceScalars {  // one small block of u64 counters, zeroed per stage
   PairCounters pc;
   uint32_t list_counts[4];
   uint32_t row_cursor[32];
-  uint32_t bin_counts[16];
+  uint32_t bin_counts[32];
   uint32_t n_overflow;
   uint32_t pad2;
   uint32_t shard_rows[2];
@@ -284,7 +284,7 @@ int launch_hash(kc_engine* e, uint8_t bin, const EdgeSink& sink) {
   const uint32_t grid = (uint32_t)(e->num_sm * per_sm);
   KC_LAUNCH(e, kern, grid, CTA_WARPS * 32, smem, e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(),
             e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), e->d_rowbin.as<uint8_t>(), bin, (uint32_t)e->n,
-            &e->ds->row_cursor[bin], sink, &e->ds->pc);
+            &e->ds->row_cursor[bin], e->ds->bin_counts, sink, &e->ds->pc);
   return KC_OK;
 }
 
@@ -300,7 +300,7 @@ int launch_packed(kc_engine* e, uint8_t bin, uint32_t count_bits, const EdgeSink
   const uint32_t grid = (uint32_t)(e->num_sm * per_sm);
   KC_LAUNCH(e, kern, grid, CTA_WARPS * 32, smem, e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(),
             e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), e->d_rowbin.as<uint8_t>(), bin, (uint32_t)e->n,
-            count_bits, &e->ds->row_cursor[bin], sink, &e->ds->pc);
+            count_bits, &e->ds->row_cursor[bin], e->ds->bin_counts, sink, &e->ds->pc);
   return KC_OK;
 }
 
@@ -871,8 +871,8 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
       KC_LAUNCH(e, pairs_main_kernel, (uint32_t)(e->num_sm * per_sm), kMainWarps * 32, smem,
                 e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(), e->d_suf.as<uint2>(),
                 e->d_col.as<uint32_t>(), e->d_rowbin.as<uint8_t>(), e->d_rowsafe.as<uint8_t>(),
-                e->d_rowlogh.as<uint8_t>(), n, count_bits, &ds->row_cursor[kBinMain], &ds->n_overflow, sink,
-                &ds->pc);
+                e->d_rowlogh.as<uint8_t>(), n, count_bits, &ds->row_cursor[kBinMain], &ds->n_overflow,
+                ds->bin_counts, sink, &ds->pc);
     }
     if ((rc = launch_packed<8, 1, 4>(e, kBinPack8, count_bits, sink))) return rc;
     if ((rc = launch_packed<9, 1, 4>(e, kBinPack9, count_bits, sink))) return rc;
@@ -899,11 +899,11 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
       if (wide)
         KC_LAUNCH(e, pairs_dense_kernel<true>, grid, 256, dense_smem, e->d_pstart.as<uint32_t>(),
                   e->d_rowlen.as<uint32_t>(), e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), fa,
-                  e->d_rowbin.as<uint8_t>(), n, dense_cols, &ds->row_cursor[kBinDense], sink, &ds->pc);
+                  e->d_rowbin.as<uint8_t>(), n, dense_cols, &ds->row_cursor[kBinDense], ds->bin_counts, sink, &ds->pc);
       else
         KC_LAUNCH(e, pairs_dense_kernel<false>, grid, 256, dense_smem, e->d_pstart.as<uint32_t>(),
                   e->d_rowlen.as<uint32_t>(), e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), fa,
-                  e->d_rowbin.as<uint8_t>(), n, dense_cols, &ds->row_cursor[kBinDense], sink, &ds->pc);
+                  e->d_rowbin.as<uint8_t>(), n, dense_cols, &ds->row_cursor[kBinDense], ds->bin_counts, sink, &ds->pc);
     }
     mark(e, EV_PK1);
     DeviceScalars hs{};

@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(256)
                          uint32_t dense_single_pass_cols, uint32_t count_bits, uint8_t* __restrict__ rowbin,
                          uint8_t* __restrict__ rowsafe, uint8_t* __restrict__ rowlogh,
                          uint32_t* __restrict__ bin_counts) {
-  __shared__ uint32_t s_cnt[kNumBins];
-  if (threadIdx.x < kNumBins) s_cnt[threadIdx.x] = 0;
+  __shared__ uint32_t s_cnt[16];
+  if (threadIdx.x < 16) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t row_lo = bounds[0], row_hi = bounds[1];
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -137,11 +137,11 @@ __global__ void __launch_bounds__(256)
       if (bin >= kBinPack8 && bin <= kBinPack14) {
         // U counts every multi-edge as a new partner, but related proteins meet the same partners
         // again and again.  The main kernel counts distinct partners exactly as it goes and gives
-        // a row up when they pass kMainCap, so any row may be tried there; rows that certainly
-        // (inline partners are distinct) or very probably (far more multi-edges than any
-        // plausible duplication explains) exceed the cap go straight to their safe bin.
+        // a row up when they pass kMainCap (a bounded loss: at most kMainCap insertions), so a row
+        // is tried there unless a lower bound on its partners (inline partners are distinct; the
+        // longest suffix holds distinct partners) already comes close to the cap.
         const uint32_t lower = max(rowinl[r], rowmaxlen[r]);
-        if (U <= kMainCap || (lower <= kMainCap && P <= 16u * max(lower, 16u))) {
+        if (U <= kMainCap || lower <= kMainCap / 2) {
           bin = kBinMain;
           rowlogh[r] = (uint8_t)kMainLogHMax;
         }
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256)
     rowbin[r] = bin;
   }
   __syncthreads();
-  if (threadIdx.x < kNumBins && s_cnt[threadIdx.x]) atomicAdd(&bin_counts[threadIdx.x], s_cnt[threadIdx.x]);
+  if (threadIdx.x < 16 && s_cnt[threadIdx.x]) atomicAdd(&bin_counts[threadIdx.x], s_cnt[threadIdx.x]);
 }
 
 template <int LOG_H>
@@ -201,8 +201,10 @@ __global__ void __launch_bounds__(CTA_WARPS * 32)
     pairs_hash_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen,
                       const uint2* __restrict__ suf, const uint32_t* __restrict__ col,
                       const uint8_t* __restrict__ rowbin, uint8_t my_bin, uint32_t n,
-                      uint32_t* __restrict__ row_cursor, EdgeSink sink, PairCounters* __restrict__ counters) {
+                      uint32_t* __restrict__ row_cursor, const uint32_t* __restrict__ bin_counts, EdgeSink sink,
+                      PairCounters* __restrict__ counters) {
   static_assert(GROUP_WARPS == 1 || GROUP_WARPS == CTA_WARPS, "group = warp or CTA");
+  if (bin_counts[my_bin] == 0) return;  // nothing in this bin
   constexpr uint32_t H = 1u << LOG_H;
   constexpr int GROUPS = CTA_WARPS / GROUP_WARPS;
   constexpr uint32_t GSIZE = GROUP_WARPS * 32;
@@ -427,8 +429,10 @@ __global__ void __launch_bounds__(CTA_WARPS * 32)
     pairs_packed_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen,
                         const uint2* __restrict__ suf, const uint32_t* __restrict__ col,
                         const uint8_t* __restrict__ rowbin, uint8_t my_bin, uint32_t n, uint32_t count_bits,
-                        uint32_t* __restrict__ row_cursor, EdgeSink sink, PairCounters* __restrict__ counters) {
+                        uint32_t* __restrict__ row_cursor, const uint32_t* __restrict__ bin_counts, EdgeSink sink,
+                        PairCounters* __restrict__ counters) {
   static_assert(GROUP_WARPS == 1 || GROUP_WARPS == CTA_WARPS, "group = warp or CTA");
+  if (bin_counts[my_bin] == 0) return;  // nothing in this bin
   constexpr uint32_t H = 1u << LOG_H;
   constexpr uint32_t GROUPS = CTA_WARPS / GROUP_WARPS;
   constexpr uint32_t GSIZE = GROUP_WARPS * 32;
@@ -552,8 +556,9 @@ __global__ void __launch_bounds__(kMainWarps * 32)
                       const uint2* __restrict__ suf, const uint32_t* __restrict__ col, uint8_t* __restrict__ rowbin,
                       const uint8_t* __restrict__ rowsafe, const uint8_t* __restrict__ rowlogh, uint32_t n,
                       uint32_t count_bits, uint32_t* __restrict__ row_cursor, uint32_t* __restrict__ n_overflow,
-                      EdgeSink sink, PairCounters* __restrict__ counters) {
+                      uint32_t* __restrict__ bin_counts, EdgeSink sink, PairCounters* __restrict__ counters) {
   constexpr uint32_t HMAX = 1u << kMainLogHMax;
+  if (bin_counts[kBinMain] == 0) return;
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   // per warp: table (HMAX words) | idx buffer 0 | idx buffer 1 (doubles as the edge stage) |
@@ -658,6 +663,7 @@ __global__ void __launch_bounds__(kMainWarps * 32)
         if (lane == 0) {
           rowbin[r] = (uint8_t)(kBinRetry + rowsafe[r]);
           atomicAdd(n_overflow, 1u);
+          atomicAdd(&bin_counts[kBinRetry + rowsafe[r]], 1u);
           *dirty_cnt = 0;
         }
         __syncwarp();
@@ -709,15 +715,14 @@ __global__ void __launch_bounds__(256)
     pairs_dense_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen,
                        const uint2* __restrict__ suf, const uint32_t* __restrict__ col,
                        const uint32_t* __restrict__ first_after, const uint8_t* __restrict__ rowbin, uint32_t n,
-                       uint32_t block_cols, uint32_t* __restrict__ row_cursor, EdgeSink sink,
-                       PairCounters* __restrict__ counters) {
+                       uint32_t block_cols, uint32_t* __restrict__ row_cursor, const uint32_t* __restrict__ bin_counts,
+                       EdgeSink sink, PairCounters* __restrict__ counters) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
+  if (bin_counts[kBinDense] == 0) return;
   __shared__ uint32_t s_base;
   __shared__ uint32_t s_stage[8][kStageWords];
   uint32_t* acc = reinterpret_cast<uint32_t*>(dyn_smem);
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  const uint32_t words = WIDE ? block_cols : (block_cols + 1) / 2;
-  const uint32_t words4 = (words + 3u) & ~3u;
   unsigned long long n_pairs = 0, n_edges = 0, sum_count = 0, n_multi = 0;
   EdgeStage stage{s_stage[warp], 0u};
   for (;;) {
@@ -735,6 +740,9 @@ __global__ void __launch_bounds__(256)
       const bool multipass = n - first > block_cols;
       for (uint32_t blk_lo = first; blk_lo < n; blk_lo += block_cols) {
         const uint32_t blk_hi = min(n, blk_lo + block_cols);
+        const uint32_t ncols = blk_hi - blk_lo;
+        const uint32_t words = WIDE ? ncols : (ncols + 1) / 2;  // only what this block needs
+        const uint32_t words4 = (words + 3u) & ~3u;
         for (uint32_t i = threadIdx.x * 4; i < words4; i += 256 * 4)
           *reinterpret_cast<uint4*>(acc + i) = make_uint4(0, 0, 0, 0);
         __syncthreads();
@@ -763,7 +771,6 @@ __global__ void __launch_bounds__(256)
           });
         }
         __syncthreads();
-        const uint32_t ncols = blk_hi - blk_lo;
         for (uint32_t i0 = warp * 32; i0 < words; i0 += 256) {  // warp-uniform trip count
           const uint32_t i = i0 + lane;
           const uint32_t x = i < words ? acc[i] : 0u;
