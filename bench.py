@@ -179,6 +179,7 @@ def main():
 
     import torch
     import uniprot_kmer_based_clustering_b200 as kc
+    from uniprot_kmer_based_clustering_b200 import sharded
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -206,35 +207,37 @@ def main():
     eng = kc.Engine(k, device=local_rank, threshold=THRESHOLD, cross_class_only=cross, want_blosum=True)
     eng.set_stream(stream.cuda_stream)
 
-    def gather_edges(edges_np):
-        """edge lists -> rank 0 over NCCL (variable length: sizes first, then padded gather)"""
-        if world == 1:
-            return edges_np
-        cnt = torch.tensor([edges_np.size], dtype=torch.int64, device="cuda")
-        counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-        dist.all_gather(counts, cnt)
-        mx = int(max(c.item() for c in counts))
-        buf = torch.zeros(max(mx, 1) * 4, dtype=torch.int32, device="cuda")
-        if edges_np.size:
-            buf[:edges_np.size * 4] = torch.from_numpy(edges_np.view(np.int32).reshape(-1)).cuda()
-        out = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
-        dist.gather(buf, out, dst=0)
-        if rank != 0:
-            return None
-        parts = [o[:int(c.item()) * 4].cpu().numpy().view(kc.EDGE_DTYPE) for o, c in zip(out, counts)]
-        return np.concatenate(parts)
-
     def step_resident():
         ist = eng.build_index()
         pst = eng.score_pairs(rank, world)
         return ist, pst
 
+    e2e_parts = {"stage_h2d": 0.0, "build_index": 0.0, "score_pairs": 0.0, "edges_d2h": 0.0, "gather": 0.0}
+
     def step_e2e():
+        t0 = time.perf_counter()
         eng.set_proteins_ptr(h_res.data_ptr(), h_off.data_ptr(), h_cls.data_ptr(), n, on_device=False)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
         ist = eng.build_index()
+        t2 = time.perf_counter()
         pst = eng.score_pairs(rank, world)
-        edges = eng.get_edges()
-        return ist, pst, gather_edges(edges)
+        t3 = time.perf_counter()
+        n_e = pst["n_edges_out"]
+        if world == 1:
+            if h_edges.numel() < n_e * 4:
+                raise RuntimeError("edge staging buffer too small")
+            eng.get_edges_into(h_edges.data_ptr(), h_edges.numel() // 4)
+            out = h_edges[:n_e * 4].numpy().view(kc.EDGE_DTYPE)
+            t4 = t5 = time.perf_counter()
+        else:
+            t4 = time.perf_counter()
+            out = sharded.gather_edges_device(eng, dist, rank, world, pinned_out=h_edges,
+                                              rows_in_input_order=not cross)
+            t5 = time.perf_counter()
+        for key, dt in zip(e2e_parts, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+            e2e_parts[key] += dt * 1e3
+        return ist, pst, out
 
     def barrier():
         if world > 1:
@@ -267,8 +270,14 @@ def main():
         stage_ms[key] /= args.steps
 
     # ---- e2e: host buffers, H2D + D2H (+ NCCL gather) inside the timed region, wall clock ------
+    n_e_all = torch.tensor([pst["n_edges_out"]], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(n_e_all)
+    h_edges = torch.empty(max(int(n_e_all.item() * 1.25) + 1024, 1 << 16) * 4, dtype=torch.int32).pin_memory()
     for _ in range(2):
         step_e2e()
+    for key in e2e_parts:
+        e2e_parts[key] = 0.0
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -324,12 +333,14 @@ def main():
                                "achieved": idx_achieved, "peak": peak, "unit": "GB/s", "frac": idx_achieved / peak,
                                "algorithmic_bytes": idx_bytes},
             "e2e": {"value": pairs_total / e2e_s, "unit": "pairs/s", "ms_per_step": e2e_s * 1e3,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "breakdown_ms": {key: v / args.steps for key, v in e2e_parts.items()}},
             "gpu_launches": launches_all,
             "clocks": clocks,
         }
-        if world == 1:
-            assert edges.size == pst_e["n_edges_out"]
+        assert edges.size == e_out, (edges.size, e_out)
+        ekey = (edges["a"].astype(np.uint64) << np.uint64(32)) | edges["b"].astype(np.uint64)
+        assert bool(np.all(ekey[1:] > ekey[:-1])), "gathered edge list is not sorted by (a, b)"
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             r = oracle_run(ps, k, cross, CPU_SAMPLE[args.workload], threads)

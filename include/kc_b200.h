@@ -134,6 +134,9 @@ int kc_score_pairs(kc_engine* e, kc_pair_stats* stats);
 int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pair_stats* stats);
 /* the surviving pairs of the last kc_score_pairs*, sorted by (a, b) */
 int kc_get_edges(kc_engine* e, kc_edge* edges_out, uint64_t capacity);
+/* device-resident view of the same list (valid until the next kc_score_pairs* / kc_destroy):
+ * lets a multi-GPU host gather edge lists GPU-to-GPU (NCCL) without a host round trip */
+int kc_get_edges_device(kc_engine* e, const kc_edge** d_edges_out, uint64_t* n_edges_out);
 /* KmerEdgeGroup.kmers (src/graph/edge.rs:49,74) for edge i of the last result, as k-mer
  * VALUES ascending; kmers_out holds edges[i].count entries */
 int kc_get_edge_kmers(kc_engine* e, uint64_t edge_index, uint32_t* kmers_out, uint64_t capacity);

@@ -997,6 +997,14 @@ int kc_get_edges(kc_engine* e, kc_edge* out, uint64_t capacity) {
   return KC_OK;
 }
 
+int kc_get_edges_device(kc_engine* e, const kc_edge** d_edges_out, uint64_t* n_edges_out) {
+  if (!e || !d_edges_out || !n_edges_out) return KC_EINVAL;
+  if (!e->have_pairs) return fail(e, KC_EINVAL, "kc_score_pairs first");
+  *d_edges_out = e->n_edges ? reinterpret_cast<const kc_edge*>(e->d_edges_sorted.p) : nullptr;
+  *n_edges_out = e->n_edges;
+  return KC_OK;
+}
+
 int kc_get_edge_kmers(kc_engine* e, uint64_t edge_index, uint32_t* kmers_out, uint64_t capacity) {
   if (!e || !kmers_out) return KC_EINVAL;
   if (!e->have_pairs) return fail(e, KC_EINVAL, "kc_score_pairs first");

@@ -81,6 +81,51 @@ __device__ __forceinline__ void warp_bitonic(uint32_t* keys, uint32_t np2, uint3
   }
 }
 
+// In-register bitonic sort of 32*E keys held in shared memory (blocked layout: lane l owns
+// keys[l*E .. l*E+E)).  Strides below E are compare-exchanges between a lane's own registers,
+// strides of E and more are one shuffle per register (15 of the 45 stages at E = 16).  About
+// 2.5x fewer instructions than the shared-memory network above and no bank conflicts.
+template <int E>
+__device__ __forceinline__ void warp_sort_blocked(uint32_t* keys, uint32_t lane) {
+  uint32_t a[E];
+#pragma unroll
+  for (int j = 0; j < E; j += 4) {
+    const uint4 v = *reinterpret_cast<const uint4*>(keys + lane * E + j);
+    a[j] = v.x;
+    a[j + 1] = v.y;
+    a[j + 2] = v.z;
+    a[j + 3] = v.w;
+  }
+#pragma unroll
+  for (int size = 2; size <= 32 * E; size <<= 1) {
+    const bool up_lane = ((lane * E) & size) == 0;  // direction when it depends on the lane
+#pragma unroll
+    for (int d = size >> 1; d > 0; d >>= 1) {
+      if (d >= E) {
+        const bool takemin = ((lane & (d / E)) == 0) == up_lane;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          const uint32_t p = __shfl_xor_sync(kFullMask, a[j], d / E);
+          a[j] = takemin ? min(a[j], p) : max(a[j], p);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          if ((j & d) == 0) {
+            const bool up = size < E ? ((j & size) == 0) : up_lane;
+            const uint32_t lo = min(a[j], a[j | d]), hi = max(a[j], a[j | d]);
+            a[j] = up ? lo : hi;
+            a[j | d] = up ? hi : lo;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < E; j += 4)
+    *reinterpret_cast<uint4*>(keys + lane * E + j) = make_uint4(a[j], a[j + 1], a[j + 2], a[j + 3]);
+}
+
 // block-wide bitonic sort (keys may live in shared or global memory)
 __device__ __forceinline__ void block_bitonic(uint32_t* keys, uint32_t np2) {
   for (uint32_t size = 2; size <= np2; size <<= 1) {
@@ -115,7 +160,7 @@ __global__ void __launch_bounds__(kExtractWarps * 32)
                               uint32_t* __restrict__ ndist, uint32_t slice_shift, uint32_t n_slices,
                               uint32_t* __restrict__ ksplit, unsigned long long* __restrict__ n_incid) {
   __shared__ uint8_t s_lut[256];
-  __shared__ uint32_t s_keys[kExtractWarps][kWarpMaxPos];
+  __shared__ __align__(16) uint32_t s_keys[kExtractWarps][kWarpMaxPos];
   __shared__ __align__(4) uint8_t s_codes[kExtractWarps][kWarpMaxPos + 8];
   const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
   s_lut[threadIdx.x] = c_residue_lut[threadIdx.x];
@@ -136,10 +181,14 @@ __global__ void __launch_bounds__(kExtractWarps * 32)
     const uint32_t ps = pstart[r];
     stage_codes(res, ps, len, codes, s_lut, lane, 32);
     __syncwarp();
-    const uint32_t np2 = next_pow2_u32(npos);
+    const uint32_t np2 = npos <= 128 ? 128u : next_pow2_u32(npos);
     for (uint32_t i = lane; i < np2; i += 32) keys[i] = i < npos ? pack_kmer<K>(codes + i) : kSentinel;
     __syncwarp();
-    warp_bitonic(keys, np2, lane);
+    if (np2 == 128) warp_sort_blocked<4>(keys, lane);
+    else if (np2 == 256) warp_sort_blocked<8>(keys, lane);
+    else if (np2 == 512) warp_sort_blocked<16>(keys, lane);
+    else warp_sort_blocked<32>(keys, lane);
+    __syncwarp();
     uint32_t base = 0;
     for (uint32_t c = 0; c < npos; c += 32) {
       const uint32_t i = c + lane;

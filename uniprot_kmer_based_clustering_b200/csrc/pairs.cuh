@@ -588,7 +588,6 @@ __global__ void __launch_bounds__(kMainWarps * 32)
       mine = true;
       m_len = rowlen[base + lane];
       m_ps = pstart[base + lane];
-      m_lh = rowlogh[base + lane];
     }
     uint32_t todo = __ballot_sync(kFullMask, mine);
     while (todo) {

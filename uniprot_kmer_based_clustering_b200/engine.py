@@ -216,6 +216,12 @@ class Engine:
         self._check(self._L.kc_get_edges(self._h, _ptr(out), out.size))
         return out
 
+    def edges_device(self):
+        """(device pointer, n_edges) of the sorted edge list in HBM (16 bytes per edge)"""
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self._L.kc_get_edges_device(self._h, C.byref(p), C.byref(n)))
+        return (p.value or 0), int(n.value)
+
     def get_edges_into(self, out_ptr: int, capacity: int):
         self._check(self._L.kc_get_edges(self._h, C.c_void_p(out_ptr), capacity))
 

@@ -64,6 +64,61 @@ def gather_edges(edges: np.ndarray, dist, rank: int, world: int, device=None, ds
     return merge_edge_lists(parts)
 
 
+class _DeviceWords:
+    """CUDA array interface over a raw device pointer (int32 words), so torch can wrap engine memory"""
+
+    def __init__(self, ptr: int, n_words: int):
+        self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+
+
+def gather_edges_device(engine, dist, rank: int, world: int, pinned_out=None, dst: int = 0,
+                        rows_in_input_order: bool = True):
+    """NCCL path: the per-rank sorted edge lists go GPU-to-GPU (send/recv of the engine's device
+    buffers over NVLink) into one device buffer on `dst`, then one D2H copy.  With the input-order
+    pair order (all-classes mode) the shards are contiguous row blocks, so the concatenation in
+    rank order is already sorted by (a, b); otherwise the merged list is sorted on the host."""
+    import torch
+    from .engine import EDGE_DTYPE
+    ptr, n_e = engine.edges_device()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    mine = (torch.as_tensor(_DeviceWords(ptr, n_e * EDGE_WORDS), device=dev) if n_e
+            else torch.zeros(0, dtype=torch.int32, device=dev))
+    if world == 1:
+        counts = [n_e]
+    else:
+        cnt = torch.tensor([n_e], dtype=torch.int64, device=dev)
+        allc = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, cnt)
+        counts = [int(c) for c in allc.tolist()]
+    total = sum(counts)
+    if rank != dst:
+        if n_e:
+            dist.send(mine, dst=dst)
+        return None
+    buf = torch.empty(total * EDGE_WORDS, dtype=torch.int32, device=dev)
+    off = 0
+    reqs = []
+    for src, c in enumerate(counts):
+        part = buf[off * EDGE_WORDS:(off + c) * EDGE_WORDS]
+        if src == dst:
+            part.copy_(mine)
+        elif c:
+            reqs.append(dist.irecv(part, src=src))
+        off += c
+    for q in reqs:
+        q.wait()
+    if pinned_out is not None and pinned_out.numel() >= buf.numel():
+        host = pinned_out[:buf.numel()]
+        host.copy_(buf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    else:
+        host = buf.cpu()
+    edges = host.numpy().view(EDGE_DTYPE)
+    if not rows_in_input_order and world > 1:
+        edges = edges[np.lexsort((edges["b"], edges["a"]))]
+    return edges
+
+
 def reduce_pair_stats(stats: dict, dist, world: int, device=None) -> dict:
     """Whole-job counters from per-shard counters (n_multi_edges is a whole-set constant)."""
     import torch
