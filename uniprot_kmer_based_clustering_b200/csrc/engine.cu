@@ -583,13 +583,17 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
   const bool narrow = P >= 4;  // few entries per (row, slice): 8 lanes per row instead of 32
   const uint32_t pass_grid = blocks_for(n, narrow ? 32 : 8, e->num_sm * 8);
   auto split = [&](DBuf& b, uint32_t q) { return b.as<uint32_t>() + (size_t)q * n; };
-  for (uint32_t q = 0; q < P && n; ++q) {
-    if (narrow)
+  // the census state is only 2 bits per k-mer: it can take coarser slices (longer row runs)
+  const uint32_t cmerge = std::getenv("KC_B200_CENSUS_MERGE") ? std::max(1, std::atoi(std::getenv("KC_B200_CENSUS_MERGE"))) : 1;
+  for (uint32_t q = 0; q < P && n; q += cmerge) {
+    const uint32_t q1 = std::min(P, q + cmerge);
+    if (narrow && cmerge < 4)
       KC_LAUNCH(e, census_pass_kernel<8>, pass_grid, 256, 0, e->d_pk.as<uint32_t>(), e->d_pstart.as<uint32_t>(),
-                split(e->d_ksplit, q), split(e->d_ksplit, q + 1), n, e->d_seen.as<uint32_t>());
+                split(e->d_ksplit, q), split(e->d_ksplit, q1), n, e->d_seen.as<uint32_t>());
     else
-      KC_LAUNCH(e, census_pass_kernel<32>, pass_grid, 256, 0, e->d_pk.as<uint32_t>(), e->d_pstart.as<uint32_t>(),
-                split(e->d_ksplit, q), split(e->d_ksplit, q + 1), n, e->d_seen.as<uint32_t>());
+      KC_LAUNCH(e, census_pass_kernel<32>, blocks_for(n, 8, e->num_sm * 8), 256, 0, e->d_pk.as<uint32_t>(),
+                e->d_pstart.as<uint32_t>(), split(e->d_ksplit, q), split(e->d_ksplit, q1), n,
+                e->d_seen.as<uint32_t>());
   }
   mark(e, EV_IC1);
   // K4: rank dictionary over "held by >= 2 proteins"

@@ -536,6 +536,8 @@ constexpr int kMainWarps = 4;
 
 // flatten the short postings suffixes (2..15 holders) of one 32-entry chunk into `idx` and start
 // the gathers of the first 128 flattened postings; returns the number of flattened postings
+// (`idx` must be spelled as <shared array> + offset at the call site: a pointer picked from an array
+// of pointers makes ptxas fall back to generic LD/ST, ~10 % of the kernel's instructions)
 __device__ __forceinline__ uint32_t chunk_prepare(const uint32_t* __restrict__ col, uint2 e, uint32_t* idx,
                                                   uint32_t (&v)[4]) {
   const uint32_t lane = lane_id();
@@ -566,11 +568,11 @@ __global__ void __launch_bounds__(kMainWarps * 32)
   constexpr uint32_t kWarpWords = HMAX + 2 * kIdxPerWarp + kMainCap / 2 + 4;
   uint32_t* wbase = reinterpret_cast<uint32_t*>(dyn_smem) + (size_t)warp * kWarpWords;
   uint32_t* tab = wbase;
-  uint32_t* idxbuf[2] = {wbase + HMAX, wbase + HMAX + kIdxPerWarp};
+  uint32_t* idx0 = wbase + HMAX;  // idx buffer k lives at idx0 + k * kIdxPerWarp
   uint16_t* dirty = reinterpret_cast<uint16_t*>(wbase + HMAX + 2 * kIdxPerWarp);
   uint32_t* dirty_cnt = wbase + HMAX + 2 * kIdxPerWarp + kMainCap / 2;
   if (lane == 0) *dirty_cnt = 0;
-  EdgeStage stage{idxbuf[1], 0u};
+  EdgeStage stage{idx0 + kIdxPerWarp, 0u};
   const uint32_t cb = count_bits, cmask = (1u << count_bits) - 1u;
   unsigned long long n_pairs = 0, n_edges = 0, sum_count = 0, n_multi = 0;
   for (uint32_t i = lane * 4; i < HMAX; i += 128)
@@ -603,14 +605,14 @@ __global__ void __launch_bounds__(kMainWarps * 32)
       uint2 e_cur = lane < nl ? ld_stream_u32x2(suf + ps + lane) : make_uint2(0, 0);
       uint2 e_nxt = 32 + lane < nl ? ld_stream_u32x2(suf + ps + 32 + lane) : make_uint2(0, 0);
       uint32_t v[4], w[4];
-      uint32_t tot_cur = chunk_prepare(col, e_cur, idxbuf[0], v), tot_nxt = 0;
+      uint32_t tot_cur = chunk_prepare(col, e_cur, idx0, v), tot_nxt = 0;
       uint32_t k = 0;
       for (uint32_t c = 0; c < nl; c += 32, k ^= 1u) {
         const bool more = c + 32 < nl;
         uint2 e_nn = make_uint2(0, 0);
         if (more) {
           e_nn = c + 64 + lane < nl ? ld_stream_u32x2(suf + ps + c + 64 + lane) : make_uint2(0, 0);
-          tot_nxt = chunk_prepare(col, e_nxt, idxbuf[k ^ 1u], w);
+          tot_nxt = chunk_prepare(col, e_nxt, idx0 + (k ^ 1u) * kIdxPerWarp, w);
         }
         // consume chunk c
         if (e_cur.y == kSentinel) bump(e_cur.x);  // inline single partner
@@ -621,7 +623,7 @@ __global__ void __launch_bounds__(kMainWarps * 32)
           const uint32_t t0 = t00 + lane;
           uint32_t x[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) x[u] = t0 + 32 * u < tot_cur ? col[idxbuf[k][t0 + 32 * u]] : kSentinel;
+          for (int u = 0; u < 4; ++u) x[u] = t0 + 32 * u < tot_cur ? col[idx0[k * kIdxPerWarp + t0 + 32 * u]] : kSentinel;
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             if (x[u] != kSentinel) bump(x[u]);
