@@ -416,3 +416,19 @@ def test_cli_prints_the_reference_counters(tmp_path, arg_fasta_bytes, golden):
     r7 = subprocess.run([exe, str(fa), "2", "--k", "7"], capture_output=True, text=True, timeout=120)
     assert "Number of 7mers found in at least two proteins: 288551" in r7.stderr
     assert r7.stderr.count("Cross-checking:") == 463
+
+
+def test_device_edge_view_matches_host_copy(arg_set):
+    """kc_get_edges_device: the sorted edge list in HBM (what the NCCL gather sends)"""
+    torch = pytest.importorskip("torch")
+    from uniprot_kmer_based_clustering_b200.sharded import _DeviceWords, gather_edges_device
+    with kc.Engine(7, threshold=10, cross_class_only=False, want_blosum=True) as e:
+        e.set_protein_set(arg_set)
+        e.build_index()
+        e.score_pairs()
+        host = e.get_edges()
+        ptr, n = e.edges_device()
+        assert n == host.size and ptr != 0
+        dev = torch.as_tensor(_DeviceWords(ptr, n * 4), device="cuda")
+        assert np.array_equal(dev.cpu().numpy().view(kc.EDGE_DTYPE), host)
+        assert np.array_equal(gather_edges_device(e, None, 0, 1), host)

@@ -816,18 +816,19 @@ __global__ void __launch_bounds__(256)
 // shorter row's ids and binary-search the longer row.  MODE 0: sum of BLOSUM62 self-scores of
 // the shared k-mers -> edge.w.  (The list itself is produced by shared_kmers_kernel.)
 // ---------------------------------------------------------------------------------------
-constexpr uint32_t kBlosumSlots = 2048;  // per-warp id hash: rows of up to 1024 ids
+// per-warp id hash of SLOTS entries: rows of up to 0.7 * SLOTS ids (longer rows: binary search)
 // Runs over the SORTED edge list (keys = a << 32 | b in input order).  A warp takes a window of
 // 32 consecutive edges; while `a` stays the same it keeps row a's ids in a shared-memory hash
 // set (id -> BLOSUM62 self-score), streams row b's ids with coalesced loads and probes.
 // vals = count | blosum << 32 (blosum filled in here).
+template <uint32_t SLOTS, uint32_t SHIFT>
 __global__ void __launch_bounds__(128)
     edge_blosum_kernel(const unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals,
                        unsigned long long n_edges, const uint32_t* __restrict__ rank_of,
                        const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen,
                        const uint32_t* __restrict__ ids, const uint8_t* __restrict__ selfscore) {
-  __shared__ uint32_t s_key[4][kBlosumSlots];
-  __shared__ uint8_t s_val[4][kBlosumSlots];
+  __shared__ uint32_t s_key[4][SLOTS];
+  __shared__ uint8_t s_val[4][SLOTS];
   const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
   uint32_t* hk = s_key[w];
   uint8_t* hv = s_val[w];
@@ -880,10 +881,10 @@ __global__ void __launch_bounds__(128)
         cur_a = a;
         A = ids + pa;
         na = na_l;
-        hashed = na <= kBlosumSlots / 2;
+        hashed = 10u * na <= 7u * SLOTS;
         __syncwarp();
         if (hashed) {
-          for (uint32_t i = lane * 4; i < kBlosumSlots; i += 128)
+          for (uint32_t i = lane * 4; i < SLOTS; i += 128)
             *reinterpret_cast<uint4*>(hk + i) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
           __syncwarp();
           for (uint32_t i0 = lane; i0 < na; i0 += 256) {
@@ -897,8 +898,8 @@ __global__ void __launch_bounds__(128)
             for (int u = 0; u < 8; ++u) {
               const uint32_t x = as[u];
               if (x == kSentinel) continue;
-              uint32_t h = (x * 2654435761u) >> 21;
-              while (atomicCAS(&hk[h], kSentinel, x) != kSentinel) h = (h + 1u) & (kBlosumSlots - 1u);
+              uint32_t h = (x * 2654435761u) >> SHIFT;
+              while (atomicCAS(&hk[h], kSentinel, x) != kSentinel) h = (h + 1u) & (SLOTS - 1u);
               hv[h] = sc[u];
             }
           }
@@ -918,7 +919,7 @@ __global__ void __launch_bounds__(128)
           for (int u = 0; u < 8; ++u) {
             const uint32_t x = xs[u];
             if (x == kSentinel) continue;
-            uint32_t h = (x * 2654435761u) >> 21;
+            uint32_t h = (x * 2654435761u) >> SHIFT;
             for (;;) {
               const uint32_t k = hk[h];
               if (k == x) {
@@ -926,7 +927,7 @@ __global__ void __launch_bounds__(128)
                 break;
               }
               if (k == kSentinel) break;
-              h = (h + 1u) & (kBlosumSlots - 1u);
+              h = (h + 1u) & (SLOTS - 1u);
             }
           }
         }
