@@ -90,7 +90,7 @@ struct kc_engine {
   kc_index_stats istats{};
   uint64_t multi_total = 0, work_total = 0;
   DBuf d_pk, d_ndist, d_rowlen, d_seen, d_dict, d_vocab, d_freq, d_self, d_colptr, d_cursor, d_col,
-      d_suf, d_rowwork, d_lists, d_colscratch, d_workprefix, d_ksplit, d_isplit, d_rowwork64, d_rowinl, d_rowmaxlen;
+      d_suf, d_sufss, d_rowwork, d_lists, d_colscratch, d_workprefix, d_ksplit, d_isplit, d_rowwork64, d_rowinl, d_rowmaxlen;
   uint32_t slice_shift = 31, n_slices = 1;
   // pairs
   DBuf d_rowbin, d_rowsafe, d_rowlogh, d_edges, d_keys_a, d_keys_b, d_vals_a, d_vals_b, d_hist, d_edges_sorted;
@@ -424,7 +424,7 @@ void kc_destroy(kc_engine* e) {
   DBuf* all[] = {&e->d_res, &e->d_off, &e->d_kpos, &e->d_pstart, &e->d_plen, &e->d_orig, &e->d_rank,
                  &e->d_first_after, &e->d_long, &e->d_huge, &e->d_huge_off, &e->d_huge_scratch, &e->d_pk,
                  &e->d_ndist, &e->d_rowlen, &e->d_seen, &e->d_dict, &e->d_vocab, &e->d_freq,
-                 &e->d_self, &e->d_colptr, &e->d_cursor, &e->d_col, &e->d_suf, &e->d_rowwork, &e->d_lists,
+                 &e->d_self, &e->d_colptr, &e->d_cursor, &e->d_col, &e->d_suf, &e->d_sufss, &e->d_rowwork, &e->d_lists,
                  &e->d_colscratch, &e->d_workprefix, &e->d_ksplit, &e->d_isplit, &e->d_rowwork64, &e->d_rowinl, &e->d_rowmaxlen, &e->d_rowbin, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
                  &e->d_vals_a, &e->d_vals_b, &e->d_hist, &e->d_edges_sorted, &e->d_scalars, &e->d_scan_tiles,
                  &e->d_tmp};
@@ -616,6 +616,7 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
   KC_CUDA(e, e->d_cursor.ensure((V + 2) * 4));
   KC_CUDA(e, e->d_col.ensure((n_incid + 64) * 4));
   KC_CUDA(e, e->d_suf.ensure((R + 64) * 8));
+  if (e->cfg.want_blosum) KC_CUDA(e, e->d_sufss.ensure(R + 64));
   KC_CUDA(e, e->d_rowwork.ensure(((uint64_t)n + 1) * 4));
   KC_CUDA(e, e->d_workprefix.ensure(((uint64_t)n + 2) * 8));
   const uint64_t list_cap = n_incid / 33 + 16;
@@ -687,12 +688,14 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
       if (narrow)
         KC_LAUNCH(e, suffix_ranges_kernel<8>, pass_grid, 256, 0, e->d_pstart.as<uint32_t>(), split(e->d_isplit, q),
                   split(e->d_isplit, q + 1), n, e->d_pk.as<uint32_t>(), e->d_colptr.as<uint32_t>(),
-                  e->d_col.as<uint32_t>(), fa, e->d_suf.as<uint2>(), e->d_rowwork64.as<unsigned long long>(),
+                  e->d_col.as<uint32_t>(), fa, e->d_self.as<uint8_t>(), e->d_suf.as<uint2>(),
+                  e->cfg.want_blosum ? e->d_sufss.as<uint8_t>() : nullptr, e->d_rowwork64.as<unsigned long long>(),
                   e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>(), &ds->work_total);
       else
         KC_LAUNCH(e, suffix_ranges_kernel<32>, pass_grid, 256, 0, e->d_pstart.as<uint32_t>(), split(e->d_isplit, q),
                   split(e->d_isplit, q + 1), n, e->d_pk.as<uint32_t>(), e->d_colptr.as<uint32_t>(),
-                  e->d_col.as<uint32_t>(), fa, e->d_suf.as<uint2>(), e->d_rowwork64.as<unsigned long long>(),
+                  e->d_col.as<uint32_t>(), fa, e->d_self.as<uint8_t>(), e->d_suf.as<uint2>(),
+                  e->cfg.want_blosum ? e->d_sufss.as<uint8_t>() : nullptr, e->d_rowwork64.as<unsigned long long>(),
                   e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>(), &ds->work_total);
     }
     KC_LAUNCH(e, clamp_rowwork_kernel, (n + 255) / 256, 256, 0, e->d_rowwork64.as<unsigned long long>(), n,
@@ -863,10 +866,22 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
               e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr, n,
               ds->shard_rows, dense_cols, count_bits, e->d_rowbin.as<uint8_t>(), e->d_rowsafe.as<uint8_t>(),
               e->d_rowlogh.as<uint8_t>(), ds->bin_counts);
-    EdgeSink sink{e->d_edges.as<uint4>(), &ds->edge_cursor, e->edge_cap, e->cfg.threshold};
+    EdgeSink sink{e->d_edges.as<uint4>(), &ds->edge_cursor, e->edge_cap, e->cfg.threshold,
+                  e->cfg.want_blosum ? kUnscored : 0u};
     mark(e, EV_PK0);
     int rc;
-    {
+    if (e->cfg.want_blosum) {
+      constexpr size_t smem = (size_t)kScoredWarps * kScoredWarpWords * 4;
+      KC_CUDA(e, cudaFuncSetAttribute(pairs_main_scored_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 1;
+      KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairs_main_scored_kernel, kScoredWarps * 32, smem));
+      if (per_sm < 1) per_sm = 1;
+      KC_LAUNCH(e, pairs_main_scored_kernel, (uint32_t)(e->num_sm * per_sm), kScoredWarps * 32, smem,
+                e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(), e->d_suf.as<uint2>(),
+                e->d_sufss.as<uint8_t>(), e->d_col.as<uint32_t>(), e->d_rowbin.as<uint8_t>(),
+                e->d_rowsafe.as<uint8_t>(), n, &ds->row_cursor[kBinMain], &ds->n_overflow, ds->bin_counts, sink,
+                &ds->pc);
+    } else {
       constexpr size_t smem = (size_t)kMainWarps * ((1u << kMainLogHMax) + 2 * kIdxPerWarp + kMainCap / 2 + 4) * 4;
       KC_CUDA(e, cudaFuncSetAttribute(pairs_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 1;

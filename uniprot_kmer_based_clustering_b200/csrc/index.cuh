@@ -284,7 +284,8 @@ __global__ void __launch_bounds__(256)
     suffix_ranges_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ lo,
                          const uint32_t* __restrict__ hi, uint32_t n, const uint32_t* __restrict__ ids,
                          const uint32_t* __restrict__ colptr, const uint32_t* __restrict__ col,
-                         const uint32_t* __restrict__ first_after, uint2* __restrict__ suf,
+                         const uint32_t* __restrict__ first_after, const uint8_t* __restrict__ selfscore,
+                         uint2* __restrict__ suf, uint8_t* __restrict__ sufss,
                          unsigned long long* __restrict__ rowwork64, uint32_t* __restrict__ rowinl,
                          uint32_t* __restrict__ rowmaxlen, unsigned long long* __restrict__ work_total) {
   const uint32_t lane = lane_id(), gl = lane % G;
@@ -308,6 +309,7 @@ __global__ void __launch_bounds__(256)
       // a single partner is stored inline ({rank, sentinel}): the pair stage then needs no
       // postings gather for it (a 4-byte read there costs a whole random 32-byte sector)
       suf[ps + i] = end - a == 1u ? make_uint2(col[a], kSentinel) : make_uint2(a, end);
+      if (sufss) sufss[ps + i] = selfscore[id];  // BLOSUM62 self-score of the entry's k-mer (K9 fused into K7)
       work += end - a;
       n_inl += end - a == 1u;
       max_len = max(max_len, end - a == 1u ? 0u : end - a);

@@ -27,7 +27,11 @@ struct EdgeSink {
   unsigned long long* cursor;   // edges wanted so far (may exceed cap: caller grows + retries)
   unsigned long long cap;
   uint32_t threshold;
+  uint32_t unscored;            // blosum word written by kernels that do not accumulate scores:
+                                // kUnscored when a score is wanted (edge_blosum_kernel fills it), else 0
 };
+constexpr uint32_t kUnscored = 0x80000000u;
+constexpr uint32_t kScoreShift = 12;  // scored tables: value = score << 12 | count (rows of < 4096 ids)
 
 struct PairCounters {            // device-side totals (u64 each)
   unsigned long long n_pairs;    // distinct (row, partner) pairs with count >= 1
@@ -64,7 +68,8 @@ __device__ __forceinline__ void stage_flush(EdgeStage& st, const EdgeSink& sink)
   base = __shfl_sync(kFullMask, base, 0);
   for (uint32_t i = lane_id(); i < st.cnt; i += 32) {
     const unsigned long long idx = base + i;
-    if (idx < sink.cap) sink.buf[idx] = make_uint4(st.buf[3 * i], st.buf[3 * i + 1], st.buf[3 * i + 2], 0u);
+    if (idx < sink.cap)
+      sink.buf[idx] = make_uint4(st.buf[3 * i], st.buf[3 * i + 1], st.buf[3 * i + 2], sink.unscored);
   }
   __syncwarp();
   st.cnt = 0;
@@ -78,6 +83,32 @@ __device__ __forceinline__ void stage_push(EdgeStage& st, bool pred, uint32_t r,
     st.buf[3 * pos] = r;
     st.buf[3 * pos + 1] = b;
     st.buf[3 * pos + 2] = c;
+  }
+  st.cnt += __popc(m);
+}
+
+// scored variant: {row, partner, count, score}
+constexpr uint32_t kStageEdges4 = 128;
+__device__ __forceinline__ void stage4_flush(EdgeStage& st, const EdgeSink& sink) {
+  if (st.cnt == 0) return;
+  __syncwarp();
+  unsigned long long base = 0;
+  if (lane_id() == 0) base = atomicAdd(sink.cursor, (unsigned long long)st.cnt);
+  base = __shfl_sync(kFullMask, base, 0);
+  for (uint32_t i = lane_id(); i < st.cnt; i += 32) {
+    const unsigned long long idx = base + i;
+    if (idx < sink.cap) sink.buf[idx] = *reinterpret_cast<const uint4*>(st.buf + 4 * i);
+  }
+  __syncwarp();
+  st.cnt = 0;
+}
+__device__ __forceinline__ void stage4_push(EdgeStage& st, bool pred, uint32_t r, uint32_t b, uint32_t c,
+                                            uint32_t score) {
+  const uint32_t m = __ballot_sync(kFullMask, pred);
+  if (!m) return;
+  if (pred) {
+    const uint32_t pos = st.cnt + __popc(m & lanemask_lt());
+    *reinterpret_cast<uint4*>(st.buf + 4 * pos) = make_uint4(r, b, c, score);
   }
   st.cnt += __popc(m);
 }
@@ -141,7 +172,7 @@ __global__ void __launch_bounds__(256)
         // is tried there unless a lower bound on its partners (inline partners are distinct; the
         // longest suffix holds distinct partners) already comes close to the cap.
         const uint32_t lower = max(rowinl[r], rowmaxlen[r]);
-        if (U <= kMainCap || lower <= kMainCap / 2) {
+        if ((U <= kMainCap || lower <= kMainCap / 2) && rowlen[r] < (1u << kScoreShift)) {
           bin = kBinMain;
           rowlogh[r] = (uint8_t)kMainLogHMax;
         }
@@ -285,6 +316,37 @@ __global__ void __launch_bounds__(CTA_WARPS * 32)
 // The read-out pass clears the table for the next row.
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t kIdxPerWarp = 512;  // >= 32 lanes x 15 postings
+
+// scored main-kernel variant: keys and values in separate words; value = score << 12 | count, so
+// the count and the BLOSUM self-score sum of a pair grow with ONE shared-memory atomic
+__device__ __forceinline__ void scored_bump_dirty(uint32_t* key, uint32_t* val, uint32_t mask, uint32_t log_h,
+                                                  uint32_t b, uint32_t inc, uint32_t* dirty_cnt, uint16_t* dirty,
+                                                  uint32_t cap, bool& full) {
+  if (full) return;
+  uint32_t h = (b * 2654435761u) >> (32u - log_h);
+  for (;;) {
+    const uint32_t k = key[h];
+    if (k == b) {
+      atomicAdd(&val[h], inc);
+      return;
+    }
+    if (k == kSentinel) {
+      const uint32_t old = atomicCAS(&key[h], kSentinel, b);
+      if (old == kSentinel) {
+        atomicAdd(&val[h], inc);
+        const uint32_t pos = atomicAdd(dirty_cnt, 1u);
+        if (pos < cap) dirty[pos] = (uint16_t)h;
+        else full = true;
+        return;
+      }
+      if (old == b) {
+        atomicAdd(&val[h], inc);
+        return;
+      }
+    }
+    h = (h + 1u) & mask;
+  }
+}
 
 // main-kernel variant: every new key's slot is appended to the warp's dirty list (so the read-out
 // touches only occupied slots and the distinct-partner count is exact); gives up beyond `cap`
@@ -708,6 +770,212 @@ __global__ void __launch_bounds__(kMainWarps * 32)
 }
 
 // ---------------------------------------------------------------------------------------
+// Scored main kernel (want_blosum): same walk as pairs_main_kernel, but every multi-edge also
+// carries the BLOSUM62 self-score of its k-mer (sufss, one byte per row entry), accumulated in
+// the same atomic as the count.  K9 fused into K7: no per-edge list intersection afterwards.
+// ---------------------------------------------------------------------------------------
+constexpr int kScoredWarps = 5;
+constexpr uint32_t kScoredWarpWords = 2 * (1u << kMainLogHMax) + 2 * kIdxPerWarp + 2 * (kIdxPerWarp / 4) + kMainCap / 2 + 4;
+
+__device__ __forceinline__ uint32_t chunk_prepare_scored(const uint32_t* __restrict__ col, uint2 e, uint32_t ss,
+                                                         uint32_t* idx, uint8_t* idxs, uint32_t (&v)[4],
+                                                         uint32_t (&sv)[4]) {
+  const uint32_t lane = lane_id();
+  const uint32_t len = e.y == kSentinel ? 0u : e.y - e.x;
+  const uint32_t slen = len < 16u ? len : 0u;
+  const uint32_t incl = warp_scan_incl(slen);
+  const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+  uint32_t w = incl - slen;
+  for (uint32_t j = e.x; j < e.x + slen; ++j) {
+    idx[w] = j;
+    idxs[w++] = (uint8_t)ss;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const uint32_t t = lane + 32 * u;
+    v[u] = t < total ? col[idx[t]] : kSentinel;
+    sv[u] = t < total ? idxs[t] : 0u;
+  }
+  return total;
+}
+
+__global__ void __launch_bounds__(kScoredWarps * 32)
+    pairs_main_scored_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen,
+                             const uint2* __restrict__ suf, const uint8_t* __restrict__ sufss,
+                             const uint32_t* __restrict__ col, uint8_t* __restrict__ rowbin,
+                             const uint8_t* __restrict__ rowsafe, uint32_t n, uint32_t* __restrict__ row_cursor,
+                             uint32_t* __restrict__ n_overflow, uint32_t* __restrict__ bin_counts, EdgeSink sink,
+                             PairCounters* __restrict__ counters) {
+  constexpr uint32_t HMAX = 1u << kMainLogHMax;
+  constexpr uint32_t log_h = kMainLogHMax;
+  if (bin_counts[kBinMain] == 0) return;
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  // per warp: keys | values | idx buffers 0,1 (buffer 1 doubles as the edge stage) | idx score
+  // buffers 0,1 | dirty list | dirty count
+  uint32_t* wbase = reinterpret_cast<uint32_t*>(dyn_smem) + (size_t)warp * kScoredWarpWords;
+  uint32_t* key = wbase;
+  uint32_t* val = wbase + HMAX;
+  uint32_t* idx0 = wbase + 2 * HMAX;
+  uint8_t* idxs0 = reinterpret_cast<uint8_t*>(wbase + 2 * HMAX + 2 * kIdxPerWarp);
+  uint16_t* dirty = reinterpret_cast<uint16_t*>(wbase + 2 * HMAX + 2 * kIdxPerWarp + 2 * (kIdxPerWarp / 4));
+  uint32_t* dirty_cnt = wbase + 2 * HMAX + 2 * kIdxPerWarp + 2 * (kIdxPerWarp / 4) + kMainCap / 2;
+  if (lane == 0) *dirty_cnt = 0;
+  EdgeStage stage{idx0 + kIdxPerWarp, 0u};
+  unsigned long long n_pairs = 0, n_edges = 0, sum_count = 0, n_multi = 0;
+  for (uint32_t i = lane * 4; i < HMAX; i += 128) {
+    *reinterpret_cast<uint4*>(key + i) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+    *reinterpret_cast<uint4*>(val + i) = make_uint4(0, 0, 0, 0);
+  }
+  __syncwarp();
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(row_cursor, 4u);
+    base = __shfl_sync(kFullMask, base, 0);
+    if (base >= n) break;
+    uint32_t m_len = 0, m_ps = 0;
+    bool mine = false;
+    if (lane < 4 && base + lane < n && rowbin[base + lane] == kBinMain) {
+      mine = true;
+      m_len = rowlen[base + lane];
+      m_ps = pstart[base + lane];
+    }
+    uint32_t todo = __ballot_sync(kFullMask, mine);
+    while (todo) {
+      const uint32_t l = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t r = base + l;
+      const uint32_t nl = __shfl_sync(kFullMask, m_len, l), ps = __shfl_sync(kFullMask, m_ps, l);
+      bool full = false, overflow = false;
+      auto bump = [&](uint32_t b, uint32_t ss) {
+        scored_bump_dirty(key, val, HMAX - 1u, log_h, b, (ss << kScoreShift) | 1u, dirty_cnt, dirty, kMainCap, full);
+      };
+      uint2 e_cur = lane < nl ? ld_stream_u32x2(suf + ps + lane) : make_uint2(0, 0);
+      uint32_t s_cur = lane < nl ? sufss[ps + lane] : 0u;
+      uint2 e_nxt = 32 + lane < nl ? ld_stream_u32x2(suf + ps + 32 + lane) : make_uint2(0, 0);
+      uint32_t s_nxt = 32 + lane < nl ? sufss[ps + 32 + lane] : 0u;
+      uint32_t v[4], sv[4], w[4], sw[4];
+      uint32_t tot_cur = chunk_prepare_scored(col, e_cur, s_cur, idx0, idxs0, v, sv), tot_nxt = 0;
+      uint32_t k = 0;
+      for (uint32_t c = 0; c < nl; c += 32, k ^= 1u) {
+        const bool more = c + 32 < nl;
+        uint2 e_nn = make_uint2(0, 0);
+        uint32_t s_nn = 0;
+        if (more) {
+          if (c + 64 + lane < nl) {
+            e_nn = ld_stream_u32x2(suf + ps + c + 64 + lane);
+            s_nn = sufss[ps + c + 64 + lane];
+          }
+          tot_nxt = chunk_prepare_scored(col, e_nxt, s_nxt, idx0 + (k ^ 1u) * kIdxPerWarp,
+                                         idxs0 + (k ^ 1u) * kIdxPerWarp, w, sw);
+        }
+        if (e_cur.y == kSentinel) bump(e_cur.x, s_cur);  // inline single partner
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (v[u] != kSentinel) bump(v[u], sv[u]);
+        for (uint32_t t00 = 128; t00 < tot_cur; t00 += 128) {  // rare: more than 128 short postings
+          const uint32_t t0 = t00 + lane;
+          uint32_t x[4], sx[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t t = t0 + 32 * u;
+            x[u] = t < tot_cur ? col[idx0[k * kIdxPerWarp + t]] : kSentinel;
+            sx[u] = t < tot_cur ? idxs0[k * kIdxPerWarp + t] : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (x[u] != kSentinel) bump(x[u], sx[u]);
+        }
+        {  // long suffixes: the whole warp reads 32 consecutive postings at a time
+          const uint32_t len = e_cur.y == kSentinel ? 0u : e_cur.y - e_cur.x;
+          uint32_t m = __ballot_sync(kFullMask, len >= 16u);
+          while (m) {
+            const uint32_t src = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t s0 = __shfl_sync(kFullMask, e_cur.x, src), t1 = __shfl_sync(kFullMask, e_cur.y, src);
+            const uint32_t ssl = __shfl_sync(kFullMask, s_cur, src);
+            for (uint32_t j0 = s0; j0 < t1; j0 += 128) {
+              const uint32_t j = j0 + lane;
+              uint32_t x[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) x[u] = j + 32 * u < t1 ? col[j + 32 * u] : kSentinel;
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (x[u] != kSentinel) bump(x[u], ssl);
+              if (__any_sync(kFullMask, full)) break;
+            }
+          }
+        }
+        if (__any_sync(kFullMask, full)) {
+          overflow = true;
+          break;
+        }
+        e_cur = e_nxt;
+        s_cur = s_nxt;
+        e_nxt = e_nn;
+        s_nxt = s_nn;
+        tot_cur = tot_nxt;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[u] = w[u];
+          sv[u] = sw[u];
+        }
+      }
+      __syncwarp();
+      if (overflow) {
+        for (uint32_t i = lane * 4; i < HMAX; i += 128) {
+          *reinterpret_cast<uint4*>(key + i) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+          *reinterpret_cast<uint4*>(val + i) = make_uint4(0, 0, 0, 0);
+        }
+        if (lane == 0) {
+          rowbin[r] = (uint8_t)(kBinRetry + rowsafe[r]);
+          atomicAdd(n_overflow, 1u);
+          atomicAdd(&bin_counts[kBinRetry + rowsafe[r]], 1u);
+          *dirty_cnt = 0;
+        }
+        __syncwarp();
+        continue;
+      }
+      const uint32_t n_dirty = *dirty_cnt;
+      __syncwarp();
+      for (uint32_t i0 = 0; i0 < n_dirty; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        uint32_t b = kSentinel, vv = 0;
+        if (i < n_dirty) {
+          const uint32_t h = dirty[i];
+          b = key[h];
+          vv = val[h];
+          key[h] = kSentinel;
+          val[h] = 0;
+        }
+        const uint32_t cq = vv & ((1u << kScoreShift) - 1u);
+        const bool out = cq > sink.threshold;
+        n_pairs += cq != 0;
+        n_multi += cq;
+        n_edges += out;
+        sum_count += out ? cq : 0u;
+        if (stage.cnt + 32u > kStageEdges4) stage4_flush(stage, sink);
+        stage4_push(stage, out, r, b, cq, vv >> kScoreShift);
+      }
+      if (lane == 0) *dirty_cnt = 0;
+      stage4_flush(stage, sink);  // the stage shares idx buffer 1 with the next row's walk
+      __syncwarp();
+    }
+  }
+  n_pairs = warp_sum64(n_pairs);
+  n_edges = warp_sum64(n_edges);
+  sum_count = warp_sum64(sum_count);
+  n_multi = warp_sum64(n_multi);
+  if (lane == 0) {
+    if (n_multi) atomicAdd(&counters->n_multi, n_multi);
+    if (n_pairs) atomicAdd(&counters->n_pairs, n_pairs);
+    if (n_edges) atomicAdd(&counters->n_edges, n_edges);
+    if (sum_count) atomicAdd(&counters->sum_count, sum_count);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // dense accumulators: one CTA per row, one counter per candidate partner, in column blocks of
 // `block_cols` partners.  WIDE = u32 counters (rows with >= 65535 ids), else two u16 per word.
 // ---------------------------------------------------------------------------------------
@@ -865,6 +1133,10 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
       for (int u = 0; u < 8; ++u) nxt[u] = lane + 32 * u < nb0 ? B0[lane + 32 * u] : kSentinel;
     }
+    // edges whose score came out of the scored pair kernel keep it; only the rest is intersected
+    const uint32_t need = __ballot_sync(kFullMask, my_e < n_edges && (m_val >> 63) != 0);
+    if (!need) continue;
+    m_score = (uint32_t)(m_val >> 32);
     for (uint32_t l = 0; l < n_in_win; ++l) {
       uint32_t xs[8];
 #pragma unroll
@@ -877,6 +1149,7 @@ __global__ void __launch_bounds__(128)
       }
       const uint32_t a = __shfl_sync(kFullMask, m_a, l);
       const uint32_t pa = __shfl_sync(kFullMask, m_pa, l), na_l = __shfl_sync(kFullMask, m_na, l);
+      if (!((need >> l) & 1u)) continue;
       if (a != cur_a) {
         cur_a = a;
         A = ids + pa;
