@@ -46,8 +46,11 @@ typedef struct kc_config {
   uint32_t threshold;       /* emit pairs with count > threshold; reference 10, src/graph/mod.rs:242 */
   int32_t cross_class_only; /* 1 = reference (remove_uninteresting_edges, src/graph/mod.rs:580-587) */
   int32_t want_blosum;      /* 1 = fill kc_edge.blosum (src/blosum.rs table, framework-defined score) */
-  uint32_t reserved0;
+  uint32_t sample_every;    /* 0/1 = every k-mer position (reference's live path); d > 1 = keep
+                             * floor(positions / d) random start positions per protein, without
+                             * replacement (Protein::new_with_rand_fivemers, d = 10, src/protein.rs:77-104) */
   uint64_t max_edges;       /* device edge-buffer capacity; 0 = automatic (grows and retries) */
+  uint64_t sample_seed;     /* seed of the counter-based position sampler (kc_sample_position) */
 } kc_config;
 
 /* src/main.rs:84-147 census + split; nnz = sum over proteins of |get_five_hash()| */
@@ -86,6 +89,12 @@ typedef struct kc_timings {
   float pair_kernel_ms;     /* accumulation kernels only (the roofline kernel family) */
   float census_kernel_ms;   /* extract+dedup+census kernel only */
 } kc_timings;
+
+/* The sampler (host-callable, same integer arithmetic as the kernels): the x-th sampled start
+ * position, x < floor(n_positions / sample_every), of the protein with input index `protein`.
+ * A 4-round Feistel permutation of [0, n_positions) with cycle walking, keyed by (seed, protein):
+ * distinct positions, reproducible, order-independent. */
+uint32_t kc_sample_position(uint64_t seed, uint32_t protein, uint32_t n_positions, uint32_t x);
 
 int kc_abi_version(void);
 int kc_device_count(void);

@@ -47,6 +47,22 @@ int kc_synth_layout(uint64_t n, int length_law, uint64_t seed, uint64_t* offsets
 int kc_synth_residues(uint64_t n, int length_law, uint64_t seed, int threads, const uint64_t* offsets,
                       uint8_t* residues);
 
+/* Host tree clustering: the reference's src/tree.rs (Tree::new + add_protein for every protein in
+ * input order, src/tree.rs:519-536) over the engine's per-protein id lists
+ * (kc_get_protein_ids: row_offsets[n+1], ids ascending within a row, ids < n_ids).
+ * Stays on the host (north star); see csrc/tree.cpp for what is cached. */
+typedef struct kc_tree kc_tree;
+int kc_tree_build(const uint64_t* row_offsets, const uint32_t* ids, uint64_t n_proteins, uint32_t n_ids,
+                  kc_tree** out);
+void kc_tree_free(kc_tree* t);
+uint64_t kc_tree_n_merges(const kc_tree* t);     /* "Merging" events, src/tree.rs:227 */
+uint64_t kc_tree_n_no_common(const kc_tree* t);  /* "No kmers in common" events, src/tree.rs:379 */
+/* preorder tokens: leaf = protein index, internal node = -(number of children) then its children;
+ * returns the token count (out may be NULL to size the buffer) */
+uint64_t kc_tree_serialize(const kc_tree* t, int64_t* out, uint64_t capacity);
+/* cluster_of[p] = index of the root child (top-level cluster) holding protein p */
+int kc_tree_clusters(const kc_tree* t, uint32_t* cluster_of, uint32_t* n_clusters);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,9 +58,41 @@ struct PairStats {
   uint64_t sum_count_out;
 };
 
+// Position sampler of the optional subsampling mode (Protein::new_with_rand_fivemers,
+// src/protein.rs:77-104: a tenth of the start positions, without replacement).  The reference
+// draws from a thread-local RNG (not reproducible); the framework defines a counter-based
+// sampler instead (include/kc_b200.h, kc_sample_position) and this is its restatement.
+uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+uint32_t sample_position(uint64_t seed, uint32_t protein, uint32_t n, uint32_t x) {
+  const uint32_t key = mix32((uint32_t)seed ^ mix32(protein ^ (uint32_t)(seed >> 32) ^ 0x9E3779B9u));
+  uint32_t half = 1;
+  while ((1ull << (2 * half)) < (uint64_t)n) ++half;
+  const uint32_t mask = (1u << half) - 1u;
+  uint32_t y = x;
+  do {
+    uint32_t L = y >> half, R = y & mask;
+    for (uint32_t round = 0; round < 4; ++round) {
+      const uint32_t t = L ^ (mix32(R ^ key ^ (round * 0x9E3779B9u)) & mask);
+      L = R;
+      R = t;
+    }
+    y = (L << half) | R;
+  } while (y >= n);
+  return y;
+}
+
 struct Oracle {
   int k = 5;
   int threads = 1;
+  uint32_t sample_every = 0;
+  uint64_t sample_seed = 0;
   uint64_t n = 0;
   std::vector<uint8_t> res;
   std::vector<uint64_t> off;
@@ -133,6 +165,10 @@ Oracle* ko_create(int k, int threads) {
 }
 
 void ko_destroy(Oracle* o) { delete o; }
+void ko_set_sampling(Oracle* o, uint32_t every, uint64_t seed) {
+  o->sample_every = every;
+  o->sample_seed = seed;
+}
 const char* ko_last_error(Oracle* o) { return o->err.c_str(); }
 
 int ko_set_proteins(Oracle* o, const uint8_t* residues, const uint64_t* offsets,
@@ -151,9 +187,10 @@ int ko_extract(Oracle* o) {
   double t0 = now_s();
   const int k = o->k;
   o->kpos_off.assign(o->n + 1, 0);
+  const uint64_t every = o->sample_every > 1 ? o->sample_every : 1;
   for (uint64_t p = 0; p < o->n; ++p) {
     uint64_t len = o->off[p + 1] - o->off[p];
-    o->kpos_off[p + 1] = o->kpos_off[p] + (len >= (uint64_t)k ? len - k + 1 : 0);
+    o->kpos_off[p + 1] = o->kpos_off[p] + (len >= (uint64_t)k ? (len - k + 1) / every : 0);
   }
   o->kmers.resize(o->kpos_off[o->n]);
   parallel_for(o->threads, o->n, 256, [&](int, uint64_t lo, uint64_t hi) {
@@ -161,9 +198,12 @@ int ko_extract(Oracle* o) {
       const uint8_t* s = o->res.data() + o->off[p];
       uint64_t npos = o->kpos_off[p + 1] - o->kpos_off[p];
       uint32_t* out = o->kmers.data() + o->kpos_off[p];
+      const uint64_t len = o->off[p + 1] - o->off[p];
       for (uint64_t i = 0; i < npos; ++i) {
+        const uint64_t pos =
+            every > 1 ? sample_position(o->sample_seed, (uint32_t)p, (uint32_t)(len - k + 1), (uint32_t)i) : i;
         uint32_t v = 0;
-        for (int j = 0; j < k; ++j) v = v * 21u + o->lut[s[i + j]];
+        for (int j = 0; j < k; ++j) v = v * 21u + o->lut[s[pos + j]];
         out[i] = v;
       }
     }

@@ -49,6 +49,7 @@ def lib():
         L.ko_create.restype = vp
         L.ko_create.argtypes = [i32, i32]
         L.ko_destroy.argtypes = [vp]
+        L.ko_set_sampling.argtypes = [vp, u32, u64]
         L.ko_last_error.restype = C.c_char_p
         L.ko_last_error.argtypes = [vp]
         L.ko_set_proteins.argtypes = [vp, vp, vp, vp, u64]
@@ -97,11 +98,13 @@ class PairResult:
 class Oracle:
     """CPU restatement of the hot path; stage names follow the reference's modules."""
 
-    def __init__(self, k: int = 5, threads: int = 1):
+    def __init__(self, k: int = 5, threads: int = 1, sample_every: int = 0, sample_seed: int = 0):
         self._L = lib()
         self._h = self._L.ko_create(k, threads)
         if not self._h:
             raise ValueError("k must be 5 or 7")
+        if sample_every > 1:
+            self._L.ko_set_sampling(self._h, sample_every, sample_seed)
         self.k = k
         self.n = 0
 

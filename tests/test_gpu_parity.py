@@ -432,3 +432,73 @@ def test_device_edge_view_matches_host_copy(arg_set):
         dev = torch.as_tensor(_DeviceWords(ptr, n * 4), device="cuda")
         assert np.array_equal(dev.cpu().numpy().view(kc.EDGE_DTYPE), host)
         assert np.array_equal(gather_edges_device(e, None, 0, 1), host)
+
+
+@pytest.mark.parametrize("k", [5, 7])
+def test_subsampling_mode_matches_oracle(k):
+    """Protein::new_with_rand_fivemers (src/protein.rs:77-104): a tenth of the start positions; the
+    engine and the oracle share the counter-based sampler definition (kc_sample_position)"""
+    ps = random_protein_set(9, 400, min_len=0, max_len=500, n_classes=3, family=8, mutate=0.03)
+    lens = [40000, 1500, 36000, 1030]  # block / global-scratch extract paths under sampling
+    rng = np.random.default_rng(3)
+    letters = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)
+    base = letters[rng.integers(0, 8, size=max(lens))]
+    extra = np.concatenate([base[:L] for L in lens])
+    res = np.concatenate([ps.residues, extra])
+    off = np.concatenate([ps.offsets, ps.offsets[-1] + np.cumsum(lens).astype(np.uint64)])
+    cls = np.concatenate([ps.class_id, np.array([0, 1, 2, 0], np.uint32)])
+    seed = 0xB2005EED
+    o = Oracle(k, 4, sample_every=10, sample_seed=seed)
+    o.set_proteins(res, off, cls)
+    km = o.extract_kmers()
+    ix = o.build_index()
+    pr = o.score_pairs(3, False, True, mode=1)
+    with kc.Engine(k, threshold=3, cross_class_only=False, want_blosum=True, sample_every=10, sample_seed=seed) as e:
+        e.set_proteins(res, off, cls)
+        got = e.extract_kmers()
+        assert got.size == km.size == sum(max(0, int(L) - k + 1) // 10 for L in np.diff(off.astype(np.int64)))
+        assert np.array_equal(got, km)
+        e.build_index()
+        check_index(e, ix)
+        check_pairs(e.score_pairs(), e.get_edges(), pr)
+    # sampled k-mers are a subset of the full k-mers
+    with kc.Engine(k) as e:
+        e.set_proteins(res, off, cls)
+        full = e.extract_kmers()
+    assert np.isin(km, full).all()
+
+
+def test_tree_from_engine_index(arg_set, arg_oracle):
+    from uniprot_kmer_based_clustering_b200.tree import Tree
+    n = 600
+    sub = kc.ProteinSet(arg_set.residues[:int(arg_set.offsets[n])], arg_set.offsets[:n + 1], arg_set.class_id[:n])
+    o = Oracle(7, 4)
+    o.set_proteins(sub.residues, sub.offsets, sub.class_id)
+    o.extract_kmers()
+    ix = o.build_index()
+    exp = Tree.from_id_rows(ix.row_offsets, ix.ids, ix.stats["n_repeated"])
+    with kc.Engine(7) as e:
+        e.set_protein_set(sub)
+        e.build_index()
+        got = Tree.from_engine(e)
+    assert np.array_equal(got.serialize(), exp.serialize())
+    assert np.array_equal(got.clusters(), exp.clusters())
+
+
+def test_cli_tree_and_sampling(tmp_path, arg_fasta_bytes):
+    import json
+    import os
+    import subprocess
+    from conftest import GOLDEN_DIR, ROOT
+    exe = os.path.join(ROOT, "uniprot_kmer_based_clustering_b200", "bin", "kmer_cluster")
+    fa = tmp_path / "arg.fasta"
+    fa.write_bytes(arg_fasta_bytes)
+    g = json.load(open(os.path.join(GOLDEN_DIR, "tree_golden.json")))["k7"]
+    r = subprocess.run([exe, str(fa), "4", "--k", "7", "--tree"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-400:]
+    assert f"Tree: {g['n_clusters']} top-level clusters, {g['n_merges']} merges" in r.stderr
+    rows = [ln for ln in r.stdout.splitlines() if ln.startswith("#") and not ln.startswith("#protein")]
+    assert len(rows) == 10619
+    r2 = subprocess.run([exe, str(fa), "2", "--sample-every", "10", "--seed", "7"], capture_output=True, text=True,
+                        timeout=120)
+    assert r2.returncode == 0 and "Number of 5mers found in at least two proteins:" in r2.stderr

@@ -240,7 +240,7 @@ def test_reference_api_mirror_names():
 
 
 def test_engine_fails_loudly_without_gpu_and_on_bad_k():
-    cfg_bad = kc._lib.Config(6, 0, 10, 1, 0, 0, 0)
+    cfg_bad = kc._lib.Config(6, 0, 10, 1, 0, 0, 0, 0)
     h = ctypes.c_void_p()
     assert kc.lib().kc_create(ctypes.byref(cfg_bad), ctypes.byref(h)) == kc._lib.KC_EINVAL
     if not has_gpu():
@@ -256,3 +256,34 @@ def test_product_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or fn == "Makefile":
                 text = open(os.path.join(dirpath, fn), errors="ignore").read()
                 assert "oracle" not in text.lower().replace("no cpu fallback", ""), (dirpath, fn)
+
+
+# ---------------------------------------------------------------- subsampling mode (host side)
+def test_position_sampler_is_a_permutation_and_matches_the_oracle():
+    """kc_sample_position: distinct positions, exact count, reproducible (src/protein.rs:77-104 takes a
+    tenth of the start positions without replacement)"""
+    L = kc.lib()
+    for n in (1, 2, 7, 10, 33, 100, 1000, 4097):
+        for protein in (0, 5, 12345):
+            pos = [L.kc_sample_position(0xB2005EED, protein, n, x) for x in range(n)]
+            assert sorted(pos) == list(range(n))
+    a = [L.kc_sample_position(1, 7, 500, x) for x in range(50)]
+    b = [L.kc_sample_position(2, 7, 500, x) for x in range(50)]
+    c = [L.kc_sample_position(1, 8, 500, x) for x in range(50)]
+    assert a != b and a != c
+    # the oracle's restatement of the sampler agrees: sampled k-mers = k-mers at the sampled positions
+    ps = random_protein_set(5, 30, min_len=0, max_len=300, n_classes=2, family=3)
+    full = Oracle(5, 1)
+    full.set_proteins(ps.residues, ps.offsets, ps.class_id)
+    fk = full.extract_kmers()
+    samp = Oracle(5, 1, sample_every=10, sample_seed=0xB2005EED)
+    samp.set_proteins(ps.residues, ps.offsets, ps.class_id)
+    sk = samp.extract_kmers()
+    lens = np.diff(ps.offsets.astype(np.int64))
+    npos = np.maximum(lens - 4, 0)
+    fo = np.concatenate([[0], np.cumsum(npos)])
+    so = np.concatenate([[0], np.cumsum(npos // 10)])
+    assert sk.size == so[-1]
+    for p in range(ps.n):
+        exp = [fk[fo[p] + L.kc_sample_position(0xB2005EED, p, int(npos[p]), x)] for x in range(int(npos[p]) // 10)]
+        assert sk[so[p]:so[p + 1]].tolist() == exp

@@ -26,8 +26,8 @@ class KcError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("k", C.c_int32), ("device", C.c_int32), ("threshold", C.c_uint32),
-                ("cross_class_only", C.c_int32), ("want_blosum", C.c_int32), ("reserved0", C.c_uint32),
-                ("max_edges", C.c_uint64)]
+                ("cross_class_only", C.c_int32), ("want_blosum", C.c_int32), ("sample_every", C.c_uint32),
+                ("max_edges", C.c_uint64), ("sample_seed", C.c_uint64)]
 
 
 class IndexStats(C.Structure):
@@ -54,7 +54,7 @@ def stats_dict(s: C.Structure) -> dict:
 
 # every symbol the two headers declare; tests check the library exports all of them
 EXPORTED = [
-    "kc_abi_version", "kc_device_count", "kc_create", "kc_destroy", "kc_last_error", "kc_set_stream",
+    "kc_sample_position", "kc_abi_version", "kc_device_count", "kc_create", "kc_destroy", "kc_last_error", "kc_set_stream",
     "kc_set_proteins", "kc_set_proteins_device", "kc_extract_kmers", "kc_build_index",
     "kc_get_distinct_kmers", "kc_get_vocab", "kc_get_protein_ids", "kc_lookup_kmers", "kc_score_pairs",
     "kc_score_pairs_shard", "kc_get_edges", "kc_get_edges_device", "kc_get_edge_kmers", "kc_get_timings", "kc_reset_timings",
@@ -63,6 +63,8 @@ EXPORTED = [
     "kc_fasta_n_residues", "kc_fasta_residues", "kc_fasta_offsets", "kc_fasta_class_ids",
     "kc_fasta_n_classes", "kc_fasta_n_missing_class", "kc_fasta_class_name", "kc_fasta_id",
     "kc_synth_layout", "kc_synth_residues",
+    "kc_tree_build", "kc_tree_free", "kc_tree_n_merges", "kc_tree_n_no_common", "kc_tree_serialize",
+    "kc_tree_clusters",
 ]
 
 
@@ -88,6 +90,7 @@ def lib():
     vp, u64, u32, i32, cp = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_char_p
     P = C.POINTER
     sig = {
+        "kc_sample_position": (u32, [u64, u32, u32, u32]),
         "kc_abi_version": (i32, []),
         "kc_device_count": (i32, []),
         "kc_create": (i32, [P(Config), P(vp)]),
@@ -124,6 +127,12 @@ def lib():
         "kc_fasta_id": (cp, [vp, u64]),
         "kc_synth_layout": (i32, [u64, i32, u64, vp, vp]),
         "kc_synth_residues": (i32, [u64, i32, u64, i32, vp, vp]),
+        "kc_tree_build": (i32, [vp, vp, u64, u32, P(vp)]),
+        "kc_tree_free": (None, [vp]),
+        "kc_tree_n_merges": (u64, [vp]),
+        "kc_tree_n_no_common": (u64, [vp]),
+        "kc_tree_serialize": (u64, [vp, vp, u64]),
+        "kc_tree_clusters": (i32, [vp, vp, P(u32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

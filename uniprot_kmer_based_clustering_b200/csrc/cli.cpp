@@ -39,7 +39,7 @@ int main(int argc, char** argv) {
   cfg.threshold = 10;
   cfg.cross_class_only = 1;
   cfg.want_blosum = 0;
-  bool list_kmers = false;
+  bool list_kmers = false, want_tree = false;
   for (int i = 3; i < argc; ++i) {
     const std::string a = argv[i];
     if (a == "--k" && i + 1 < argc) cfg.k = std::atoi(argv[++i]);
@@ -48,6 +48,9 @@ int main(int argc, char** argv) {
     else if (a == "--all-classes") cfg.cross_class_only = 0;
     else if (a == "--blosum") cfg.want_blosum = 1;
     else if (a == "--kmers") list_kmers = true;
+    else if (a == "--tree") want_tree = true;
+    else if (a == "--sample-every" && i + 1 < argc) cfg.sample_every = (uint32_t)std::atoi(argv[++i]);
+    else if (a == "--seed" && i + 1 < argc) cfg.sample_seed = std::strtoull(argv[++i], nullptr, 0);
     else {
       std::fprintf(stderr, "unknown option %s\n", a.c_str());
       return 101;
@@ -108,6 +111,25 @@ int main(int argc, char** argv) {
       for (size_t j = 0; j < kms.size(); ++j) std::printf(j ? ",%u" : "%u", kms[j]);
     }
     std::printf("\n");
+  }
+  if (want_tree) {
+    // src/tree.rs (host): Tree::new + add_protein in input order over the per-protein id lists
+    std::vector<uint64_t> ro(n + 1);
+    std::vector<uint32_t> ids(is.nnz);
+    rc = kc_get_protein_ids(e, ro.data(), ids.data(), ids.size());
+    if (rc) die("kc_get_protein_ids", e, rc);
+    kc_tree* tree = nullptr;
+    rc = kc_tree_build(ro.data(), ids.data(), n, (uint32_t)is.n_repeated, &tree);
+    if (rc) die("kc_tree_build", e, rc);
+    std::vector<uint32_t> cluster(n);
+    uint32_t n_clusters = 0;
+    kc_tree_clusters(tree, cluster.data(), &n_clusters);
+    std::fprintf(stderr, "Tree: %u top-level clusters, %llu merges, %llu proteins without k-mers in common\n",
+                 n_clusters, (unsigned long long)kc_tree_n_merges(tree),
+                 (unsigned long long)kc_tree_n_no_common(tree));
+    std::printf("#protein\tcluster\n");
+    for (uint64_t p = 0; p < n; ++p) std::printf("#%s\t%u\n", kc_fasta_id(fa, p), cluster[p]);
+    kc_tree_free(tree);
   }
   kc_destroy(e);
   kc_fasta_free(fa);

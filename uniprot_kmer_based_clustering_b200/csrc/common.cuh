@@ -105,6 +105,37 @@ __host__ __device__ __forceinline__ uint32_t next_pow2_u32(uint32_t v) {
   return v + 1;
 }
 
+// ---- counter-based position sampler (kc_sample_position, include/kc_b200.h) ----------------
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t sample_key(unsigned long long seed, uint32_t protein) {
+  return mix32((uint32_t)seed ^ mix32(protein ^ (uint32_t)(seed >> 32) ^ 0x9E3779B9u));
+}
+// bijection of [0, n): balanced 4-round Feistel over 2*half bits, cycle-walked into range
+__host__ __device__ __forceinline__ uint32_t sample_perm(uint32_t key, uint32_t n, uint32_t x) {
+  uint32_t half = 1;
+  while ((1ull << (2 * half)) < (unsigned long long)n) ++half;
+  const uint32_t mask = (1u << half) - 1u;
+  uint32_t y = x;
+  do {
+    uint32_t L = y >> half, R = y & mask;
+#pragma unroll
+    for (uint32_t round = 0; round < 4; ++round) {
+      const uint32_t t = L ^ (mix32(R ^ key ^ (round * 0x9E3779B9u)) & mask);
+      L = R;
+      R = t;
+    }
+    y = (L << half) | R;
+  } while (y >= n);
+  return y;
+}
+
 __host__ __device__ constexpr uint32_t pow21(int k) {
   uint32_t v = 1;
   for (int i = 0; i < k; ++i) v *= 21u;

@@ -245,7 +245,8 @@ int run_extract_census(kc_engine* e) {
   if (n) {
     const uint32_t grid = blocks_for(n, kExtractWarps, e->num_sm * 5);
     KC_LAUNCH(e, extract_dedup_warp_kernel<K>, grid, kExtractWarps * 32, 0, res, e->d_pstart.as<uint32_t>(),
-              e->d_plen.as<uint32_t>(), n, pk, ndist, e->slice_shift, e->n_slices, ksplit, &ds->n_incid);
+              e->d_plen.as<uint32_t>(), n, pk, ndist, e->slice_shift, e->n_slices, ksplit, e->cfg.sample_every,
+              e->cfg.sample_seed, e->d_orig.as<uint32_t>(), &ds->n_incid);
   }
   if (!e->h_long.empty()) {
     const size_t smem = (size_t)e->max_block_np2 * 4 + e->max_block_len + 16;
@@ -253,19 +254,28 @@ int run_extract_census(kc_engine* e) {
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KC_LAUNCH(e, (extract_dedup_block_kernel<K, false>), (uint32_t)e->h_long.size(), 512, smem, res,
               e->d_pstart.as<uint32_t>(), e->d_plen.as<uint32_t>(), e->d_long.as<uint32_t>(), nullptr, nullptr,
-              pk, ndist, n, e->slice_shift, e->n_slices, ksplit, &ds->n_incid);
+              pk, ndist, n, e->slice_shift, e->n_slices, ksplit, e->cfg.sample_every, e->cfg.sample_seed,
+              e->d_orig.as<uint32_t>(), &ds->n_incid);
   }
   if (!e->h_huge.empty()) {
     KC_LAUNCH(e, (extract_dedup_block_kernel<K, true>), (uint32_t)e->h_huge.size(), 512, 0, res,
               e->d_pstart.as<uint32_t>(), e->d_plen.as<uint32_t>(), e->d_huge.as<uint32_t>(),
               e->d_huge_off.as<unsigned long long>(), e->d_huge_scratch.as<uint32_t>(), pk, ndist, n,
-              e->slice_shift, e->n_slices, ksplit, &ds->n_incid);
+              e->slice_shift, e->n_slices, ksplit, e->cfg.sample_every, e->cfg.sample_seed,
+              e->d_orig.as<uint32_t>(), &ds->n_incid);
   }
   return KC_OK;
 }
 
 template <int K>
 int run_positions(kc_engine* e, uint32_t* out) {
+  if (e->cfg.sample_every > 1) {
+    if (e->n)
+      KC_LAUNCH(e, kmers_sampled_kernel<K>, blocks_for(e->n, 8, e->num_sm * 8), 256, 0, e->d_res.as<uint8_t>(),
+                e->d_off.as<unsigned long long>(), e->d_kpos.as<unsigned long long>(), (uint32_t)e->n,
+                e->cfg.sample_every, e->cfg.sample_seed, out);
+    return KC_OK;
+  }
   const uint32_t grid = (uint32_t)((e->R + kTileRes - 1) / kTileRes);
   if (grid)
     KC_LAUNCH(e, kmers_per_position_kernel<K>, grid, 256, 0, e->d_res.as<uint8_t>(), e->R,
@@ -362,6 +372,10 @@ struct ColptrOut {
 extern "C" {
 
 int kc_abi_version(void) { return KC_ABI_VERSION; }
+
+uint32_t kc_sample_position(uint64_t seed, uint32_t protein, uint32_t n_positions, uint32_t x) {
+  return n_positions ? sample_perm(sample_key(seed, protein), n_positions, x % n_positions) : 0u;
+}
 
 int kc_device_count(void) {
   int n = 0;
@@ -509,7 +523,8 @@ int kc_extract_kmers(kc_engine* e, uint32_t* kmers_out, uint64_t capacity, uint6
   std::vector<unsigned long long> kpos(n + 1, 0);
   for (uint64_t p = 0; p < n; ++p) {
     const uint64_t len = e->h_off[p + 1] - e->h_off[p];
-    kpos[p + 1] = kpos[p] + (len >= (uint64_t)k ? len - k + 1 : 0);
+    const uint64_t every = e->cfg.sample_every > 1 ? e->cfg.sample_every : 1;
+    kpos[p + 1] = kpos[p] + (len >= (uint64_t)k ? (len - k + 1) / every : 0);
   }
   const uint64_t npos = kpos[n];
   if (n_positions) *n_positions = npos;
@@ -573,8 +588,9 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
   KC_CUDA(e, cudaMemsetAsync(ds, 0, sizeof(DeviceScalars), e->stream));
   // positions are known on the host
   unsigned long long n_positions = 0;
+  const uint32_t every = e->cfg.sample_every > 1 ? e->cfg.sample_every : 1;
   for (uint32_t r = 0; r < n; ++r)
-    if (e->h_plen[r] >= (uint32_t)e->cfg.k) n_positions += e->h_plen[r] - e->cfg.k + 1;
+    if (e->h_plen[r] >= (uint32_t)e->cfg.k) n_positions += (e->h_plen[r] - e->cfg.k + 1) / every;
 
   // K1-K3: extract, per-protein dedup, census bitmaps
   mark(e, EV_IC0);

@@ -158,7 +158,8 @@ __global__ void __launch_bounds__(kExtractWarps * 32)
     extract_dedup_warp_kernel(const uint8_t* __restrict__ res, const uint32_t* __restrict__ pstart,
                               const uint32_t* __restrict__ plen, uint32_t n, uint32_t* __restrict__ pk,
                               uint32_t* __restrict__ ndist, uint32_t slice_shift, uint32_t n_slices,
-                              uint32_t* __restrict__ ksplit, unsigned long long* __restrict__ n_incid) {
+                              uint32_t* __restrict__ ksplit, uint32_t sample_every, unsigned long long sample_seed,
+                              const uint32_t* __restrict__ orig_of, unsigned long long* __restrict__ n_incid) {
   __shared__ uint8_t s_lut[256];
   __shared__ __align__(16) uint32_t s_keys[kExtractWarps][kWarpMaxPos];
   __shared__ __align__(4) uint8_t s_codes[kExtractWarps][kWarpMaxPos + 8];
@@ -176,13 +177,26 @@ __global__ void __launch_bounds__(kExtractWarps * 32)
       for (uint32_t q = lane; q <= n_slices; q += 32) ksplit[(size_t)q * n + r] = 0;
       continue;
     }
-    const uint32_t npos = len - K + 1;
-    if (npos > kWarpMaxPos) continue;  // handled by the block kernels
+    const uint32_t npos_all = len - K + 1;
+    if (npos_all > kWarpMaxPos) continue;  // handled by the block kernels
+    // optional subsampling (Protein::new_with_rand_fivemers): floor(positions / d) distinct positions
+    const uint32_t npos = sample_every > 1 ? npos_all / sample_every : npos_all;
+    if (npos == 0) {
+      if (lane == 0) ndist[r] = 0;
+      for (uint32_t q = lane; q <= n_slices; q += 32) ksplit[(size_t)q * n + r] = 0;
+      continue;
+    }
     const uint32_t ps = pstart[r];
     stage_codes(res, ps, len, codes, s_lut, lane, 32);
     __syncwarp();
     const uint32_t np2 = npos <= 128 ? 128u : next_pow2_u32(npos);
-    for (uint32_t i = lane; i < np2; i += 32) keys[i] = i < npos ? pack_kmer<K>(codes + i) : kSentinel;
+    if (sample_every > 1) {
+      const uint32_t skey = sample_key(sample_seed, orig_of ? orig_of[r] : r);
+      for (uint32_t i = lane; i < np2; i += 32)
+        keys[i] = i < npos ? pack_kmer<K>(codes + sample_perm(skey, npos_all, i)) : kSentinel;
+    } else {
+      for (uint32_t i = lane; i < np2; i += 32) keys[i] = i < npos ? pack_kmer<K>(codes + i) : kSentinel;
+    }
     __syncwarp();
     if (np2 == 128) warp_sort_blocked<4>(keys, lane);
     else if (np2 == 256) warp_sort_blocked<8>(keys, lane);
@@ -222,14 +236,17 @@ __global__ void __launch_bounds__(512)
                                const unsigned long long* __restrict__ scratch_off,
                                uint32_t* __restrict__ scratch, uint32_t* __restrict__ pk,
                                uint32_t* __restrict__ ndist, uint32_t n, uint32_t slice_shift, uint32_t n_slices,
-                               uint32_t* __restrict__ ksplit, unsigned long long* __restrict__ n_incid) {
+                               uint32_t* __restrict__ ksplit, uint32_t sample_every, unsigned long long sample_seed,
+                               const uint32_t* __restrict__ orig_of, unsigned long long* __restrict__ n_incid) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ uint8_t s_lut[256];
   __shared__ uint32_t s_wcnt[32];
   if (threadIdx.x < 256) s_lut[threadIdx.x] = c_residue_lut[threadIdx.x];
   const uint32_t r = list[blockIdx.x];
   const uint32_t len = plen[r], ps = pstart[r];
-  const uint32_t npos = len - K + 1;
+  const uint32_t npos_all = len - K + 1;
+  const uint32_t npos = sample_every > 1 ? npos_all / sample_every : npos_all;  // >= 1: long proteins only
+  const uint32_t skey = sample_key(sample_seed, orig_of ? orig_of[r] : r);
   const uint32_t np2 = next_pow2_u32(npos);
   uint32_t* keys;
   __syncthreads();
@@ -238,19 +255,20 @@ __global__ void __launch_bounds__(512)
     for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x) {
       uint32_t v = kSentinel;
       if (i < npos) {
+        const uint32_t pos = sample_every > 1 ? sample_perm(skey, npos_all, i) : i;
         v = 0;
 #pragma unroll
-        for (int j = 0; j < K; ++j) v = v * 21u + s_lut[res[ps + i + j]];
+        for (int j = 0; j < K; ++j) v = v * 21u + s_lut[res[ps + pos + j]];
       }
       keys[i] = v;
     }
   } else {
     keys = reinterpret_cast<uint32_t*>(dyn_smem);
-    uint8_t* codes = dyn_smem + (size_t)np2 * 4;
+    uint8_t* codes = dyn_smem + (size_t)next_pow2_u32(npos_all) * 4;
     stage_codes(res, ps, len, codes, s_lut, threadIdx.x, blockDim.x);
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x)
-      keys[i] = i < npos ? pack_kmer<K>(codes + i) : kSentinel;
+      keys[i] = i < npos ? pack_kmer<K>(codes + (sample_every > 1 ? sample_perm(skey, npos_all, i) : i)) : kSentinel;
   }
   __syncthreads();
   block_bitonic(keys, np2);
@@ -390,6 +408,32 @@ __global__ void __launch_bounds__(256)
     const uint64_t pbeg = local ? s_off[lo] : off[p0 + lo];
     const uint64_t pend = local ? s_off[lo + 1] : off[p0 + lo + 1];
     if (g + K <= pend) out[kpos_off[p0 + lo] + (g - pbeg)] = pack_kmer<K>(s_codes + li);
+  }
+}
+
+// K1 in subsampling mode: the x-th sampled k-mer of every protein (input order), x ascending
+template <int K>
+__global__ void __launch_bounds__(256)
+    kmers_sampled_kernel(const uint8_t* __restrict__ res, const unsigned long long* __restrict__ off,
+                         const unsigned long long* __restrict__ kpos_off, uint32_t n_prot, uint32_t sample_every,
+                         unsigned long long sample_seed, uint32_t* __restrict__ out) {
+  __shared__ uint8_t s_lut[256];
+  s_lut[threadIdx.x] = c_residue_lut[threadIdx.x];
+  __syncthreads();
+  const uint32_t lane = lane_id();
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t p = gw; p < n_prot; p += nw) {
+    const unsigned long long b = off[p], len = off[p + 1] - b;
+    if (len < (unsigned long long)K) continue;
+    const uint32_t npos_all = (uint32_t)(len - K + 1), m = npos_all / sample_every;
+    const uint32_t skey = sample_key(sample_seed, p);
+    for (uint32_t x = lane; x < m; x += 32) {
+      const uint32_t pos = sample_perm(skey, npos_all, x);
+      uint32_t v = 0;
+#pragma unroll
+      for (int j = 0; j < K; ++j) v = v * 21u + s_lut[res[b + pos + j]];
+      out[kpos_off[p] + x] = v;
+    }
   }
 }
 

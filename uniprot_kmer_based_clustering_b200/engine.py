@@ -109,10 +109,11 @@ class Engine:
     """One engine per GPU.  Method names follow include/kc_b200.h."""
 
     def __init__(self, k: int = 5, device: int = 0, threshold: int = 10, cross_class_only: bool = True,
-                 want_blosum: bool = False, max_edges: int = 0):
+                 want_blosum: bool = False, max_edges: int = 0, sample_every: int = 0, sample_seed: int = 0):
         self._L = _lib.lib()
         self._h = C.c_void_p()
-        cfg = Config(k, device, threshold, int(cross_class_only), int(want_blosum), 0, max_edges)
+        cfg = Config(k, device, threshold, int(cross_class_only), int(want_blosum), sample_every, max_edges,
+                     sample_seed)
         rc = self._L.kc_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             self._h = None
