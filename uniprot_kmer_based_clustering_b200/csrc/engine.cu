@@ -603,13 +603,17 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
   const uint32_t cmerge = std::getenv("KC_B200_CENSUS_MERGE") ? std::max(1, std::atoi(std::getenv("KC_B200_CENSUS_MERGE"))) : 1;
   for (uint32_t q = 0; q < P && n; q += cmerge) {
     const uint32_t q1 = std::min(P, q + cmerge);
-    if (narrow && cmerge < 4)
-      KC_LAUNCH(e, census_pass_kernel<8>, pass_grid, 256, 0, e->d_pk.as<uint32_t>(), e->d_pstart.as<uint32_t>(),
-                split(e->d_ksplit, q), split(e->d_ksplit, q1), n, e->d_seen.as<uint32_t>());
-    else
-      KC_LAUNCH(e, census_pass_kernel<32>, blocks_for(n, 8, e->num_sm * 8), 256, 0, e->d_pk.as<uint32_t>(),
-                e->d_pstart.as<uint32_t>(), split(e->d_ksplit, q), split(e->d_ksplit, q1), n,
-                e->d_seen.as<uint32_t>());
+    const bool preread = e->universe <= (1u << 24);  // hot k-mers (k=5): skip marks that are no-ops
+    const uint32_t cgrid = narrow && cmerge < 4 ? pass_grid : blocks_for(n, 8, e->num_sm * 8);
+#define KC_CENSUS(G, PRE)                                                                              \
+  KC_LAUNCH(e, (census_pass_kernel<G, PRE>), cgrid, 256, 0, e->d_pk.as<uint32_t>(), e->d_pstart.as<uint32_t>(), \
+            split(e->d_ksplit, q), split(e->d_ksplit, q1), n, e->d_seen.as<uint32_t>())
+    if (narrow && cmerge < 4) {
+      if (preread) KC_CENSUS(8, true); else KC_CENSUS(8, false);
+    } else {
+      if (preread) KC_CENSUS(32, true); else KC_CENSUS(32, false);
+    }
+#undef KC_CENSUS
   }
   mark(e, EV_IC1);
   // K4: rank dictionary over "held by >= 2 proteins"

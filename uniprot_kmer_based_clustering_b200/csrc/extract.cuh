@@ -20,10 +20,13 @@ __constant__ uint8_t c_residue_lut[256];
 // within the protein) finds it set and sets the high bit.  Both bits live in the same 32-byte
 // sector, so one incidence costs one random sector.  The plain pre-read may be stale; it only
 // skips work that is idempotent.
+// PREREAD: worth it when k-mers are hot (small universe: many holders per k-mer, most marks are
+// no-ops); with a sparse universe (k=7) it only adds a dependent round trip.
+template <bool PREREAD>
 __device__ __forceinline__ void census_mark(uint32_t kmer, uint32_t* __restrict__ seen) {
   const uint32_t w = kmer >> 4, sh = (kmer & 15u) * 2u;
   const uint32_t lo = 1u << sh, hi = 2u << sh;
-  if (seen[w] & hi) return;
+  if (PREREAD && (seen[w] & hi)) return;
   const uint32_t old = atomicOr(&seen[w], lo);
   if ((old & lo) && !(old & hi)) atomicOr(&seen[w], hi);
 }
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(512)
 // done slice by slice; lo[r]..hi[r] is the run of row r that falls into the slice.
 // G lanes work on one row.
 // ---------------------------------------------------------------------------------------
-template <int G>
+template <int G, bool PREREAD>
 __global__ void __launch_bounds__(256)
     census_pass_kernel(const uint32_t* __restrict__ pk, const uint32_t* __restrict__ pstart,
                        const uint32_t* __restrict__ lo, const uint32_t* __restrict__ hi, uint32_t n,
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(256)
   const uint32_t gg = (blockIdx.x * blockDim.x + threadIdx.x) / G, ng = (gridDim.x * blockDim.x) / G;
   for (uint32_t r = gg; r < n; r += ng) {
     const uint32_t i0 = lo[r], i1 = hi[r], ps = pstart[r];
-    for (uint32_t i = i0 + gl; i < i1; i += G) census_mark(pk[ps + i], seen);
+    for (uint32_t i = i0 + gl; i < i1; i += G) census_mark<PREREAD>(pk[ps + i], seen);
   }
 }
 

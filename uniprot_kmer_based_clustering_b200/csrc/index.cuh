@@ -301,14 +301,29 @@ __global__ void __launch_bounds__(256)
       const uint32_t id = ids[ps + i];
       uint32_t a = colptr[id];
       const uint32_t end = colptr[id + 1];
-      uint32_t b = end;
-      while (a < b) {  // lower_bound(col[a..b), target)
-        const uint32_t mid = (a + b) >> 1;
-        if (col[mid] < target) a = mid + 1; else b = mid;
+      uint32_t partner = kSentinel;  // the holder at position a, when it is already in a register
+      if (end - a <= 4u) {
+        // short posting list (most k-mers): fetch it whole with independent loads instead of a
+        // dependent binary search; padding with the sentinel keeps the comparison branch-free
+        const uint32_t f = end - a;
+        const uint32_t c0 = col[a];
+        const uint32_t c1 = f > 1 ? col[a + 1] : kSentinel;
+        const uint32_t c2 = f > 2 ? col[a + 2] : kSentinel;
+        const uint32_t c3 = f > 3 ? col[a + 3] : kSentinel;
+        const uint32_t below = (c0 < target) + (c1 < target) + (c2 < target) + (c3 < target);
+        partner = below == 0 ? c0 : (below == 1 ? c1 : (below == 2 ? c2 : c3));
+        a += below;
+      } else {
+        uint32_t b = end;
+        while (a < b) {  // lower_bound(col[a..b), target)
+          const uint32_t mid = (a + b) >> 1;
+          if (col[mid] < target) a = mid + 1; else b = mid;
+        }
+        if (end - a == 1u) partner = col[a];
       }
       // a single partner is stored inline ({rank, sentinel}): the pair stage then needs no
       // postings gather for it (a 4-byte read there costs a whole random 32-byte sector)
-      suf[ps + i] = end - a == 1u ? make_uint2(col[a], kSentinel) : make_uint2(a, end);
+      suf[ps + i] = end - a == 1u ? make_uint2(partner, kSentinel) : make_uint2(a, end);
       if (sufss) sufss[ps + i] = selfscore[id];  // BLOSUM62 self-score of the entry's k-mer (K9 fused into K7)
       work += end - a;
       n_inl += end - a == 1u;
