@@ -502,3 +502,22 @@ def test_cli_tree_and_sampling(tmp_path, arg_fasta_bytes):
     r2 = subprocess.run([exe, str(fa), "2", "--sample-every", "10", "--seed", "7"], capture_output=True, text=True,
                         timeout=120)
     assert r2.returncode == 0 and "Number of 5mers found in at least two proteins:" in r2.stderr
+
+
+@pytest.mark.parametrize("blosum", [True, False])
+def test_stream_pair_kernel_over_materialised_lists(blosum, monkeypatch, arg_set, arg_oracle):
+    """KC_B200_PLIST=1 materialises the multi-edge lists and scores them with the stream kernel
+    (opt-in: the fill costs more than the stream kernel saves); both paths must give identical results"""
+    monkeypatch.setenv("KC_B200_PLIST", "1")
+    for k, cross, thr in ((5, True, 10), (7, False, 10)):
+        pr = arg_oracle[k][0].score_pairs(thr, cross, blosum, mode=1)
+        with kc.Engine(k, threshold=thr, cross_class_only=cross, want_blosum=blosum) as e:
+            e.set_protein_set(arg_set)
+            e.build_index()
+            check_pairs(e.score_pairs(), e.get_edges(), pr)
+    ps = kc.ProteinSet.synthetic(20000, "A", 0xB2000004, threads=8)
+    km, ix, pr = run_oracle(ps, 7, 10, False, blosum=blosum)
+    with kc.Engine(7, threshold=10, cross_class_only=False, want_blosum=blosum) as e:
+        e.set_protein_set(ps)
+        e.build_index()
+        check_pairs(e.score_pairs(), e.get_edges(), pr)

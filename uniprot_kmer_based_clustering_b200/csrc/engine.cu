@@ -67,6 +67,7 @@ struct kc_engine {
   int dev = 0;
   int num_sm = kNumSM;
   size_t smem_optin = 0;
+  size_t total_mem = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::string err;
@@ -90,7 +91,8 @@ struct kc_engine {
   kc_index_stats istats{};
   uint64_t multi_total = 0, work_total = 0;
   DBuf d_pk, d_ndist, d_rowlen, d_seen, d_dict, d_vocab, d_freq, d_self, d_colptr, d_cursor, d_col,
-      d_suf, d_sufss, d_rowwork, d_lists, d_colscratch, d_workprefix, d_ksplit, d_isplit, d_rowwork64, d_rowinl, d_rowmaxlen;
+      d_suf, d_sufss, d_rowwork, d_lists, d_colscratch, d_workprefix, d_ksplit, d_isplit, d_rowwork64, d_rowinl, d_rowmaxlen, d_psplit, d_rowbase, d_plist, d_pss;
+  bool have_plist = false;
   uint32_t slice_shift = 31, n_slices = 1;
   // pairs
   DBuf d_rowbin, d_rowsafe, d_rowlogh, d_edges, d_keys_a, d_keys_b, d_vals_a, d_vals_b, d_hist, d_edges_sorted;
@@ -407,6 +409,7 @@ int kc_create(const kc_config* cfg, kc_engine** out) {
   cudaGetDeviceProperties(&prop, e->dev);
   e->num_sm = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : kNumSM;
   e->smem_optin = prop.sharedMemPerBlockOptin;
+  e->total_mem = prop.totalGlobalMem;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete e;
     return KC_ECUDA;
@@ -439,7 +442,7 @@ void kc_destroy(kc_engine* e) {
                  &e->d_first_after, &e->d_long, &e->d_huge, &e->d_huge_off, &e->d_huge_scratch, &e->d_pk,
                  &e->d_ndist, &e->d_rowlen, &e->d_seen, &e->d_dict, &e->d_vocab, &e->d_freq,
                  &e->d_self, &e->d_colptr, &e->d_cursor, &e->d_col, &e->d_suf, &e->d_sufss, &e->d_rowwork, &e->d_lists,
-                 &e->d_colscratch, &e->d_workprefix, &e->d_ksplit, &e->d_isplit, &e->d_rowwork64, &e->d_rowinl, &e->d_rowmaxlen, &e->d_rowbin, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
+                 &e->d_colscratch, &e->d_workprefix, &e->d_ksplit, &e->d_isplit, &e->d_rowwork64, &e->d_rowinl, &e->d_rowmaxlen, &e->d_psplit, &e->d_rowbase, &e->d_plist, &e->d_pss, &e->d_rowbin, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
                  &e->d_vals_a, &e->d_vals_b, &e->d_hist, &e->d_edges_sorted, &e->d_scalars, &e->d_scan_tiles,
                  &e->d_tmp};
   for (DBuf* b : all) b->release();
@@ -572,6 +575,9 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
   const uint32_t P = e->n_slices;
   KC_CUDA(e, e->d_ksplit.ensure(((uint64_t)P + 1) * std::max<uint64_t>(n, 1) * 4));
   KC_CUDA(e, e->d_isplit.ensure(((uint64_t)P + 1) * std::max<uint64_t>(n, 1) * 4));
+  KC_CUDA(e, e->d_psplit.ensure(((uint64_t)P + 1) * std::max<uint64_t>(n, 1) * 4));
+  KC_CUDA(e, e->d_rowbase.ensure(((uint64_t)n + 2) * 8));
+  e->have_plist = false;
   KC_CUDA(e, e->d_rowwork64.ensure(((uint64_t)n + 1) * 8));
   KC_CUDA(e, e->d_rowinl.ensure(((uint64_t)n + 1) * 4));
   KC_CUDA(e, e->d_rowmaxlen.ensure(((uint64_t)n + 1) * 4));
@@ -710,13 +716,13 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
                   split(e->d_isplit, q + 1), n, e->d_pk.as<uint32_t>(), e->d_colptr.as<uint32_t>(),
                   e->d_col.as<uint32_t>(), fa, e->d_self.as<uint8_t>(), e->d_suf.as<uint2>(),
                   e->cfg.want_blosum ? e->d_sufss.as<uint8_t>() : nullptr, e->d_rowwork64.as<unsigned long long>(),
-                  e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>(), &ds->work_total);
+                  e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>(), split(e->d_psplit, q), &ds->work_total);
       else
         KC_LAUNCH(e, suffix_ranges_kernel<32>, pass_grid, 256, 0, e->d_pstart.as<uint32_t>(), split(e->d_isplit, q),
                   split(e->d_isplit, q + 1), n, e->d_pk.as<uint32_t>(), e->d_colptr.as<uint32_t>(),
                   e->d_col.as<uint32_t>(), fa, e->d_self.as<uint8_t>(), e->d_suf.as<uint2>(),
                   e->cfg.want_blosum ? e->d_sufss.as<uint8_t>() : nullptr, e->d_rowwork64.as<unsigned long long>(),
-                  e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>(), &ds->work_total);
+                  e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>(), split(e->d_psplit, q), &ds->work_total);
     }
     KC_LAUNCH(e, clamp_rowwork_kernel, (n + 255) / 256, 256, 0, e->d_rowwork64.as<unsigned long long>(), n,
               e->d_rowwork.as<uint32_t>());
@@ -729,9 +735,35 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
                                   U64ExclOutWithTail{e->d_workprefix.as<unsigned long long>(), n}, n, e->scan,
                                   e->stream);
   }
-  mark(e, EV_I1);
   KC_CUDA(e, cudaMemcpyAsync(&hs, ds, sizeof(hs), cudaMemcpyDeviceToHost, e->stream));
   KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  KC_CUDA(e, cudaGetLastError());
+  // Materialised multi-edge lists for the stream pair kernel (opt-in, KC_B200_PLIST=1): 4 bytes
+  // (+1 with BLOSUM) per multi-edge.  Measured on synth_1m_k7: the fill costs 12 ms, the stream
+  // kernel saves 3 ms over the gather kernels, so the default is the gather kernels.
+  if (n && V && hs.work_total && std::getenv("KC_B200_PLIST")) {
+    // budget: a quarter of the device memory (no cudaMemGetInfo here: it stalls for milliseconds)
+    const unsigned long long need = hs.work_total * (4ull + (e->cfg.want_blosum ? 1ull : 0ull)) + (1ull << 20);
+    if (need <= (unsigned long long)e->total_mem / 4) {
+      KC_CUDA(e, e->d_plist.ensure((hs.work_total + 64) * 4));
+      if (e->cfg.want_blosum) KC_CUDA(e, e->d_pss.ensure(hs.work_total + 64));
+      e->launches += exclusive_scan(U64In{e->d_rowwork64.as<unsigned long long>()},
+                                    U64ExclOutWithTail{e->d_rowbase.as<unsigned long long>(), n}, n, e->scan,
+                                    e->stream);
+      for (uint32_t q = 0; q < P; ++q) {
+#define KC_PFILL(G)                                                                                          \
+  KC_LAUNCH(e, products_fill_kernel<G>, pass_grid, 256, 0, e->d_pstart.as<uint32_t>(), split(e->d_isplit, q),   \
+            split(e->d_isplit, q + 1), n, e->d_suf.as<uint2>(),                                                  \
+            e->cfg.want_blosum ? e->d_sufss.as<uint8_t>() : nullptr, e->d_col.as<uint32_t>(),                  \
+            e->d_rowbase.as<unsigned long long>(), e->d_rowwork64.as<unsigned long long>(), split(e->d_psplit, q), \
+            e->d_plist.as<uint32_t>(), e->cfg.want_blosum ? e->d_pss.as<uint8_t>() : nullptr)
+        if (narrow) KC_PFILL(8); else KC_PFILL(32);
+#undef KC_PFILL
+      }
+      e->have_plist = true;
+    }
+  }
+  mark(e, EV_I1);
   KC_CUDA(e, cudaGetLastError());
   e->istats.n_positions = n_positions;
   e->istats.n_incidences = n_incid;
@@ -890,7 +922,22 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
                   e->cfg.want_blosum ? kUnscored : 0u};
     mark(e, EV_PK0);
     int rc;
-    if (e->cfg.want_blosum) {
+    if (e->have_plist) {
+#define KC_STREAM(SC)                                                                                         \
+  do {                                                                                                        \
+    constexpr size_t smem = (size_t)kStreamWarps * stream_warp_words<SC>() * 4;                               \
+    KC_CUDA(e, cudaFuncSetAttribute(pairs_stream_kernel<SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    int per_sm = 1;                                                                                           \
+    KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairs_stream_kernel<SC>, kStreamWarps * 32, smem)); \
+    if (per_sm < 1) per_sm = 1;                                                                               \
+    KC_LAUNCH(e, pairs_stream_kernel<SC>, (uint32_t)(e->num_sm * per_sm), kStreamWarps * 32, smem,            \
+              e->d_rowbase.as<unsigned long long>(), e->d_rowwork.as<uint32_t>(), e->d_plist.as<uint32_t>(),  \
+              SC ? e->d_pss.as<uint8_t>() : nullptr, e->d_rowbin.as<uint8_t>(), e->d_rowsafe.as<uint8_t>(), n, \
+              count_bits, &ds->row_cursor[kBinMain], &ds->n_overflow, ds->bin_counts, sink, &ds->pc);         \
+  } while (0)
+      if (e->cfg.want_blosum) KC_STREAM(true); else KC_STREAM(false);
+#undef KC_STREAM
+    } else     if (e->cfg.want_blosum) {
       constexpr size_t smem = (size_t)kScoredWarps * kScoredWarpWords * 4;
       KC_CUDA(e, cudaFuncSetAttribute(pairs_main_scored_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 1;

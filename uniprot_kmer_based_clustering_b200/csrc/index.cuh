@@ -287,12 +287,15 @@ __global__ void __launch_bounds__(256)
                          const uint32_t* __restrict__ first_after, const uint8_t* __restrict__ selfscore,
                          uint2* __restrict__ suf, uint8_t* __restrict__ sufss,
                          unsigned long long* __restrict__ rowwork64, uint32_t* __restrict__ rowinl,
-                         uint32_t* __restrict__ rowmaxlen, unsigned long long* __restrict__ work_total) {
+                         uint32_t* __restrict__ rowmaxlen, uint32_t* __restrict__ pslo,
+                         unsigned long long* __restrict__ work_total) {
   const uint32_t lane = lane_id(), gl = lane % G;
   const uint32_t gg = (blockIdx.x * blockDim.x + threadIdx.x) / G, ng = (gridDim.x * blockDim.x) / G;
   unsigned long long tot = 0;
   for (uint32_t r = gg; r < n; r += ng) {
     const uint32_t i0 = lo[r], i1 = hi[r], ps = pstart[r];
+    // where this slice's multi-edges start in the row's materialised list (products_fill_kernel)
+    if (pslo && gl == 0) pslo[r] = (uint32_t)min(rowwork64[r], 0xFFFFFFFFull);
     if (i0 >= i1) continue;
     const uint32_t target = first_after ? first_after[r] : r + 1;  // first rank that pairs with r
     unsigned long long work = 0;
@@ -345,6 +348,77 @@ __global__ void __launch_bounds__(256)
   tot = warp_sum64(tot);
   if (lane == 0 && tot) atomicAdd(work_total, tot);
 }
+
+// Materialised multi-edge lists ("plist"): row r's partners, one u32 per multi-edge, in entry order
+// at plist[rowbase[r] ..], plus the entry's BLOSUM self-score per multi-edge (pss).  Filled slice
+// by slice like the suffix pass (the postings slice stays L2-resident); the pair kernel then
+// streams exactly 4 bytes per multi-edge with coalesced loads instead of gathering postings.
+template <int G>
+__global__ void __launch_bounds__(256)
+    products_fill_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ lo,
+                         const uint32_t* __restrict__ hi, uint32_t n, const uint2* __restrict__ suf,
+                         const uint8_t* __restrict__ sufss, const uint32_t* __restrict__ col,
+                         const unsigned long long* __restrict__ rowbase, const unsigned long long* __restrict__ rowwork64,
+                         const uint32_t* __restrict__ pslo, uint32_t* __restrict__ plist, uint8_t* __restrict__ pss) {
+  const uint32_t lane = lane_id(), gl = lane % G, gshift = (lane / G) * G;
+  const uint32_t gmask = group_mask<G>();
+  const uint32_t gg = (blockIdx.x * blockDim.x + threadIdx.x) / G, ng = (gridDim.x * blockDim.x) / G;
+  for (uint32_t r = gg; r < n; r += ng) {
+    const uint32_t i0 = lo[r], i1 = hi[r], ps = pstart[r];
+    if (i0 >= i1 || rowwork64[r] > 0xFFFFFFFFull) continue;  // monstrous rows are never streamed
+    unsigned long long dst0 = rowbase[r] + pslo[r];
+    for (uint32_t c = i0; c < i1; c += G) {
+      const uint32_t i = c + gl;
+      uint2 e = make_uint2(0, 0);
+      uint32_t ss = 0;
+      if (i < i1) {
+        e = suf[ps + i];
+        if (pss) ss = sufss[ps + i];
+      }
+      const bool inl = e.y == kSentinel;
+      const uint32_t len = inl ? 1u : e.y - e.x;
+      // exclusive scan of len over the G lanes of the group
+      uint32_t incl = len;
+#pragma unroll
+      for (int o = 1; o < G; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(gmask, incl, o, G);
+        if (gl >= (uint32_t)o) incl += t;
+      }
+      const uint32_t total = __shfl_sync(gmask, incl, gshift + G - 1);
+      const unsigned long long dst = dst0 + incl - len;
+      if (inl) {
+        plist[dst] = e.x;
+        if (pss) pss[dst] = (uint8_t)ss;
+      } else if (len < 32u) {
+        for (uint32_t j = 0; j < len; ++j) {
+          plist[dst + j] = col[e.x + j];
+          if (pss) pss[dst + j] = (uint8_t)ss;
+        }
+      }
+      // long posting suffixes: the whole group copies them, one after the other
+      uint32_t m = (__ballot_sync(gmask, !inl && len >= 32u) >> gshift) & (G == 32 ? kFullMask : ((1u << (G & 31)) - 1u));
+      while (m) {
+        const uint32_t src = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t sx = __shfl_sync(gmask, e.x, gshift + src), sl = __shfl_sync(gmask, len, gshift + src);
+        const uint32_t sss = __shfl_sync(gmask, ss, gshift + src);
+        const unsigned long long sd =
+            (unsigned long long)__shfl_sync(gmask, (uint32_t)(dst >> 32), gshift + src) << 32 |
+            __shfl_sync(gmask, (uint32_t)dst, gshift + src);
+        for (uint32_t j = gl; j < sl; j += G) {
+          plist[sd + j] = col[sx + j];
+          if (pss) pss[sd + j] = (uint8_t)sss;
+        }
+      }
+      dst0 += total;
+    }
+  }
+}
+
+struct U64In {
+  const unsigned long long* p;
+  __device__ unsigned long long operator()(uint64_t i) const { return p[i] > 0xFFFFFFFFull ? 0ull : p[i]; }
+};
 
 // clamp the 64-bit per-row work to the 32-bit value the row classifier uses
 __global__ void clamp_rowwork_kernel(const unsigned long long* __restrict__ w64, uint32_t n,

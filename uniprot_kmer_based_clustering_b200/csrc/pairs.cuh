@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256)
         // is tried there unless a lower bound on its partners (inline partners are distinct; the
         // longest suffix holds distinct partners) already comes close to the cap.
         const uint32_t lower = max(rowinl[r], rowmaxlen[r]);
-        if ((U <= kMainCap || lower <= kMainCap / 2) && rowlen[r] < (1u << kScoreShift)) {
+        if ((U <= kMainCap || lower <= kMainCap / 2) && rowlen[r] < (1u << kScoreShift) && P != 0xFFFFFFFFu) {
           bin = kBinMain;
           rowlogh[r] = (uint8_t)kMainLogHMax;
         }
@@ -963,6 +963,169 @@ __global__ void __launch_bounds__(kScoredWarps * 32)
       __syncwarp();
     }
   }
+  n_pairs = warp_sum64(n_pairs);
+  n_edges = warp_sum64(n_edges);
+  sum_count = warp_sum64(sum_count);
+  n_multi = warp_sum64(n_multi);
+  if (lane == 0) {
+    if (n_multi) atomicAdd(&counters->n_multi, n_multi);
+    if (n_pairs) atomicAdd(&counters->n_pairs, n_pairs);
+    if (n_edges) atomicAdd(&counters->n_edges, n_edges);
+    if (sum_count) atomicAdd(&counters->sum_count, sum_count);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Stream kernel (the fast path when the materialised multi-edge lists fit in HBM): row r's
+// partners are plist[rowbase[r] .. +rowwork[r]), one u32 per multi-edge, written by the index
+// stage.  A warp streams them with coalesced 128-byte loads (next 128 in flight while the
+// current 128 are bumped) into its shared-memory table: exactly the 4 algorithmic bytes per
+// multi-edge, no postings gather, no flattening.  Same table / dirty-list / overflow protocol
+// as pairs_main_kernel; SCORED adds the BLOSUM self-score stream (one byte per multi-edge).
+// ---------------------------------------------------------------------------------------
+constexpr int kStreamWarps = 4;
+constexpr uint32_t kStreamStageWords = 256;  // 64 scored or 85 unscored edges per flush
+template <bool SCORED>
+__host__ __device__ constexpr uint32_t stream_warp_words() {
+  return (SCORED ? 2u : 1u) * (1u << kMainLogHMax) + kMainCap / 2 + 4 + kStreamStageWords;
+}
+
+template <bool SCORED>
+__global__ void __launch_bounds__(kStreamWarps * 32)
+    pairs_stream_kernel(const unsigned long long* __restrict__ rowbase, const uint32_t* __restrict__ rowwork,
+                        const uint32_t* __restrict__ plist, const uint8_t* __restrict__ pss,
+                        uint8_t* __restrict__ rowbin, const uint8_t* __restrict__ rowsafe, uint32_t n,
+                        uint32_t count_bits, uint32_t* __restrict__ row_cursor, uint32_t* __restrict__ n_overflow,
+                        uint32_t* __restrict__ bin_counts, EdgeSink sink, PairCounters* __restrict__ counters) {
+  constexpr uint32_t HMAX = 1u << kMainLogHMax;
+  constexpr uint32_t log_h = kMainLogHMax;
+  if (bin_counts[kBinMain] == 0) return;
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  uint32_t* wbase = reinterpret_cast<uint32_t*>(dyn_smem) + (size_t)warp * stream_warp_words<SCORED>();
+  uint32_t* key = wbase;                              // SCORED: keys; else packed key|count slots
+  uint32_t* val = wbase + HMAX;                       // SCORED only: score << 12 | count
+  uint32_t* after = wbase + (SCORED ? 2u : 1u) * HMAX;
+  uint16_t* dirty = reinterpret_cast<uint16_t*>(after);
+  uint32_t* dirty_cnt = after + kMainCap / 2;
+  EdgeStage stage{after + kMainCap / 2 + 4, 0u};
+  const uint32_t cb = count_bits, cmask = (1u << count_bits) - 1u;
+  unsigned long long n_pairs = 0, n_edges = 0, sum_count = 0, n_multi = 0;
+  if (lane == 0) *dirty_cnt = 0;
+  for (uint32_t i = lane * 4; i < HMAX; i += 128) {
+    *reinterpret_cast<uint4*>(key + i) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+    if (SCORED) *reinterpret_cast<uint4*>(val + i) = make_uint4(0, 0, 0, 0);
+  }
+  __syncwarp();
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(row_cursor, 4u);
+    base = __shfl_sync(kFullMask, base, 0);
+    if (base >= n) break;
+    uint32_t m_work = 0, m_lo = 0, m_hi = 0;
+    bool mine = false;
+    if (lane < 4 && base + lane < n && rowbin[base + lane] == kBinMain) {
+      mine = true;
+      m_work = rowwork[base + lane];
+      const unsigned long long rb = rowbase[base + lane];
+      m_lo = (uint32_t)rb;
+      m_hi = (uint32_t)(rb >> 32);
+    }
+    uint32_t todo = __ballot_sync(kFullMask, mine);
+    while (todo) {
+      const uint32_t l = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t r = base + l;
+      const uint32_t P = __shfl_sync(kFullMask, m_work, l);
+      const unsigned long long rb =
+          ((unsigned long long)__shfl_sync(kFullMask, m_hi, l) << 32) | __shfl_sync(kFullMask, m_lo, l);
+      const uint32_t* pl = plist + rb;
+      const uint8_t* sl = SCORED ? pss + rb : nullptr;
+      bool full = false;
+      uint32_t v[4], sv[4], w[4], sw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t t = lane + 32 * u;
+        v[u] = t < P ? ld_stream_u32(pl + t) : kSentinel;
+        sv[u] = SCORED && t < P ? sl[t] : 0u;
+      }
+      for (uint32_t t0 = 0; t0 < P; t0 += 128) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {  // next 128 multi-edges in flight while these are bumped
+          const uint32_t t = t0 + 128 + lane + 32 * u;
+          w[u] = t < P ? ld_stream_u32(pl + t) : kSentinel;
+          sw[u] = SCORED && t < P ? sl[t] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (v[u] == kSentinel) continue;
+          if (SCORED)
+            scored_bump_dirty(key, val, HMAX - 1u, log_h, v[u], (sv[u] << kScoreShift) | 1u, dirty_cnt, dirty,
+                              kMainCap, full);
+          else
+            packed_bump_dirty(key, HMAX - 1u, log_h, cb, v[u], dirty_cnt, dirty, kMainCap, full);
+        }
+        if (__any_sync(kFullMask, full)) break;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[u] = w[u];
+          sv[u] = sw[u];
+        }
+      }
+      __syncwarp();
+      if (__any_sync(kFullMask, full)) {  // more distinct partners than the table takes: safe kernels
+        for (uint32_t i = lane * 4; i < HMAX; i += 128) {
+          *reinterpret_cast<uint4*>(key + i) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+          if (SCORED) *reinterpret_cast<uint4*>(val + i) = make_uint4(0, 0, 0, 0);
+        }
+        if (lane == 0) {
+          rowbin[r] = (uint8_t)(kBinRetry + rowsafe[r]);
+          atomicAdd(n_overflow, 1u);
+          atomicAdd(&bin_counts[kBinRetry + rowsafe[r]], 1u);
+          *dirty_cnt = 0;
+        }
+        __syncwarp();
+        continue;
+      }
+      const uint32_t n_dirty = *dirty_cnt;
+      __syncwarp();
+      for (uint32_t i0 = 0; i0 < n_dirty; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        uint32_t b = kSentinel, cq = 0, score = 0;
+        if (i < n_dirty) {
+          const uint32_t h = dirty[i];
+          if (SCORED) {
+            b = key[h];
+            const uint32_t vv = val[h];
+            key[h] = kSentinel;
+            val[h] = 0;
+            cq = vv & ((1u << kScoreShift) - 1u);
+            score = vv >> kScoreShift;
+          } else {
+            const uint32_t sv0 = key[h];
+            key[h] = kSentinel;
+            b = sv0 >> cb;
+            cq = sv0 & cmask;
+          }
+        }
+        const bool out = cq > sink.threshold;
+        n_pairs += cq != 0;
+        n_multi += cq;
+        n_edges += out;
+        sum_count += out ? cq : 0u;
+        if (SCORED) {
+          if (stage.cnt + 32u > kStreamStageWords / 4) stage4_flush(stage, sink);
+          stage4_push(stage, out, r, b, cq, score);
+        } else {
+          if (stage.cnt + 32u > kStreamStageWords / 3) stage_flush(stage, sink);
+          stage_push(stage, out, r, b, cq);
+        }
+      }
+      if (lane == 0) *dirty_cnt = 0;
+      __syncwarp();
+    }
+  }
+  if (SCORED) stage4_flush(stage, sink); else stage_flush(stage, sink);
   n_pairs = warp_sum64(n_pairs);
   n_edges = warp_sum64(n_edges);
   sum_count = warp_sum64(sum_count);
