@@ -133,6 +133,14 @@ int kc_get_vocab(kc_engine* e, uint32_t* kmers_out, uint32_t* freq_out, uint64_t
 int kc_get_protein_ids(kc_engine* e, uint64_t* row_offsets, uint32_t* ids_out, uint64_t capacity);
 /* Mphf::hash (src/main.rs:145,192): id of each k-mer, 0xFFFFFFFF if not a repeated k-mer */
 int kc_lookup_kmers(kc_engine* e, const uint32_t* kmers, uint64_t n, uint32_t* ids_out);
+/* The index exactly as the pair stage reads it: the minimal perfect hash the build assigned
+ * (like boomphf's ids at src/main.rs:139-147 it is an arbitrary bijection onto [0, n_repeated);
+ * kc_get_vocab / kc_get_protein_ids / kc_lookup_kmers present the canonical ascending-k-mer view).
+ * kmers_out[id] / freq_out[id] / self_out[id] (BLOSUM62 self-score) per id, row_offsets[n+1] and
+ * ids_out[nnz] = every protein's ids in input protein order, unsorted within a row.
+ * Any output pointer may be NULL. */
+int kc_get_pair_index(kc_engine* e, uint32_t* kmers_out, uint32_t* freq_out, uint8_t* self_out,
+                      uint64_t capacity_vocab, uint64_t* row_offsets, uint32_t* ids_out, uint64_t capacity_ids);
 
 /* Graph::new + remove_uninteresting_edges + combine_edges + the threshold of
  * align_and_output_pairs (src/graph/mod.rs:39-193, 549-697, 322-546, 242) in one pass;

@@ -10,6 +10,14 @@ from oracle.oracle import Oracle
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["bucket", "table"])
+def index_flavour(request, monkeypatch):
+    """every test runs against both index builds: the partitioned one (csrc/bucket.cuh) and the
+    universe-table one (csrc/index.cuh); KC_B200_INDEX overrides the engine's own choice"""
+    monkeypatch.setenv("KC_B200_INDEX", request.param)
+    return request.param
+
+
 def run_oracle(ps, k, thr, cross, blosum=True, threads=8):
     o = Oracle(k, threads)
     o.set_proteins(ps.residues, ps.offsets, ps.class_id)
@@ -520,4 +528,50 @@ def test_stream_pair_kernel_over_materialised_lists(blosum, monkeypatch, arg_set
     with kc.Engine(7, threshold=10, cross_class_only=False, want_blosum=blosum) as e:
         e.set_protein_set(ps)
         e.build_index()
+        check_pairs(e.score_pairs(), e.get_edges(), pr)
+
+
+@pytest.mark.parametrize("k,cross", [(5, True), (7, False), (7, True)])
+def test_pair_index_is_a_perfect_hash_of_the_canonical_one(k, cross, arg_set, arg_oracle):
+    """kc_get_pair_index (the ids the pair stage really uses) against the oracle's canonical index:
+    same vocabulary, same kmer_freq, same BLOSUM self-scores, same per-protein k-mer sets"""
+    ix = arg_oracle[k][2]
+    diag = np.array([9, 4, 5, 4, 6, 7, 6, 5, 5, 6, 8, 5, 5, 5, 4, 4, 4, 11, 7, 6, 0])
+    with kc.Engine(k, cross_class_only=cross, want_blosum=True) as e:
+        e.set_protein_set(arg_set)
+        e.build_index()
+        v, f, ss, ro, ids = e.get_pair_index()
+    assert np.unique(v).size == v.size == ix.vocab.size
+    order = np.argsort(v, kind="stable")
+    assert np.array_equal(v[order], ix.vocab)
+    assert np.array_equal(f[order], ix.freq)
+    digits = (v[:, None].astype(np.int64) // (21 ** np.arange(k))[None, :]) % 21
+    assert np.array_equal(ss, diag[digits].sum(axis=1))
+    assert np.array_equal(ro, ix.row_offsets)
+    canon = np.empty(v.size, dtype=np.int64)
+    canon[order] = np.arange(v.size)
+    got = canon[ids]
+    for p in (0, 1, 26, 2838, arg_set.n - 1):
+        a, b = int(ro[p]), int(ro[p + 1])
+        assert np.array_equal(np.sort(got[a:b]), ix.ids[a:b])
+    # every row at once: sort within rows via a (row, id) key
+    row_of = np.repeat(np.arange(arg_set.n), np.diff(ro).astype(np.int64))
+    key = row_of * np.int64(v.size + 1) + got
+    assert np.array_equal(np.sort(key) - row_of * np.int64(v.size + 1), ix.ids)
+
+
+def test_bucket_overflow_falls_back_to_the_table_build(index_flavour):
+    """one k-mer held by more proteins than a shared-memory bucket takes (kBkCap = 8192): the
+    partitioned build reports it and the engine builds the universe-table index instead"""
+    n = 9000
+    seq = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+    res = np.tile(seq[:9], n)
+    off = (np.arange(n + 1) * 9).astype(np.uint64)
+    cls = (np.arange(n) % 3).astype(np.uint32)
+    ps = kc.ProteinSet(res, off, cls, [], ["a", "b", "c"])
+    km, ix, pr = run_oracle(ps, 7, 3, True)
+    with kc.Engine(7, threshold=3, cross_class_only=True, want_blosum=True) as e:
+        e.set_protein_set(ps)
+        e.build_index()
+        check_index(e, ix)
         check_pairs(e.score_pairs(), e.get_edges(), pr)

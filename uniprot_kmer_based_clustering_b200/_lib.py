@@ -56,7 +56,7 @@ def stats_dict(s: C.Structure) -> dict:
 EXPORTED = [
     "kc_sample_position", "kc_abi_version", "kc_device_count", "kc_create", "kc_destroy", "kc_last_error", "kc_set_stream",
     "kc_set_proteins", "kc_set_proteins_device", "kc_extract_kmers", "kc_build_index",
-    "kc_get_distinct_kmers", "kc_get_vocab", "kc_get_protein_ids", "kc_lookup_kmers", "kc_score_pairs",
+    "kc_get_distinct_kmers", "kc_get_vocab", "kc_get_protein_ids", "kc_lookup_kmers", "kc_get_pair_index", "kc_score_pairs",
     "kc_score_pairs_shard", "kc_get_edges", "kc_get_edges_device", "kc_get_edge_kmers", "kc_get_timings", "kc_reset_timings",
     "kc_bitset_pair_counts",
     "kc_fasta_parse_file", "kc_fasta_parse_buffer", "kc_fasta_free", "kc_fasta_n_proteins",
@@ -110,6 +110,7 @@ def lib():
         "kc_get_edges": (i32, [vp, vp, u64]),
         "kc_get_edges_device": (i32, [vp, P(vp), P(u64)]),
         "kc_get_edge_kmers": (i32, [vp, u64, vp, u64]),
+        "kc_get_pair_index": (i32, [vp, vp, vp, vp, u64, vp, vp, u64]),
         "kc_get_timings": (i32, [vp, P(Timings)]),
         "kc_reset_timings": (i32, [vp]),
         "kc_bitset_pair_counts": (i32, [vp, vp, u32, vp]),

@@ -1,0 +1,392 @@
+// bucket.cuh — K3/K4/K5 for sparse k-mer universes: the index built by PARTITIONING instead of
+// by random access into universe-sized tables (index.cuh).
+//
+// Replaces (reference root relative), same stages as index.cuh:
+//   merge_sort census                        src/main.rs:23-48,103-116
+//   split unique/repeated + Mphf::new x2     src/main.rs:127-147
+//   remove_unique_five_mers + modify_hash_five_mer + kmer_freq   src/protein.rs:151-174, src/main.rs:182-193
+//   times_kmer_visited / triangular layout   src/graph/vertex.rs:92-136
+//
+// Flow (every random access is either a shared-memory access or an append through an L2-resident
+// cursor, whose 8/16-byte writes merge into full sectors in L2 before they reach HBM):
+//   1. The extract kernels (extract.cuh) append every (distinct k-mer, row) incidence to the
+//      bucket its k-mer hashes to: n_buckets fixed-size slots of kBkCap records, one cursor each.
+//   2. One CTA per bucket: hash-group the bucket in shared memory (the census: holders per
+//      k-mer), give every repeated k-mer an id and a postings range, rank-sort the holders of
+//      every k-mer, and emit postings (col), vocabulary (k-mer, freq, BLOSUM self-score per id)
+//      and one entry {row, id, postings suffix of the holders after row} per (row, repeated
+//      k-mer), appended to the entry bin of the row's 64-row block.
+//   3. One CTA per entry bin: split the bin by row into the CSR the pair stage reads (ids /
+//      suffix ranges / self-scores per row) and sum the per-row totals the row classifier needs.
+// The ids are a minimal perfect hash of the repeated k-mers in bucket order (boomphf's ids are
+// arbitrary too); the canonical (ascending k-mer) view is derived on demand.
+#pragma once
+#include "common.cuh"
+#include "extract.cuh"
+#include "index.cuh"
+
+namespace kc {
+
+constexpr uint32_t kBkSlots = 8192;   // hash slots per bucket (>= kBkCap: distinct <= incidences)
+constexpr int kBkThreads = 1024;
+constexpr int kBkPerThread = kBkCap / kBkThreads;
+constexpr uint32_t kBkTargetFill = 5120;  // mean records per bucket (62 % of a slot)
+constexpr uint32_t kBinRowsLog = 6;       // entry bins of 64 rows
+constexpr uint32_t kBinRows = 1u << kBinRowsLog;
+
+struct BucketGlobals {
+  unsigned long long col_cursor;  // postings / entries written so far (= nnz at the end)
+  unsigned long long id_cursor;   // ids handed out (= n_repeated at the end)
+  unsigned long long n_distinct, multi_total, work_total;
+  uint32_t overflow;              // some bucket was sent more than kBkCap records
+  uint32_t max_bucket;
+};
+
+// ---------------------------------------------------------------------------------------
+// The bucket kernel.  Shared memory per CTA (208 KB): the hash table of the bucket's k-mers
+// (key, counter/cursor, id|self-score, holders), the records (row, slot) and the grouped +
+// sorted holders.  The next bucket's records are prefetched into registers while the current
+// one is processed.
+// ---------------------------------------------------------------------------------------
+constexpr size_t kBkSmemBytes = (size_t)kBkSlots * (4 + 4 + 4 + 2) + (size_t)kBkCap * (4 + 2 + 4 + 2);
+
+__device__ __forceinline__ uint32_t bucket_slot_hash(uint32_t kmer) {
+  uint32_t h = kmer ^ (kmer >> 15);
+  h *= 0x2C1B3C6Du;
+  h ^= h >> 12;
+  return h & (kBkSlots - 1u);
+}
+
+template <bool CROSS>
+__global__ void __launch_bounds__(kBkThreads, 1)
+    bucket_build_kernel(const uint2* __restrict__ rec, const uint32_t* __restrict__ bucket_cnt, uint32_t n_buckets,
+                        const uint32_t* __restrict__ first_after, int k, uint32_t* __restrict__ col,
+                        uint4* __restrict__ entries, const uint32_t* __restrict__ rowcap_prefix,
+                        uint32_t* __restrict__ bin_cursor, uint32_t* __restrict__ vocab,
+                        uint32_t* __restrict__ freq, uint8_t* __restrict__ selfscore, BucketGlobals* __restrict__ g) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  uint32_t* s_key = reinterpret_cast<uint32_t*>(dyn_smem);      // [slots] k-mer
+  uint32_t* s_val = s_key + kBkSlots;                           // [slots] holders -> cursor -> group end
+  uint32_t* s_meta = s_val + kBkSlots;                          // [slots] local id | self-score << 16
+  uint32_t* s_row = s_meta + kBkSlots;                          // [cap] record rows -> sorted holders
+  uint32_t* s_col = s_row + kBkCap;                             // [cap] grouped holders (arrival order)
+  uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_col + kBkCap);  // [slots] holders
+  uint16_t* s_slot = s_cnt + kBkSlots;                          // [cap] record slots -> suffix starts (CROSS)
+  uint16_t* s_grp = s_slot + kBkCap;                            // [cap] slot of every grouped holder
+  __shared__ uint32_t s_wsum[32];
+  __shared__ unsigned long long s_base[2];
+  __shared__ uint32_t s_nnz;
+  const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+  unsigned long long n_distinct = 0, multi = 0, work = 0;
+  uint32_t max_bucket = 0;
+
+  uint2 nxt[kBkPerThread];
+  uint32_t b = blockIdx.x;
+  uint32_t n_cur = 0;
+  if (b < n_buckets) {
+    n_cur = bucket_cnt[b];
+    const uint2* src = rec + (size_t)b * kBkCap;
+#pragma unroll
+    for (int j = 0; j < kBkPerThread; ++j) {
+      const uint32_t i = tid + j * kBkThreads;
+      if (i < n_cur && n_cur <= kBkCap) nxt[j] = ld_stream_u32x2(src + i);
+    }
+  }
+  for (; b < n_buckets; b += gridDim.x) {
+    const uint32_t nrec = n_cur;
+    max_bucket = max(max_bucket, nrec);
+    // ---- P0: clear the table
+#pragma unroll
+    for (int j = 0; j < (int)(kBkSlots / kBkThreads); ++j) {
+      const uint32_t s = tid + j * kBkThreads;
+      s_key[s] = kSentinel;
+      s_val[s] = 0;
+    }
+    __syncthreads();
+    const bool ok = nrec <= kBkCap;
+    // ---- P1: insert this bucket's records (from registers), prefetch the next bucket's
+    if (ok) {
+#pragma unroll
+      for (int j = 0; j < kBkPerThread; ++j) {
+        const uint32_t i = tid + j * kBkThreads;
+        if (i < nrec) {
+          const uint32_t km = nxt[j].x;
+          uint32_t h = bucket_slot_hash(km);
+          for (;;) {
+            const uint32_t cur = s_key[h];
+            if (cur == km) break;
+            if (cur == kSentinel) {
+              const uint32_t old = atomicCAS(&s_key[h], kSentinel, km);
+              if (old == kSentinel || old == km) break;
+            }
+            h = (h + 1u) & (kBkSlots - 1u);
+          }
+          atomicAdd(&s_val[h], 1u);
+          s_slot[i] = (uint16_t)h;
+          s_row[i] = nxt[j].y;
+        }
+      }
+    } else if (tid == 0) {
+      atomicOr(&g->overflow, 1u);
+    }
+    {
+      const uint32_t bn = b + gridDim.x;
+      if (bn < n_buckets) {
+        n_cur = bucket_cnt[bn];
+        const uint2* src = rec + (size_t)bn * kBkCap;
+#pragma unroll
+        for (int j = 0; j < kBkPerThread; ++j) {
+          const uint32_t i = tid + j * kBkThreads;
+          if (i < n_cur && n_cur <= kBkCap) nxt[j] = ld_stream_u32x2(src + i);
+        }
+      }
+    }
+    __syncthreads();
+    if (!ok) continue;  // uniform: the host falls back to the universe-table index
+    // ---- P2: every thread owns kBkSlots / kBkThreads consecutive slots; block scan of
+    // (repeated k-mers, their holders) packed as holders << 16 | repeated
+    constexpr int SPT = kBkSlots / kBkThreads;
+    uint32_t cnts[SPT];
+    uint32_t local = 0;
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) {
+      const uint32_t s = tid * SPT + j;
+      const uint32_t c = s_key[s] != kSentinel ? s_val[s] : 0u;
+      cnts[j] = c;
+      s_cnt[s] = (uint16_t)c;
+      n_distinct += c != 0;
+      if (c >= 2u) {
+        local += (c << 16) | 1u;
+        multi += (unsigned long long)c * (c - 1u) / 2u;
+      }
+    }
+    uint32_t incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFullMask, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const uint32_t x = s_wsum[lane];
+      uint32_t xs = x;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFullMask, xs, o);
+        if (lane >= (uint32_t)o) xs += t;
+      }
+      s_wsum[lane] = xs - x;
+      if (lane == 31) {  // block totals: reserve the bucket's ids and postings
+        s_nnz = xs >> 16;
+        s_base[0] = atomicAdd(&g->col_cursor, (unsigned long long)(xs >> 16));
+        s_base[1] = atomicAdd(&g->id_cursor, (unsigned long long)(xs & 0xFFFFu));
+      }
+    }
+    __syncthreads();
+    const uint32_t excl = incl - local + s_wsum[warp];
+    const unsigned long long col_base = s_base[0], id_base = s_base[1];
+    const uint32_t nnz = s_nnz;
+    {
+      uint32_t lid = excl & 0xFFFFu, coff = excl >> 16;
+#pragma unroll
+      for (int j = 0; j < SPT; ++j) {
+        const uint32_t s = tid * SPT + j;
+        const uint32_t c = cnts[j];
+        if (c >= 2u) {
+          const uint32_t km = s_key[s];
+          const uint32_t ss = (uint32_t)kmer_self_score(km, k);
+          s_val[s] = coff;
+          s_meta[s] = lid | (ss << 16);
+          vocab[id_base + lid] = km;
+          freq[id_base + lid] = c;
+          selfscore[id_base + lid] = (uint8_t)ss;
+          ++lid;
+          coff += c;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- P3: group the holders of every repeated k-mer
+#pragma unroll
+    for (int j = 0; j < kBkPerThread; ++j) {
+      const uint32_t i = tid + j * kBkThreads;
+      if (i < nrec) {
+        const uint32_t s = s_slot[i];
+        if (s_cnt[s] >= 2u) {
+          const uint32_t pos = atomicAdd(&s_val[s], 1u);
+          s_col[pos] = s_row[i];
+          s_grp[pos] = (uint16_t)s;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- P4: rank-sort every group (holders are distinct rows): s_row[start + rank] = holder;
+    // CROSS: the suffix of a holder starts at the first holder of a later class block
+#pragma unroll
+    for (int j = 0; j < kBkPerThread; ++j) {
+      const uint32_t p = tid + j * kBkThreads;
+      if (p < nnz) {
+        const uint32_t s = s_grp[p];
+        const uint32_t end = s_val[s], start = end - s_cnt[s];
+        const uint32_t v = s_col[p];
+        uint32_t target = 0;
+        if (CROSS) target = first_after[v];
+        uint32_t rank = 0, below = 0;
+        for (uint32_t q = start; q < end; ++q) {
+          const uint32_t x = s_col[q];
+          rank += x < v;
+          if (CROSS) below += x < target;
+        }
+        s_row[start + rank] = v;
+        if (CROSS) s_slot[start + rank] = (uint16_t)(start + below);
+      }
+    }
+    __syncthreads();
+    // ---- P5: emit postings (contiguous per bucket) and entries (appended to the row block's bin;
+    // lanes that hit the same bin share one atomic)
+#pragma unroll
+    for (int j = 0; j < kBkPerThread; ++j) {
+      const uint32_t q = tid + j * kBkThreads;
+      const bool act = q < nnz;
+      uint32_t row = 0, bin = kSentinel;
+      uint4 ent = make_uint4(0, 0, 0, 0);
+      if (act) {
+        const uint32_t s = s_grp[q];
+        const uint32_t end = s_val[s];
+        const uint32_t a = CROSS ? (uint32_t)s_slot[q] : q + 1u;
+        row = s_row[q];
+        const uint32_t meta = s_meta[s];
+        const uint32_t len = end - a;
+        // a single partner is stored inline ({rank, sentinel}): no postings gather in the pair stage
+        const uint2 sf = len == 1u ? make_uint2(s_row[a], kSentinel)
+                                   : make_uint2((uint32_t)col_base + a, (uint32_t)col_base + end);
+        col[col_base + q] = row;
+        ent = make_uint4(row | ((meta >> 16) << 24), (uint32_t)id_base + (meta & 0xFFFFu), sf.x, sf.y);
+        work += len;
+        bin = row >> kBinRowsLog;
+      }
+      const uint32_t peers = __match_any_sync(kFullMask, bin);
+      if (act) {
+        const uint32_t leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&bin_cursor[bin], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        entries[(size_t)rowcap_prefix[bin << kBinRowsLog] + base + __popc(peers & lanemask_lt())] = ent;
+      }
+    }
+    __syncthreads();
+  }
+  n_distinct = warp_sum64(n_distinct);
+  multi = warp_sum64(multi);
+  work = warp_sum64(work);
+  if (lane == 0) {
+    if (n_distinct) atomicAdd(&g->n_distinct, n_distinct);
+    if (multi) atomicAdd(&g->multi_total, multi);
+    if (work) atomicAdd(&g->work_total, work);
+    atomicMax(&g->max_bucket, max_bucket);
+  }
+}
+
+// distinct k-mers of the rows before row r (entry capacity of the rows' bins): prefix[r], prefix[n]
+struct RowCapOut {
+  uint32_t* p;
+  uint64_t n;
+  __device__ void operator()(uint64_t i, unsigned long long excl, unsigned long long v) const {
+    p[i] = (uint32_t)excl;
+    if (i + 1 == n) p[n] = (uint32_t)(excl + v);
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// One CTA per entry bin (64 rows): count per row, CSR offsets (binptr = exclusive scan of the bin
+// fill counts), then the split into ids / suffix ranges / self-scores.  The bin is read twice (the
+// second time from L2).  Also sums what the pair stage's row classifier needs (rowwork = multi-
+// edges of the row, rowinl = inline partners, rowmaxlen = longest suffix; suffix_ranges_kernel
+// in index.cuh produces the same numbers for the table build).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    rows_finalize_kernel(const uint4* __restrict__ entries, const uint32_t* __restrict__ rowcap_prefix,
+                         const uint32_t* __restrict__ bin_cnt, const uint32_t* __restrict__ binptr, uint32_t n,
+                         uint32_t n_bins, uint32_t* __restrict__ rowptr, uint32_t* __restrict__ rowlen,
+                         uint32_t* __restrict__ ids, uint2* __restrict__ suf, uint8_t* __restrict__ sufss,
+                         unsigned long long* __restrict__ rowwork64, uint32_t* __restrict__ rowwork,
+                         uint32_t* __restrict__ rowinl, uint32_t* __restrict__ rowmaxlen) {
+  __shared__ uint32_t s_cnt[kBinRows], s_off[kBinRows], s_inl[kBinRows], s_max[kBinRows];
+  __shared__ unsigned long long s_work[kBinRows];
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t bin = blockIdx.x; bin < n_bins; bin += gridDim.x) {
+    const uint32_t r0 = bin << kBinRowsLog;
+    const uint32_t nrows = min(kBinRows, n - r0);
+    const uint4* src = entries + rowcap_prefix[r0];
+    const uint32_t cnt = bin_cnt[bin], dst0 = binptr[bin];
+    if (tid < kBinRows) {
+      s_cnt[tid] = 0;
+      s_inl[tid] = 0;
+      s_max[tid] = 0;
+      s_work[tid] = 0;
+    }
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < cnt; i0 += 1024) {
+      uint4 e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * 256 + tid < cnt) e[u] = ld_stream_u32x4(src + i0 + u * 256 + tid);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (i0 + u * 256 + tid >= cnt) continue;
+        const uint32_t lr = (e[u].x & 0xFFFFFFu) - r0;
+        const bool inl = e[u].w == kSentinel;
+        const uint32_t len = inl ? 1u : e[u].w - e[u].z;
+        atomicAdd(&s_cnt[lr], 1u);
+        if (len) atomicAdd(&s_work[lr], (unsigned long long)len);
+        if (inl) atomicAdd(&s_inl[lr], 1u);
+        else if (len > 1u) atomicMax(&s_max[lr], len);
+      }
+    }
+    __syncthreads();
+    if (tid < 32) {  // exclusive scan of the 64 row counts by one warp
+      const uint32_t c0 = s_cnt[2 * tid], c1 = s_cnt[2 * tid + 1];
+      uint32_t incl = c0 + c1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFullMask, incl, o);
+        if (tid >= (uint32_t)o) incl += t;
+      }
+      const uint32_t ex = incl - c0 - c1;
+      s_off[2 * tid] = dst0 + ex;
+      s_off[2 * tid + 1] = dst0 + ex + c0;
+    }
+    __syncthreads();
+    if (tid < nrows) {
+      const uint32_t r = r0 + tid;
+      const unsigned long long w = s_work[tid];
+      rowptr[r] = s_off[tid];
+      rowlen[r] = s_cnt[tid];
+      rowwork64[r] = w;
+      rowwork[r] = w > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)w;
+      rowinl[r] = s_inl[tid];
+      rowmaxlen[r] = s_max[tid];
+      if (r + 1 == n) rowptr[n] = dst0 + cnt;
+    }
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < cnt; i0 += 1024) {
+      uint4 e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * 256 + tid < cnt) e[u] = src[i0 + u * 256 + tid];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (i0 + u * 256 + tid >= cnt) continue;
+        const uint32_t lr = (e[u].x & 0xFFFFFFu) - r0;
+        const uint32_t pos = atomicAdd(&s_off[lr], 1u);
+        ids[pos] = e[u].y;
+        suf[pos] = make_uint2(e[u].z, e[u].w);
+        if (sufss) sufss[pos] = (uint8_t)(e[u].x >> 24);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace kc

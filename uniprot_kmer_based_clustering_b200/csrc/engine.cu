@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "extract.cuh"
 #include "index.cuh"
+#include "bucket.cuh"
 #include "pairs.cuh"
 #include "primitives.cuh"
 
@@ -56,6 +57,9 @@ struct DeviceScalars {  // one small block of u64 counters, zeroed per stage
   uint32_t shard_rows[2];
   uint32_t n_shared;
   uint32_t pad;
+  BucketGlobals bg;
+  uint32_t ent_seg[2];  // {0, nnz}: the one segment of the first entry-partition pass
+  uint32_t pad3[2];
 };
 
 enum Ev { EV_H2D0, EV_H2D1, EV_X0, EV_X1, EV_I0, EV_IC0, EV_IC1, EV_I1, EV_P0, EV_PK0, EV_PK1, EV_P1, EV_E1, EV_D0, EV_D1, EV_COUNT };
@@ -94,6 +98,15 @@ struct kc_engine {
       d_suf, d_sufss, d_rowwork, d_lists, d_colscratch, d_workprefix, d_ksplit, d_isplit, d_rowwork64, d_rowinl, d_rowmaxlen, d_psplit, d_rowbase, d_plist, d_pss;
   bool have_plist = false;
   uint32_t slice_shift = 31, n_slices = 1;
+  // partitioned index (bucket.cuh): the pair stage reads d_rowptr / d_ids / d_self_h instead of
+  // d_pstart / d_pk / d_self; the canonical view (legacy arrays) is derived on demand
+  bool bucketed = false, canonical_ready = false;
+  DBuf d_recA, d_recB, d_histA, d_histB, d_segoff, d_bucketoff, d_rowptr, d_ids, d_vocab_h, d_freq_h, d_self_h,
+      d_zero, d_rowlen_c, d_islo_c;
+  const uint32_t* pair_rowptr() const { return (bucketed ? d_rowptr : d_pstart).as<uint32_t>(); }
+  const uint32_t* pair_ids() const { return (bucketed ? d_ids : d_pk).as<uint32_t>(); }
+  const uint8_t* pair_self() const { return (bucketed ? d_self_h : d_self).as<uint8_t>(); }
+  const uint32_t* canon_rowlen() const { return (bucketed ? d_rowlen_c : d_rowlen).as<uint32_t>(); }
   // pairs
   DBuf d_rowbin, d_rowsafe, d_rowlogh, d_edges, d_keys_a, d_keys_b, d_vals_a, d_vals_b, d_hist, d_edges_sorted;
   uint64_t edge_cap = 0, n_edges = 0;
@@ -237,7 +250,7 @@ int stage_layout(kc_engine* e) {
 size_t padded_res_bytes(uint64_t R) { return (size_t)((R + kTileRes - 1) / kTileRes + 1) * kTileRes; }
 
 template <int K>
-int run_extract_census(kc_engine* e) {
+int run_extract_census(kc_engine* e, BucketScatter scatter = BucketScatter{nullptr, nullptr, 0u}) {
   const uint32_t n = (uint32_t)e->n;
   DeviceScalars* ds = e->ds;
   const uint8_t* res = e->d_res.as<uint8_t>();
@@ -248,7 +261,7 @@ int run_extract_census(kc_engine* e) {
     const uint32_t grid = blocks_for(n, kExtractWarps, e->num_sm * 5);
     KC_LAUNCH(e, extract_dedup_warp_kernel<K>, grid, kExtractWarps * 32, 0, res, e->d_pstart.as<uint32_t>(),
               e->d_plen.as<uint32_t>(), n, pk, ndist, e->slice_shift, e->n_slices, ksplit, e->cfg.sample_every,
-              e->cfg.sample_seed, e->d_orig.as<uint32_t>(), &ds->n_incid);
+              e->cfg.sample_seed, e->d_orig.as<uint32_t>(), &ds->n_incid, scatter);
   }
   if (!e->h_long.empty()) {
     const size_t smem = (size_t)e->max_block_np2 * 4 + e->max_block_len + 16;
@@ -257,14 +270,14 @@ int run_extract_census(kc_engine* e) {
     KC_LAUNCH(e, (extract_dedup_block_kernel<K, false>), (uint32_t)e->h_long.size(), 512, smem, res,
               e->d_pstart.as<uint32_t>(), e->d_plen.as<uint32_t>(), e->d_long.as<uint32_t>(), nullptr, nullptr,
               pk, ndist, n, e->slice_shift, e->n_slices, ksplit, e->cfg.sample_every, e->cfg.sample_seed,
-              e->d_orig.as<uint32_t>(), &ds->n_incid);
+              e->d_orig.as<uint32_t>(), &ds->n_incid, scatter);
   }
   if (!e->h_huge.empty()) {
     KC_LAUNCH(e, (extract_dedup_block_kernel<K, true>), (uint32_t)e->h_huge.size(), 512, 0, res,
               e->d_pstart.as<uint32_t>(), e->d_plen.as<uint32_t>(), e->d_huge.as<uint32_t>(),
               e->d_huge_off.as<unsigned long long>(), e->d_huge_scratch.as<uint32_t>(), pk, ndist, n,
               e->slice_shift, e->n_slices, ksplit, e->cfg.sample_every, e->cfg.sample_seed,
-              e->d_orig.as<uint32_t>(), &ds->n_incid);
+              e->d_orig.as<uint32_t>(), &ds->n_incid, scatter);
   }
   return KC_OK;
 }
@@ -294,7 +307,7 @@ int launch_hash(kc_engine* e, uint8_t bin, const EdgeSink& sink) {
   KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CTA_WARPS * 32, smem));
   if (per_sm < 1) per_sm = 1;
   const uint32_t grid = (uint32_t)(e->num_sm * per_sm);
-  KC_LAUNCH(e, kern, grid, CTA_WARPS * 32, smem, e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(),
+  KC_LAUNCH(e, kern, grid, CTA_WARPS * 32, smem, e->pair_rowptr(), e->d_rowlen.as<uint32_t>(),
             e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), e->d_rowbin.as<uint8_t>(), bin, (uint32_t)e->n,
             &e->ds->row_cursor[bin], e->ds->bin_counts, sink, &e->ds->pc);
   return KC_OK;
@@ -310,7 +323,7 @@ int launch_packed(kc_engine* e, uint8_t bin, uint32_t count_bits, const EdgeSink
   KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CTA_WARPS * 32, smem));
   if (per_sm < 1) per_sm = 1;
   const uint32_t grid = (uint32_t)(e->num_sm * per_sm);
-  KC_LAUNCH(e, kern, grid, CTA_WARPS * 32, smem, e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(),
+  KC_LAUNCH(e, kern, grid, CTA_WARPS * 32, smem, e->pair_rowptr(), e->d_rowlen.as<uint32_t>(),
             e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), e->d_rowbin.as<uint8_t>(), bin, (uint32_t)e->n,
             count_bits, &e->ds->row_cursor[bin], e->ds->bin_counts, sink, &e->ds->pc);
   return KC_OK;
@@ -369,6 +382,161 @@ struct ColptrOut {
 };
 
 }  // namespace
+
+
+// ---- the partitioned index build (bucket.cuh) -----------------------------------------------
+static int build_index_bucketed(kc_engine* e, kc_index_stats* stats, bool* overflow) {
+  const uint32_t n = (uint32_t)e->n;
+  const uint64_t R = e->R;
+  DeviceScalars* ds = e->ds;
+  *overflow = false;
+  unsigned long long n_positions = 0;
+  const uint32_t every = e->cfg.sample_every > 1 ? e->cfg.sample_every : 1;
+  for (uint32_t r = 0; r < n; ++r)
+    if (e->h_plen[r] >= (uint32_t)e->cfg.k) n_positions += (e->h_plen[r] - e->cfg.k + 1) / every;
+  const uint64_t E = std::max<unsigned long long>(n_positions, 1);  // upper bound on the incidences
+  const uint32_t NB = (uint32_t)((E + kBkTargetFill - 1) / kBkTargetFill);  // buckets
+  const uint32_t n_bins = (n + kBinRows - 1) >> kBinRowsLog;                // entry bins
+  KC_CUDA(e, e->d_pk.ensure((R + 64) * 4));
+  KC_CUDA(e, e->d_ndist.ensure(((uint64_t)n + 1) * 4));
+  KC_CUDA(e, e->d_rowlen.ensure(((uint64_t)n + 1) * 4));
+  KC_CUDA(e, e->d_recA.ensure((uint64_t)NB * kBkCap * 8));
+  KC_CUDA(e, e->d_recB.ensure((E + 64) * 16));
+  KC_CUDA(e, e->d_bucketoff.ensure(((uint64_t)NB + 2) * 4));                // bucket cursors
+  KC_CUDA(e, e->d_segoff.ensure(((uint64_t)n + 2) * 4));                    // rowcap prefix
+  KC_CUDA(e, e->d_histA.ensure(((uint64_t)n_bins + 2) * 4));                // bin cursors
+  KC_CUDA(e, e->d_histB.ensure(((uint64_t)n_bins + 2) * 4));                // bin CSR bases
+  KC_CUDA(e, e->d_rowptr.ensure(((uint64_t)n + 2) * 4));
+  KC_CUDA(e, e->d_ids.ensure((E + 64) * 4));
+  KC_CUDA(e, e->d_col.ensure((E + 64) * 4));
+  KC_CUDA(e, e->d_suf.ensure((E + 64) * 8));
+  if (e->cfg.want_blosum) KC_CUDA(e, e->d_sufss.ensure(E + 64));
+  KC_CUDA(e, e->d_vocab_h.ensure((E / 2 + 2) * 4));
+  KC_CUDA(e, e->d_freq_h.ensure((E / 2 + 2) * 4));
+  KC_CUDA(e, e->d_self_h.ensure(E / 2 + 16));
+  KC_CUDA(e, e->d_rowwork.ensure(((uint64_t)n + 1) * 4));
+  KC_CUDA(e, e->d_rowwork64.ensure(((uint64_t)n + 1) * 8));
+  KC_CUDA(e, e->d_rowinl.ensure(((uint64_t)n + 1) * 4));
+  KC_CUDA(e, e->d_rowmaxlen.ensure(((uint64_t)n + 1) * 4));
+  KC_CUDA(e, e->d_workprefix.ensure(((uint64_t)n + 2) * 8));
+  int rc = ensure_scan(e, (uint64_t)n + 1);
+  if (rc) return rc;
+  e->have_plist = false;
+  e->n_slices = 0;
+  uint32_t* bucket_cnt = e->d_bucketoff.as<uint32_t>();
+  uint32_t* rowcap = e->d_segoff.as<uint32_t>();
+  uint32_t* bin_cnt = e->d_histA.as<uint32_t>();
+  uint32_t* binptr = e->d_histB.as<uint32_t>();
+  uint2* rec = e->d_recA.as<uint2>();
+  uint4* ent = e->d_recB.as<uint4>();
+
+  mark(e, EV_I0);
+  KC_CUDA(e, cudaMemsetAsync(ds, 0, sizeof(DeviceScalars), e->stream));
+  KC_CUDA(e, cudaMemsetAsync(bucket_cnt, 0, ((uint64_t)NB + 1) * 4, e->stream));
+  KC_CUDA(e, cudaMemsetAsync(bin_cnt, 0, ((uint64_t)n_bins + 1) * 4, e->stream));
+  // K1/K2: extract + per-protein dedup; every (distinct k-mer, row) is appended to its bucket
+  mark(e, EV_IC0);
+  {
+    DBuf none;
+    std::swap(none, e->d_ksplit);  // the rows are not sliced: run_extract_census passes ksplit = null
+    const BucketScatter scatter{rec, bucket_cnt, NB};
+    rc = e->cfg.k == 5 ? run_extract_census<5>(e, scatter) : run_extract_census<7>(e, scatter);
+    std::swap(none, e->d_ksplit);
+    if (rc) return rc;
+  }
+  mark(e, EV_IC1);
+  // entry capacity of every row block: the rows' distinct k-mers
+  e->launches += exclusive_scan(U32In{e->d_ndist.as<uint32_t>()}, RowCapOut{rowcap, n}, n, e->scan, e->stream);
+  // buckets: census, ids, postings, entries
+  {
+    const uint32_t grid = std::min<uint32_t>(NB, (uint32_t)e->num_sm);
+    const uint32_t* fa = e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr;
+#define KC_BUCKETS(CROSS)                                                                                       \
+  do {                                                                                                          \
+    KC_CUDA(e, cudaFuncSetAttribute(bucket_build_kernel<CROSS>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                    (int)kBkSmemBytes));                                                        \
+    KC_LAUNCH(e, bucket_build_kernel<CROSS>, grid, kBkThreads, kBkSmemBytes, rec, bucket_cnt, NB, fa, e->cfg.k, \
+              e->d_col.as<uint32_t>(), ent, rowcap, bin_cnt, e->d_vocab_h.as<uint32_t>(),                       \
+              e->d_freq_h.as<uint32_t>(), e->d_self_h.as<uint8_t>(), &ds->bg);                                  \
+  } while (0)
+    if (fa) KC_BUCKETS(true); else KC_BUCKETS(false);
+#undef KC_BUCKETS
+  }
+  // entry bins -> CSR
+  e->launches += exclusive_scan(U32In{bin_cnt}, U32ExclOut{binptr}, n_bins, e->scan, e->stream);
+  KC_LAUNCH(e, rows_finalize_kernel, std::min<uint32_t>(n_bins, (uint32_t)e->num_sm * 8), 256, 0, ent, rowcap, bin_cnt,
+            binptr, n, n_bins, e->d_rowptr.as<uint32_t>(), e->d_rowlen.as<uint32_t>(), e->d_ids.as<uint32_t>(),
+            e->d_suf.as<uint2>(), e->cfg.want_blosum ? e->d_sufss.as<uint8_t>() : nullptr,
+            e->d_rowwork64.as<unsigned long long>(), e->d_rowwork.as<uint32_t>(), e->d_rowinl.as<uint32_t>(),
+            e->d_rowmaxlen.as<uint32_t>());
+  e->launches += exclusive_scan(WorkIn{e->d_rowwork.as<uint32_t>(), e->d_rowlen.as<uint32_t>()},
+                                U64ExclOutWithTail{e->d_workprefix.as<unsigned long long>(), n}, n, e->scan, e->stream);
+  mark(e, EV_I1);
+  DeviceScalars hs{};
+  KC_CUDA(e, cudaMemcpyAsync(&hs, ds, sizeof(hs), cudaMemcpyDeviceToHost, e->stream));
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  KC_CUDA(e, cudaGetLastError());
+  if (hs.bg.overflow) {
+    *overflow = true;
+    return KC_OK;
+  }
+  e->istats.n_positions = n_positions;
+  e->istats.n_incidences = hs.n_incid;
+  e->istats.n_distinct = hs.bg.n_distinct;
+  e->istats.n_repeated = hs.bg.id_cursor;
+  e->istats.n_singleton = hs.bg.n_distinct - hs.bg.id_cursor;
+  e->istats.nnz = hs.bg.col_cursor;
+  e->multi_total = hs.bg.multi_total;
+  e->work_total = hs.bg.work_total;
+  if (stats) *stats = e->istats;
+  e->bucketed = true;
+  e->canonical_ready = false;
+  e->have_index = true;
+  return KC_OK;
+}
+
+// The canonical view of a partitioned index: ascending-k-mer ids, sorted id rows, kmer_freq by
+// canonical id — the universe-table stages of index.cuh, unsliced, run on demand for the readback
+// / lookup entry points (never on the hot path).  d_pk still holds every row's sorted distinct
+// k-mers; it is rewritten to canonical ids in place exactly like the table build does.
+static int ensure_canonical(kc_engine* e) {
+  if (!e->bucketed || e->canonical_ready) return KC_OK;
+  const uint32_t n = (uint32_t)e->n;
+  const uint64_t W = e->n_words, V = e->istats.n_repeated;
+  DeviceScalars* ds = e->ds;
+  KC_CUDA(e, e->d_seen.ensure(W * 8));
+  KC_CUDA(e, e->d_dict.ensure(W * 8));
+  KC_CUDA(e, e->d_zero.ensure(((uint64_t)n + 1) * 4));
+  KC_CUDA(e, e->d_rowlen_c.ensure(((uint64_t)n + 1) * 4));
+  KC_CUDA(e, e->d_islo_c.ensure(((uint64_t)n + 1) * 4));
+  KC_CUDA(e, e->d_vocab.ensure((V + 1) * 4));
+  KC_CUDA(e, e->d_freq.ensure((V + 1) * 4));
+  KC_CUDA(e, e->d_self.ensure(V + 16));
+  int rc = ensure_scan(e, std::max<uint64_t>(W, (uint64_t)n + 1));
+  if (rc) return rc;
+  KC_CUDA(e, cudaMemsetAsync(e->d_seen.p, 0, W * 8, e->stream));
+  KC_CUDA(e, cudaMemsetAsync(e->d_zero.p, 0, ((uint64_t)n + 1) * 4, e->stream));
+  KC_CUDA(e, cudaMemsetAsync(e->d_rowlen_c.p, 0, ((uint64_t)n + 1) * 4, e->stream));
+  KC_CUDA(e, cudaMemsetAsync(e->d_freq.p, 0, (V + 1) * 4, e->stream));
+  const uint32_t grid = blocks_for(n, 8, e->num_sm * 8);
+  KC_LAUNCH(e, (census_pass_kernel<32, false>), grid, 256, 0, e->d_pk.as<uint32_t>(), e->d_pstart.as<uint32_t>(),
+            e->d_zero.as<uint32_t>(), e->d_ndist.as<uint32_t>(), n, e->d_seen.as<uint32_t>());
+  e->launches += exclusive_scan(PopcIn<1>{e->d_seen.as<uint32_t>()},
+                                DictOut<1>{e->d_seen.as<uint32_t>(), e->d_dict.as<uint2>()}, W, e->scan, e->stream);
+  unsigned long long v_check = 0;
+  KC_CUDA(e, cudaMemcpyAsync(&v_check, &ds->scan_total, 8, cudaMemcpyDeviceToHost, e->stream));
+  if (V)
+    KC_LAUNCH(e, expand_bitmap_kernel, blocks_for(W, 256, e->num_sm * 16), 256, 0, e->d_dict.as<uint2>(), W,
+              e->d_vocab.as<uint32_t>(), e->d_self.as<uint8_t>(), e->cfg.k);
+  KC_LAUNCH(e, ids_freq_kernel<32>, grid, 256, 0, e->d_dict.as<uint2>(), e->d_pstart.as<uint32_t>(),
+            e->d_zero.as<uint32_t>(), e->d_ndist.as<uint32_t>(), n, e->d_pk.as<uint32_t>(),
+            e->d_rowlen_c.as<uint32_t>(), e->d_islo_c.as<uint32_t>(), nullptr, e->d_freq.as<uint32_t>(), &ds->nnz);
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  KC_CUDA(e, cudaGetLastError());
+  if (v_check != V) return fail(e, KC_ECUDA, "partitioned index and canonical view disagree on the vocabulary size");
+  e->canonical_ready = true;
+  return KC_OK;
+}
 
 // =========================================================================================
 extern "C" {
@@ -442,7 +610,9 @@ void kc_destroy(kc_engine* e) {
                  &e->d_first_after, &e->d_long, &e->d_huge, &e->d_huge_off, &e->d_huge_scratch, &e->d_pk,
                  &e->d_ndist, &e->d_rowlen, &e->d_seen, &e->d_dict, &e->d_vocab, &e->d_freq,
                  &e->d_self, &e->d_colptr, &e->d_cursor, &e->d_col, &e->d_suf, &e->d_sufss, &e->d_rowwork, &e->d_lists,
-                 &e->d_colscratch, &e->d_workprefix, &e->d_ksplit, &e->d_isplit, &e->d_rowwork64, &e->d_rowinl, &e->d_rowmaxlen, &e->d_psplit, &e->d_rowbase, &e->d_plist, &e->d_pss, &e->d_rowbin, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
+                 &e->d_colscratch, &e->d_workprefix, &e->d_ksplit, &e->d_isplit, &e->d_rowwork64, &e->d_rowinl, &e->d_rowmaxlen, &e->d_psplit, &e->d_rowbase, &e->d_plist, &e->d_pss,
+                 &e->d_recA, &e->d_recB, &e->d_histA, &e->d_histB, &e->d_segoff, &e->d_bucketoff, &e->d_rowptr, &e->d_ids,
+                 &e->d_vocab_h, &e->d_freq_h, &e->d_self_h, &e->d_zero, &e->d_rowlen_c, &e->d_islo_c, &e->d_rowbin, &e->d_rowsafe, &e->d_rowlogh, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
                  &e->d_vals_a, &e->d_vals_b, &e->d_hist, &e->d_edges_sorted, &e->d_scalars, &e->d_scan_tiles,
                  &e->d_tmp};
   for (DBuf* b : all) b->release();
@@ -554,6 +724,22 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
   const uint64_t R = e->R, W = e->n_words;
   DeviceScalars* ds = e->ds;
   e->have_index = e->have_pairs = false;
+  e->bucketed = e->canonical_ready = false;
+  {
+    // Index flavour: the partitioned build (bucket.cuh) for sparse universes (k = 7: 21^7 k-mers,
+    // random access into universe-sized tables misses L2), the universe-table build (index.cuh)
+    // for k = 5.  KC_B200_INDEX=bucket|table overrides (tests run both).
+    const char* env = std::getenv("KC_B200_INDEX");
+    bool want = e->cfg.k == 7;
+    if (env && !std::strcmp(env, "bucket")) want = true;
+    if (env && !std::strcmp(env, "table")) want = false;
+    if (want && n > 0 && n <= (1u << 24)) {
+      bool overflow = false;
+      int rc = build_index_bucketed(e, stats, &overflow);
+      if (rc != KC_OK || !overflow) return rc;
+      // a k-mer (or a clump of them) with more holders than a shared-memory bucket takes: table build
+    }
+  }
   KC_CUDA(e, e->d_pk.ensure((R + 64) * 4));
   KC_CUDA(e, e->d_ndist.ensure(((uint64_t)n + 1) * 4));
   KC_CUDA(e, e->d_rowlen.ensure(((uint64_t)n + 1) * 4));
@@ -783,6 +969,7 @@ int kc_get_distinct_kmers(kc_engine* e, uint32_t* out, uint64_t capacity) {
   if (!e->have_index) return fail(e, KC_EINVAL, "kc_build_index first");
   if (capacity < e->istats.n_distinct) return fail(e, KC_EINVAL, "capacity too small");
   KC_CUDA(e, cudaSetDevice(e->dev));
+  if (int rc = ensure_canonical(e)) return rc;
   const uint64_t W = e->n_words, D = e->istats.n_distinct;
   DBuf dict1, list;
   cudaError_t a = dict1.ensure(W * 8), b = list.ensure((D + 1) * 4);
@@ -809,6 +996,7 @@ int kc_get_vocab(kc_engine* e, uint32_t* kmers_out, uint32_t* freq_out, uint64_t
   const uint64_t V = e->istats.n_repeated;
   if (capacity < V) return fail(e, KC_EINVAL, "capacity too small");
   KC_CUDA(e, cudaSetDevice(e->dev));
+  if (int rc = ensure_canonical(e)) return rc;
   if (kmers_out && V) KC_CUDA(e, cudaMemcpyAsync(kmers_out, e->d_vocab.p, V * 4, cudaMemcpyDeviceToHost, e->stream));
   if (freq_out && V) KC_CUDA(e, cudaMemcpyAsync(freq_out, e->d_freq.p, V * 4, cudaMemcpyDeviceToHost, e->stream));
   KC_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -819,9 +1007,10 @@ int kc_get_protein_ids(kc_engine* e, uint64_t* row_offsets, uint32_t* ids_out, u
   if (!e || !row_offsets) return KC_EINVAL;
   if (!e->have_index) return fail(e, KC_EINVAL, "kc_build_index first");
   KC_CUDA(e, cudaSetDevice(e->dev));
+  if (int rc = ensure_canonical(e)) return rc;
   const uint32_t n = (uint32_t)e->n;
   std::vector<uint32_t> rowlen(n);
-  if (n) KC_CUDA(e, cudaMemcpyAsync(rowlen.data(), e->d_rowlen.p, (uint64_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (n) KC_CUDA(e, cudaMemcpyAsync(rowlen.data(), e->canon_rowlen(), (uint64_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
   KC_CUDA(e, cudaStreamSynchronize(e->stream));
   row_offsets[0] = 0;
   for (uint32_t p = 0; p < n; ++p) row_offsets[p + 1] = row_offsets[p] + rowlen[e->h_rank[p]];
@@ -838,7 +1027,7 @@ int kc_get_protein_ids(kc_engine* e, uint64_t* row_offsets, uint32_t* ids_out, u
   }
   cudaMemcpyAsync(d_ro.p, row_offsets, ((uint64_t)n + 1) * 8, cudaMemcpyHostToDevice, e->stream);
   KC_LAUNCH(e, compact_rows_kernel, blocks_for(n, 8, e->num_sm * 8), 256, 0, e->d_pstart.as<uint32_t>(),
-            e->d_rowlen.as<uint32_t>(), d_ro.as<unsigned long long>(), e->d_rank.as<uint32_t>(), n,
+            e->canon_rowlen(), d_ro.as<unsigned long long>(), e->d_rank.as<uint32_t>(), n,
             e->d_pk.as<uint32_t>(), d_out.as<uint32_t>());
   cudaError_t rc = cudaMemcpyAsync(ids_out, d_out.p, nnz * 4, cudaMemcpyDeviceToHost, e->stream);
   if (rc == cudaSuccess) rc = cudaStreamSynchronize(e->stream);
@@ -853,6 +1042,7 @@ int kc_lookup_kmers(kc_engine* e, const uint32_t* kmers, uint64_t n, uint32_t* i
   if (!e->have_index) return fail(e, KC_EINVAL, "kc_build_index first");
   if (!n) return KC_OK;
   KC_CUDA(e, cudaSetDevice(e->dev));
+  if (int rc = ensure_canonical(e)) return rc;
   KC_CUDA(e, e->d_tmp.ensure(n * 8));
   uint32_t* d_in = e->d_tmp.as<uint32_t>();
   uint32_t* d_out = d_in + n;
@@ -861,6 +1051,48 @@ int kc_lookup_kmers(kc_engine* e, const uint32_t* kmers, uint64_t n, uint32_t* i
             e->universe, d_out);
   KC_CUDA(e, cudaMemcpyAsync(ids_out, d_out, n * 4, cudaMemcpyDeviceToHost, e->stream));
   KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  return KC_OK;
+}
+
+int kc_get_pair_index(kc_engine* e, uint32_t* kmers_out, uint32_t* freq_out, uint8_t* self_out,
+                      uint64_t capacity_vocab, uint64_t* row_offsets, uint32_t* ids_out, uint64_t capacity_ids) {
+  if (!e) return KC_EINVAL;
+  if (!e->have_index) return fail(e, KC_EINVAL, "kc_build_index first");
+  KC_CUDA(e, cudaSetDevice(e->dev));
+  const uint64_t V = e->istats.n_repeated;
+  const uint32_t n = (uint32_t)e->n;
+  if ((kmers_out || freq_out || self_out) && capacity_vocab < V) return fail(e, KC_EINVAL, "capacity too small");
+  const DBuf& vb = e->bucketed ? e->d_vocab_h : e->d_vocab;
+  const DBuf& fb = e->bucketed ? e->d_freq_h : e->d_freq;
+  if (kmers_out && V) KC_CUDA(e, cudaMemcpyAsync(kmers_out, vb.p, V * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (freq_out && V) KC_CUDA(e, cudaMemcpyAsync(freq_out, fb.p, V * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (self_out && V) KC_CUDA(e, cudaMemcpyAsync(self_out, e->pair_self(), V, cudaMemcpyDeviceToHost, e->stream));
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (!row_offsets) return KC_OK;
+  std::vector<uint32_t> rowlen(n);
+  if (n) KC_CUDA(e, cudaMemcpyAsync(rowlen.data(), e->d_rowlen.p, (uint64_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  row_offsets[0] = 0;
+  for (uint32_t p = 0; p < n; ++p) row_offsets[p + 1] = row_offsets[p] + rowlen[e->h_rank[p]];
+  const uint64_t nnz = row_offsets[n];
+  if (!ids_out || !nnz) return KC_OK;
+  if (capacity_ids < nnz) return fail(e, KC_EINVAL, "capacity too small");
+  DBuf d_ro, d_out;
+  cudaError_t a = d_ro.ensure(((uint64_t)n + 1) * 8), b = d_out.ensure(nnz * 4);
+  if (a != cudaSuccess || b != cudaSuccess) {
+    d_ro.release();
+    d_out.release();
+    return fail(e, KC_ENOMEM, "out of device memory");
+  }
+  cudaMemcpyAsync(d_ro.p, row_offsets, ((uint64_t)n + 1) * 8, cudaMemcpyHostToDevice, e->stream);
+  KC_LAUNCH(e, compact_rows_kernel, blocks_for(n, 8, e->num_sm * 8), 256, 0, e->pair_rowptr(),
+            e->d_rowlen.as<uint32_t>(), d_ro.as<unsigned long long>(), e->d_rank.as<uint32_t>(), n, e->pair_ids(),
+            d_out.as<uint32_t>());
+  cudaError_t rc = cudaMemcpyAsync(ids_out, d_out.p, nnz * 4, cudaMemcpyDeviceToHost, e->stream);
+  if (rc == cudaSuccess) rc = cudaStreamSynchronize(e->stream);
+  d_ro.release();
+  d_out.release();
+  KC_CUDA(e, rc);
   return KC_OK;
 }
 
@@ -944,7 +1176,7 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
       KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairs_main_scored_kernel, kScoredWarps * 32, smem));
       if (per_sm < 1) per_sm = 1;
       KC_LAUNCH(e, pairs_main_scored_kernel, (uint32_t)(e->num_sm * per_sm), kScoredWarps * 32, smem,
-                e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(), e->d_suf.as<uint2>(),
+                e->pair_rowptr(), e->d_rowlen.as<uint32_t>(), e->d_suf.as<uint2>(),
                 e->d_sufss.as<uint8_t>(), e->d_col.as<uint32_t>(), e->d_rowbin.as<uint8_t>(),
                 e->d_rowsafe.as<uint8_t>(), n, &ds->row_cursor[kBinMain], &ds->n_overflow, ds->bin_counts, sink,
                 &ds->pc);
@@ -955,7 +1187,7 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
       KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairs_main_kernel, kMainWarps * 32, smem));
       if (per_sm < 1) per_sm = 1;
       KC_LAUNCH(e, pairs_main_kernel, (uint32_t)(e->num_sm * per_sm), kMainWarps * 32, smem,
-                e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(), e->d_suf.as<uint2>(),
+                e->pair_rowptr(), e->d_rowlen.as<uint32_t>(), e->d_suf.as<uint2>(),
                 e->d_col.as<uint32_t>(), e->d_rowbin.as<uint8_t>(), e->d_rowsafe.as<uint8_t>(),
                 e->d_rowlogh.as<uint8_t>(), n, count_bits, &ds->row_cursor[kBinMain], &ds->n_overflow,
                 ds->bin_counts, sink, &ds->pc);
@@ -983,11 +1215,11 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
       const uint32_t grid = (uint32_t)(e->num_sm * per_sm);
       const uint32_t* fa = e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr;
       if (wide)
-        KC_LAUNCH(e, pairs_dense_kernel<true>, grid, 256, dense_smem, e->d_pstart.as<uint32_t>(),
+        KC_LAUNCH(e, pairs_dense_kernel<true>, grid, 256, dense_smem, e->pair_rowptr(),
                   e->d_rowlen.as<uint32_t>(), e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), fa,
                   e->d_rowbin.as<uint8_t>(), n, dense_cols, &ds->row_cursor[kBinDense], ds->bin_counts, sink, &ds->pc);
       else
-        KC_LAUNCH(e, pairs_dense_kernel<false>, grid, 256, dense_smem, e->d_pstart.as<uint32_t>(),
+        KC_LAUNCH(e, pairs_dense_kernel<false>, grid, 256, dense_smem, e->pair_rowptr(),
                   e->d_rowlen.as<uint32_t>(), e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), fa,
                   e->d_rowbin.as<uint8_t>(), n, dense_cols, &ds->row_cursor[kBinDense], ds->bin_counts, sink, &ds->pc);
     }
@@ -1058,12 +1290,12 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
       unsigned long long* svals = (in_b ? e->d_vals_b : e->d_vals_a).as<unsigned long long>();
       if (small_rows)
         KC_LAUNCH(e, (edge_blosum_kernel<1024, 22>), bgrid, 128, 0, skeys, svals, ne, e->d_rank.as<uint32_t>(),
-                  e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(), e->d_pk.as<uint32_t>(),
-                  e->d_self.as<uint8_t>());
+                  e->pair_rowptr(), e->d_rowlen.as<uint32_t>(), e->pair_ids(),
+                  e->pair_self());
       else
         KC_LAUNCH(e, (edge_blosum_kernel<2048, 21>), bgrid, 128, 0, skeys, svals, ne, e->d_rank.as<uint32_t>(),
-                  e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(), e->d_pk.as<uint32_t>(),
-                  e->d_self.as<uint8_t>());
+                  e->pair_rowptr(), e->d_rowlen.as<uint32_t>(), e->pair_ids(),
+                  e->pair_self());
     }
     KC_LAUNCH(e, assemble_edges_kernel, blocks_for(ne, 256, e->num_sm * 8), 256, 0,
               (in_b ? e->d_keys_b : e->d_keys_a).as<unsigned long long>(),
@@ -1105,13 +1337,14 @@ int kc_get_edge_kmers(kc_engine* e, uint64_t edge_index, uint32_t* kmers_out, ui
   if (!e->have_pairs) return fail(e, KC_EINVAL, "kc_score_pairs first");
   if (edge_index >= e->n_edges) return fail(e, KC_EINVAL, "edge index out of range");
   KC_CUDA(e, cudaSetDevice(e->dev));
+  if (int rc = ensure_canonical(e)) return rc;
   uint4 ed;
   KC_CUDA(e, cudaMemcpyAsync(&ed, e->d_edges_sorted.as<uint4>() + edge_index, 16, cudaMemcpyDeviceToHost, e->stream));
   KC_CUDA(e, cudaStreamSynchronize(e->stream));
   if (capacity < ed.z) return fail(e, KC_EINVAL, "capacity too small");
   KC_CUDA(e, e->d_tmp.ensure((uint64_t)ed.z * 4 + 16));
   KC_LAUNCH(e, shared_kmers_kernel, 1, 32, 0, e->h_rank[ed.x], e->h_rank[ed.y], e->d_pstart.as<uint32_t>(),
-            e->d_rowlen.as<uint32_t>(), e->d_pk.as<uint32_t>(), e->d_vocab.as<uint32_t>(), e->d_tmp.as<uint32_t>(),
+            e->canon_rowlen(), e->d_pk.as<uint32_t>(), e->d_vocab.as<uint32_t>(), e->d_tmp.as<uint32_t>(),
             ed.z, &e->ds->n_shared);
   KC_CUDA(e, cudaMemcpyAsync(kmers_out, e->d_tmp.p, (uint64_t)ed.z * 4, cudaMemcpyDeviceToHost, e->stream));
   KC_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -1149,6 +1382,7 @@ int kc_bitset_pair_counts(kc_engine* e, const uint32_t* rows, uint32_t n_rows, u
   for (uint32_t i = 0; i < n_rows; ++i)
     if (rows[i] >= e->n) return fail(e, KC_EINVAL, "row out of range");
   KC_CUDA(e, cudaSetDevice(e->dev));
+  if (int rc = ensure_canonical(e)) return rc;
   const uint32_t words = (uint32_t)((e->istats.n_repeated + 31) / 32) + 1;
   std::vector<uint32_t> ranks(n_rows);
   for (uint32_t i = 0; i < n_rows; ++i) ranks[i] = e->h_rank[rows[i]];
@@ -1164,7 +1398,7 @@ int kc_bitset_pair_counts(kc_engine* e, const uint32_t* rows, uint32_t n_rows, u
   cudaMemcpyAsync(d_rows.p, ranks.data(), (size_t)n_rows * 4, cudaMemcpyHostToDevice, e->stream);
   cudaMemsetAsync(d_bits.p, 0, (size_t)n_rows * words * 4, e->stream);
   KC_LAUNCH(e, bitset_fill_kernel, blocks_for(n_rows, 8, e->num_sm * 8), 256, 0, d_rows.as<uint32_t>(), n_rows,
-            e->d_pstart.as<uint32_t>(), e->d_rowlen.as<uint32_t>(), e->d_pk.as<uint32_t>(), words,
+            e->d_pstart.as<uint32_t>(), e->canon_rowlen(), e->d_pk.as<uint32_t>(), words,
             d_bits.as<uint32_t>());
   const uint32_t tiles = (n_rows + kBitTile - 1) / kBitTile;
   KC_LAUNCH(e, bitset_pairs_kernel, dim3(tiles, tiles), kBitTile * 32, 0, d_bits.as<uint32_t>(), n_rows, words,

@@ -14,6 +14,24 @@ namespace kc {
 
 __constant__ uint8_t c_residue_lut[256];
 
+// ---- partitioned index (bucket.cuh): the extract kernels append every (distinct k-mer, row)
+// incidence to the bucket its k-mer hashes to
+constexpr uint32_t kBkCap = 8192;  // records per bucket slot
+__host__ __device__ __forceinline__ uint32_t kmer_bucket_hash(uint32_t kmer) { return kmer * 0x9E3779B1u; }
+
+// where the extract kernels append the incidences (rec == nullptr: the universe-table build)
+struct BucketScatter {
+  uint2* rec;          // n_buckets slots of kBkCap {k-mer, row} records
+  uint32_t* cursor;    // records appended per bucket (may pass kBkCap: overflow, the build falls back)
+  uint32_t n_buckets;
+  __device__ __forceinline__ void put(uint32_t kmer, uint32_t row) const {
+    const uint32_t b = __umulhi(kmer_bucket_hash(kmer), n_buckets);
+    const uint32_t pos = atomicAdd(&cursor[b], 1u);
+    if (pos < kBkCap) rec[(size_t)b * kBkCap + pos] = make_uint2(kmer, row);
+  }
+};
+
+
 // ---- census: two bits of state per k-mer, interleaved in one word (16 k-mers per u32):
 // bit 2j = "held by >= 1 protein", bit 2j+1 = "held by >= 2 proteins".  The first holder sets
 // the low bit; every later holder (a different protein, because the caller has deduplicated
@@ -37,6 +55,7 @@ __device__ __forceinline__ void census_mark(uint32_t kmer, uint32_t* __restrict_
 // over one slice reads one contiguous run of each row without searching.
 __device__ __forceinline__ void record_slice_starts(uint32_t* __restrict__ ksplit, uint32_t n, uint32_t r,
                                                     uint32_t q_from, uint32_t q_to, uint32_t j) {
+  if (!ksplit) return;  // the partitioned index (bucket.cuh) does not slice the rows
   for (uint32_t q = q_from; q <= q_to; ++q) ksplit[(size_t)q * n + r] = j;
 }
 
@@ -162,7 +181,8 @@ __global__ void __launch_bounds__(kExtractWarps * 32)
                               const uint32_t* __restrict__ plen, uint32_t n, uint32_t* __restrict__ pk,
                               uint32_t* __restrict__ ndist, uint32_t slice_shift, uint32_t n_slices,
                               uint32_t* __restrict__ ksplit, uint32_t sample_every, unsigned long long sample_seed,
-                              const uint32_t* __restrict__ orig_of, unsigned long long* __restrict__ n_incid) {
+                              const uint32_t* __restrict__ orig_of, unsigned long long* __restrict__ n_incid,
+                              BucketScatter scatter) {
   __shared__ uint8_t s_lut[256];
   __shared__ __align__(16) uint32_t s_keys[kExtractWarps][kWarpMaxPos];
   __shared__ __align__(4) uint8_t s_codes[kExtractWarps][kWarpMaxPos + 8];
@@ -177,7 +197,8 @@ __global__ void __launch_bounds__(kExtractWarps * 32)
     const uint32_t len = plen[r];
     if (len < (uint32_t)K) {
       if (lane == 0) ndist[r] = 0;
-      for (uint32_t q = lane; q <= n_slices; q += 32) ksplit[(size_t)q * n + r] = 0;
+      if (ksplit)
+        for (uint32_t q = lane; q <= n_slices; q += 32) ksplit[(size_t)q * n + r] = 0;
       continue;
     }
     const uint32_t npos_all = len - K + 1;
@@ -186,7 +207,8 @@ __global__ void __launch_bounds__(kExtractWarps * 32)
     const uint32_t npos = sample_every > 1 ? npos_all / sample_every : npos_all;
     if (npos == 0) {
       if (lane == 0) ndist[r] = 0;
-      for (uint32_t q = lane; q <= n_slices; q += 32) ksplit[(size_t)q * n + r] = 0;
+      if (ksplit)
+        for (uint32_t q = lane; q <= n_slices; q += 32) ksplit[(size_t)q * n + r] = 0;
       continue;
     }
     const uint32_t ps = pstart[r];
@@ -216,12 +238,14 @@ __global__ void __launch_bounds__(kExtractWarps * 32)
         const uint32_t j = base + __popc(m & lanemask_lt());
         pk[ps + j] = v;
         record_slice_starts(ksplit, n, r, i == 0 ? 0u : (keys[i - 1] >> slice_shift) + 1u, v >> slice_shift, j);
+        if (scatter.rec) scatter.put(v, r);
       }
       base += __popc(m);
     }
     if (lane == 0) ndist[r] = base;
-    for (uint32_t q = (keys[npos - 1] >> slice_shift) + 1u + lane; q <= n_slices; q += 32)
-      ksplit[(size_t)q * n + r] = base;
+    if (ksplit)
+      for (uint32_t q = (keys[npos - 1] >> slice_shift) + 1u + lane; q <= n_slices; q += 32)
+        ksplit[(size_t)q * n + r] = base;
     incid += base;
     __syncwarp();
   }
@@ -240,7 +264,8 @@ __global__ void __launch_bounds__(512)
                                uint32_t* __restrict__ scratch, uint32_t* __restrict__ pk,
                                uint32_t* __restrict__ ndist, uint32_t n, uint32_t slice_shift, uint32_t n_slices,
                                uint32_t* __restrict__ ksplit, uint32_t sample_every, unsigned long long sample_seed,
-                               const uint32_t* __restrict__ orig_of, unsigned long long* __restrict__ n_incid) {
+                               const uint32_t* __restrict__ orig_of, unsigned long long* __restrict__ n_incid,
+                               BucketScatter scatter) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ uint8_t s_lut[256];
   __shared__ uint32_t s_wcnt[32];
@@ -301,11 +326,13 @@ __global__ void __launch_bounds__(512)
       const uint32_t j = base + __popc(m & lanemask_lt());
       pk[ps + j] = v;
       record_slice_starts(ksplit, n, r, i == 0 ? 0u : (keys[i - 1] >> slice_shift) + 1u, v >> slice_shift, j);
+      if (scatter.rec) scatter.put(v, r);
     }
     base += __popc(m);
   }
-  for (uint32_t q = (keys[npos - 1] >> slice_shift) + 1u + threadIdx.x; q <= n_slices; q += blockDim.x)
-    ksplit[(size_t)q * n + r] = total;
+  if (ksplit)
+    for (uint32_t q = (keys[npos - 1] >> slice_shift) + 1u + threadIdx.x; q <= n_slices; q += blockDim.x)
+      ksplit[(size_t)q * n + r] = total;
   if (threadIdx.x == 0) {
     ndist[r] = total;
     atomicAdd(n_incid, (unsigned long long)total);

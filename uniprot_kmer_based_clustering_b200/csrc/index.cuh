@@ -55,12 +55,12 @@ __global__ void popc_reduce_kernel(const uint32_t* __restrict__ bits, uint64_t n
   if (lane_id() == 0 && s) atomicAdd(total, s);
 }
 
+// B62[r][r] in the reference's residue order (src/blosum.rs:8-30 diagonal); code 20 -> 0
+__constant__ uint8_t c_blosum_diag[21] = {9, 4, 5, 4, 6, 7, 6, 5, 5, 6, 8, 5, 5, 5, 4, 4, 4, 11, 7, 6, 0};
 __device__ __forceinline__ int kmer_self_score(uint32_t kmer, int k) {
-  // B62[r][r] in the reference's residue order (src/blosum.rs:8-30 diagonal); code 20 -> 0
-  const int diag[21] = {9, 4, 5, 4, 6, 7, 6, 5, 5, 6, 8, 5, 5, 5, 4, 4, 4, 11, 7, 6, 0};
   int s = 0;
   for (int i = 0; i < k; ++i) {
-    s += diag[kmer % 21u];
+    s += c_blosum_diag[kmer % 21u];
     kmer /= 21u;
   }
   return s;

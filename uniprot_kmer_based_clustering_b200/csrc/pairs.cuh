@@ -1313,34 +1313,47 @@ __global__ void __launch_bounds__(128)
       const uint32_t a = __shfl_sync(kFullMask, m_a, l);
       const uint32_t pa = __shfl_sync(kFullMask, m_pa, l), na_l = __shfl_sync(kFullMask, m_na, l);
       if (!((need >> l) & 1u)) continue;
+      // hash (a chunk of) row a's ids into the warp's table: id -> self-score
+      auto build = [&](uint32_t c0, uint32_t c1) {
+        __syncwarp();
+        for (uint32_t i = lane * 4; i < SLOTS; i += 128)
+          *reinterpret_cast<uint4*>(hk + i) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+        __syncwarp();
+        for (uint32_t i0 = c0 + lane; i0 < c1; i0 += 256) {
+          uint32_t as[8];
+          uint8_t sc[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) as[u] = i0 + 32 * u < c1 ? A[i0 + 32 * u] : kSentinel;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) sc[u] = as[u] != kSentinel ? selfscore[as[u]] : (uint8_t)0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t x = as[u];
+            if (x == kSentinel) continue;
+            uint32_t h = (x * 2654435761u) >> SHIFT;
+            while (atomicCAS(&hk[h], kSentinel, x) != kSentinel) h = (h + 1u) & (SLOTS - 1u);
+            hv[h] = sc[u];
+          }
+        }
+        __syncwarp();
+      };
+      auto probe = [&](uint32_t x) -> int {
+        if (x == kSentinel) return 0;
+        uint32_t h = (x * 2654435761u) >> SHIFT;
+        for (;;) {
+          const uint32_t k = hk[h];
+          if (k == x) return hv[h];
+          if (k == kSentinel) return 0;
+          h = (h + 1u) & (SLOTS - 1u);
+        }
+      };
+      constexpr uint32_t kChunk = 7u * SLOTS / 10u;
       if (a != cur_a) {
         cur_a = a;
         A = ids + pa;
         na = na_l;
-        hashed = 10u * na <= 7u * SLOTS;
-        __syncwarp();
-        if (hashed) {
-          for (uint32_t i = lane * 4; i < SLOTS; i += 128)
-            *reinterpret_cast<uint4*>(hk + i) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
-          __syncwarp();
-          for (uint32_t i0 = lane; i0 < na; i0 += 256) {
-            uint32_t as[8];
-            uint8_t sc[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) as[u] = i0 + 32 * u < na ? A[i0 + 32 * u] : kSentinel;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) sc[u] = as[u] != kSentinel ? selfscore[as[u]] : (uint8_t)0;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const uint32_t x = as[u];
-              if (x == kSentinel) continue;
-              uint32_t h = (x * 2654435761u) >> SHIFT;
-              while (atomicCAS(&hk[h], kSentinel, x) != kSentinel) h = (h + 1u) & (SLOTS - 1u);
-              hv[h] = sc[u];
-            }
-          }
-          __syncwarp();
-        }
+        hashed = na <= kChunk;
+        if (hashed) build(0, na);
       }
       const uint32_t* B = ids + __shfl_sync(kFullMask, m_pb, l);
       const uint32_t nb = __shfl_sync(kFullMask, m_nb, l);
@@ -1352,31 +1365,16 @@ __global__ void __launch_bounds__(128)
             for (int u = 0; u < 8; ++u) xs[u] = i0 + 32 * u < nb ? B[i0 + 32 * u] : kSentinel;
           }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const uint32_t x = xs[u];
-            if (x == kSentinel) continue;
-            uint32_t h = (x * 2654435761u) >> SHIFT;
-            for (;;) {
-              const uint32_t k = hk[h];
-              if (k == x) {
-                s += hv[h];
-                break;
-              }
-              if (k == kSentinel) break;
-              h = (h + 1u) & (SLOTS - 1u);
-            }
-          }
+          for (int u = 0; u < 8; ++u) s += probe(xs[u]);
         }
       } else {
-        for (uint32_t i = lane; i < nb; i += 32) {
-          const uint32_t x = B[i];
-          uint32_t lo = 0, hi = na;
-          while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (A[mid] < x) lo = mid + 1; else hi = mid;
-          }
-          if (lo < na && A[lo] == x) s += selfscore[x];
+        // row a does not fit the table: hash it chunk by chunk and stream row b against every
+        // chunk (the id rows need not be sorted: the partitioned index leaves them in arrival order)
+        for (uint32_t c0 = 0; c0 < na; c0 += kChunk) {
+          build(c0, min(na, c0 + kChunk));
+          for (uint32_t i = lane; i < nb; i += 32) s += probe(B[i]);
         }
+        cur_a = kSentinel;  // the table holds the last chunk only
       }
       s = warp_sum_i(s);
       if (lane == l) m_score = (uint32_t)s;

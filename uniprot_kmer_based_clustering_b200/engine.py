@@ -199,6 +199,17 @@ class Engine:
         self._check(self._L.kc_get_protein_ids(self._h, _ptr(ro), _ptr(ids), ids.size))
         return ro, ids
 
+    def get_pair_index(self):
+        """(kmers[id], freq[id], self_score[id], row_offsets, ids): the index as the pair stage reads it"""
+        V, nnz = self.index_stats["n_repeated"], self.index_stats["nnz"]
+        v = np.empty(V, dtype=np.uint32)
+        f = np.empty(V, dtype=np.uint32)
+        ss = np.empty(V, dtype=np.uint8)
+        ro = np.empty(self.n + 1, dtype=np.uint64)
+        ids = np.empty(nnz, dtype=np.uint32)
+        self._check(self._L.kc_get_pair_index(self._h, _ptr(v), _ptr(f), _ptr(ss), V, _ptr(ro), _ptr(ids), nnz))
+        return v, f, ss, ro, ids
+
     def lookup_kmers(self, kmers: np.ndarray) -> np.ndarray:
         kmers = np.ascontiguousarray(kmers, dtype=np.uint32)
         out = np.empty(kmers.size, dtype=np.uint32)
