@@ -43,12 +43,12 @@ struct BucketGlobals {
 };
 
 // ---------------------------------------------------------------------------------------
-// The bucket kernel.  Shared memory per CTA (208 KB): the hash table of the bucket's k-mers
+// The bucket kernel.  Shared memory per CTA (216 KB): the hash table of the bucket's k-mers
 // (key, counter/cursor, id|self-score, holders), the records (row, slot) and the grouped +
 // sorted holders.  The next bucket's records are prefetched into registers while the current
 // one is processed.
 // ---------------------------------------------------------------------------------------
-constexpr size_t kBkSmemBytes = (size_t)kBkSlots * (4 + 4 + 4 + 2) + (size_t)kBkCap * (4 + 2 + 4 + 2);
+constexpr size_t kBkSmemBytes = (size_t)kBkSlots * (4 + 4 + 4 + 2) + (size_t)kBkCap * (4 + 2 + 4 + 2) + (size_t)(kBkCap / 2) * 2;
 
 __device__ __forceinline__ uint32_t bucket_slot_hash(uint32_t kmer) {
   uint32_t h = kmer ^ (kmer >> 15);
@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(kBkThreads, 1)
   uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_col + kBkCap);  // [slots] holders
   uint16_t* s_slot = s_cnt + kBkSlots;                          // [cap] record slots -> suffix starts (CROSS)
   uint16_t* s_grp = s_slot + kBkCap;                            // [cap] slot of every grouped holder
+  uint16_t* s_rep = s_grp + kBkCap;                             // [cap / 2] slot of every repeated k-mer, by local id
   __shared__ uint32_t s_wsum[32];
   __shared__ unsigned long long s_base[2];
   __shared__ uint32_t s_nnz;
@@ -143,23 +144,24 @@ __global__ void __launch_bounds__(kBkThreads, 1)
     }
     __syncthreads();
     if (!ok) continue;  // uniform: the host falls back to the universe-table index
-    // ---- P2: every thread owns kBkSlots / kBkThreads consecutive slots; block scan of
-    // (repeated k-mers, their holders) packed as holders << 16 | repeated
+    // ---- P2: every thread owns kBkSlots / kBkThreads slots (strided: no bank conflicts); block
+    // scan of (repeated k-mers, their holders) packed as holders << 16 | repeated
     constexpr int SPT = kBkSlots / kBkThreads;
     uint32_t cnts[SPT];
-    uint32_t local = 0;
+    uint32_t local = 0, multi32 = 0;
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
-      const uint32_t s = tid * SPT + j;
+      const uint32_t s = tid + j * kBkThreads;
       const uint32_t c = s_key[s] != kSentinel ? s_val[s] : 0u;
       cnts[j] = c;
       s_cnt[s] = (uint16_t)c;
       n_distinct += c != 0;
       if (c >= 2u) {
         local += (c << 16) | 1u;
-        multi += (unsigned long long)c * (c - 1u) / 2u;
+        multi32 += c * (c - 1u) / 2u;  // <= 8192^2 / 2 per slot, <= 2^25 per bucket
       }
     }
+    multi += multi32;
     uint32_t incl = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(kBkThreads, 1)
       }
       s_wsum[lane] = xs - x;
       if (lane == 31) {  // block totals: reserve the bucket's ids and postings
-        s_nnz = xs >> 16;
+        s_nnz = xs;
         s_base[0] = atomicAdd(&g->col_cursor, (unsigned long long)(xs >> 16));
         s_base[1] = atomicAdd(&g->id_cursor, (unsigned long long)(xs & 0xFFFFu));
       }
@@ -186,27 +188,33 @@ __global__ void __launch_bounds__(kBkThreads, 1)
     __syncthreads();
     const uint32_t excl = incl - local + s_wsum[warp];
     const unsigned long long col_base = s_base[0], id_base = s_base[1];
-    const uint32_t nnz = s_nnz;
+    const uint32_t nnz = s_nnz >> 16, nrep = s_nnz & 0xFFFFu;
     {
       uint32_t lid = excl & 0xFFFFu, coff = excl >> 16;
 #pragma unroll
       for (int j = 0; j < SPT; ++j) {
-        const uint32_t s = tid * SPT + j;
         const uint32_t c = cnts[j];
         if (c >= 2u) {
-          const uint32_t km = s_key[s];
-          const uint32_t ss = (uint32_t)kmer_self_score(km, k);
+          const uint32_t s = tid + j * kBkThreads;
           s_val[s] = coff;
-          s_meta[s] = lid | (ss << 16);
-          vocab[id_base + lid] = km;
-          freq[id_base + lid] = c;
-          selfscore[id_base + lid] = (uint8_t)ss;
+          s_rep[lid] = (uint16_t)s;
           ++lid;
           coff += c;
         }
       }
     }
     __syncthreads();
+    // vocabulary of the bucket, one thread per repeated k-mer (dense: the self-score costs k
+    // divisions, and the global writes are coalesced)
+    for (uint32_t l = tid; l < nrep; l += kBkThreads) {
+      const uint32_t s = s_rep[l];
+      const uint32_t km = s_key[s];
+      const uint32_t ss = (uint32_t)kmer_self_score(km, k);
+      s_meta[s] = l | (ss << 16);
+      vocab[id_base + l] = km;
+      freq[id_base + l] = s_cnt[s];
+      selfscore[id_base + l] = (uint8_t)ss;
+    }
     // ---- P3: group the holders of every repeated k-mer
 #pragma unroll
     for (int j = 0; j < kBkPerThread; ++j) {
@@ -244,35 +252,46 @@ __global__ void __launch_bounds__(kBkThreads, 1)
     }
     __syncthreads();
     // ---- P5: emit postings (contiguous per bucket) and entries (appended to the row block's bin;
-    // lanes that hit the same bin share one atomic)
+    // lanes that hit the same bin share one reservation, and four reservations per thread are in
+    // flight before the first entry is stored)
 #pragma unroll
-    for (int j = 0; j < kBkPerThread; ++j) {
-      const uint32_t q = tid + j * kBkThreads;
-      const bool act = q < nnz;
-      uint32_t row = 0, bin = kSentinel;
-      uint4 ent = make_uint4(0, 0, 0, 0);
-      if (act) {
-        const uint32_t s = s_grp[q];
-        const uint32_t end = s_val[s];
-        const uint32_t a = CROSS ? (uint32_t)s_slot[q] : q + 1u;
-        row = s_row[q];
-        const uint32_t meta = s_meta[s];
-        const uint32_t len = end - a;
-        // a single partner is stored inline ({rank, sentinel}): no postings gather in the pair stage
-        const uint2 sf = len == 1u ? make_uint2(s_row[a], kSentinel)
-                                   : make_uint2((uint32_t)col_base + a, (uint32_t)col_base + end);
-        col[col_base + q] = row;
-        ent = make_uint4(row | ((meta >> 16) << 24), (uint32_t)id_base + (meta & 0xFFFFu), sf.x, sf.y);
-        work += len;
-        bin = row >> kBinRowsLog;
-      }
-      const uint32_t peers = __match_any_sync(kFullMask, bin);
-      if (act) {
+    for (int j0 = 0; j0 < kBkPerThread; j0 += 4) {
+      uint4 ent[4];
+      uint32_t who[4], pend[4];  // who = leader lane << 8 | rank among the lanes of the same bin
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t q = tid + (j0 + u) * kBkThreads;
+        const bool act = q < nnz;
+        uint32_t bin = kSentinel;
+        ent[u].x = kSentinel;
+        if (act) {
+          const uint32_t s = s_grp[q];
+          const uint32_t end = s_val[s];
+          const uint32_t a = CROSS ? (uint32_t)s_slot[q] : q + 1u;
+          const uint32_t row = s_row[q];
+          const uint32_t meta = s_meta[s];
+          const uint32_t len = end - a;
+          // a single partner is stored inline ({rank, sentinel}): no postings gather in the pair stage
+          const uint2 sf = len == 1u ? make_uint2(s_row[a], kSentinel)
+                                     : make_uint2((uint32_t)col_base + a, (uint32_t)col_base + end);
+          col[col_base + q] = row;
+          ent[u] = make_uint4(row | ((meta >> 16) << 24), (uint32_t)id_base + (meta & 0xFFFFu), sf.x, sf.y);
+          work += len;
+          bin = row >> kBinRowsLog;
+        }
+        const uint32_t peers = __match_any_sync(kFullMask, bin);
         const uint32_t leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(&bin_cursor[bin], (uint32_t)__popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        entries[(size_t)rowcap_prefix[bin << kBinRowsLog] + base + __popc(peers & lanemask_lt())] = ent;
+        who[u] = (leader << 8) | __popc(peers & lanemask_lt());
+        pend[u] = 0;
+        if (act && lane == leader) pend[u] = atomicAdd(&bin_cursor[bin], (uint32_t)__popc(peers));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t base = __shfl_sync(kFullMask, pend[u], who[u] >> 8);
+        if (ent[u].x != kSentinel) {
+          const uint32_t r0 = (ent[u].x & 0xFFFFFFu) & ~(kBinRows - 1u);
+          entries[(size_t)rowcap_prefix[r0] + base + (who[u] & 31u)] = ent[u];
+        }
       }
     }
     __syncthreads();
@@ -305,7 +324,8 @@ struct RowCapOut {
 // edges of the row, rowinl = inline partners, rowmaxlen = longest suffix; suffix_ranges_kernel
 // in index.cuh produces the same numbers for the table build).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int kFinThreads = 512;
+__global__ void __launch_bounds__(kFinThreads)
     rows_finalize_kernel(const uint4* __restrict__ entries, const uint32_t* __restrict__ rowcap_prefix,
                          const uint32_t* __restrict__ bin_cnt, const uint32_t* __restrict__ binptr, uint32_t n,
                          uint32_t n_bins, uint32_t* __restrict__ rowptr, uint32_t* __restrict__ rowlen,
@@ -313,7 +333,7 @@ __global__ void __launch_bounds__(256)
                          unsigned long long* __restrict__ rowwork64, uint32_t* __restrict__ rowwork,
                          uint32_t* __restrict__ rowinl, uint32_t* __restrict__ rowmaxlen) {
   __shared__ uint32_t s_cnt[kBinRows], s_off[kBinRows], s_inl[kBinRows], s_max[kBinRows];
-  __shared__ unsigned long long s_work[kBinRows];
+  __shared__ uint32_t s_wlo[kBinRows], s_whi[kBinRows];  // multi-edges of the row: low word + carries
   const uint32_t tid = threadIdx.x;
   for (uint32_t bin = blockIdx.x; bin < n_bins; bin += gridDim.x) {
     const uint32_t r0 = bin << kBinRowsLog;
@@ -324,24 +344,31 @@ __global__ void __launch_bounds__(256)
       s_cnt[tid] = 0;
       s_inl[tid] = 0;
       s_max[tid] = 0;
-      s_work[tid] = 0;
+      s_wlo[tid] = 0;
+      s_whi[tid] = 0;
     }
     __syncthreads();
-    for (uint32_t i0 = 0; i0 < cnt; i0 += 1024) {
+    for (uint32_t i0 = 0; i0 < cnt; i0 += 4 * kFinThreads) {
       uint4 e[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (i0 + u * 256 + tid < cnt) e[u] = ld_stream_u32x4(src + i0 + u * 256 + tid);
+        if (i0 + u * kFinThreads + tid < cnt) e[u] = ld_stream_u32x4(src + i0 + u * kFinThreads + tid);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (i0 + u * 256 + tid >= cnt) continue;
+        if (i0 + u * kFinThreads + tid >= cnt) continue;
         const uint32_t lr = (e[u].x & 0xFFFFFFu) - r0;
         const bool inl = e[u].w == kSentinel;
         const uint32_t len = inl ? 1u : e[u].w - e[u].z;
         atomicAdd(&s_cnt[lr], 1u);
-        if (len) atomicAdd(&s_work[lr], (unsigned long long)len);
-        if (inl) atomicAdd(&s_inl[lr], 1u);
-        else if (len > 1u) atomicMax(&s_max[lr], len);
+        if (inl) {
+          atomicAdd(&s_inl[lr], 1u);
+        } else if (len > 1u) {
+          atomicMax(&s_max[lr], len);
+        }
+        if (len) {
+          const uint32_t old = atomicAdd(&s_wlo[lr], len);
+          if (old + len < old) atomicAdd(&s_whi[lr], 1u);
+        }
       }
     }
     __syncthreads();
@@ -360,7 +387,7 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
     if (tid < nrows) {
       const uint32_t r = r0 + tid;
-      const unsigned long long w = s_work[tid];
+      const unsigned long long w = ((unsigned long long)s_whi[tid] << 32) | s_wlo[tid];
       rowptr[r] = s_off[tid];
       rowlen[r] = s_cnt[tid];
       rowwork64[r] = w;
@@ -370,14 +397,14 @@ __global__ void __launch_bounds__(256)
       if (r + 1 == n) rowptr[n] = dst0 + cnt;
     }
     __syncthreads();
-    for (uint32_t i0 = 0; i0 < cnt; i0 += 1024) {
+    for (uint32_t i0 = 0; i0 < cnt; i0 += 4 * kFinThreads) {  // second read of the bin: L2
       uint4 e[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (i0 + u * 256 + tid < cnt) e[u] = src[i0 + u * 256 + tid];
+        if (i0 + u * kFinThreads + tid < cnt) e[u] = src[i0 + u * kFinThreads + tid];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (i0 + u * 256 + tid >= cnt) continue;
+        if (i0 + u * kFinThreads + tid >= cnt) continue;
         const uint32_t lr = (e[u].x & 0xFFFFFFu) - r0;
         const uint32_t pos = atomicAdd(&s_off[lr], 1u);
         ids[pos] = e[u].y;

@@ -87,6 +87,7 @@ struct kc_engine {
   std::vector<uint32_t> h_long, h_huge;
   std::vector<unsigned long long> h_huge_off;
   uint32_t max_block_np2 = 0, max_block_len = 0;
+  uint32_t n_mid_rows = 0;  // proteins of kHashMaxPos+1 .. kWarpMaxPos positions
   DBuf d_res, d_off, d_kpos, d_pstart, d_plen, d_orig, d_rank, d_first_after, d_long, d_huge, d_huge_off,
       d_huge_scratch;
   // index
@@ -208,6 +209,7 @@ int stage_layout(kc_engine* e) {
   e->h_huge_off.clear();
   e->max_block_np2 = 0;
   e->max_block_len = 0;
+  e->n_mid_rows = 0;
   unsigned long long huge_total = 0;
   for (uint64_t r = 0; r < n; ++r) {
     const uint32_t p = e->h_orig[r];
@@ -224,6 +226,8 @@ int stage_layout(kc_engine* e) {
         e->h_long.push_back((uint32_t)r);
         e->max_block_np2 = std::max(e->max_block_np2, next_pow2_u32(npos));
         e->max_block_len = std::max(e->max_block_len, (uint32_t)len);
+      } else if (npos > kHashMaxPos) {
+        ++e->n_mid_rows;
       }
     }
   }
@@ -257,11 +261,21 @@ int run_extract_census(kc_engine* e, BucketScatter scatter = BucketScatter{nullp
   uint32_t* pk = e->d_pk.as<uint32_t>();
   uint32_t* ndist = e->d_ndist.as<uint32_t>();
   uint32_t* ksplit = e->d_ksplit.as<uint32_t>();
-  if (n) {
+  // partitioned build: short proteins are deduplicated by hashing (no pk), the sorting warp kernel
+  // only takes the proteins of more than kHashMaxPos positions
+  uint32_t min_pos = 0;
+  if (n && scatter.rec) {
+    min_pos = kHashMaxPos;
+    const uint32_t grid = blocks_for(n, kXsWarps, e->num_sm * 5);
+    KC_LAUNCH(e, extract_scatter_warp_kernel<K>, grid, kXsWarps * 32, 0, res, e->d_pstart.as<uint32_t>(),
+              e->d_plen.as<uint32_t>(), n, ndist, e->cfg.sample_every, e->cfg.sample_seed, e->d_orig.as<uint32_t>(),
+              &ds->n_incid, scatter);
+  }
+  if (n && (!scatter.rec || e->n_mid_rows)) {
     const uint32_t grid = blocks_for(n, kExtractWarps, e->num_sm * 5);
     KC_LAUNCH(e, extract_dedup_warp_kernel<K>, grid, kExtractWarps * 32, 0, res, e->d_pstart.as<uint32_t>(),
               e->d_plen.as<uint32_t>(), n, pk, ndist, e->slice_shift, e->n_slices, ksplit, e->cfg.sample_every,
-              e->cfg.sample_seed, e->d_orig.as<uint32_t>(), &ds->n_incid, scatter);
+              e->cfg.sample_seed, e->d_orig.as<uint32_t>(), &ds->n_incid, scatter, min_pos);
   }
   if (!e->h_long.empty()) {
     const size_t smem = (size_t)e->max_block_np2 * 4 + e->max_block_len + 16;
@@ -464,7 +478,7 @@ static int build_index_bucketed(kc_engine* e, kc_index_stats* stats, bool* overf
   }
   // entry bins -> CSR
   e->launches += exclusive_scan(U32In{bin_cnt}, U32ExclOut{binptr}, n_bins, e->scan, e->stream);
-  KC_LAUNCH(e, rows_finalize_kernel, std::min<uint32_t>(n_bins, (uint32_t)e->num_sm * 8), 256, 0, ent, rowcap, bin_cnt,
+  KC_LAUNCH(e, rows_finalize_kernel, std::min<uint32_t>(n_bins, (uint32_t)e->num_sm * 2), kFinThreads, 0, ent, rowcap, bin_cnt,
             binptr, n, n_bins, e->d_rowptr.as<uint32_t>(), e->d_rowlen.as<uint32_t>(), e->d_ids.as<uint32_t>(),
             e->d_suf.as<uint2>(), e->cfg.want_blosum ? e->d_sufss.as<uint8_t>() : nullptr,
             e->d_rowwork64.as<unsigned long long>(), e->d_rowwork.as<uint32_t>(), e->d_rowinl.as<uint32_t>(),
@@ -514,6 +528,13 @@ static int ensure_canonical(kc_engine* e) {
   KC_CUDA(e, e->d_self.ensure(V + 16));
   int rc = ensure_scan(e, std::max<uint64_t>(W, (uint64_t)n + 1));
   if (rc) return rc;
+  {  // the rows' sorted distinct k-mers (the partitioned build does not write them)
+    DBuf none;
+    std::swap(none, e->d_ksplit);
+    rc = e->cfg.k == 5 ? run_extract_census<5>(e) : run_extract_census<7>(e);
+    std::swap(none, e->d_ksplit);
+    if (rc) return rc;
+  }
   KC_CUDA(e, cudaMemsetAsync(e->d_seen.p, 0, W * 8, e->stream));
   KC_CUDA(e, cudaMemsetAsync(e->d_zero.p, 0, ((uint64_t)n + 1) * 4, e->stream));
   KC_CUDA(e, cudaMemsetAsync(e->d_rowlen_c.p, 0, ((uint64_t)n + 1) * 4, e->stream));

@@ -24,11 +24,16 @@ struct BucketScatter {
   uint2* rec;          // n_buckets slots of kBkCap {k-mer, row} records
   uint32_t* cursor;    // records appended per bucket (may pass kBkCap: overflow, the build falls back)
   uint32_t n_buckets;
-  __device__ __forceinline__ void put(uint32_t kmer, uint32_t row) const {
+  // two steps so that a caller can keep several reservations (L2 atomics) in flight
+  __device__ __forceinline__ unsigned long long reserve(uint32_t kmer) const {
     const uint32_t b = __umulhi(kmer_bucket_hash(kmer), n_buckets);
     const uint32_t pos = atomicAdd(&cursor[b], 1u);
-    if (pos < kBkCap) rec[(size_t)b * kBkCap + pos] = make_uint2(kmer, row);
+    return pos < kBkCap ? (unsigned long long)b * kBkCap + pos : ~0ull;
   }
+  __device__ __forceinline__ void store(unsigned long long at, uint32_t kmer, uint32_t row) const {
+    if (at != ~0ull) rec[at] = make_uint2(kmer, row);
+  }
+  __device__ __forceinline__ void put(uint32_t kmer, uint32_t row) const { store(reserve(kmer), kmer, row); }
 };
 
 
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(kExtractWarps * 32)
                               uint32_t* __restrict__ ndist, uint32_t slice_shift, uint32_t n_slices,
                               uint32_t* __restrict__ ksplit, uint32_t sample_every, unsigned long long sample_seed,
                               const uint32_t* __restrict__ orig_of, unsigned long long* __restrict__ n_incid,
-                              BucketScatter scatter) {
+                              BucketScatter scatter, uint32_t min_pos) {
   __shared__ uint8_t s_lut[256];
   __shared__ __align__(16) uint32_t s_keys[kExtractWarps][kWarpMaxPos];
   __shared__ __align__(4) uint8_t s_codes[kExtractWarps][kWarpMaxPos + 8];
@@ -203,6 +208,7 @@ __global__ void __launch_bounds__(kExtractWarps * 32)
     }
     const uint32_t npos_all = len - K + 1;
     if (npos_all > kWarpMaxPos) continue;  // handled by the block kernels
+    if (npos_all <= min_pos) continue;     // handled by extract_scatter_warp_kernel
     // optional subsampling (Protein::new_with_rand_fivemers): floor(positions / d) distinct positions
     const uint32_t npos = sample_every > 1 ? npos_all / sample_every : npos_all;
     if (npos == 0) {
@@ -229,18 +235,35 @@ __global__ void __launch_bounds__(kExtractWarps * 32)
     else warp_sort_blocked<32>(keys, lane);
     __syncwarp();
     uint32_t base = 0;
-    for (uint32_t c = 0; c < npos; c += 32) {
-      const uint32_t i = c + lane;
-      const uint32_t v = i < npos ? keys[i] : kSentinel;
-      const bool first = i < npos && (i == 0 || v != keys[i - 1]);
-      const uint32_t m = __ballot_sync(kFullMask, first);
-      if (first) {
-        const uint32_t j = base + __popc(m & lanemask_lt());
-        pk[ps + j] = v;
-        record_slice_starts(ksplit, n, r, i == 0 ? 0u : (keys[i - 1] >> slice_shift) + 1u, v >> slice_shift, j);
-        if (scatter.rec) scatter.put(v, r);
+    for (uint32_t c = 0; c < npos; c += 128) {  // four 32-key chunks at a time: four bucket reservations in flight
+      uint32_t v[4], j[4];
+      bool first[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = c + 32 * u + lane;
+        v[u] = i < npos ? keys[i] : kSentinel;
+        first[u] = i < npos && (i == 0 || v[u] != keys[i - 1]);
+        const uint32_t m = __ballot_sync(kFullMask, first[u]);
+        j[u] = base + __popc(m & lanemask_lt());
+        base += __popc(m);
       }
-      base += __popc(m);
+      unsigned long long at[4];
+      if (scatter.rec) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) at[u] = first[u] ? scatter.reserve(v[u]) : ~0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (first[u]) {
+          const uint32_t i = c + 32 * u + lane;
+          pk[ps + j[u]] = v[u];
+          record_slice_starts(ksplit, n, r, i == 0 ? 0u : (keys[i - 1] >> slice_shift) + 1u, v[u] >> slice_shift, j[u]);
+        }
+      }
+      if (scatter.rec) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) scatter.store(at[u], v[u], r);
+      }
     }
     if (lane == 0) ndist[r] = base;
     if (ksplit)
@@ -337,6 +360,98 @@ __global__ void __launch_bounds__(512)
     ndist[r] = total;
     atomicAdd(n_incid, (unsigned long long)total);
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2 for the partitioned index (bucket.cuh), proteins of <= kHashMaxPos positions: one warp per
+// protein, dedup through a per-warp shared-memory hash set instead of a sort (the buckets do not
+// need the row's k-mers in order), every newly seen k-mer appended to its bucket right away.
+// Nothing but ndist is written per row: the sorted distinct k-mers (pk) are only needed by the
+// canonical view, which runs extract_dedup_warp_kernel on demand.
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t kHashSlots = 1024;
+constexpr uint32_t kHashMaxPos = 716;  // load factor <= 0.7
+constexpr int kXsWarps = 8;
+
+template <int K>
+__global__ void __launch_bounds__(kXsWarps * 32)
+    extract_scatter_warp_kernel(const uint8_t* __restrict__ res, const uint32_t* __restrict__ pstart,
+                                const uint32_t* __restrict__ plen, uint32_t n, uint32_t* __restrict__ ndist,
+                                uint32_t sample_every, unsigned long long sample_seed,
+                                const uint32_t* __restrict__ orig_of, unsigned long long* __restrict__ n_incid,
+                                BucketScatter scatter) {
+  __shared__ uint8_t s_lut[256];
+  __shared__ __align__(16) uint32_t s_tab[kXsWarps][kHashSlots];
+  __shared__ __align__(4) uint8_t s_codes[kXsWarps][kHashMaxPos + K + 8];
+  const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
+  s_lut[threadIdx.x] = c_residue_lut[threadIdx.x];
+  __syncthreads();
+  uint32_t* tab = s_tab[w];
+  uint8_t* codes = s_codes[w];
+  unsigned long long incid = 0;
+  const uint32_t nwarps = gridDim.x * kXsWarps;
+  for (uint32_t r = blockIdx.x * kXsWarps + w; r < n; r += nwarps) {
+    const uint32_t len = plen[r];
+    if (len < (uint32_t)K) {
+      if (lane == 0) ndist[r] = 0;
+      continue;
+    }
+    const uint32_t npos_all = len - K + 1;
+    if (npos_all > kHashMaxPos) continue;  // sorted by the warp / block kernels
+    const uint32_t npos = sample_every > 1 ? npos_all / sample_every : npos_all;
+    if (npos == 0) {
+      if (lane == 0) ndist[r] = 0;
+      continue;
+    }
+    const uint32_t ps = pstart[r];
+#pragma unroll
+    for (int i = 0; i < (int)(kHashSlots / 128); ++i)
+      *reinterpret_cast<uint4*>(tab + i * 128 + lane * 4) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+    stage_codes(res, ps, len, codes, s_lut, lane, 32);
+    __syncwarp();
+    const uint32_t skey = sample_every > 1 ? sample_key(sample_seed, orig_of ? orig_of[r] : r) : 0u;
+    uint32_t fresh = 0;
+    for (uint32_t c = 0; c < npos; c += 128) {  // four k-mers per lane: four bucket reservations in flight
+      uint32_t v[4];
+      bool first[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = c + 32 * u + lane;
+        first[u] = false;
+        v[u] = 0;
+        if (i < npos) {
+          v[u] = pack_kmer<K>(codes + (sample_every > 1 ? sample_perm(skey, npos_all, i) : i));
+          uint32_t h = (v[u] * 2654435761u) >> 22;
+          for (;;) {
+            const uint32_t cur = tab[h];
+            if (cur == v[u]) break;
+            if (cur == kSentinel) {
+              const uint32_t old = atomicCAS(&tab[h], kSentinel, v[u]);
+              if (old == kSentinel) {
+                first[u] = true;
+                break;
+              }
+              if (old == v[u]) break;
+            }
+            h = (h + 1u) & (kHashSlots - 1u);
+          }
+        }
+      }
+      unsigned long long at[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) at[u] = first[u] ? scatter.reserve(v[u]) : ~0ull;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        scatter.store(at[u], v[u], r);
+        fresh += first[u];
+      }
+    }
+    fresh = warp_sum(fresh);
+    if (lane == 0) ndist[r] = fresh;
+    incid += fresh;
+    __syncwarp();
+  }
+  if (lane == 0 && incid) atomicAdd(n_incid, incid);
 }
 
 // ---------------------------------------------------------------------------------------
