@@ -27,10 +27,10 @@
 
 namespace kc {
 
-constexpr uint32_t kBkSlots = 8192;   // hash slots per bucket (>= kBkCap: distinct <= incidences)
-constexpr int kBkThreads = 1024;
+constexpr uint32_t kBkSlots = 4096;   // hash slots per bucket (>= kBkCap: distinct <= incidences)
+constexpr int kBkThreads = 512;
 constexpr int kBkPerThread = kBkCap / kBkThreads;
-constexpr uint32_t kBkTargetFill = 5120;  // mean records per bucket (62 % of a slot)
+constexpr uint32_t kBkTargetFill = 2560;  // mean records per bucket (62 % of a slot)
 constexpr uint32_t kBinRowsLog = 6;       // entry bins of 64 rows
 constexpr uint32_t kBinRows = 1u << kBinRowsLog;
 
@@ -58,7 +58,7 @@ __device__ __forceinline__ uint32_t bucket_slot_hash(uint32_t kmer) {
 }
 
 template <bool CROSS>
-__global__ void __launch_bounds__(kBkThreads, 1)
+__global__ void __launch_bounds__(kBkThreads, 2)
     bucket_build_kernel(const uint2* __restrict__ rec, const uint32_t* __restrict__ bucket_cnt, uint32_t n_buckets,
                         const uint32_t* __restrict__ first_after, int k, uint32_t* __restrict__ col,
                         uint4* __restrict__ entries, const uint32_t* __restrict__ rowcap_prefix,
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kBkThreads, 1)
     if (lane == 31) s_wsum[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-      const uint32_t x = s_wsum[lane];
+      const uint32_t x = lane < (uint32_t)(kBkThreads / 32) ? s_wsum[lane] : 0u;
       uint32_t xs = x;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -318,29 +318,39 @@ struct RowCapOut {
 };
 
 // ---------------------------------------------------------------------------------------
-// One CTA per entry bin (64 rows): count per row, CSR offsets (binptr = exclusive scan of the bin
-// fill counts), then the split into ids / suffix ranges / self-scores.  The bin is read twice (the
-// second time from L2).  Also sums what the pair stage's row classifier needs (rowwork = multi-
-// edges of the row, rowinl = inline partners, rowmaxlen = longest suffix; suffix_ranges_kernel
-// in index.cuh produces the same numbers for the table build).
+// One CTA per entry bin (64 rows): ONE pass over the bin splits it by row into the arrays the
+// pair stage reads (ids / suffix ranges / self-scores).  The bin is taken in chunks of 4096
+// entries that are counting-sorted by row in shared memory first, so that the global stores
+// are runs of consecutive entries of one row (full sectors) instead of one scattered 4/8/1-byte
+// store per entry.  The rows are laid out by capacity (row r starts at rowcap_prefix[r], room
+// for all its distinct k-mers; the pair stage reads rowlen[r] entries from there), so no
+// counting pass over the whole bin and no scan are needed.  Also sums what the pair stage's row
+// classifier needs (rowwork = multi-edges of the row, rowinl = inline partners, rowmaxlen =
+// longest suffix; suffix_ranges_kernel in index.cuh produces the same numbers for the table build).
 // ---------------------------------------------------------------------------------------
 constexpr int kFinThreads = 512;
+constexpr int kFinPer = 8;
+constexpr uint32_t kFinChunk = kFinThreads * kFinPer;
+constexpr size_t kFinSmemBytes = (size_t)kFinChunk * 16;
 __global__ void __launch_bounds__(kFinThreads)
     rows_finalize_kernel(const uint4* __restrict__ entries, const uint32_t* __restrict__ rowcap_prefix,
-                         const uint32_t* __restrict__ bin_cnt, const uint32_t* __restrict__ binptr, uint32_t n,
-                         uint32_t n_bins, uint32_t* __restrict__ rowptr, uint32_t* __restrict__ rowlen,
-                         uint32_t* __restrict__ ids, uint2* __restrict__ suf, uint8_t* __restrict__ sufss,
-                         unsigned long long* __restrict__ rowwork64, uint32_t* __restrict__ rowwork,
-                         uint32_t* __restrict__ rowinl, uint32_t* __restrict__ rowmaxlen) {
-  __shared__ uint32_t s_cnt[kBinRows], s_off[kBinRows], s_inl[kBinRows], s_max[kBinRows];
+                         const uint32_t* __restrict__ bin_cnt, uint32_t n, uint32_t n_bins,
+                         uint32_t* __restrict__ rowlen, uint32_t* __restrict__ ids, uint2* __restrict__ suf,
+                         uint8_t* __restrict__ sufss, unsigned long long* __restrict__ rowwork64,
+                         uint32_t* __restrict__ rowwork, uint32_t* __restrict__ rowinl,
+                         uint32_t* __restrict__ rowmaxlen) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  uint4* s_ent = reinterpret_cast<uint4*>(dyn_smem);
+  __shared__ uint32_t s_off[kBinRows], s_cnt[kBinRows], s_start[kBinRows], s_inl[kBinRows], s_max[kBinRows];
   __shared__ uint32_t s_wlo[kBinRows], s_whi[kBinRows];  // multi-edges of the row: low word + carries
   const uint32_t tid = threadIdx.x;
   for (uint32_t bin = blockIdx.x; bin < n_bins; bin += gridDim.x) {
     const uint32_t r0 = bin << kBinRowsLog;
     const uint32_t nrows = min(kBinRows, n - r0);
     const uint4* src = entries + rowcap_prefix[r0];
-    const uint32_t cnt = bin_cnt[bin], dst0 = binptr[bin];
+    const uint32_t cnt = bin_cnt[bin];
     if (tid < kBinRows) {
+      s_off[tid] = tid < nrows ? rowcap_prefix[r0 + tid] : 0u;
       s_cnt[tid] = 0;
       s_inl[tid] = 0;
       s_max[tid] = 0;
@@ -348,18 +358,20 @@ __global__ void __launch_bounds__(kFinThreads)
       s_whi[tid] = 0;
     }
     __syncthreads();
-    for (uint32_t i0 = 0; i0 < cnt; i0 += 4 * kFinThreads) {
-      uint4 e[4];
+    for (uint32_t c0 = 0; c0 < cnt; c0 += kFinChunk) {
+      const uint32_t m = min(kFinChunk, cnt - c0);
+      uint4 e[kFinPer];
+      uint32_t rk[kFinPer];  // row << 16 | rank of the entry among the chunk's entries of its row
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (i0 + u * kFinThreads + tid < cnt) e[u] = ld_stream_u32x4(src + i0 + u * kFinThreads + tid);
+      for (int u = 0; u < kFinPer; ++u)
+        if (u * kFinThreads + tid < m) e[u] = ld_stream_u32x4(src + c0 + u * kFinThreads + tid);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (i0 + u * kFinThreads + tid >= cnt) continue;
+      for (int u = 0; u < kFinPer; ++u) {
+        if (u * kFinThreads + tid >= m) continue;
         const uint32_t lr = (e[u].x & 0xFFFFFFu) - r0;
         const bool inl = e[u].w == kSentinel;
         const uint32_t len = inl ? 1u : e[u].w - e[u].z;
-        atomicAdd(&s_cnt[lr], 1u);
+        rk[u] = (lr << 16) | atomicAdd(&s_cnt[lr], 1u);
         if (inl) {
           atomicAdd(&s_inl[lr], 1u);
         } else if (len > 1u) {
@@ -370,47 +382,46 @@ __global__ void __launch_bounds__(kFinThreads)
           if (old + len < old) atomicAdd(&s_whi[lr], 1u);
         }
       }
-    }
-    __syncthreads();
-    if (tid < 32) {  // exclusive scan of the 64 row counts by one warp
-      const uint32_t c0 = s_cnt[2 * tid], c1 = s_cnt[2 * tid + 1];
-      uint32_t incl = c0 + c1;
+      __syncthreads();
+      if (tid < 32) {  // exclusive scan of the 64 per-row counts of the chunk by one warp
+        const uint32_t a = s_cnt[2 * tid], b = s_cnt[2 * tid + 1];
+        uint32_t incl = a + b;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(kFullMask, incl, o);
-        if (tid >= (uint32_t)o) incl += t;
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(kFullMask, incl, o);
+          if (tid >= (uint32_t)o) incl += t;
+        }
+        s_start[2 * tid] = incl - a - b;
+        s_start[2 * tid + 1] = incl - b;
       }
-      const uint32_t ex = incl - c0 - c1;
-      s_off[2 * tid] = dst0 + ex;
-      s_off[2 * tid + 1] = dst0 + ex + c0;
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < kFinPer; ++u)
+        if (u * kFinThreads + tid < m) s_ent[s_start[rk[u] >> 16] + (rk[u] & 0xFFFFu)] = e[u];
+      __syncthreads();
+      for (uint32_t i = tid; i < m; i += kFinThreads) {
+        const uint4 v = s_ent[i];
+        const uint32_t lr = (v.x & 0xFFFFFFu) - r0;
+        const uint32_t pos = s_off[lr] + (i - s_start[lr]);
+        ids[pos] = v.y;
+        suf[pos] = make_uint2(v.z, v.w);
+        if (sufss) sufss[pos] = (uint8_t)(v.x >> 24);
+      }
+      __syncthreads();
+      if (tid < kBinRows) {
+        s_off[tid] += s_cnt[tid];
+        s_cnt[tid] = 0;
+      }
+      __syncthreads();
     }
-    __syncthreads();
     if (tid < nrows) {
       const uint32_t r = r0 + tid;
       const unsigned long long w = ((unsigned long long)s_whi[tid] << 32) | s_wlo[tid];
-      rowptr[r] = s_off[tid];
-      rowlen[r] = s_cnt[tid];
+      rowlen[r] = s_off[tid] - rowcap_prefix[r];
       rowwork64[r] = w;
       rowwork[r] = w > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)w;
       rowinl[r] = s_inl[tid];
       rowmaxlen[r] = s_max[tid];
-      if (r + 1 == n) rowptr[n] = dst0 + cnt;
-    }
-    __syncthreads();
-    for (uint32_t i0 = 0; i0 < cnt; i0 += 4 * kFinThreads) {  // second read of the bin: L2
-      uint4 e[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (i0 + u * kFinThreads + tid < cnt) e[u] = src[i0 + u * kFinThreads + tid];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (i0 + u * kFinThreads + tid >= cnt) continue;
-        const uint32_t lr = (e[u].x & 0xFFFFFFu) - r0;
-        const uint32_t pos = atomicAdd(&s_off[lr], 1u);
-        ids[pos] = e[u].y;
-        suf[pos] = make_uint2(e[u].z, e[u].w);
-        if (sufss) sufss[pos] = (uint8_t)(e[u].x >> 24);
-      }
     }
     __syncthreads();
   }

@@ -104,7 +104,7 @@ struct kc_engine {
   bool bucketed = false, canonical_ready = false;
   DBuf d_recA, d_recB, d_histA, d_histB, d_segoff, d_bucketoff, d_rowptr, d_ids, d_vocab_h, d_freq_h, d_self_h,
       d_zero, d_rowlen_c, d_islo_c;
-  const uint32_t* pair_rowptr() const { return (bucketed ? d_rowptr : d_pstart).as<uint32_t>(); }
+  const uint32_t* pair_rowptr() const { return (bucketed ? d_segoff : d_pstart).as<uint32_t>(); }  // d_segoff: capacity prefix
   const uint32_t* pair_ids() const { return (bucketed ? d_ids : d_pk).as<uint32_t>(); }
   const uint8_t* pair_self() const { return (bucketed ? d_self_h : d_self).as<uint8_t>(); }
   const uint32_t* canon_rowlen() const { return (bucketed ? d_rowlen_c : d_rowlen).as<uint32_t>(); }
@@ -419,8 +419,6 @@ static int build_index_bucketed(kc_engine* e, kc_index_stats* stats, bool* overf
   KC_CUDA(e, e->d_bucketoff.ensure(((uint64_t)NB + 2) * 4));                // bucket cursors
   KC_CUDA(e, e->d_segoff.ensure(((uint64_t)n + 2) * 4));                    // rowcap prefix
   KC_CUDA(e, e->d_histA.ensure(((uint64_t)n_bins + 2) * 4));                // bin cursors
-  KC_CUDA(e, e->d_histB.ensure(((uint64_t)n_bins + 2) * 4));                // bin CSR bases
-  KC_CUDA(e, e->d_rowptr.ensure(((uint64_t)n + 2) * 4));
   KC_CUDA(e, e->d_ids.ensure((E + 64) * 4));
   KC_CUDA(e, e->d_col.ensure((E + 64) * 4));
   KC_CUDA(e, e->d_suf.ensure((E + 64) * 8));
@@ -440,7 +438,6 @@ static int build_index_bucketed(kc_engine* e, kc_index_stats* stats, bool* overf
   uint32_t* bucket_cnt = e->d_bucketoff.as<uint32_t>();
   uint32_t* rowcap = e->d_segoff.as<uint32_t>();
   uint32_t* bin_cnt = e->d_histA.as<uint32_t>();
-  uint32_t* binptr = e->d_histB.as<uint32_t>();
   uint2* rec = e->d_recA.as<uint2>();
   uint4* ent = e->d_recB.as<uint4>();
 
@@ -463,12 +460,15 @@ static int build_index_bucketed(kc_engine* e, kc_index_stats* stats, bool* overf
   e->launches += exclusive_scan(U32In{e->d_ndist.as<uint32_t>()}, RowCapOut{rowcap, n}, n, e->scan, e->stream);
   // buckets: census, ids, postings, entries
   {
-    const uint32_t grid = std::min<uint32_t>(NB, (uint32_t)e->num_sm);
     const uint32_t* fa = e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr;
 #define KC_BUCKETS(CROSS)                                                                                       \
   do {                                                                                                          \
     KC_CUDA(e, cudaFuncSetAttribute(bucket_build_kernel<CROSS>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                     (int)kBkSmemBytes));                                                        \
+    int per_sm = 1;                                                                                             \
+    KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bucket_build_kernel<CROSS>, kBkThreads,   \
+                                                             kBkSmemBytes));                                    \
+    const uint32_t grid = std::min<uint32_t>(NB, (uint32_t)(e->num_sm * std::max(per_sm, 1)));                   \
     KC_LAUNCH(e, bucket_build_kernel<CROSS>, grid, kBkThreads, kBkSmemBytes, rec, bucket_cnt, NB, fa, e->cfg.k, \
               e->d_col.as<uint32_t>(), ent, rowcap, bin_cnt, e->d_vocab_h.as<uint32_t>(),                       \
               e->d_freq_h.as<uint32_t>(), e->d_self_h.as<uint8_t>(), &ds->bg);                                  \
@@ -476,13 +476,12 @@ static int build_index_bucketed(kc_engine* e, kc_index_stats* stats, bool* overf
     if (fa) KC_BUCKETS(true); else KC_BUCKETS(false);
 #undef KC_BUCKETS
   }
-  // entry bins -> CSR
-  e->launches += exclusive_scan(U32In{bin_cnt}, U32ExclOut{binptr}, n_bins, e->scan, e->stream);
-  KC_LAUNCH(e, rows_finalize_kernel, std::min<uint32_t>(n_bins, (uint32_t)e->num_sm * 2), kFinThreads, 0, ent, rowcap, bin_cnt,
-            binptr, n, n_bins, e->d_rowptr.as<uint32_t>(), e->d_rowlen.as<uint32_t>(), e->d_ids.as<uint32_t>(),
-            e->d_suf.as<uint2>(), e->cfg.want_blosum ? e->d_sufss.as<uint8_t>() : nullptr,
-            e->d_rowwork64.as<unsigned long long>(), e->d_rowwork.as<uint32_t>(), e->d_rowinl.as<uint32_t>(),
-            e->d_rowmaxlen.as<uint32_t>());
+  // entry bins -> rows (laid out by capacity: row r starts at rowcap[r])
+  KC_CUDA(e, cudaFuncSetAttribute(rows_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmemBytes));
+  KC_LAUNCH(e, rows_finalize_kernel, std::min<uint32_t>(n_bins, (uint32_t)e->num_sm * 3), kFinThreads, kFinSmemBytes, ent, rowcap,
+            bin_cnt, n, n_bins, e->d_rowlen.as<uint32_t>(), e->d_ids.as<uint32_t>(), e->d_suf.as<uint2>(),
+            e->cfg.want_blosum ? e->d_sufss.as<uint8_t>() : nullptr, e->d_rowwork64.as<unsigned long long>(),
+            e->d_rowwork.as<uint32_t>(), e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>());
   e->launches += exclusive_scan(WorkIn{e->d_rowwork.as<uint32_t>(), e->d_rowlen.as<uint32_t>()},
                                 U64ExclOutWithTail{e->d_workprefix.as<unsigned long long>(), n}, n, e->scan, e->stream);
   mark(e, EV_I1);

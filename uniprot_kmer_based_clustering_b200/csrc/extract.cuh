@@ -16,7 +16,7 @@ __constant__ uint8_t c_residue_lut[256];
 
 // ---- partitioned index (bucket.cuh): the extract kernels append every (distinct k-mer, row)
 // incidence to the bucket its k-mer hashes to
-constexpr uint32_t kBkCap = 8192;  // records per bucket slot
+constexpr uint32_t kBkCap = 4096;  // records per bucket slot
 __host__ __device__ __forceinline__ uint32_t kmer_bucket_hash(uint32_t kmer) { return kmer * 0x9E3779B1u; }
 
 // where the extract kernels append the incidences (rec == nullptr: the universe-table build)
