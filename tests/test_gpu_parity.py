@@ -575,3 +575,47 @@ def test_bucket_overflow_falls_back_to_the_table_build(index_flavour):
         e.build_index()
         check_index(e, ix)
         check_pairs(e.score_pairs(), e.get_edges(), pr)
+
+
+@pytest.mark.parametrize("n_shards", [2, 3, 5])
+@pytest.mark.parametrize("k,cross", [(7, False), (7, True), (5, False)])
+def test_sharded_index_build_adds_up_to_the_whole(n_shards, k, cross, index_flavour):
+    """kc_build_index_shard + kc_score_pairs_shard for every shard in turn (one GPU standing in for
+    n_shards ranks): the index stats and pair counters add up to the oracle's whole-set numbers and
+    the union of the edge lists is the oracle's edge list.  With the universe-table build every
+    shard holds the whole index (stats are whole-set numbers on every rank)."""
+    ps = kc.ProteinSet.synthetic(6000, "A", 0xB2000004, threads=8)
+    km, ix, pr = run_oracle(ps, k, 10, cross)
+    tot_i = {name: 0 for name in ("n_positions", "n_incidences", "n_distinct", "n_singleton", "n_repeated", "nnz")}
+    tot_p = {name: 0 for name in ("n_multi_edges", "n_multi_edges_kept", "n_pairs_kept", "n_edges_out",
+                                  "sum_count_out", "n_rows")}
+    parts = []
+    sharded = None
+    with kc.Engine(k, threshold=10, cross_class_only=cross, want_blosum=True) as e:
+        e.set_protein_set(ps)
+        for s in range(n_shards):
+            ist = e.build_index(s, n_shards)
+            info = e.index_shard_info()
+            sharded = info["n_shards"] > 1
+            assert sharded == (index_flavour == "bucket")
+            pst = e.score_pairs(s, n_shards)
+            parts.append(e.get_edges())
+            for name in tot_i:
+                tot_i[name] += ist[name]
+            for name in tot_p:
+                tot_p[name] += pst[name]
+            if sharded:
+                assert info["shard"] == s and info["row_lo"] <= info["row_hi"] <= ps.n
+                with pytest.raises(kc.KcError):
+                    e.get_vocab()
+                with pytest.raises(kc.KcError):
+                    e.score_pairs((s + 1) % n_shards, n_shards)
+    scale = 1 if sharded else n_shards
+    for name in tot_i:
+        assert tot_i[name] == ix.stats[name] * scale, name
+    assert tot_p["n_multi_edges"] == pr.stats["n_multi_edges"] * scale
+    assert tot_p["n_rows"] == ps.n
+    for name in ("n_multi_edges_kept", "n_pairs_kept", "n_edges_out", "sum_count_out"):
+        assert tot_p[name] == pr.stats[name], name
+    from uniprot_kmer_based_clustering_b200.sharded import merge_edge_lists
+    assert np.array_equal(merge_edge_lists(parts), pr.edges)

@@ -37,7 +37,9 @@ constexpr uint32_t kBinRows = 1u << kBinRowsLog;
 struct BucketGlobals {
   unsigned long long col_cursor;  // postings / entries written so far (= nnz at the end)
   unsigned long long id_cursor;   // ids handed out (= n_repeated at the end)
-  unsigned long long n_distinct, multi_total, work_total;
+  // totals over the k-mers this build OWNS (the first holder is one of its rows; every k-mer
+  // when the build is not sharded): summed over the ranks they are the whole-set numbers
+  unsigned long long n_distinct, n_repeated, nnz, multi_total, work_total;
   uint32_t overflow;              // some bucket was sent more than kBkCap records
   uint32_t max_bucket;
 };
@@ -63,7 +65,8 @@ __global__ void __launch_bounds__(kBkThreads, 2)
                         const uint32_t* __restrict__ first_after, int k, uint32_t* __restrict__ col,
                         uint4* __restrict__ entries, const uint32_t* __restrict__ rowcap_prefix,
                         uint32_t* __restrict__ bin_cursor, uint32_t* __restrict__ vocab,
-                        uint32_t* __restrict__ freq, uint8_t* __restrict__ selfscore, BucketGlobals* __restrict__ g) {
+                        uint32_t* __restrict__ freq, uint8_t* __restrict__ selfscore, uint32_t row_lo,
+                        uint32_t row_hi, BucketGlobals* __restrict__ g) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   uint32_t* s_key = reinterpret_cast<uint32_t*>(dyn_smem);      // [slots] k-mer
   uint32_t* s_val = s_key + kBkSlots;                           // [slots] holders -> cursor -> group end
@@ -78,7 +81,8 @@ __global__ void __launch_bounds__(kBkThreads, 2)
   __shared__ unsigned long long s_base[2];
   __shared__ uint32_t s_nnz;
   const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-  unsigned long long n_distinct = 0, multi = 0, work = 0;
+  unsigned long long multi = 0, work = 0;
+  uint32_t n_distinct = 0, n_rep_owned = 0, nnz_owned = 0;  // per thread: far below 2^32
   uint32_t max_bucket = 0;
 
   uint2 nxt[kBkPerThread];
@@ -148,20 +152,15 @@ __global__ void __launch_bounds__(kBkThreads, 2)
     // scan of (repeated k-mers, their holders) packed as holders << 16 | repeated
     constexpr int SPT = kBkSlots / kBkThreads;
     uint32_t cnts[SPT];
-    uint32_t local = 0, multi32 = 0;
+    uint32_t local = 0;
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
       const uint32_t s = tid + j * kBkThreads;
       const uint32_t c = s_key[s] != kSentinel ? s_val[s] : 0u;
       cnts[j] = c;
       s_cnt[s] = (uint16_t)c;
-      n_distinct += c != 0;
-      if (c >= 2u) {
-        local += (c << 16) | 1u;
-        multi32 += c * (c - 1u) / 2u;  // <= 8192^2 / 2 per slot, <= 2^25 per bucket
-      }
+      if (c >= 2u) local += (c << 16) | 1u;
     }
-    multi += multi32;
     uint32_t incl = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -221,10 +220,14 @@ __global__ void __launch_bounds__(kBkThreads, 2)
       const uint32_t i = tid + j * kBkThreads;
       if (i < nrec) {
         const uint32_t s = s_slot[i];
-        if (s_cnt[s] >= 2u) {
+        const uint32_t c = s_cnt[s];
+        if (c >= 2u) {
           const uint32_t pos = atomicAdd(&s_val[s], 1u);
           s_col[pos] = s_row[i];
           s_grp[pos] = (uint16_t)s;
+        } else {  // a k-mer with one holder: owned by that holder's rank
+          const uint32_t row = s_row[i];
+          n_distinct += row >= row_lo && row < row_hi;
         }
       }
     }
@@ -269,21 +272,33 @@ __global__ void __launch_bounds__(kBkThreads, 2)
           const uint32_t end = s_val[s];
           const uint32_t a = CROSS ? (uint32_t)s_slot[q] : q + 1u;
           const uint32_t row = s_row[q];
+          const bool mine = row >= row_lo && row < row_hi;
+          col[col_base + q] = row;
+          const uint32_t c = s_cnt[s];
+          if (mine && q == end - c) {  // first holder: this build owns the k-mer's totals
+            ++n_distinct;
+            ++n_rep_owned;
+            nnz_owned += c;
+            multi += (unsigned long long)c * (c - 1u) / 2u;
+          }
+          // Every holder gets its entry, also the rows of other shards that passed the filter: the
+          // pair stage scores this build's rows only, but the BLOSUM pass over unscored edges
+          // (edge_blosum_kernel) intersects the id lists of BOTH endpoints, and the k-mers a foreign
+          // row shares with this build's rows are exactly the ones that passed.
           const uint32_t meta = s_meta[s];
           const uint32_t len = end - a;
           // a single partner is stored inline ({rank, sentinel}): no postings gather in the pair stage
           const uint2 sf = len == 1u ? make_uint2(s_row[a], kSentinel)
                                      : make_uint2((uint32_t)col_base + a, (uint32_t)col_base + end);
-          col[col_base + q] = row;
           ent[u] = make_uint4(row | ((meta >> 16) << 24), (uint32_t)id_base + (meta & 0xFFFFu), sf.x, sf.y);
-          work += len;
+          if (mine) work += len;
           bin = row >> kBinRowsLog;
         }
         const uint32_t peers = __match_any_sync(kFullMask, bin);
         const uint32_t leader = __ffs(peers) - 1;
         who[u] = (leader << 8) | __popc(peers & lanemask_lt());
         pend[u] = 0;
-        if (act && lane == leader) pend[u] = atomicAdd(&bin_cursor[bin], (uint32_t)__popc(peers));
+        if (bin != kSentinel && lane == leader) pend[u] = atomicAdd(&bin_cursor[bin], (uint32_t)__popc(peers));
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -296,11 +311,14 @@ __global__ void __launch_bounds__(kBkThreads, 2)
     }
     __syncthreads();
   }
-  n_distinct = warp_sum64(n_distinct);
+  const unsigned long long n_dist64 = warp_sum64(n_distinct), n_rep64 = warp_sum64(n_rep_owned),
+                           nnz64 = warp_sum64(nnz_owned);
   multi = warp_sum64(multi);
   work = warp_sum64(work);
   if (lane == 0) {
-    if (n_distinct) atomicAdd(&g->n_distinct, n_distinct);
+    if (n_dist64) atomicAdd(&g->n_distinct, n_dist64);
+    if (n_rep64) atomicAdd(&g->n_repeated, n_rep64);
+    if (nnz64) atomicAdd(&g->nnz, nnz64);
     if (multi) atomicAdd(&g->multi_total, multi);
     if (work) atomicAdd(&g->work_total, work);
     atomicMax(&g->max_bucket, max_bucket);
@@ -334,7 +352,7 @@ constexpr uint32_t kFinChunk = kFinThreads * kFinPer;
 constexpr size_t kFinSmemBytes = (size_t)kFinChunk * 16;
 __global__ void __launch_bounds__(kFinThreads)
     rows_finalize_kernel(const uint4* __restrict__ entries, const uint32_t* __restrict__ rowcap_prefix,
-                         const uint32_t* __restrict__ bin_cnt, uint32_t n, uint32_t n_bins,
+                         const uint32_t* __restrict__ bin_cnt, uint32_t n, uint32_t bin_lo, uint32_t n_bins,
                          uint32_t* __restrict__ rowlen, uint32_t* __restrict__ ids, uint2* __restrict__ suf,
                          uint8_t* __restrict__ sufss, unsigned long long* __restrict__ rowwork64,
                          uint32_t* __restrict__ rowwork, uint32_t* __restrict__ rowinl,
@@ -344,7 +362,7 @@ __global__ void __launch_bounds__(kFinThreads)
   __shared__ uint32_t s_off[kBinRows], s_cnt[kBinRows], s_start[kBinRows], s_inl[kBinRows], s_max[kBinRows];
   __shared__ uint32_t s_wlo[kBinRows], s_whi[kBinRows];  // multi-edges of the row: low word + carries
   const uint32_t tid = threadIdx.x;
-  for (uint32_t bin = blockIdx.x; bin < n_bins; bin += gridDim.x) {
+  for (uint32_t bin = bin_lo + blockIdx.x; bin < n_bins; bin += gridDim.x) {  // [bin_lo, n_bins): this build's rows
     const uint32_t r0 = bin << kBinRowsLog;
     const uint32_t nrows = min(kBinRows, n - r0);
     const uint4* src = entries + rowcap_prefix[r0];

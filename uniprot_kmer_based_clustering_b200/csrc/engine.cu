@@ -102,6 +102,12 @@ struct kc_engine {
   // partitioned index (bucket.cuh): the pair stage reads d_rowptr / d_ids / d_self_h instead of
   // d_pstart / d_pk / d_self; the canonical view (legacy arrays) is derived on demand
   bool bucketed = false, canonical_ready = false;
+  // sharded build (kc_build_index_shard with n_shards > 1): this engine holds the index of the row
+  // block [row_bounds[0], row_bounds[1]) of the pair order only
+  uint32_t ishard = 0, ishards = 1;
+  uint32_t row_bounds[2] = {0, 0};
+  uint64_t v_local = 0;  // ids handed out by this build (= n_repeated when not sharded)
+  DBuf d_filter;
   DBuf d_recA, d_recB, d_histA, d_histB, d_segoff, d_bucketoff, d_rowptr, d_ids, d_vocab_h, d_freq_h, d_self_h,
       d_zero, d_rowlen_c, d_islo_c;
   const uint32_t* pair_rowptr() const { return (bucketed ? d_segoff : d_pstart).as<uint32_t>(); }  // d_segoff: capacity prefix
@@ -254,7 +260,7 @@ int stage_layout(kc_engine* e) {
 size_t padded_res_bytes(uint64_t R) { return (size_t)((R + kTileRes - 1) / kTileRes + 1) * kTileRes; }
 
 template <int K>
-int run_extract_census(kc_engine* e, BucketScatter scatter = BucketScatter{nullptr, nullptr, 0u}) {
+int run_extract_census(kc_engine* e, BucketScatter scatter = BucketScatter{nullptr, nullptr, 0u, nullptr, 0u, 0u, 0u}) {
   const uint32_t n = (uint32_t)e->n;
   DeviceScalars* ds = e->ds;
   const uint8_t* res = e->d_res.as<uint8_t>();
@@ -399,7 +405,8 @@ struct ColptrOut {
 
 
 // ---- the partitioned index build (bucket.cuh) -----------------------------------------------
-static int build_index_bucketed(kc_engine* e, kc_index_stats* stats, bool* overflow) {
+static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_index_stats* stats,
+                                bool* overflow) {
   const uint32_t n = (uint32_t)e->n;
   const uint64_t R = e->R;
   DeviceScalars* ds = e->ds;
@@ -409,8 +416,36 @@ static int build_index_bucketed(kc_engine* e, kc_index_stats* stats, bool* overf
   for (uint32_t r = 0; r < n; ++r)
     if (e->h_plen[r] >= (uint32_t)e->cfg.k) n_positions += (e->h_plen[r] - e->cfg.k + 1) / every;
   const uint64_t E = std::max<unsigned long long>(n_positions, 1);  // upper bound on the incidences
-  const uint32_t NB = (uint32_t)((E + kBkTargetFill - 1) / kBkTargetFill);  // buckets
   const uint32_t n_bins = (n + kBinRows - 1) >> kBinRowsLog;                // entry bins
+  // sharded build: this rank's row block = an equal share of the k-mer positions, cut at bin borders
+  uint32_t row_lo = 0, row_hi = n;
+  unsigned long long own_positions = n_positions;
+  if (n_shards > 1) {
+    auto cut = [&](uint32_t s) -> uint32_t {
+      if (s == 0) return 0u;
+      if (s >= n_shards) return n;
+      const unsigned long long target = n_positions / n_shards * s + (n_positions % n_shards) * s / n_shards;
+      unsigned long long acc = 0;
+      uint32_t r = 0;
+      for (; r < n && acc < target; ++r)
+        if (e->h_plen[r] >= (uint32_t)e->cfg.k) acc += (e->h_plen[r] - e->cfg.k + 1) / every;
+      return std::min<uint32_t>(n, (r + kBinRows - 1) & ~(kBinRows - 1u));
+    };
+    row_lo = cut(shard);
+    row_hi = std::max(row_lo, cut(shard + 1));
+    own_positions = 0;
+    for (uint32_t r = row_lo; r < row_hi; ++r)
+      if (e->h_plen[r] >= (uint32_t)e->cfg.k) own_positions += (e->h_plen[r] - e->cfg.k + 1) / every;
+  }
+  // the records this build keeps: all of its own rows' plus what passes the filter (bounded by E)
+  const uint32_t NB = (uint32_t)((E + kBkTargetFill - 1) / kBkTargetFill);  // buckets
+  uint32_t filter_bits = 0;
+  if (n_shards > 1) {
+    filter_bits = 1u << 20;
+    while (filter_bits < (1u << 30) && (unsigned long long)filter_bits < 8ull * std::max<unsigned long long>(own_positions, 1))
+      filter_bits <<= 1;
+    KC_CUDA(e, e->d_filter.ensure((size_t)filter_bits / 8 + 64));
+  }
   KC_CUDA(e, e->d_pk.ensure((R + 64) * 4));
   KC_CUDA(e, e->d_ndist.ensure(((uint64_t)n + 1) * 4));
   KC_CUDA(e, e->d_rowlen.ensure(((uint64_t)n + 1) * 4));
@@ -447,10 +482,25 @@ static int build_index_bucketed(kc_engine* e, kc_index_stats* stats, bool* overf
   KC_CUDA(e, cudaMemsetAsync(bin_cnt, 0, ((uint64_t)n_bins + 1) * 4, e->stream));
   // K1/K2: extract + per-protein dedup; every (distinct k-mer, row) is appended to its bucket
   mark(e, EV_IC0);
+  if (n_shards > 1) {  // filter of the k-mers this rank's rows hold
+    KC_CUDA(e, cudaMemsetAsync(e->d_filter.p, 0, (size_t)filter_bits / 8, e->stream));
+    if (row_hi > row_lo) {
+      const uint32_t fgrid = blocks_for(row_hi - row_lo, 8, e->num_sm * 8);
+      if (e->cfg.k == 5)
+        KC_LAUNCH(e, kmer_filter_build_kernel<5>, fgrid, 256, 0, e->d_res.as<uint8_t>(), e->d_pstart.as<uint32_t>(),
+                  e->d_plen.as<uint32_t>(), row_lo, row_hi, e->cfg.sample_every, e->cfg.sample_seed,
+                  e->d_orig.as<uint32_t>(), e->d_filter.as<uint32_t>(), filter_bits - 1u);
+      else
+        KC_LAUNCH(e, kmer_filter_build_kernel<7>, fgrid, 256, 0, e->d_res.as<uint8_t>(), e->d_pstart.as<uint32_t>(),
+                  e->d_plen.as<uint32_t>(), row_lo, row_hi, e->cfg.sample_every, e->cfg.sample_seed,
+                  e->d_orig.as<uint32_t>(), e->d_filter.as<uint32_t>(), filter_bits - 1u);
+    }
+  }
   {
     DBuf none;
     std::swap(none, e->d_ksplit);  // the rows are not sliced: run_extract_census passes ksplit = null
-    const BucketScatter scatter{rec, bucket_cnt, NB};
+    const BucketScatter scatter{rec, bucket_cnt, NB, n_shards > 1 ? e->d_filter.as<uint32_t>() : nullptr,
+                                filter_bits - 1u, row_lo, row_hi};
     rc = e->cfg.k == 5 ? run_extract_census<5>(e, scatter) : run_extract_census<7>(e, scatter);
     std::swap(none, e->d_ksplit);
     if (rc) return rc;
@@ -471,15 +521,17 @@ static int build_index_bucketed(kc_engine* e, kc_index_stats* stats, bool* overf
     const uint32_t grid = std::min<uint32_t>(NB, (uint32_t)(e->num_sm * std::max(per_sm, 1)));                   \
     KC_LAUNCH(e, bucket_build_kernel<CROSS>, grid, kBkThreads, kBkSmemBytes, rec, bucket_cnt, NB, fa, e->cfg.k, \
               e->d_col.as<uint32_t>(), ent, rowcap, bin_cnt, e->d_vocab_h.as<uint32_t>(),                       \
-              e->d_freq_h.as<uint32_t>(), e->d_self_h.as<uint8_t>(), &ds->bg);                                  \
+              e->d_freq_h.as<uint32_t>(), e->d_self_h.as<uint8_t>(), row_lo, row_hi, &ds->bg);                  \
   } while (0)
     if (fa) KC_BUCKETS(true); else KC_BUCKETS(false);
 #undef KC_BUCKETS
   }
   // entry bins -> rows (laid out by capacity: row r starts at rowcap[r])
   KC_CUDA(e, cudaFuncSetAttribute(rows_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmemBytes));
-  KC_LAUNCH(e, rows_finalize_kernel, std::min<uint32_t>(n_bins, (uint32_t)e->num_sm * 3), kFinThreads, kFinSmemBytes, ent, rowcap,
-            bin_cnt, n, n_bins, e->d_rowlen.as<uint32_t>(), e->d_ids.as<uint32_t>(), e->d_suf.as<uint2>(),
+  const uint32_t bin_lo = 0, bin_hi = n_bins;  // foreign rows keep (short) id lists too: see bucket_build_kernel
+  if (bin_hi > bin_lo)
+    KC_LAUNCH(e, rows_finalize_kernel, std::min<uint32_t>(bin_hi - bin_lo, (uint32_t)e->num_sm * 3), kFinThreads,
+              kFinSmemBytes, ent, rowcap, bin_cnt, n, bin_lo, bin_hi, e->d_rowlen.as<uint32_t>(), e->d_ids.as<uint32_t>(), e->d_suf.as<uint2>(),
             e->cfg.want_blosum ? e->d_sufss.as<uint8_t>() : nullptr, e->d_rowwork64.as<unsigned long long>(),
             e->d_rowwork.as<uint32_t>(), e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>());
   e->launches += exclusive_scan(WorkIn{e->d_rowwork.as<uint32_t>(), e->d_rowlen.as<uint32_t>()},
@@ -493,14 +545,27 @@ static int build_index_bucketed(kc_engine* e, kc_index_stats* stats, bool* overf
     *overflow = true;
     return KC_OK;
   }
-  e->istats.n_positions = n_positions;
-  e->istats.n_incidences = hs.n_incid;
+  // totals over the k-mers this build owns: the whole-set numbers when summed over the shards
+  unsigned long long own_incid = hs.n_incid;
+  if (n_shards > 1) {
+    uint32_t cap[2] = {0, 0};
+    KC_CUDA(e, cudaMemcpy(&cap[0], rowcap + row_lo, 4, cudaMemcpyDeviceToHost));
+    KC_CUDA(e, cudaMemcpy(&cap[1], rowcap + row_hi, 4, cudaMemcpyDeviceToHost));
+    own_incid = cap[1] - cap[0];
+  }
+  e->istats.n_positions = own_positions;
+  e->istats.n_incidences = own_incid;
   e->istats.n_distinct = hs.bg.n_distinct;
-  e->istats.n_repeated = hs.bg.id_cursor;
-  e->istats.n_singleton = hs.bg.n_distinct - hs.bg.id_cursor;
-  e->istats.nnz = hs.bg.col_cursor;
+  e->istats.n_repeated = hs.bg.n_repeated;
+  e->istats.n_singleton = hs.bg.n_distinct - hs.bg.n_repeated;
+  e->istats.nnz = hs.bg.nnz;
+  e->v_local = hs.bg.id_cursor;
   e->multi_total = hs.bg.multi_total;
   e->work_total = hs.bg.work_total;
+  e->ishard = shard;
+  e->ishards = n_shards;
+  e->row_bounds[0] = row_lo;
+  e->row_bounds[1] = row_hi;
   if (stats) *stats = e->istats;
   e->bucketed = true;
   e->canonical_ready = false;
@@ -513,6 +578,8 @@ static int build_index_bucketed(kc_engine* e, kc_index_stats* stats, bool* overf
 // / lookup entry points (never on the hot path).  d_pk still holds every row's sorted distinct
 // k-mers; it is rewritten to canonical ids in place exactly like the table build does.
 static int ensure_canonical(kc_engine* e) {
+  if (e->ishards > 1)
+    return fail(e, KC_EINVAL, "the readback / lookup entry points need a whole index: kc_build_index, not a shard");
   if (!e->bucketed || e->canonical_ready) return KC_OK;
   const uint32_t n = (uint32_t)e->n;
   const uint64_t W = e->n_words, V = e->istats.n_repeated;
@@ -632,7 +699,7 @@ void kc_destroy(kc_engine* e) {
                  &e->d_self, &e->d_colptr, &e->d_cursor, &e->d_col, &e->d_suf, &e->d_sufss, &e->d_rowwork, &e->d_lists,
                  &e->d_colscratch, &e->d_workprefix, &e->d_ksplit, &e->d_isplit, &e->d_rowwork64, &e->d_rowinl, &e->d_rowmaxlen, &e->d_psplit, &e->d_rowbase, &e->d_plist, &e->d_pss,
                  &e->d_recA, &e->d_recB, &e->d_histA, &e->d_histB, &e->d_segoff, &e->d_bucketoff, &e->d_rowptr, &e->d_ids,
-                 &e->d_vocab_h, &e->d_freq_h, &e->d_self_h, &e->d_zero, &e->d_rowlen_c, &e->d_islo_c, &e->d_rowbin, &e->d_rowsafe, &e->d_rowlogh, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
+                 &e->d_vocab_h, &e->d_freq_h, &e->d_self_h, &e->d_zero, &e->d_rowlen_c, &e->d_islo_c, &e->d_filter, &e->d_rowbin, &e->d_rowsafe, &e->d_rowlogh, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
                  &e->d_vals_a, &e->d_vals_b, &e->d_hist, &e->d_edges_sorted, &e->d_scalars, &e->d_scan_tiles,
                  &e->d_tmp};
   for (DBuf* b : all) b->release();
@@ -736,8 +803,20 @@ int kc_extract_kmers(kc_engine* e, uint32_t* kmers_out, uint64_t capacity, uint6
   return KC_OK;
 }
 
-int kc_build_index(kc_engine* e, kc_index_stats* stats) {
-  if (!e) return KC_EINVAL;
+int kc_build_index(kc_engine* e, kc_index_stats* stats) { return kc_build_index_shard(e, 0, 1, stats); }
+
+int kc_index_shard_info(kc_engine* e, uint32_t info[4]) {
+  if (!e || !info) return KC_EINVAL;
+  if (!e->have_index) return fail(e, KC_EINVAL, "kc_build_index first");
+  info[0] = e->ishard;
+  info[1] = e->ishards;
+  info[2] = e->ishards > 1 ? e->row_bounds[0] : 0u;
+  info[3] = e->ishards > 1 ? e->row_bounds[1] : (uint32_t)e->n;
+  return KC_OK;
+}
+
+int kc_build_index_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_index_stats* stats) {
+  if (!e || n_shards == 0 || shard >= n_shards) return KC_EINVAL;
   if (!e->have_proteins) return fail(e, KC_EINVAL, "kc_set_proteins first");
   KC_CUDA(e, cudaSetDevice(e->dev));
   const uint32_t n = (uint32_t)e->n;
@@ -745,6 +824,8 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
   DeviceScalars* ds = e->ds;
   e->have_index = e->have_pairs = false;
   e->bucketed = e->canonical_ready = false;
+  e->ishard = 0;
+  e->ishards = 1;
   {
     // Index flavour: the partitioned build (bucket.cuh) for sparse universes (k = 7: 21^7 k-mers,
     // random access into universe-sized tables misses L2), the universe-table build (index.cuh)
@@ -755,7 +836,7 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
     if (env && !std::strcmp(env, "table")) want = false;
     if (want && n > 0 && n <= (1u << 24)) {
       bool overflow = false;
-      int rc = build_index_bucketed(e, stats, &overflow);
+      int rc = build_index_bucketed(e, shard, n_shards, stats, &overflow);
       if (rc != KC_OK || !overflow) return rc;
       // a k-mer (or a clump of them) with more holders than a shared-memory bucket takes: table build
     }
@@ -975,6 +1056,7 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats) {
   e->istats.n_incidences = n_incid;
   e->istats.n_distinct = hs.n_distinct;
   e->istats.n_repeated = V;
+  e->v_local = V;
   e->istats.n_singleton = hs.n_distinct - V;
   e->istats.nnz = hs.nnz;
   e->multi_total = hs.multi_total;
@@ -1079,6 +1161,7 @@ int kc_get_pair_index(kc_engine* e, uint32_t* kmers_out, uint32_t* freq_out, uin
   if (!e) return KC_EINVAL;
   if (!e->have_index) return fail(e, KC_EINVAL, "kc_build_index first");
   KC_CUDA(e, cudaSetDevice(e->dev));
+  if (e->ishards > 1) return fail(e, KC_EINVAL, "kc_get_pair_index needs a whole index: kc_build_index, not a shard");
   const uint64_t V = e->istats.n_repeated;
   const uint32_t n = (uint32_t)e->n;
   if ((kmers_out || freq_out || self_out) && capacity_vocab < V) return fail(e, KC_EINVAL, "capacity too small");
@@ -1121,6 +1204,8 @@ int kc_score_pairs(kc_engine* e, kc_pair_stats* stats) { return kc_score_pairs_s
 int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pair_stats* stats) {
   if (!e || n_shards == 0 || shard >= n_shards) return KC_EINVAL;
   if (!e->have_index) return fail(e, KC_EINVAL, "kc_build_index first");
+  if (e->ishards > 1 && (shard != e->ishard || n_shards != e->ishards))
+    return fail(e, KC_EINVAL, "the index was built for another shard (kc_build_index_shard)");
   KC_CUDA(e, cudaSetDevice(e->dev));
   const uint32_t n = (uint32_t)e->n;
   DeviceScalars* ds = e->ds;
@@ -1128,7 +1213,7 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
   e->n_edges = 0;
   kc_pair_stats ps{};
   ps.n_multi_edges = e->multi_total;
-  if (n == 0 || e->istats.n_repeated == 0) {
+  if (n == 0 || e->v_local == 0) {
     e->pstats = ps;
     if (stats) *stats = ps;
     e->have_pairs = true;
@@ -1163,8 +1248,11 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
   for (int attempt = 0;; ++attempt) {
     KC_CUDA(e, cudaMemsetAsync(&ds->edge_cursor, 0,
                                sizeof(DeviceScalars) - offsetof(DeviceScalars, edge_cursor), e->stream));
-    KC_LAUNCH(e, shard_bounds_kernel, 1, 32, 0, e->d_workprefix.as<unsigned long long>(), n, shard, n_shards,
-              ds->shard_rows);
+    if (e->ishards > 1)  // sharded index: the row block was fixed when the index was built
+      KC_CUDA(e, cudaMemcpyAsync(ds->shard_rows, e->row_bounds, 8, cudaMemcpyHostToDevice, e->stream));
+    else
+      KC_LAUNCH(e, shard_bounds_kernel, 1, 32, 0, e->d_workprefix.as<unsigned long long>(), n, shard, n_shards,
+                ds->shard_rows);
     KC_LAUNCH(e, classify_rows_kernel, (n + 255) / 256, 256, 0, e->d_rowwork.as<uint32_t>(),
               e->d_rowlen.as<uint32_t>(), e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>(),
               e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr, n,

@@ -19,13 +19,28 @@ __constant__ uint8_t c_residue_lut[256];
 constexpr uint32_t kBkCap = 4096;  // records per bucket slot
 __host__ __device__ __forceinline__ uint32_t kmer_bucket_hash(uint32_t kmer) { return kmer * 0x9E3779B1u; }
 
-// where the extract kernels append the incidences (rec == nullptr: the universe-table build)
+// where the extract kernels append the incidences (rec == nullptr: the universe-table build).
+// Sharded build (multi-GPU, one row block [row_lo, row_hi) of the pair triangle per rank): a rank
+// only needs the k-mers its own rows hold, with ALL their holders.  `filter` is a bitmap over a
+// hash of the k-mers of the rank's own rows (kmer_filter_build_kernel); the incidences of the
+// other rows are appended only when their k-mer passes it (false positives only cost work).
 struct BucketScatter {
   uint2* rec;          // n_buckets slots of kBkCap {k-mer, row} records
   uint32_t* cursor;    // records appended per bucket (may pass kBkCap: overflow, the build falls back)
   uint32_t n_buckets;
+  const uint32_t* filter;  // null: every incidence is kept
+  uint32_t filter_mask;    // filter bits - 1 (power of two)
+  uint32_t row_lo, row_hi;
+  __device__ __forceinline__ static uint32_t filter_hash(uint32_t kmer) {
+    uint32_t h = kmer * 0x85EBCA6Bu;
+    return h ^ (h >> 13);
+  }
   // two steps so that a caller can keep several reservations (L2 atomics) in flight
-  __device__ __forceinline__ unsigned long long reserve(uint32_t kmer) const {
+  __device__ __forceinline__ unsigned long long reserve(uint32_t kmer, uint32_t row) const {
+    if (filter && (row < row_lo || row >= row_hi)) {
+      const uint32_t f = filter_hash(kmer) & filter_mask;
+      if (!((__ldg(filter + (f >> 5)) >> (f & 31u)) & 1u)) return ~0ull;
+    }
     const uint32_t b = __umulhi(kmer_bucket_hash(kmer), n_buckets);
     const uint32_t pos = atomicAdd(&cursor[b], 1u);
     return pos < kBkCap ? (unsigned long long)b * kBkCap + pos : ~0ull;
@@ -33,9 +48,8 @@ struct BucketScatter {
   __device__ __forceinline__ void store(unsigned long long at, uint32_t kmer, uint32_t row) const {
     if (at != ~0ull) rec[at] = make_uint2(kmer, row);
   }
-  __device__ __forceinline__ void put(uint32_t kmer, uint32_t row) const { store(reserve(kmer), kmer, row); }
+  __device__ __forceinline__ void put(uint32_t kmer, uint32_t row) const { store(reserve(kmer, row), kmer, row); }
 };
-
 
 // ---- census: two bits of state per k-mer, interleaved in one word (16 k-mers per u32):
 // bit 2j = "held by >= 1 protein", bit 2j+1 = "held by >= 2 proteins".  The first holder sets
@@ -250,7 +264,7 @@ __global__ void __launch_bounds__(kExtractWarps * 32)
       unsigned long long at[4];
       if (scatter.rec) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) at[u] = first[u] ? scatter.reserve(v[u]) : ~0ull;
+        for (int u = 0; u < 4; ++u) at[u] = first[u] ? scatter.reserve(v[u], r) : ~0ull;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -439,7 +453,7 @@ __global__ void __launch_bounds__(kXsWarps * 32)
       }
       unsigned long long at[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) at[u] = first[u] ? scatter.reserve(v[u]) : ~0ull;
+      for (int u = 0; u < 4; ++u) at[u] = first[u] ? scatter.reserve(v[u], r) : ~0ull;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         scatter.store(at[u], v[u], r);
@@ -452,6 +466,37 @@ __global__ void __launch_bounds__(kXsWarps * 32)
     __syncwarp();
   }
   if (lane == 0 && incid) atomicAdd(n_incid, incid);
+}
+
+// Sharded build: mark (a hash of) every k-mer of the rows [row_lo, row_hi) in the filter bitmap.
+// One warp per row, any length; duplicates are harmless.
+template <int K>
+__global__ void __launch_bounds__(256)
+    kmer_filter_build_kernel(const uint8_t* __restrict__ res, const uint32_t* __restrict__ pstart,
+                             const uint32_t* __restrict__ plen, uint32_t row_lo, uint32_t row_hi,
+                             uint32_t sample_every, unsigned long long sample_seed,
+                             const uint32_t* __restrict__ orig_of, uint32_t* __restrict__ filter,
+                             uint32_t filter_mask) {
+  __shared__ uint8_t s_lut[256];
+  s_lut[threadIdx.x] = c_residue_lut[threadIdx.x];
+  __syncthreads();
+  const uint32_t lane = lane_id();
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t r = row_lo + gw; r < row_hi; r += nw) {
+    const uint32_t len = plen[r], ps = pstart[r];
+    if (len < (uint32_t)K) continue;
+    const uint32_t npos_all = len - K + 1;
+    const uint32_t npos = sample_every > 1 ? npos_all / sample_every : npos_all;
+    const uint32_t skey = sample_every > 1 ? sample_key(sample_seed, orig_of ? orig_of[r] : r) : 0u;
+    for (uint32_t i = lane; i < npos; i += 32) {
+      const uint32_t pos = sample_every > 1 ? sample_perm(skey, npos_all, i) : i;
+      uint32_t v = 0;
+#pragma unroll
+      for (int j = 0; j < K; ++j) v = v * 21u + s_lut[res[ps + pos + j]];
+      const uint32_t f = BucketScatter::filter_hash(v) & filter_mask;
+      atomicOr(&filter[f >> 5], 1u << (f & 31u));
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -176,11 +176,19 @@ class Engine:
         return out
 
     # ---- K2-K5 ----------------------------------------------------------------------
-    def build_index(self) -> dict:
+    def build_index(self, shard: int = 0, n_shards: int = 1) -> dict:
+        """n_shards > 1: the index of one row block of the pair triangle (kc_build_index_shard);
+        the stats then add up to the whole-set numbers over the shards"""
         st = IndexStats()
-        self._check(self._L.kc_build_index(self._h, C.byref(st)))
+        self._check(self._L.kc_build_index_shard(self._h, shard, n_shards, C.byref(st)))
         self.index_stats = stats_dict(st)
         return self.index_stats
+
+    def index_shard_info(self) -> dict:
+        """what the current index covers; n_shards == 1: a whole index (whole-set stats)"""
+        info = np.zeros(4, dtype=np.uint32)
+        self._check(self._L.kc_index_shard_info(self._h, _ptr(info)))
+        return {"shard": int(info[0]), "n_shards": int(info[1]), "row_lo": int(info[2]), "row_hi": int(info[3])}
 
     def get_distinct_kmers(self) -> np.ndarray:
         out = np.empty(self.index_stats["n_distinct"], dtype=np.uint32)

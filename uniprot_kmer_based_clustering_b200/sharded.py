@@ -119,13 +119,34 @@ def gather_edges_device(engine, dist, rank: int, world: int, pinned_out=None, ds
     return edges
 
 
-def reduce_pair_stats(stats: dict, dist, world: int, device=None) -> dict:
-    """Whole-job counters from per-shard counters (n_multi_edges is a whole-set constant)."""
+INDEX_STAT_KEYS = ["n_positions", "n_incidences", "n_distinct", "n_singleton", "n_repeated", "nnz"]
+
+
+def reduce_index_stats(stats: dict, dist, world: int, device=None, sharded_index: bool = True) -> dict:
+    """Whole-set index counters.  A sharded build (kc_build_index_shard) reports totals over the
+    k-mers each rank owns, which add up; a whole index per rank already holds the whole-set numbers."""
+    import torch
+    if world == 1 or not sharded_index:
+        return dict(stats)
+    device = device or torch.device("cpu")
+    t = torch.tensor([stats[k] for k in INDEX_STAT_KEYS], dtype=torch.int64, device=device)
+    dist.all_reduce(t)
+    out = dict(stats)
+    for k, v in zip(INDEX_STAT_KEYS, t.tolist()):
+        out[k] = int(v)
+    return out
+
+
+def reduce_pair_stats(stats: dict, dist, world: int, device=None, sharded_index: bool = False) -> dict:
+    """Whole-job counters from per-shard counters (n_multi_edges is a whole-set constant when every
+    rank holds the whole index, a per-rank share when the index is sharded)."""
     import torch
     if world == 1:
         return dict(stats)
     device = device or torch.device("cpu")
     keys = ["n_multi_edges_kept", "n_pairs_kept", "n_edges_out", "sum_count_out", "n_rows"]
+    if sharded_index:
+        keys = keys + ["n_multi_edges"]
     t = torch.tensor([stats[k] for k in keys], dtype=torch.int64, device=device)
     dist.all_reduce(t)
     out = dict(stats)
