@@ -11,9 +11,10 @@ one GPU.  One "step" = one pass of the hot path over the whole protein set:
 `value` is measured with the residue stream already resident in HBM, CUDA events on the
 launching stream; `e2e` is the same step through the C ABI from pinned HOST buffers with the
 H2D staging and the D2H edge readback inside the timed region (wall clock around a sync).
-At N > 1 every rank holds the full index (replicated build) and scores its own work-balanced
-shard of the pair triangle; the sorted edge lists are gathered to rank 0 over NCCL inside the
-timed region.  Total work is fixed, so "scaling" is "strong".
+At N > 1 the pair triangle is cut into N row blocks (an equal share of the k-mer positions each);
+every rank builds the index of its own block from the whole residue stream (kc_build_index_shard:
+owner computes, no exchange) and scores it; the sorted edge lists are gathered to rank 0 over NCCL
+inside the timed region.  Total work is fixed, so "scaling" is "strong".
 """
 from __future__ import annotations
 
@@ -208,7 +209,7 @@ def main():
     eng.set_stream(stream.cuda_stream)
 
     def step_resident():
-        ist = eng.build_index()
+        ist = eng.build_index(rank, world)
         pst = eng.score_pairs(rank, world)
         return ist, pst
 
@@ -219,7 +220,7 @@ def main():
         eng.set_proteins_ptr(h_res.data_ptr(), h_off.data_ptr(), h_cls.data_ptr(), n, on_device=False)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        ist = eng.build_index()
+        ist = eng.build_index(rank, world)
         t2 = time.perf_counter()
         pst = eng.score_pairs(rank, world)
         t3 = time.perf_counter()
@@ -295,15 +296,22 @@ def main():
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     dev_ms, e2e_s, index_ms, pairs_ms, pair_kernel_ms, census_ms, edges_ms = red.tolist()
     m_kept, e_out, p_kept, launches_all = (int(x) for x in sums.tolist())
+    # a sharded index build reports per-rank shares that add up; a whole index per rank (k = 5: the
+    # universe-table build) reports the whole-set numbers on every rank
+    sharded_index = eng.index_shard_info()["n_shards"] > 1
+    ist_rank = dict(ist)
+    ist = sharded.reduce_index_stats(ist, dist, world, torch.device("cuda"), sharded_index)
+    pst_all = sharded.reduce_pair_stats(pst, dist, world, torch.device("cuda"), sharded_index)
 
     if rank == 0:
         peak, peak_src = measured_peak()
         nnz = ist["nnz"]
         # 4 B per multi-edge + 4 B per CSR nonzero + 16 B per emitted edge; at N > 1 every
         # rank streams its own rows' suffixes, so the per-rank figure uses the rank-0 share
-        algo_bytes = 4 * pst["n_multi_edges_kept"] + 4 * nnz // world + 16 * pst["n_edges_out"]
+        nnz_rank = ist_rank["nnz"] if sharded_index else nnz // world
+        algo_bytes = 4 * pst["n_multi_edges_kept"] + 4 * nnz_rank + 16 * pst["n_edges_out"]
         achieved = algo_bytes / (stage_ms["pair_kernel_ms"] * 1e-3) / 1e9 if stage_ms["pair_kernel_ms"] > 0 else 0.0
-        idx_bytes = 9 * ist["n_positions"]
+        idx_bytes = 9 * (ist_rank["n_positions"] if sharded_index else ist["n_positions"])
         idx_achieved = idx_bytes / (stage_ms["index_ms"] * 1e-3) / 1e9 if stage_ms["index_ms"] > 0 else 0.0
         h2d = int(h_res.numel() + h_off.numel() * 8 + h_cls.numel() * 4 + 16 * n)
         d2h = int(pst_e["n_edges_out"] * 16 + 12 * n + 512)
@@ -317,19 +325,24 @@ def main():
                        "generator": "G1 (include/kc_host.h)", "seed": hex(WORKLOADS[args.workload][3]),
                        "l2_policy": f"inputs larger than L2 ({ps.residues.size / 1e6:.0f} MB residues, "
                                     f"{4 * nnz / 1e6:.0f} MB postings); no flush needed",
-                       "parallelism": "replicated index, row-block sharded pair triangle" if world > 1 else "1 GPU"},
+                       "parallelism": ("1 GPU" if world == 1 else
+                                       "row-block sharded index + pair triangle (owner computes, no exchange)"
+                                       if sharded_index else
+                                       "replicated index, row-block sharded pair triangle")},
             "kmers_indexed_per_s": ist["n_positions"] / (index_ms * 1e-3),
             "pair_stage_pairs_per_s": pairs_total / (pairs_ms * 1e-3) if pairs_ms > 0 else None,
             "multi_edges_per_s": m_kept / (pair_kernel_ms * 1e-3) if pair_kernel_ms > 0 else None,
             "stage_ms": {"index": index_ms, "census_kernel": census_ms, "pairs": pairs_ms,
                          "pair_kernels": pair_kernel_ms, "edges_sort_blosum": edges_ms},
             "counts": {"n_positions": ist["n_positions"], "n_repeated": ist["n_repeated"], "nnz": nnz,
-                       "n_multi_edges": pst["n_multi_edges"], "n_pairs_nonzero": p_kept, "n_edges_out": e_out},
-            "roofline": {"bound": "hbm", "kernel": "pairs_hash_kernel/pairs_dense_kernel (K7-K8)",
+                       "n_multi_edges": pst_all["n_multi_edges"], "n_pairs_nonzero": p_kept, "n_edges_out": e_out},
+            "roofline": {"bound": "hbm", "kernel": "pairs_main_scored_kernel + packed/dense retries (K7-K9)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes": algo_bytes},
-            "roofline_index": {"bound": "hbm", "kernel": "K1-K5 (extract, dedup, census, index, postings)",
+            "roofline_index": {"bound": "hbm",
+                               "kernel": "K1-K5 (extract_scatter, bucket_build, rows_finalize)" if k == 7
+                               else "K1-K5 (extract, census, ids, postings, suffix ranges)",
                                "achieved": idx_achieved, "peak": peak, "unit": "GB/s", "frac": idx_achieved / peak,
                                "algorithmic_bytes": idx_bytes},
             "e2e": {"value": pairs_total / e2e_s, "unit": "pairs/s", "ms_per_step": e2e_s * 1e3,

@@ -124,17 +124,22 @@ int kc_extract_kmers(kc_engine* e, uint32_t* kmers_out, uint64_t capacity, uint6
 /* Census, unique/repeated split, perfect k-mer index, per-protein id lists, kmer_freq
  * (src/main.rs:84-199; replaces boomphf Mphf::new at :139-140). */
 int kc_build_index(kc_engine* e, kc_index_stats* stats);
-/* Multi-GPU: the index of ONE row block of the pair triangle (block `shard` of `n_shards`, an equal
- * share of the k-mer positions each).  A rank only needs the k-mers its own rows hold, with all
+/* Multi-GPU: the index of ONE rank's rows of the pair triangle.  The pair order is cut into
+ * 2 * n_shards row blocks of equal k-mer positions; rank `shard` owns blocks shard and
+ * 2 * n_shards - 1 - shard (one early, one late: a row is scored against the rows after it, so its
+ * work falls with its position).  A rank only needs the k-mers its own rows hold, with all
  * their holders, so every rank builds its part from the whole residue stream with no exchange
  * (owner computes): the stats are totals over the k-mers whose first holder is in the block and
  * add up to kc_build_index's over the shards.  Follow with kc_score_pairs_shard(shard, n_shards).
  * The readback / lookup entry points need a whole index.  With the universe-table build (k = 5)
  * every rank builds the whole index and the stats are the whole-set numbers on every rank. */
 int kc_build_index_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_index_stats* stats);
-/* What the engine's current index covers: info[0..3] = {shard, n_shards, first row, end row} of the
- * row block in the pair order; n_shards == 1 means a whole index (stats are whole-set numbers). */
+/* What the engine's current index covers: info[0..3] = {shard, n_shards, n_blocks, rows owned};
+ * n_shards == 1 means a whole index (stats are whole-set numbers). */
 int kc_index_shard_info(kc_engine* e, uint32_t info[4]);
+/* bounds[n_blocks + 1]: the row blocks of the pair order (block b is owned by rank b if b < n_shards,
+ * else by rank n_blocks - 1 - b); a whole index has the one block {0, n}. */
+int kc_index_shard_blocks(kc_engine* e, uint32_t* bounds, uint32_t capacity);
 /* all distinct k-mers, ascending (the census keys, src/main.rs:138) */
 int kc_get_distinct_kmers(kc_engine* e, uint32_t* kmers_out, uint64_t capacity);
 /* repeated k-mers ascending (= id order) and kmer_freq[id] (src/main.rs:135,187-193) */

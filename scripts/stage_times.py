@@ -21,26 +21,28 @@ ap.add_argument("--n-proteins", type=int, default=None)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--cross", action="store_true")
 ap.add_argument("--no-blosum", action="store_true")
+ap.add_argument("--shard", type=int, default=0)
+ap.add_argument("--n-shards", type=int, default=1)
 args = ap.parse_args()
 ps, k, cross = make_set(args.workload, args.n_proteins)
 cross = cross or args.cross
 with kc.Engine(k, threshold=THRESHOLD, cross_class_only=cross, want_blosum=not args.no_blosum) as e:
     e.set_protein_set(ps)
     for _ in range(2):
-        ist = e.build_index()
-        pst = e.score_pairs()
+        ist = e.build_index(args.shard, args.n_shards)
+        pst = e.score_pairs(args.shard, args.n_shards)
     torch.cuda.synchronize()
     tot = {}
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e.reset_timings()
-        ist = e.build_index()
-        pst = e.score_pairs()
+        ist = e.build_index(args.shard, args.n_shards)
+        pst = e.score_pairs(args.shard, args.n_shards)
         for key, v in e.timings().items():
             tot[key] = tot.get(key, 0.0) + v
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / args.steps * 1e3
     avg = {key: round(v / args.steps, 3) for key, v in tot.items()}
-    print(args.workload, os.environ.get("KC_B200_INDEX", "default"), f"wall {wall:.2f} ms/step", avg)
+    print(args.workload, f"shard {args.shard}/{args.n_shards}", os.environ.get("KC_B200_INDEX", "default"), f"wall {wall:.2f} ms/step", avg)
     print("  index", ist)
     print("  pairs", pst)

@@ -605,7 +605,8 @@ def test_sharded_index_build_adds_up_to_the_whole(n_shards, k, cross, index_flav
             for name in tot_p:
                 tot_p[name] += pst[name]
             if sharded:
-                assert info["shard"] == s and info["row_lo"] <= info["row_hi"] <= ps.n
+                assert info["shard"] == s and info["n_blocks"] == 2 * n_shards
+                assert info["block_bounds"][0] == 0 and info["block_bounds"][-1] == ps.n
                 with pytest.raises(kc.KcError):
                     e.get_vocab()
                 with pytest.raises(kc.KcError):

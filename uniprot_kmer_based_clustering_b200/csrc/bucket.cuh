@@ -31,8 +31,6 @@ constexpr uint32_t kBkSlots = 4096;   // hash slots per bucket (>= kBkCap: disti
 constexpr int kBkThreads = 512;
 constexpr int kBkPerThread = kBkCap / kBkThreads;
 constexpr uint32_t kBkTargetFill = 2560;  // mean records per bucket (62 % of a slot)
-constexpr uint32_t kBinRowsLog = 6;       // entry bins of 64 rows
-constexpr uint32_t kBinRows = 1u << kBinRowsLog;
 
 struct BucketGlobals {
   unsigned long long col_cursor;  // postings / entries written so far (= nnz at the end)
@@ -40,6 +38,7 @@ struct BucketGlobals {
   // totals over the k-mers this build OWNS (the first holder is one of its rows; every k-mer
   // when the build is not sharded): summed over the ranks they are the whole-set numbers
   unsigned long long n_distinct, n_repeated, nnz, multi_total, work_total;
+  unsigned long long n_records;   // records the buckets received (sizes the next build's bucket count)
   uint32_t overflow;              // some bucket was sent more than kBkCap records
   uint32_t max_bucket;
 };
@@ -65,8 +64,8 @@ __global__ void __launch_bounds__(kBkThreads, 2)
                         const uint32_t* __restrict__ first_after, int k, uint32_t* __restrict__ col,
                         uint4* __restrict__ entries, const uint32_t* __restrict__ rowcap_prefix,
                         uint32_t* __restrict__ bin_cursor, uint32_t* __restrict__ vocab,
-                        uint32_t* __restrict__ freq, uint8_t* __restrict__ selfscore, uint32_t row_lo,
-                        uint32_t row_hi, BucketGlobals* __restrict__ g) {
+                        uint32_t* __restrict__ freq, uint8_t* __restrict__ selfscore, RowOwner owner,
+                        BucketGlobals* __restrict__ g) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   uint32_t* s_key = reinterpret_cast<uint32_t*>(dyn_smem);      // [slots] k-mer
   uint32_t* s_val = s_key + kBkSlots;                           // [slots] holders -> cursor -> group end
@@ -84,6 +83,7 @@ __global__ void __launch_bounds__(kBkThreads, 2)
   unsigned long long multi = 0, work = 0;
   uint32_t n_distinct = 0, n_rep_owned = 0, nnz_owned = 0;  // per thread: far below 2^32
   uint32_t max_bucket = 0;
+  unsigned long long n_records = 0;
 
   uint2 nxt[kBkPerThread];
   uint32_t b = blockIdx.x;
@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(kBkThreads, 2)
   for (; b < n_buckets; b += gridDim.x) {
     const uint32_t nrec = n_cur;
     max_bucket = max(max_bucket, nrec);
+    if (tid == 0) n_records += nrec;
     // ---- P0: clear the table
 #pragma unroll
     for (int j = 0; j < (int)(kBkSlots / kBkThreads); ++j) {
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(kBkThreads, 2)
           s_grp[pos] = (uint16_t)s;
         } else {  // a k-mer with one holder: owned by that holder's rank
           const uint32_t row = s_row[i];
-          n_distinct += row >= row_lo && row < row_hi;
+          n_distinct += owner.mine(row);
         }
       }
     }
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(kBkThreads, 2)
           const uint32_t end = s_val[s];
           const uint32_t a = CROSS ? (uint32_t)s_slot[q] : q + 1u;
           const uint32_t row = s_row[q];
-          const bool mine = row >= row_lo && row < row_hi;
+          const bool mine = owner.mine(row);
           col[col_base + q] = row;
           const uint32_t c = s_cnt[s];
           if (mine && q == end - c) {  // first holder: this build owns the k-mer's totals
@@ -322,7 +323,18 @@ __global__ void __launch_bounds__(kBkThreads, 2)
     if (multi) atomicAdd(&g->multi_total, multi);
     if (work) atomicAdd(&g->work_total, work);
     atomicMax(&g->max_bucket, max_bucket);
+    if (n_records) atomicAdd(&g->n_records, n_records);
   }
+}
+
+// sharded build: distinct k-mers of this rank's rows (its share of n_incidences)
+__global__ void own_incidences_kernel(const uint32_t* __restrict__ ndist, uint32_t n, RowOwner owner,
+                                      unsigned long long* __restrict__ total) {
+  unsigned long long s = 0;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
+    if (owner.mine(r)) s += ndist[r];
+  s = warp_sum64(s);
+  if (lane_id() == 0 && s) atomicAdd(total, s);
 }
 
 // distinct k-mers of the rows before row r (entry capacity of the rows' bins): prefix[r], prefix[n]

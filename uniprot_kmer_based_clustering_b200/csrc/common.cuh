@@ -9,6 +9,19 @@ constexpr uint32_t kFullMask = 0xFFFFFFFFu;
 constexpr uint32_t kSentinel = 0xFFFFFFFFu;  // never a packed k-mer (21^7 < 2^31) nor a protein
 constexpr int kNumSM = 148;                  // B200: 2 dies x 74 SMs
 
+// Rows are owned in blocks of 64 consecutive rows of the pair order ("bins": the entry bins of the
+// partitioned index, bucket.cuh).  Sharded build / scoring: bin_owner[row >> 6] names the rank that
+// owns the row; null = everything is this engine's.
+constexpr uint32_t kBinRowsLog = 6;
+constexpr uint32_t kBinRows = 1u << kBinRowsLog;
+struct RowOwner {
+  const uint8_t* bin_owner;
+  uint32_t me;
+  __device__ __forceinline__ bool mine(uint32_t row) const {
+    return !bin_owner || bin_owner[row >> kBinRowsLog] == me;
+  }
+};
+
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ uint32_t lanemask_lt() {
   uint32_t m;

@@ -88,6 +88,10 @@ struct kc_engine {
   std::vector<unsigned long long> h_huge_off;
   uint32_t max_block_np2 = 0, max_block_len = 0;
   uint32_t n_mid_rows = 0;  // proteins of kHashMaxPos+1 .. kWarpMaxPos positions
+  std::vector<unsigned long long> h_pospref;  // k-mer positions (after subsampling) of the rows before row r
+  unsigned long long n_pos_unsampled = 0;
+  uint32_t max_plen = 0;
+  bool retry_full_buckets = false;
   DBuf d_res, d_off, d_kpos, d_pstart, d_plen, d_orig, d_rank, d_first_after, d_long, d_huge, d_huge_off,
       d_huge_scratch;
   // index
@@ -105,9 +109,16 @@ struct kc_engine {
   // sharded build (kc_build_index_shard with n_shards > 1): this engine holds the index of the row
   // block [row_bounds[0], row_bounds[1]) of the pair order only
   uint32_t ishard = 0, ishards = 1;
-  uint32_t row_bounds[2] = {0, 0};
-  uint64_t v_local = 0;  // ids handed out by this build (= n_repeated when not sharded)
-  DBuf d_filter;
+  std::vector<uint32_t> block_bounds;  // n_blocks + 1 rows of the pair order (2 blocks per rank, zig-zag)
+  std::vector<uint8_t> h_binowner;
+  uint32_t n_own_rows = 0;
+  uint64_t v_local = 0;    // ids handed out by this build (= n_repeated when not sharded)
+  uint64_t kept_hint = 0;  // records the last sharded build kept (sizes the bucket count of the next one)
+  uint32_t hint_shards = 0;
+  DBuf d_filter, d_binowner;
+  RowOwner owner() const {
+    return RowOwner{ishards > 1 ? d_binowner.as<uint8_t>() : nullptr, ishard};
+  }
   DBuf d_recA, d_recB, d_histA, d_histB, d_segoff, d_bucketoff, d_rowptr, d_ids, d_vocab_h, d_freq_h, d_self_h,
       d_zero, d_rowlen_c, d_islo_c;
   const uint32_t* pair_rowptr() const { return (bucketed ? d_segoff : d_pstart).as<uint32_t>(); }  // d_segoff: capacity prefix
@@ -216,12 +227,19 @@ int stage_layout(kc_engine* e) {
   e->max_block_np2 = 0;
   e->max_block_len = 0;
   e->n_mid_rows = 0;
+  e->h_pospref.assign(n + 1, 0);
+  e->n_pos_unsampled = 0;
+  e->max_plen = 0;
+  const uint64_t every = e->cfg.sample_every > 1 ? e->cfg.sample_every : 1;
   unsigned long long huge_total = 0;
   for (uint64_t r = 0; r < n; ++r) {
     const uint32_t p = e->h_orig[r];
     const uint64_t len = off[p + 1] - off[p];
     e->h_pstart[r] = (uint32_t)off[p];
     e->h_plen[r] = (uint32_t)len;
+    e->max_plen = std::max(e->max_plen, (uint32_t)len);
+    e->h_pospref[r + 1] = e->h_pospref[r] + (len >= (uint64_t)k ? (len - k + 1) / every : 0);
+    e->n_pos_unsampled += len >= (uint64_t)k ? len - k + 1 : 0;
     if (len >= (uint64_t)k) {
       const uint32_t npos = (uint32_t)(len - k + 1);
       if (npos > kBlockMaxPos) {
@@ -260,7 +278,7 @@ int stage_layout(kc_engine* e) {
 size_t padded_res_bytes(uint64_t R) { return (size_t)((R + kTileRes - 1) / kTileRes + 1) * kTileRes; }
 
 template <int K>
-int run_extract_census(kc_engine* e, BucketScatter scatter = BucketScatter{nullptr, nullptr, 0u, nullptr, 0u, 0u, 0u}) {
+int run_extract_census(kc_engine* e, BucketScatter scatter = BucketScatter{nullptr, nullptr, 0u, nullptr, 0u, RowOwner{nullptr, 0u}}) {
   const uint32_t n = (uint32_t)e->n;
   DeviceScalars* ds = e->ds;
   const uint8_t* res = e->d_res.as<uint8_t>();
@@ -411,34 +429,53 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
   const uint64_t R = e->R;
   DeviceScalars* ds = e->ds;
   *overflow = false;
-  unsigned long long n_positions = 0;
-  const uint32_t every = e->cfg.sample_every > 1 ? e->cfg.sample_every : 1;
-  for (uint32_t r = 0; r < n; ++r)
-    if (e->h_plen[r] >= (uint32_t)e->cfg.k) n_positions += (e->h_plen[r] - e->cfg.k + 1) / every;
+  const unsigned long long n_positions = e->h_pospref[n];
   const uint64_t E = std::max<unsigned long long>(n_positions, 1);  // upper bound on the incidences
   const uint32_t n_bins = (n + kBinRows - 1) >> kBinRowsLog;                // entry bins
-  // sharded build: this rank's row block = an equal share of the k-mer positions, cut at bin borders
-  uint32_t row_lo = 0, row_hi = n;
+  // Sharded build: the pair order is cut into 2 * n_shards row blocks of equal k-mer positions (at
+  // bin borders); rank g owns blocks g and 2 * n_shards - 1 - g.  The work of a row falls with its
+  // position in the pair order (it is scored against the rows after it), so the zig-zag gives every
+  // rank one early and one late block.
   unsigned long long own_positions = n_positions;
+  uint32_t n_own_rows = n;
+  std::vector<uint32_t> bounds;
   if (n_shards > 1) {
-    auto cut = [&](uint32_t s) -> uint32_t {
-      if (s == 0) return 0u;
-      if (s >= n_shards) return n;
-      const unsigned long long target = n_positions / n_shards * s + (n_positions % n_shards) * s / n_shards;
-      unsigned long long acc = 0;
-      uint32_t r = 0;
-      for (; r < n && acc < target; ++r)
-        if (e->h_plen[r] >= (uint32_t)e->cfg.k) acc += (e->h_plen[r] - e->cfg.k + 1) / every;
-      return std::min<uint32_t>(n, (r + kBinRows - 1) & ~(kBinRows - 1u));
-    };
-    row_lo = cut(shard);
-    row_hi = std::max(row_lo, cut(shard + 1));
+    const uint32_t n_blocks = 2 * n_shards;
+    bounds.assign(n_blocks + 1, n);
+    bounds[0] = 0;
+    for (uint32_t b = 1; b < n_blocks; ++b) {
+      const unsigned long long target = n_positions / n_blocks * b + (n_positions % n_blocks) * b / n_blocks;
+      const uint32_t r = (uint32_t)(std::lower_bound(e->h_pospref.begin(), e->h_pospref.end(), target) -
+                                    e->h_pospref.begin());  // first r with positions(rows < r) >= target
+      bounds[b] = std::max(bounds[b - 1], std::min<uint32_t>(n, (r + kBinRows - 1) & ~(kBinRows - 1u)));
+    }
+    e->h_binowner.assign(n_bins, 0);
     own_positions = 0;
-    for (uint32_t r = row_lo; r < row_hi; ++r)
-      if (e->h_plen[r] >= (uint32_t)e->cfg.k) own_positions += (e->h_plen[r] - e->cfg.k + 1) / every;
+    n_own_rows = 0;
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+      const uint32_t who = b < n_shards ? b : n_blocks - 1 - b;
+      for (uint32_t bin = bounds[b] >> kBinRowsLog; bin < (bounds[b + 1] + kBinRows - 1) >> kBinRowsLog; ++bin)
+        e->h_binowner[bin] = (uint8_t)who;
+      if (who != shard) continue;
+      n_own_rows += bounds[b + 1] - bounds[b];
+      own_positions += e->h_pospref[bounds[b + 1]] - e->h_pospref[bounds[b]];
+    }
+    KC_CUDA(e, e->d_binowner.ensure((size_t)n_bins + 64));
+    KC_CUDA(e, cudaMemcpyAsync(e->d_binowner.p, e->h_binowner.data(), n_bins, cudaMemcpyHostToDevice, e->stream));
   }
-  // the records this build keeps: all of its own rows' plus what passes the filter (bounded by E)
-  const uint32_t NB = (uint32_t)((E + kBkTargetFill - 1) / kBkTargetFill);  // buckets
+  const RowOwner owner{n_shards > 1 ? e->d_binowner.as<uint8_t>() : nullptr, shard};
+  // The records this build keeps: all of its own rows' plus what passes the filter.  Bucket count
+  // from what the last build of this shape kept, else from a guess (a bucket overflow retries with
+  // the whole-set count).
+  const uint32_t NB_full = (uint32_t)((E + kBkTargetFill - 1) / kBkTargetFill);
+  uint32_t NB = NB_full;
+  if (n_shards > 1) {
+    const unsigned long long guess = e->kept_hint && e->hint_shards == n_shards
+                                         ? e->kept_hint + e->kept_hint / 4
+                                         : std::min<unsigned long long>(E, 2 * own_positions + E / 16);
+    NB = (uint32_t)std::min<unsigned long long>(NB_full, (guess + kBkTargetFill - 1) / kBkTargetFill + 1);
+  }
+  if (e->retry_full_buckets) NB = NB_full;
   uint32_t filter_bits = 0;
   if (n_shards > 1) {
     filter_bits = 1u << 20;
@@ -450,6 +487,7 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
   KC_CUDA(e, e->d_ndist.ensure(((uint64_t)n + 1) * 4));
   KC_CUDA(e, e->d_rowlen.ensure(((uint64_t)n + 1) * 4));
   KC_CUDA(e, e->d_recA.ensure((uint64_t)NB * kBkCap * 8));
+  KC_CUDA(e, e->d_bucketoff.ensure(((uint64_t)NB_full + 2) * 4));
   KC_CUDA(e, e->d_recB.ensure((E + 64) * 16));
   KC_CUDA(e, e->d_bucketoff.ensure(((uint64_t)NB + 2) * 4));                // bucket cursors
   KC_CUDA(e, e->d_segoff.ensure(((uint64_t)n + 2) * 4));                    // rowcap prefix
@@ -484,15 +522,15 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
   mark(e, EV_IC0);
   if (n_shards > 1) {  // filter of the k-mers this rank's rows hold
     KC_CUDA(e, cudaMemsetAsync(e->d_filter.p, 0, (size_t)filter_bits / 8, e->stream));
-    if (row_hi > row_lo) {
-      const uint32_t fgrid = blocks_for(row_hi - row_lo, 8, e->num_sm * 8);
+    if (n_own_rows) {
+      const uint32_t fgrid = blocks_for(n, 8, e->num_sm * 8);
       if (e->cfg.k == 5)
         KC_LAUNCH(e, kmer_filter_build_kernel<5>, fgrid, 256, 0, e->d_res.as<uint8_t>(), e->d_pstart.as<uint32_t>(),
-                  e->d_plen.as<uint32_t>(), row_lo, row_hi, e->cfg.sample_every, e->cfg.sample_seed,
+                  e->d_plen.as<uint32_t>(), n, owner, e->cfg.sample_every, e->cfg.sample_seed,
                   e->d_orig.as<uint32_t>(), e->d_filter.as<uint32_t>(), filter_bits - 1u);
       else
         KC_LAUNCH(e, kmer_filter_build_kernel<7>, fgrid, 256, 0, e->d_res.as<uint8_t>(), e->d_pstart.as<uint32_t>(),
-                  e->d_plen.as<uint32_t>(), row_lo, row_hi, e->cfg.sample_every, e->cfg.sample_seed,
+                  e->d_plen.as<uint32_t>(), n, owner, e->cfg.sample_every, e->cfg.sample_seed,
                   e->d_orig.as<uint32_t>(), e->d_filter.as<uint32_t>(), filter_bits - 1u);
     }
   }
@@ -500,7 +538,7 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
     DBuf none;
     std::swap(none, e->d_ksplit);  // the rows are not sliced: run_extract_census passes ksplit = null
     const BucketScatter scatter{rec, bucket_cnt, NB, n_shards > 1 ? e->d_filter.as<uint32_t>() : nullptr,
-                                filter_bits - 1u, row_lo, row_hi};
+                                filter_bits - 1u, owner};
     rc = e->cfg.k == 5 ? run_extract_census<5>(e, scatter) : run_extract_census<7>(e, scatter);
     std::swap(none, e->d_ksplit);
     if (rc) return rc;
@@ -521,7 +559,7 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
     const uint32_t grid = std::min<uint32_t>(NB, (uint32_t)(e->num_sm * std::max(per_sm, 1)));                   \
     KC_LAUNCH(e, bucket_build_kernel<CROSS>, grid, kBkThreads, kBkSmemBytes, rec, bucket_cnt, NB, fa, e->cfg.k, \
               e->d_col.as<uint32_t>(), ent, rowcap, bin_cnt, e->d_vocab_h.as<uint32_t>(),                       \
-              e->d_freq_h.as<uint32_t>(), e->d_self_h.as<uint8_t>(), row_lo, row_hi, &ds->bg);                  \
+              e->d_freq_h.as<uint32_t>(), e->d_self_h.as<uint8_t>(), owner, &ds->bg);                           \
   } while (0)
     if (fa) KC_BUCKETS(true); else KC_BUCKETS(false);
 #undef KC_BUCKETS
@@ -534,25 +572,32 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
               kFinSmemBytes, ent, rowcap, bin_cnt, n, bin_lo, bin_hi, e->d_rowlen.as<uint32_t>(), e->d_ids.as<uint32_t>(), e->d_suf.as<uint2>(),
             e->cfg.want_blosum ? e->d_sufss.as<uint8_t>() : nullptr, e->d_rowwork64.as<unsigned long long>(),
             e->d_rowwork.as<uint32_t>(), e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>());
-  e->launches += exclusive_scan(WorkIn{e->d_rowwork.as<uint32_t>(), e->d_rowlen.as<uint32_t>()},
-                                U64ExclOutWithTail{e->d_workprefix.as<unsigned long long>(), n}, n, e->scan, e->stream);
+  if (n_shards > 1)  // distinct k-mers of the own rows (ds->multi_total is free in this build: bg holds the totals)
+    KC_LAUNCH(e, own_incidences_kernel, blocks_for(n, 256, e->num_sm * 4), 256, 0, e->d_ndist.as<uint32_t>(), n, owner,
+              &ds->multi_total);
+  else
+    e->launches += exclusive_scan(WorkIn{e->d_rowwork.as<uint32_t>(), e->d_rowlen.as<uint32_t>()},
+                                  U64ExclOutWithTail{e->d_workprefix.as<unsigned long long>(), n}, n, e->scan,
+                                  e->stream);
   mark(e, EV_I1);
   DeviceScalars hs{};
   KC_CUDA(e, cudaMemcpyAsync(&hs, ds, sizeof(hs), cudaMemcpyDeviceToHost, e->stream));
   KC_CUDA(e, cudaStreamSynchronize(e->stream));
   KC_CUDA(e, cudaGetLastError());
   if (hs.bg.overflow) {
+    if (NB < NB_full) {  // the guess of what a sharded build keeps was too small: whole-set bucket count
+      e->retry_full_buckets = true;
+      int rc2 = build_index_bucketed(e, shard, n_shards, stats, overflow);
+      e->retry_full_buckets = false;
+      return rc2;
+    }
     *overflow = true;
     return KC_OK;
   }
+  e->kept_hint = hs.bg.n_records;
+  e->hint_shards = n_shards;
   // totals over the k-mers this build owns: the whole-set numbers when summed over the shards
-  unsigned long long own_incid = hs.n_incid;
-  if (n_shards > 1) {
-    uint32_t cap[2] = {0, 0};
-    KC_CUDA(e, cudaMemcpy(&cap[0], rowcap + row_lo, 4, cudaMemcpyDeviceToHost));
-    KC_CUDA(e, cudaMemcpy(&cap[1], rowcap + row_hi, 4, cudaMemcpyDeviceToHost));
-    own_incid = cap[1] - cap[0];
-  }
+  const unsigned long long own_incid = n_shards > 1 ? hs.multi_total : hs.n_incid;  // own_incidences_kernel
   e->istats.n_positions = own_positions;
   e->istats.n_incidences = own_incid;
   e->istats.n_distinct = hs.bg.n_distinct;
@@ -564,8 +609,8 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
   e->work_total = hs.bg.work_total;
   e->ishard = shard;
   e->ishards = n_shards;
-  e->row_bounds[0] = row_lo;
-  e->row_bounds[1] = row_hi;
+  e->block_bounds = bounds;
+  e->n_own_rows = n_own_rows;
   if (stats) *stats = e->istats;
   e->bucketed = true;
   e->canonical_ready = false;
@@ -699,7 +744,7 @@ void kc_destroy(kc_engine* e) {
                  &e->d_self, &e->d_colptr, &e->d_cursor, &e->d_col, &e->d_suf, &e->d_sufss, &e->d_rowwork, &e->d_lists,
                  &e->d_colscratch, &e->d_workprefix, &e->d_ksplit, &e->d_isplit, &e->d_rowwork64, &e->d_rowinl, &e->d_rowmaxlen, &e->d_psplit, &e->d_rowbase, &e->d_plist, &e->d_pss,
                  &e->d_recA, &e->d_recB, &e->d_histA, &e->d_histB, &e->d_segoff, &e->d_bucketoff, &e->d_rowptr, &e->d_ids,
-                 &e->d_vocab_h, &e->d_freq_h, &e->d_self_h, &e->d_zero, &e->d_rowlen_c, &e->d_islo_c, &e->d_filter, &e->d_rowbin, &e->d_rowsafe, &e->d_rowlogh, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
+                 &e->d_vocab_h, &e->d_freq_h, &e->d_self_h, &e->d_zero, &e->d_rowlen_c, &e->d_islo_c, &e->d_filter, &e->d_binowner, &e->d_rowbin, &e->d_rowsafe, &e->d_rowlogh, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
                  &e->d_vals_a, &e->d_vals_b, &e->d_hist, &e->d_edges_sorted, &e->d_scalars, &e->d_scan_tiles,
                  &e->d_tmp};
   for (DBuf* b : all) b->release();
@@ -810,8 +855,22 @@ int kc_index_shard_info(kc_engine* e, uint32_t info[4]) {
   if (!e->have_index) return fail(e, KC_EINVAL, "kc_build_index first");
   info[0] = e->ishard;
   info[1] = e->ishards;
-  info[2] = e->ishards > 1 ? e->row_bounds[0] : 0u;
-  info[3] = e->ishards > 1 ? e->row_bounds[1] : (uint32_t)e->n;
+  info[2] = e->ishards > 1 ? (uint32_t)e->block_bounds.size() - 1 : 1u;
+  info[3] = e->ishards > 1 ? e->n_own_rows : (uint32_t)e->n;
+  return KC_OK;
+}
+
+int kc_index_shard_blocks(kc_engine* e, uint32_t* bounds, uint32_t capacity) {
+  if (!e || !bounds) return KC_EINVAL;
+  if (!e->have_index) return fail(e, KC_EINVAL, "kc_build_index first");
+  if (e->ishards <= 1) {
+    if (capacity < 2) return fail(e, KC_EINVAL, "capacity too small");
+    bounds[0] = 0;
+    bounds[1] = (uint32_t)e->n;
+    return KC_OK;
+  }
+  if (capacity < e->block_bounds.size()) return fail(e, KC_EINVAL, "capacity too small");
+  for (size_t i = 0; i < e->block_bounds.size(); ++i) bounds[i] = e->block_bounds[i];
   return KC_OK;
 }
 
@@ -848,9 +907,7 @@ int kc_build_index_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_ind
   // L2 blocking plan: slices of 2^slice_shift k-mers such that the randomly accessed part of
   // every sliced pass (census state / dictionary + freq / cursor + postings) is <= ~64 MB
   {
-    unsigned long long n_positions_est = 0;
-    for (uint32_t r = 0; r < n; ++r)
-      if (e->h_plen[r] >= (uint32_t)e->cfg.k) n_positions_est += e->h_plen[r] - e->cfg.k + 1;
+    const unsigned long long n_positions_est = e->n_pos_unsampled;
     const double footprint = std::max((double)e->universe / 4.0 * 1.5, (double)n_positions_est * 5.0);
     uint32_t want = (uint32_t)std::min(64.0, std::ceil(footprint / (64.0 * 1024 * 1024)));
     if (const char* env = std::getenv("KC_B200_SLICES")) want = (uint32_t)std::max(1, std::atoi(env));  // tests
@@ -879,11 +936,7 @@ int kc_build_index_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_ind
   mark(e, EV_I0);
   KC_CUDA(e, cudaMemsetAsync(e->d_seen.p, 0, W * 8, e->stream));
   KC_CUDA(e, cudaMemsetAsync(ds, 0, sizeof(DeviceScalars), e->stream));
-  // positions are known on the host
-  unsigned long long n_positions = 0;
-  const uint32_t every = e->cfg.sample_every > 1 ? e->cfg.sample_every : 1;
-  for (uint32_t r = 0; r < n; ++r)
-    if (e->h_plen[r] >= (uint32_t)e->cfg.k) n_positions += (e->h_plen[r] - e->cfg.k + 1) / every;
+  const unsigned long long n_positions = e->h_pospref[n];  // positions are known on the host
 
   // K1-K3: extract, per-protein dedup, census bitmaps
   mark(e, EV_IC0);
@@ -1232,8 +1285,7 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
     KC_CUDA(e, e->d_edges.ensure(e->edge_cap * 16));
   }
   // dense accumulators: u16 unless some row could exceed it
-  uint32_t max_rowlen = 0;
-  for (uint32_t r = 0; r < n; ++r) max_rowlen = std::max(max_rowlen, e->h_plen[r]);
+  const uint32_t max_rowlen = e->max_plen;
   const bool wide = max_rowlen >= 65535u;
   const size_t dense_budget = std::min<size_t>(e->smem_optin ? e->smem_optin : 48 * 1024, 200 * 1024);
   const uint32_t dense_cap_cols = (uint32_t)((dense_budget - 64) / (wide ? 4 : 2)) & ~7u;
@@ -1248,16 +1300,14 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
   for (int attempt = 0;; ++attempt) {
     KC_CUDA(e, cudaMemsetAsync(&ds->edge_cursor, 0,
                                sizeof(DeviceScalars) - offsetof(DeviceScalars, edge_cursor), e->stream));
-    if (e->ishards > 1)  // sharded index: the row block was fixed when the index was built
-      KC_CUDA(e, cudaMemcpyAsync(ds->shard_rows, e->row_bounds, 8, cudaMemcpyHostToDevice, e->stream));
-    else
+    if (e->ishards <= 1)  // (sharded index: the rows were fixed when the index was built, RowOwner below)
       KC_LAUNCH(e, shard_bounds_kernel, 1, 32, 0, e->d_workprefix.as<unsigned long long>(), n, shard, n_shards,
                 ds->shard_rows);
     KC_LAUNCH(e, classify_rows_kernel, (n + 255) / 256, 256, 0, e->d_rowwork.as<uint32_t>(),
               e->d_rowlen.as<uint32_t>(), e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>(),
               e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr, n,
               ds->shard_rows, dense_cols, count_bits, e->d_rowbin.as<uint8_t>(), e->d_rowsafe.as<uint8_t>(),
-              e->d_rowlogh.as<uint8_t>(), ds->bin_counts);
+              e->d_rowlogh.as<uint8_t>(), ds->bin_counts, e->owner());
     EdgeSink sink{e->d_edges.as<uint4>(), &ds->edge_cursor, e->edge_cap, e->cfg.threshold,
                   e->cfg.want_blosum ? kUnscored : 0u};
     mark(e, EV_PK0);
@@ -1360,7 +1410,7 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
     ps.n_pairs_kept = hs.pc.n_pairs;
     ps.n_edges_out = hs.pc.n_edges;
     ps.sum_count_out = hs.pc.sum_count;
-    ps.n_rows = hs.shard_rows[1] - hs.shard_rows[0];
+    ps.n_rows = e->ishards > 1 ? e->n_own_rows : hs.shard_rows[1] - hs.shard_rows[0];
     ps.n_rows_rescored = hs.n_overflow;
     e->n_edges = hs.edge_cursor;
     ps.n_multi_edges_kept = hs.pc.n_multi;

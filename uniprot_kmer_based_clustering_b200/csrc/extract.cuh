@@ -20,7 +20,7 @@ constexpr uint32_t kBkCap = 4096;  // records per bucket slot
 __host__ __device__ __forceinline__ uint32_t kmer_bucket_hash(uint32_t kmer) { return kmer * 0x9E3779B1u; }
 
 // where the extract kernels append the incidences (rec == nullptr: the universe-table build).
-// Sharded build (multi-GPU, one row block [row_lo, row_hi) of the pair triangle per rank): a rank
+// Sharded build (multi-GPU, every rank owns some row blocks of the pair triangle): a rank
 // only needs the k-mers its own rows hold, with ALL their holders.  `filter` is a bitmap over a
 // hash of the k-mers of the rank's own rows (kmer_filter_build_kernel); the incidences of the
 // other rows are appended only when their k-mer passes it (false positives only cost work).
@@ -30,14 +30,14 @@ struct BucketScatter {
   uint32_t n_buckets;
   const uint32_t* filter;  // null: every incidence is kept
   uint32_t filter_mask;    // filter bits - 1 (power of two)
-  uint32_t row_lo, row_hi;
+  RowOwner owner;
   __device__ __forceinline__ static uint32_t filter_hash(uint32_t kmer) {
     uint32_t h = kmer * 0x85EBCA6Bu;
     return h ^ (h >> 13);
   }
   // two steps so that a caller can keep several reservations (L2 atomics) in flight
   __device__ __forceinline__ unsigned long long reserve(uint32_t kmer, uint32_t row) const {
-    if (filter && (row < row_lo || row >= row_hi)) {
+    if (filter && !owner.mine(row)) {
       const uint32_t f = filter_hash(kmer) & filter_mask;
       if (!((__ldg(filter + (f >> 5)) >> (f & 31u)) & 1u)) return ~0ull;
     }
@@ -468,12 +468,12 @@ __global__ void __launch_bounds__(kXsWarps * 32)
   if (lane == 0 && incid) atomicAdd(n_incid, incid);
 }
 
-// Sharded build: mark (a hash of) every k-mer of the rows [row_lo, row_hi) in the filter bitmap.
+// Sharded build: mark (a hash of) every k-mer of this rank's rows in the filter bitmap.
 // One warp per row, any length; duplicates are harmless.
 template <int K>
 __global__ void __launch_bounds__(256)
     kmer_filter_build_kernel(const uint8_t* __restrict__ res, const uint32_t* __restrict__ pstart,
-                             const uint32_t* __restrict__ plen, uint32_t row_lo, uint32_t row_hi,
+                             const uint32_t* __restrict__ plen, uint32_t n, RowOwner owner,
                              uint32_t sample_every, unsigned long long sample_seed,
                              const uint32_t* __restrict__ orig_of, uint32_t* __restrict__ filter,
                              uint32_t filter_mask) {
@@ -482,7 +482,8 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
   const uint32_t lane = lane_id();
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t r = row_lo + gw; r < row_hi; r += nw) {
+  for (uint32_t r = gw; r < n; r += nw) {
+    if (!owner.mine(r)) continue;
     const uint32_t len = plen[r], ps = pstart[r];
     if (len < (uint32_t)K) continue;
     const uint32_t npos_all = len - K + 1;

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256)
                          const uint32_t* __restrict__ first_after, uint32_t n, const uint32_t* __restrict__ bounds,
                          uint32_t dense_single_pass_cols, uint32_t count_bits, uint8_t* __restrict__ rowbin,
                          uint8_t* __restrict__ rowsafe, uint8_t* __restrict__ rowlogh,
-                         uint32_t* __restrict__ bin_counts) {
+                         uint32_t* __restrict__ bin_counts, RowOwner owner) {
   __shared__ uint32_t s_cnt[16];
   if (threadIdx.x < 16) s_cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(256)
   if (r < n) {
     uint8_t bin = kBinSkip;
     const uint32_t P = rowwork[r];
-    if (P != 0 && r >= row_lo && r < row_hi) {
+    // the rows this call scores: the shard's row range, or (sharded index) the rows this rank owns
+    if (P != 0 && (owner.bin_owner ? owner.mine(r) : (r >= row_lo && r < row_hi))) {
       const uint32_t target = first_after ? first_after[r] : r + 1;
       const uint32_t span = n - target;
       const uint32_t U = min(P, span);  // upper bound on distinct partners

@@ -188,7 +188,10 @@ class Engine:
         """what the current index covers; n_shards == 1: a whole index (whole-set stats)"""
         info = np.zeros(4, dtype=np.uint32)
         self._check(self._L.kc_index_shard_info(self._h, _ptr(info)))
-        return {"shard": int(info[0]), "n_shards": int(info[1]), "row_lo": int(info[2]), "row_hi": int(info[3])}
+        bounds = np.zeros(int(info[2]) + 1, dtype=np.uint32)
+        self._check(self._L.kc_index_shard_blocks(self._h, _ptr(bounds), bounds.size))
+        return {"shard": int(info[0]), "n_shards": int(info[1]), "n_blocks": int(info[2]),
+                "n_own_rows": int(info[3]), "block_bounds": bounds}
 
     def get_distinct_kmers(self) -> np.ndarray:
         out = np.empty(self.index_stats["n_distinct"], dtype=np.uint32)

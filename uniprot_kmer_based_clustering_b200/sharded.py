@@ -75,8 +75,10 @@ def gather_edges_device(engine, dist, rank: int, world: int, pinned_out=None, ds
                         rows_in_input_order: bool = True):
     """NCCL path: the per-rank sorted edge lists go GPU-to-GPU (send/recv of the engine's device
     buffers over NVLink) into one device buffer on `dst`, then one D2H copy.  With the input-order
-    pair order (all-classes mode) the shards are contiguous row blocks, so the concatenation in
-    rank order is already sorted by (a, b); otherwise the merged list is sorted on the host."""
+    pair order (all-classes mode) every rank's list is one run per row block it owns, so laying the
+    runs out in block order gives the list sorted by (a, b) with no merge: one block per rank for a
+    whole index (contiguous shards), two per rank (zig-zag) for a sharded index build.  Otherwise
+    the merged list is sorted on the host."""
     import torch
     from .engine import EDGE_DTYPE
     ptr, n_e = engine.edges_device()
@@ -84,27 +86,47 @@ def gather_edges_device(engine, dist, rank: int, world: int, pinned_out=None, ds
     mine = (torch.as_tensor(_DeviceWords(ptr, n_e * EDGE_WORDS), device=dev) if n_e
             else torch.zeros(0, dtype=torch.int32, device=dev))
     if world == 1:
-        counts = [n_e]
+        runs = [[n_e, 0]]
     else:
-        cnt = torch.tensor([n_e], dtype=torch.int64, device=dev)
-        allc = torch.zeros(world, dtype=torch.int64, device=dev)
+        info = engine.index_shard_info()
+        n_low = n_e
+        if info["n_shards"] > 1 and n_e:  # edges of the rank's early block come first (sorted by a)
+            hi_start = int(info["block_bounds"][info["n_blocks"] - 1 - rank])
+            a_col = mine.view(-1, EDGE_WORDS)[:, 0].contiguous()
+            n_low = int(torch.searchsorted(a_col, torch.tensor([hi_start], dtype=torch.int32, device=dev)).item())
+        cnt = torch.tensor([n_low, n_e - n_low], dtype=torch.int64, device=dev)
+        allc = torch.zeros(2 * world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(allc, cnt)
-        counts = [int(c) for c in allc.tolist()]
-    total = sum(counts)
+        runs = allc.view(world, 2).tolist()
+    total = sum(int(a + b) for a, b in runs)
     if rank != dst:
-        if n_e:
-            dist.send(mine, dst=dst)
+        n_low = int(runs[rank][0])
+        if n_low:
+            dist.send(mine[:n_low * EDGE_WORDS], dst=dst)
+        if n_e - n_low:
+            dist.send(mine[n_low * EDGE_WORDS:], dst=dst)
         return None
-    buf = torch.empty(total * EDGE_WORDS, dtype=torch.int32, device=dev)
+    # block order: low runs of ranks 0 .. world-1, then high runs of ranks world-1 .. 0
+    order = [(r, 0) for r in range(world)] + [(r, 1) for r in reversed(range(world))]
+    place = {}
     off = 0
+    for r, part in order:
+        place[(r, part)] = off
+        off += int(runs[r][part])
+    buf = torch.empty(total * EDGE_WORDS, dtype=torch.int32, device=dev)
     reqs = []
-    for src, c in enumerate(counts):
-        part = buf[off * EDGE_WORDS:(off + c) * EDGE_WORDS]
-        if src == dst:
-            part.copy_(mine)
-        elif c:
-            reqs.append(dist.irecv(part, src=src))
-        off += c
+    for src in range(world):
+        for part in (0, 1):  # the sender posts its low run first
+            c = int(runs[src][part])
+            if not c:
+                continue
+            o = place[(src, part)]
+            seg = buf[o * EDGE_WORDS:(o + c) * EDGE_WORDS]
+            if src == dst:
+                lo = 0 if part == 0 else int(runs[src][0])
+                seg.copy_(mine[lo * EDGE_WORDS:(lo + c) * EDGE_WORDS])
+            else:
+                reqs.append(dist.irecv(seg, src=src))
     for q in reqs:
         q.wait()
     if pinned_out is not None and pinned_out.numel() >= buf.numel():
