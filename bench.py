@@ -44,6 +44,15 @@ CPU_SAMPLE = {"synth_1m_k7": 250_000, "synth_100k_k5": 50_000, "synth_20k_k5": 2
 REF_SAMPLE = {"synth_1m_k7": 250_000, "synth_100k_k5": 50_000, "synth_20k_k5": 20_000}
 
 
+def measured_traffic(workload: str, kernel: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as fh:
+            return int(json.load(fh)[workload][kernel])
+    except Exception:
+        return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -338,7 +347,9 @@ def main():
                        "n_multi_edges": pst_all["n_multi_edges"], "n_pairs_nonzero": p_kept, "n_edges_out": e_out},
             "roofline": {"bound": "hbm", "kernel": "pairs_main_scored_kernel + packed/dense retries (K7-K9)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": measured_traffic(args.workload, "pairs_main_scored_kernel")
+                         if world == 1 and not args.n_proteins else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes": algo_bytes},
             "roofline_index": {"bound": "hbm",
                                "kernel": "K1-K5 (extract_scatter, bucket_build, rows_finalize)" if k == 7
