@@ -74,6 +74,13 @@ struct kc_engine {
   size_t total_mem = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // chunked upload of the residue stream on a second stream: the extract kernels of the next
+  // kc_build_index start on the first proteins while the rest is still crossing PCIe
+  static constexpr int kUploadChunks = 8;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t chunk_ev[kUploadChunks]{}, main_ev = nullptr;
+  uint32_t chunk_row[kUploadChunks + 1]{};
+  int n_chunks = 0;  // > 0: an upload is (possibly) in flight; chunk c holds the rows [chunk_row[c], chunk_row[c+1])
   std::string err;
   uint32_t launches = 0;
   cudaEvent_t ev[EV_COUNT]{};
@@ -172,6 +179,15 @@ float elapsed(kc_engine* e, Ev a, Ev b) {
   return ms;
 }
 
+// the main stream waits for the whole chunked upload (paths that do not consume it chunk by chunk)
+int wait_upload(kc_engine* e) {
+  if (e->n_chunks) {
+    KC_CUDA(e, cudaStreamWaitEvent(e->stream, e->chunk_ev[e->n_chunks - 1], 0));
+    e->n_chunks = 0;
+  }
+  return KC_OK;
+}
+
 int ensure_scan(kc_engine* e, uint64_t n_items) {
   const uint64_t tiles = (n_items + kScanTile - 1) / kScanTile + 1;
   if (tiles > e->scan.cap_tiles) {
@@ -189,24 +205,39 @@ uint32_t blocks_for(uint64_t items, uint32_t per_block, uint32_t cap) {
   return (uint32_t)std::min<uint64_t>(b, cap);
 }
 
+// pair order = input order (all-classes mode): the row layout straight from the offsets on the device
+__global__ void layout_identity_kernel(const unsigned long long* __restrict__ off, uint32_t n,
+                                       uint32_t* __restrict__ pstart, uint32_t* __restrict__ plen,
+                                       uint32_t* __restrict__ orig, uint32_t* __restrict__ rank) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const unsigned long long a = off[r], b = off[r + 1];
+  pstart[r] = (uint32_t)a;
+  plen[r] = (uint32_t)(b - a);
+  orig[r] = r;
+  rank[r] = r;
+}
+
 // ---- host-side staging shared by both kc_set_proteins flavours ---------------------------
+// (this runs while the residue stream is crossing PCIe: one pass over the offsets)
 int stage_layout(kc_engine* e) {
   const uint64_t n = e->n;
   const int k = e->cfg.k;
   const auto& off = e->h_off;
-  for (uint64_t p = 0; p < n; ++p)
-    if (off[p + 1] < off[p]) return fail(e, KC_EINVAL, "offsets must be non-decreasing");
   if (off[0] != 0) return fail(e, KC_EINVAL, "offsets[0] must be 0");
   e->R = off[n];
   if (e->R >= 0xFFFF0000ull) return fail(e, KC_ETOOLARGE, "more than 2^32-65536 residues");
   if (n >= 0xFFFFFFF0ull) return fail(e, KC_ETOOLARGE, "too many proteins");
   // pair order: input order, or class-major (stable) when only cross-class pairs are wanted,
   // so that the same-class holders a row must skip are one contiguous run of every posting
+  const bool cross = e->cfg.cross_class_only != 0;
   e->h_orig.resize(n);
   e->h_rank.resize(n);
-  std::iota(e->h_orig.begin(), e->h_orig.end(), 0u);
   e->h_first_after.clear();
-  if (e->cfg.cross_class_only) {
+  if (cross) {
+    for (uint64_t p = 0; p < n; ++p)
+      if (off[p + 1] < off[p]) return fail(e, KC_EINVAL, "offsets must be non-decreasing");
+    std::iota(e->h_orig.begin(), e->h_orig.end(), 0u);
     std::stable_sort(e->h_orig.begin(), e->h_orig.end(),
                      [&](uint32_t a, uint32_t b) { return e->h_cls[a] < e->h_cls[b]; });
     e->h_first_after.resize(n);
@@ -217,43 +248,52 @@ int stage_layout(kc_engine* e) {
       for (uint64_t r = i; r < j; ++r) e->h_first_after[r] = (uint32_t)j;
       i = j;
     }
+    for (uint64_t r = 0; r < n; ++r) e->h_rank[e->h_orig[r]] = (uint32_t)r;
+    e->h_pstart.resize(n);
+    e->h_plen.resize(n);
   }
-  for (uint64_t r = 0; r < n; ++r) e->h_rank[e->h_orig[r]] = (uint32_t)r;
-  e->h_pstart.resize(n);
-  e->h_plen.resize(n);
   e->h_long.clear();
   e->h_huge.clear();
   e->h_huge_off.clear();
   e->max_block_np2 = 0;
   e->max_block_len = 0;
   e->n_mid_rows = 0;
-  e->h_pospref.assign(n + 1, 0);
+  e->h_pospref.resize(n + 1);
+  e->h_pospref[0] = 0;
   e->n_pos_unsampled = 0;
   e->max_plen = 0;
   const uint64_t every = e->cfg.sample_every > 1 ? e->cfg.sample_every : 1;
-  unsigned long long huge_total = 0;
+  unsigned long long huge_total = 0, pos_acc = 0;
   for (uint64_t r = 0; r < n; ++r) {
-    const uint32_t p = e->h_orig[r];
+    const uint32_t p = cross ? e->h_orig[r] : (uint32_t)r;
+    if (off[p + 1] < off[p]) return fail(e, KC_EINVAL, "offsets must be non-decreasing");
     const uint64_t len = off[p + 1] - off[p];
-    e->h_pstart[r] = (uint32_t)off[p];
-    e->h_plen[r] = (uint32_t)len;
+    if (cross) {
+      e->h_pstart[r] = (uint32_t)off[p];
+      e->h_plen[r] = (uint32_t)len;
+    } else {
+      e->h_orig[r] = e->h_rank[r] = (uint32_t)r;
+    }
     e->max_plen = std::max(e->max_plen, (uint32_t)len);
-    e->h_pospref[r + 1] = e->h_pospref[r] + (len >= (uint64_t)k ? (len - k + 1) / every : 0);
-    e->n_pos_unsampled += len >= (uint64_t)k ? len - k + 1 : 0;
     if (len >= (uint64_t)k) {
       const uint32_t npos = (uint32_t)(len - k + 1);
-      if (npos > kBlockMaxPos) {
-        e->h_huge.push_back((uint32_t)r);
-        e->h_huge_off.push_back(huge_total);
-        huge_total += next_pow2_u32(npos);
-      } else if (npos > kWarpMaxPos) {
-        e->h_long.push_back((uint32_t)r);
-        e->max_block_np2 = std::max(e->max_block_np2, next_pow2_u32(npos));
-        e->max_block_len = std::max(e->max_block_len, (uint32_t)len);
-      } else if (npos > kHashMaxPos) {
-        ++e->n_mid_rows;
+      pos_acc += npos / every;
+      e->n_pos_unsampled += npos;
+      if (npos > kHashMaxPos) {
+        if (npos > kBlockMaxPos) {
+          e->h_huge.push_back((uint32_t)r);
+          e->h_huge_off.push_back(huge_total);
+          huge_total += next_pow2_u32(npos);
+        } else if (npos > kWarpMaxPos) {
+          e->h_long.push_back((uint32_t)r);
+          e->max_block_np2 = std::max(e->max_block_np2, next_pow2_u32(npos));
+          e->max_block_len = std::max(e->max_block_len, (uint32_t)len);
+        } else {
+          ++e->n_mid_rows;
+        }
       }
     }
+    e->h_pospref[r + 1] = pos_acc;
   }
   auto up = [&](DBuf& b, const void* src, size_t bytes) -> cudaError_t {
     cudaError_t rc = b.ensure(std::max<size_t>(bytes, 16));
@@ -261,11 +301,22 @@ int stage_layout(kc_engine* e) {
     if (bytes == 0) return cudaSuccess;
     return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, e->stream);
   };
-  KC_CUDA(e, up(e->d_pstart, e->h_pstart.data(), n * 4));
-  KC_CUDA(e, up(e->d_plen, e->h_plen.data(), n * 4));
-  KC_CUDA(e, up(e->d_orig, e->h_orig.data(), n * 4));
-  KC_CUDA(e, up(e->d_rank, e->h_rank.data(), n * 4));
-  if (e->cfg.cross_class_only) KC_CUDA(e, up(e->d_first_after, e->h_first_after.data(), n * 4));
+  if (!cross) {  // d_off is already on its way on the same stream
+    KC_CUDA(e, e->d_pstart.ensure(std::max<size_t>(n * 4, 16)));
+    KC_CUDA(e, e->d_plen.ensure(std::max<size_t>(n * 4, 16)));
+    KC_CUDA(e, e->d_orig.ensure(std::max<size_t>(n * 4, 16)));
+    KC_CUDA(e, e->d_rank.ensure(std::max<size_t>(n * 4, 16)));
+    if (n)
+      KC_LAUNCH(e, layout_identity_kernel, (uint32_t)((n + 255) / 256), 256, 0, e->d_off.as<unsigned long long>(),
+                (uint32_t)n, e->d_pstart.as<uint32_t>(), e->d_plen.as<uint32_t>(), e->d_orig.as<uint32_t>(),
+                e->d_rank.as<uint32_t>());
+  } else {
+    KC_CUDA(e, up(e->d_pstart, e->h_pstart.data(), n * 4));
+    KC_CUDA(e, up(e->d_plen, e->h_plen.data(), n * 4));
+    KC_CUDA(e, up(e->d_orig, e->h_orig.data(), n * 4));
+    KC_CUDA(e, up(e->d_rank, e->h_rank.data(), n * 4));
+    KC_CUDA(e, up(e->d_first_after, e->h_first_after.data(), n * 4));
+  }
   KC_CUDA(e, up(e->d_long, e->h_long.data(), e->h_long.size() * 4));
   KC_CUDA(e, up(e->d_huge, e->h_huge.data(), e->h_huge.size() * 4));
   KC_CUDA(e, up(e->d_huge_off, e->h_huge_off.data(), e->h_huge_off.size() * 8));
@@ -290,10 +341,21 @@ int run_extract_census(kc_engine* e, BucketScatter scatter = BucketScatter{nullp
   uint32_t min_pos = 0;
   if (n && scatter.rec) {
     min_pos = kHashMaxPos;
-    const uint32_t grid = blocks_for(n, kXsWarps, e->num_sm * 5);
-    KC_LAUNCH(e, extract_scatter_warp_kernel<K>, grid, kXsWarps * 32, 0, res, e->d_pstart.as<uint32_t>(),
-              e->d_plen.as<uint32_t>(), n, ndist, e->cfg.sample_every, e->cfg.sample_seed, e->d_orig.as<uint32_t>(),
-              &ds->n_incid, scatter);
+    // chunk by chunk while the upload of the residue stream is still in flight, else one launch
+    const int chunks = e->n_chunks ? e->n_chunks : 1;
+    for (int c = 0; c < chunks; ++c) {
+      const uint32_t r0 = e->n_chunks ? e->chunk_row[c] : 0u, r1 = e->n_chunks ? e->chunk_row[c + 1] : n;
+      if (e->n_chunks) KC_CUDA(e, cudaStreamWaitEvent(e->stream, e->chunk_ev[c], 0));
+      if (r1 <= r0) continue;
+      const uint32_t grid = blocks_for(r1 - r0, kXsWarps, e->num_sm * 5);
+      KC_LAUNCH(e, extract_scatter_warp_kernel<K>, grid, kXsWarps * 32, 0, res, e->d_pstart.as<uint32_t>(),
+                e->d_plen.as<uint32_t>(), r0, r1, ndist, e->cfg.sample_every, e->cfg.sample_seed,
+                e->d_orig.as<uint32_t>(), &ds->n_incid, scatter);
+    }
+    e->n_chunks = 0;
+  } else {
+    int rcw = wait_upload(e);
+    if (rcw) return rcw;
   }
   if (n && (!scatter.rec || e->n_mid_rows)) {
     const uint32_t grid = blocks_for(n, kExtractWarps, e->num_sm * 5);
@@ -522,17 +584,25 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
   mark(e, EV_IC0);
   if (n_shards > 1) {  // filter of the k-mers this rank's rows hold
     KC_CUDA(e, cudaMemsetAsync(e->d_filter.p, 0, (size_t)filter_bits / 8, e->stream));
-    if (n_own_rows) {
-      const uint32_t fgrid = blocks_for(n, 8, e->num_sm * 8);
-      if (e->cfg.k == 5)
-        KC_LAUNCH(e, kmer_filter_build_kernel<5>, fgrid, 256, 0, e->d_res.as<uint8_t>(), e->d_pstart.as<uint32_t>(),
-                  e->d_plen.as<uint32_t>(), n, owner, e->cfg.sample_every, e->cfg.sample_seed,
-                  e->d_orig.as<uint32_t>(), e->d_filter.as<uint32_t>(), filter_bits - 1u);
-      else
-        KC_LAUNCH(e, kmer_filter_build_kernel<7>, fgrid, 256, 0, e->d_res.as<uint8_t>(), e->d_pstart.as<uint32_t>(),
-                  e->d_plen.as<uint32_t>(), n, owner, e->cfg.sample_every, e->cfg.sample_seed,
-                  e->d_orig.as<uint32_t>(), e->d_filter.as<uint32_t>(), filter_bits - 1u);
+    if (n_own_rows) {  // chunk by chunk while the upload is in flight (the extract pass needs the whole filter)
+      const int chunks = e->n_chunks ? e->n_chunks : 1;
+      for (int c = 0; c < chunks; ++c) {
+        const uint32_t r0 = e->n_chunks ? e->chunk_row[c] : 0u, r1 = e->n_chunks ? e->chunk_row[c + 1] : n;
+        if (e->n_chunks) KC_CUDA(e, cudaStreamWaitEvent(e->stream, e->chunk_ev[c], 0));
+        if (r1 <= r0) continue;
+        const uint32_t fgrid = blocks_for(r1 - r0, 8, e->num_sm * 8);
+        if (e->cfg.k == 5)
+          KC_LAUNCH(e, kmer_filter_build_kernel<5>, fgrid, 256, 0, e->d_res.as<uint8_t>(), e->d_pstart.as<uint32_t>(),
+                    e->d_plen.as<uint32_t>(), r0, r1, owner, e->cfg.sample_every, e->cfg.sample_seed,
+                    e->d_orig.as<uint32_t>(), e->d_filter.as<uint32_t>(), filter_bits - 1u);
+        else
+          KC_LAUNCH(e, kmer_filter_build_kernel<7>, fgrid, 256, 0, e->d_res.as<uint8_t>(), e->d_pstart.as<uint32_t>(),
+                    e->d_plen.as<uint32_t>(), r0, r1, owner, e->cfg.sample_every, e->cfg.sample_seed,
+                    e->d_orig.as<uint32_t>(), e->d_filter.as<uint32_t>(), filter_bits - 1u);
+      }
     }
+    rc = wait_upload(e);
+    if (rc) return rc;
   }
   {
     DBuf none;
@@ -716,6 +786,9 @@ int kc_create(const kc_config* cfg, kc_engine** out) {
   }
   e->own_stream = true;
   for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&e->ev[i]);
+  cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < kc_engine::kUploadChunks; ++i) cudaEventCreateWithFlags(&e->chunk_ev[i], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&e->main_ev, cudaEventDisableTiming);
   // residue LUT: src/protein.rs:9-13 order, everything else -> 20 (src/protein.rs:49-54)
   uint8_t lut[256];
   std::memset(lut, 20, sizeof(lut));
@@ -751,6 +824,10 @@ void kc_destroy(kc_engine* e) {
   for (int i = 0; i < EV_COUNT; ++i)
     if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  for (int i = 0; i < kc_engine::kUploadChunks; ++i)
+    if (e->chunk_ev[i]) cudaEventDestroy(e->chunk_ev[i]);
+  if (e->main_ev) cudaEventDestroy(e->main_ev);
   delete e;
 }
 
@@ -759,6 +836,8 @@ const char* kc_last_error(const kc_engine* e) { return e ? e->err.c_str() : "nul
 int kc_set_stream(kc_engine* e, void* cuda_stream) {
   if (!e) return KC_EINVAL;
   cudaSetDevice(e->dev);
+  if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+  e->n_chunks = 0;
   cudaStreamSynchronize(e->stream);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   e->own_stream = false;
@@ -784,12 +863,45 @@ int kc_set_proteins(kc_engine* e, const uint8_t* residues, const uint64_t* offse
   mark(e, EV_H2D0);
   const size_t padded = padded_res_bytes(R);
   KC_CUDA(e, e->d_res.ensure(padded));
-  if (R) KC_CUDA(e, cudaMemcpyAsync(e->d_res.p, residues, R, cudaMemcpyHostToDevice, e->stream));
-  KC_CUDA(e, cudaMemsetAsync(e->d_res.as<uint8_t>() + R, 0, padded - R, e->stream));
+  // the offsets first: the one H2D copy engine serves the copies in issue order, and the layout
+  // kernel (main stream) must not wait behind the whole residue stream
   KC_CUDA(e, e->d_off.ensure((n + 1) * 8));
   KC_CUDA(e, cudaMemcpyAsync(e->d_off.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+  e->n_chunks = 0;
+  constexpr int C = kc_engine::kUploadChunks;
+  if (!e->cfg.cross_class_only && R >= (32u << 20) && n >= 64 * C && e->copy_stream &&
+      !std::getenv("KC_B200_NO_UPLOAD_OVERLAP")) {
+    // pair order = input order: chunk c of the stream is the rows [chunk_row[c], chunk_row[c+1]).
+    // The copy stream waits for what the main stream still does with the old residues.
+    KC_CUDA(e, cudaEventRecord(e->main_ev, e->stream));
+    KC_CUDA(e, cudaStreamWaitEvent(e->copy_stream, e->main_ev, 0));
+    e->chunk_row[0] = 0;
+    for (int c = 1; c <= C; ++c) {
+      const uint64_t target = R / C * c;
+      e->chunk_row[c] = c == C ? (uint32_t)n
+                               : (uint32_t)(std::lower_bound(offsets, offsets + n + 1, target) - offsets);
+      e->chunk_row[c] = std::max(e->chunk_row[c], e->chunk_row[c - 1]);
+    }
+    for (int c = 0; c < C; ++c) {
+      const uint64_t b0 = offsets[e->chunk_row[c]], b1 = offsets[e->chunk_row[c + 1]];
+      if (b1 > b0)
+        KC_CUDA(e, cudaMemcpyAsync(e->d_res.as<uint8_t>() + b0, residues + b0, b1 - b0, cudaMemcpyHostToDevice,
+                                   e->copy_stream));
+      if (c + 1 == C) KC_CUDA(e, cudaMemsetAsync(e->d_res.as<uint8_t>() + R, 0, padded - R, e->copy_stream));
+      KC_CUDA(e, cudaEventRecord(e->chunk_ev[c], e->copy_stream));
+    }
+    e->n_chunks = C;
+  } else {
+    if (R) KC_CUDA(e, cudaMemcpyAsync(e->d_res.p, residues, R, cudaMemcpyHostToDevice, e->stream));
+    KC_CUDA(e, cudaMemsetAsync(e->d_res.as<uint8_t>() + R, 0, padded - R, e->stream));
+  }
   int rc = stage_layout(e);
-  mark(e, EV_H2D1);
+  if (e->n_chunks) {
+    cudaEventRecord(e->ev[EV_H2D1], e->copy_stream);
+    e->ev_set[EV_H2D1] = true;
+  } else {
+    mark(e, EV_H2D1);
+  }
   return rc;
 }
 
@@ -797,6 +909,7 @@ int kc_set_proteins_device(kc_engine* e, const uint8_t* d_residues, const uint64
                            const uint32_t* d_class_id, uint64_t n) {
   if (!e || !d_offsets || (n && !d_class_id)) return KC_EINVAL;
   KC_CUDA(e, cudaSetDevice(e->dev));
+  if (int rcw = wait_upload(e)) return rcw;
   e->n = n;
   e->h_off.resize(n + 1);
   e->h_cls.resize(n);
@@ -834,6 +947,7 @@ int kc_extract_kmers(kc_engine* e, uint32_t* kmers_out, uint64_t capacity, uint6
   const uint64_t npos = kpos[n];
   if (n_positions) *n_positions = npos;
   if (kmers_out && capacity < npos) return fail(e, KC_EINVAL, "kmers_out capacity too small");
+  if (int rcw = wait_upload(e)) return rcw;
   KC_CUDA(e, e->d_kpos.ensure((n + 1) * 8));
   KC_CUDA(e, cudaMemcpyAsync(e->d_kpos.p, kpos.data(), (n + 1) * 8, cudaMemcpyHostToDevice, e->stream));
   KC_CUDA(e, e->d_tmp.ensure(std::max<uint64_t>(npos, 4) * 4));

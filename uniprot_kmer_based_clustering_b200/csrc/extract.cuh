@@ -390,7 +390,8 @@ constexpr int kXsWarps = 8;
 template <int K>
 __global__ void __launch_bounds__(kXsWarps * 32)
     extract_scatter_warp_kernel(const uint8_t* __restrict__ res, const uint32_t* __restrict__ pstart,
-                                const uint32_t* __restrict__ plen, uint32_t n, uint32_t* __restrict__ ndist,
+                                const uint32_t* __restrict__ plen, uint32_t row_begin, uint32_t n,
+                                uint32_t* __restrict__ ndist,
                                 uint32_t sample_every, unsigned long long sample_seed,
                                 const uint32_t* __restrict__ orig_of, unsigned long long* __restrict__ n_incid,
                                 BucketScatter scatter) {
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__(kXsWarps * 32)
   uint8_t* codes = s_codes[w];
   unsigned long long incid = 0;
   const uint32_t nwarps = gridDim.x * kXsWarps;
-  for (uint32_t r = blockIdx.x * kXsWarps + w; r < n; r += nwarps) {
+  for (uint32_t r = row_begin + blockIdx.x * kXsWarps + w; r < n; r += nwarps) {  // rows [row_begin, n)
     const uint32_t len = plen[r];
     if (len < (uint32_t)K) {
       if (lane == 0) ndist[r] = 0;
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(kXsWarps * 32)
 template <int K>
 __global__ void __launch_bounds__(256)
     kmer_filter_build_kernel(const uint8_t* __restrict__ res, const uint32_t* __restrict__ pstart,
-                             const uint32_t* __restrict__ plen, uint32_t n, RowOwner owner,
+                             const uint32_t* __restrict__ plen, uint32_t row_begin, uint32_t n, RowOwner owner,
                              uint32_t sample_every, unsigned long long sample_seed,
                              const uint32_t* __restrict__ orig_of, uint32_t* __restrict__ filter,
                              uint32_t filter_mask) {
@@ -482,7 +483,7 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
   const uint32_t lane = lane_id();
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t r = gw; r < n; r += nw) {
+  for (uint32_t r = row_begin + gw; r < n; r += nw) {  // rows [row_begin, n)
     if (!owner.mine(r)) continue;
     const uint32_t len = plen[r], ps = pstart[r];
     if (len < (uint32_t)K) continue;
