@@ -32,6 +32,13 @@ constexpr int kBkThreads = 512;
 constexpr int kBkPerThread = kBkCap / kBkThreads;
 constexpr uint32_t kBkTargetFill = 2560;  // mean records per bucket (62 % of a slot)
 
+// Entry bin of the rows [r0, r0 + 64): room for one entry per distinct k-mer of its rows plus one run
+// record per two entries (1.5 x the capacity prefix)
+__device__ __forceinline__ size_t bin_region(const uint32_t* __restrict__ rowcap_prefix, uint32_t r0) {
+  const size_t p = rowcap_prefix[r0];
+  return p + (p >> 1);
+}
+
 struct BucketGlobals {
   unsigned long long col_cursor;  // postings / entries written so far (= nnz at the end)
   unsigned long long id_cursor;   // ids handed out (= n_repeated at the end)
@@ -66,6 +73,11 @@ __global__ void __launch_bounds__(kBkThreads, 2)
                         uint32_t* __restrict__ bin_cursor, uint32_t* __restrict__ vocab,
                         uint32_t* __restrict__ freq, uint8_t* __restrict__ selfscore, RowOwner owner,
                         BucketGlobals* __restrict__ g) {
+  // Pairs of two rows of the SAME 64-row bin are scored from "run records" (the holders of a
+  // k-mer inside one bin as a 64-bit mask) on dense shared-memory tiles (pairs_tile_kernel); the
+  // suffix of an entry then starts behind the row's bin, so the hash kernels only see the partners
+  // of other bins.  Related proteins are usually neighbours in the input: most multi-edges are
+  // bin-local and never touch a hash table or the postings.
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   uint32_t* s_key = reinterpret_cast<uint32_t*>(dyn_smem);      // [slots] k-mer
   uint32_t* s_val = s_key + kBkSlots;                           // [slots] holders -> cursor -> group end
@@ -233,8 +245,10 @@ __global__ void __launch_bounds__(kBkThreads, 2)
       }
     }
     __syncthreads();
-    // ---- P4: rank-sort every group (holders are distinct rows): s_row[start + rank] = holder;
-    // CROSS: the suffix of a holder starts at the first holder of a later class block
+    // ---- P4: rank-sort every group (holders are distinct rows): s_row[start + rank] = holder.
+    // The same pass over the group finds the run of holders inside the row's 64-row bin; the
+    // suffix of a holder starts behind that run (CROSS: and not before the first holder of a later
+    // class block).  s_slot[sorted position] = suffix start | (first holder of a run of >= 2) << 15.
 #pragma unroll
     for (int j = 0; j < kBkPerThread; ++j) {
       const uint32_t p = tid + j * kBkThreads;
@@ -242,16 +256,21 @@ __global__ void __launch_bounds__(kBkThreads, 2)
         const uint32_t s = s_grp[p];
         const uint32_t end = s_val[s], start = end - s_cnt[s];
         const uint32_t v = s_col[p];
+        const uint32_t vbin = v >> kBinRowsLog;
         uint32_t target = 0;
         if (CROSS) target = first_after[v];
-        uint32_t rank = 0, below = 0;
+        uint32_t rank = 0, below = 0, bins_lt = 0, bins_le = 0;
         for (uint32_t q = start; q < end; ++q) {
           const uint32_t x = s_col[q];
           rank += x < v;
+          bins_lt += (x >> kBinRowsLog) < vbin;
+          bins_le += (x >> kBinRowsLog) <= vbin;
           if (CROSS) below += x < target;
         }
         s_row[start + rank] = v;
-        if (CROSS) s_slot[start + rank] = (uint16_t)(start + below);
+        const uint32_t a = CROSS ? max(bins_le, below) : bins_le;  // relative to the group start
+        const bool run_leader = rank == bins_lt && bins_le - bins_lt >= 2u;
+        s_slot[start + rank] = (uint16_t)((start + a) | (run_leader ? 0x8000u : 0u));
       }
     }
     __syncthreads();
@@ -261,52 +280,68 @@ __global__ void __launch_bounds__(kBkThreads, 2)
 #pragma unroll
     for (int j0 = 0; j0 < kBkPerThread; j0 += 4) {
       uint4 ent[4];
-      uint32_t who[4], pend[4];  // who = leader lane << 8 | rank among the lanes of the same bin
+      unsigned long long rmask[4];  // holders of the k-mer in the row's bin (set by the run's first holder)
+      uint32_t who[4], pend[4];     // who = leader lane << 16 | slot among the records the bin's lanes append
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const uint32_t q = tid + (j0 + u) * kBkThreads;
         const bool act = q < nnz;
         uint32_t bin = kSentinel;
+        bool has_run = false;
         ent[u].x = kSentinel;
+        rmask[u] = 0;
         if (act) {
           const uint32_t s = s_grp[q];
           const uint32_t end = s_val[s];
-          const uint32_t a = CROSS ? (uint32_t)s_slot[q] : q + 1u;
           const uint32_t row = s_row[q];
           const bool mine = owner.mine(row);
           col[col_base + q] = row;
           const uint32_t c = s_cnt[s];
-          if (mine && q == end - c) {  // first holder: this build owns the k-mer's totals
+          const uint32_t start = end - c;
+          if (mine && q == start) {  // first holder: this build owns the k-mer's totals
             ++n_distinct;
             ++n_rep_owned;
             nnz_owned += c;
             multi += (unsigned long long)c * (c - 1u) / 2u;
           }
+          bin = row >> kBinRowsLog;
+          const uint32_t sl = s_slot[q];
+          const uint32_t a = sl & 0x7FFFu;  // the partners behind the row's bin (P4)
+          const uint32_t meta = s_meta[s];
+          if (mine && (sl & 0x8000u)) {  // first holder of a run of >= 2 holders inside the bin: its record
+            for (uint32_t p2 = q; p2 < end && (s_row[p2] >> kBinRowsLog) == bin; ++p2)
+              rmask[u] |= 1ull << (s_row[p2] & (kBinRows - 1u));
+            has_run = true;
+          }
           // Every holder gets its entry, also the rows of other shards that passed the filter: the
           // pair stage scores this build's rows only, but the BLOSUM pass over unscored edges
           // (edge_blosum_kernel) intersects the id lists of BOTH endpoints, and the k-mers a foreign
           // row shares with this build's rows are exactly the ones that passed.
-          const uint32_t meta = s_meta[s];
           const uint32_t len = end - a;
           // a single partner is stored inline ({rank, sentinel}): no postings gather in the pair stage
           const uint2 sf = len == 1u ? make_uint2(s_row[a], kSentinel)
                                      : make_uint2((uint32_t)col_base + a, (uint32_t)col_base + end);
           ent[u] = make_uint4(row | ((meta >> 16) << 24), (uint32_t)id_base + (meta & 0xFFFFu), sf.x, sf.y);
           if (mine) work += len;
-          bin = row >> kBinRowsLog;
         }
         const uint32_t peers = __match_any_sync(kFullMask, bin);
+        const uint32_t runs = __ballot_sync(kFullMask, has_run) & peers;
         const uint32_t leader = __ffs(peers) - 1;
-        who[u] = (leader << 8) | __popc(peers & lanemask_lt());
+        who[u] = (leader << 16) | (__popc(peers & lanemask_lt()) + __popc(runs & lanemask_lt()));
         pend[u] = 0;
-        if (bin != kSentinel && lane == leader) pend[u] = atomicAdd(&bin_cursor[bin], (uint32_t)__popc(peers));
+        if (bin != kSentinel && lane == leader)
+          pend[u] = atomicAdd(&bin_cursor[bin], (uint32_t)(__popc(peers) + __popc(runs)));
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const uint32_t base = __shfl_sync(kFullMask, pend[u], who[u] >> 8);
+        const uint32_t base = __shfl_sync(kFullMask, pend[u], who[u] >> 16);
         if (ent[u].x != kSentinel) {
           const uint32_t r0 = (ent[u].x & 0xFFFFFFu) & ~(kBinRows - 1u);
-          entries[(size_t)rowcap_prefix[r0] + base + (who[u] & 31u)] = ent[u];
+          uint4* dst = entries + bin_region(rowcap_prefix, r0) + base + (who[u] & 0xFFFFu);
+          dst[0] = ent[u];
+          if (rmask[u])  // run record: {tag | self-score, bin, mask}
+            dst[1] = make_uint4(0x80000000u | (ent[u].x >> 24), r0 >> kBinRowsLog, (uint32_t)rmask[u],
+                                (uint32_t)(rmask[u] >> 32));
         }
       }
     }
@@ -365,23 +400,32 @@ constexpr size_t kFinSmemBytes = (size_t)kFinChunk * 16;
 __global__ void __launch_bounds__(kFinThreads)
     rows_finalize_kernel(const uint4* __restrict__ entries, const uint32_t* __restrict__ rowcap_prefix,
                          const uint32_t* __restrict__ bin_cnt, uint32_t n, uint32_t bin_lo, uint32_t n_bins,
-                         uint32_t* __restrict__ rowlen, uint32_t* __restrict__ ids, uint2* __restrict__ suf,
+                         uint4* __restrict__ runs_out, uint32_t* __restrict__ run_cnt,
+                         uint32_t* __restrict__ rowlen, uint32_t* __restrict__ rowlen_pair,
+                         uint32_t* __restrict__ ids, uint2* __restrict__ suf,
                          uint8_t* __restrict__ sufss, unsigned long long* __restrict__ rowwork64,
                          uint32_t* __restrict__ rowwork, uint32_t* __restrict__ rowinl,
                          uint32_t* __restrict__ rowmaxlen) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   uint4* s_ent = reinterpret_cast<uint4*>(dyn_smem);
-  __shared__ uint32_t s_off[kBinRows], s_cnt[kBinRows], s_start[kBinRows], s_inl[kBinRows], s_max[kBinRows];
+  // per row of the bin: id-list cursor / chunk count / chunk start, the same for the pair list
+  // (entries with partners only), and the row totals
+  __shared__ uint32_t s_off[kBinRows], s_cnt[kBinRows], s_start[kBinRows];
+  __shared__ uint32_t s_offp[kBinRows], s_cntp[kBinRows], s_startp[kBinRows];
+  __shared__ uint32_t s_inl[kBinRows], s_max[kBinRows];
   __shared__ uint32_t s_wlo[kBinRows], s_whi[kBinRows];  // multi-edges of the row: low word + carries
+  __shared__ uint32_t s_nruns;
   const uint32_t tid = threadIdx.x;
   for (uint32_t bin = bin_lo + blockIdx.x; bin < n_bins; bin += gridDim.x) {  // [bin_lo, n_bins): this build's rows
     const uint32_t r0 = bin << kBinRowsLog;
     const uint32_t nrows = min(kBinRows, n - r0);
-    const uint4* src = entries + rowcap_prefix[r0];
+    const uint4* src = entries + bin_region(rowcap_prefix, r0);
+    uint4* rdst = runs_out + (rowcap_prefix[r0] >> 1);  // run records of the bin, compacted for pairs_tile_kernel
     const uint32_t cnt = bin_cnt[bin];
+    if (tid == 0) s_nruns = 0;
     if (tid < kBinRows) {
-      s_off[tid] = tid < nrows ? rowcap_prefix[r0 + tid] : 0u;
-      s_cnt[tid] = 0;
+      s_off[tid] = s_offp[tid] = tid < nrows ? rowcap_prefix[r0 + tid] : 0u;
+      s_cnt[tid] = s_cntp[tid] = 0;
       s_inl[tid] = 0;
       s_max[tid] = 0;
       s_wlo[tid] = 0;
@@ -391,56 +435,78 @@ __global__ void __launch_bounds__(kFinThreads)
     for (uint32_t c0 = 0; c0 < cnt; c0 += kFinChunk) {
       const uint32_t m = min(kFinChunk, cnt - c0);
       uint4 e[kFinPer];
-      uint32_t rk[kFinPer];  // row << 16 | rank of the entry among the chunk's entries of its row
+      uint32_t rk[kFinPer];  // row << 26 | rank in the row's pair list (0x1FFF: none) << 13 | rank in its id list
 #pragma unroll
       for (int u = 0; u < kFinPer; ++u)
         if (u * kFinThreads + tid < m) e[u] = ld_stream_u32x4(src + c0 + u * kFinThreads + tid);
 #pragma unroll
       for (int u = 0; u < kFinPer; ++u) {
+        rk[u] = kSentinel;
         if (u * kFinThreads + tid >= m) continue;
+        if (e[u].x >> 31) {  // run record
+          rdst[atomicAdd(&s_nruns, 1u)] = e[u];
+          continue;
+        }
         const uint32_t lr = (e[u].x & 0xFFFFFFu) - r0;
         const bool inl = e[u].w == kSentinel;
         const uint32_t len = inl ? 1u : e[u].w - e[u].z;
-        rk[u] = (lr << 16) | atomicAdd(&s_cnt[lr], 1u);
-        if (inl) {
-          atomicAdd(&s_inl[lr], 1u);
-        } else if (len > 1u) {
-          atomicMax(&s_max[lr], len);
-        }
-        if (len) {
+        uint32_t rp = 0x1FFFu;
+        if (len) {  // the pair stage only reads the entries that have partners
+          rp = atomicAdd(&s_cntp[lr], 1u);
           const uint32_t old = atomicAdd(&s_wlo[lr], len);
           if (old + len < old) atomicAdd(&s_whi[lr], 1u);
+          if (inl) atomicAdd(&s_inl[lr], 1u);
+          else if (len > 1u) atomicMax(&s_max[lr], len);
         }
+        rk[u] = (lr << 26) | (rp << 13) | atomicAdd(&s_cnt[lr], 1u);
       }
       __syncthreads();
-      if (tid < 32) {  // exclusive scan of the 64 per-row counts of the chunk by one warp
-        const uint32_t a = s_cnt[2 * tid], b = s_cnt[2 * tid + 1];
+      if (tid < 64) {  // exclusive scans of the 64 per-row counts of the chunk: warp 0 ids, warp 1 pair lists
+        const uint32_t l = tid & 31u;
+        const uint32_t* cntv = tid < 32 ? s_cnt : s_cntp;
+        uint32_t* startv = tid < 32 ? s_start : s_startp;
+        const uint32_t a = cntv[2 * l], b = cntv[2 * l + 1];
         uint32_t incl = a + b;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const uint32_t t = __shfl_up_sync(kFullMask, incl, o);
-          if (tid >= (uint32_t)o) incl += t;
+          if (l >= (uint32_t)o) incl += t;
         }
-        s_start[2 * tid] = incl - a - b;
-        s_start[2 * tid + 1] = incl - b;
+        startv[2 * l] = incl - a - b;
+        startv[2 * l + 1] = incl - b;
       }
       __syncthreads();
+      // id lists: every entry, sorted by row in shared memory, written as runs
 #pragma unroll
       for (int u = 0; u < kFinPer; ++u)
-        if (u * kFinThreads + tid < m) s_ent[s_start[rk[u] >> 16] + (rk[u] & 0xFFFFu)] = e[u];
+        if (rk[u] != kSentinel) s_ent[s_start[rk[u] >> 26] + (rk[u] & 0x1FFFu)] = e[u];
       __syncthreads();
-      for (uint32_t i = tid; i < m; i += kFinThreads) {
+      const uint32_t m_rows = s_start[kBinRows - 1] + s_cnt[kBinRows - 1];  // the chunk's entries without the runs
+      for (uint32_t i = tid; i < m_rows; i += kFinThreads) {
         const uint4 v = s_ent[i];
         const uint32_t lr = (v.x & 0xFFFFFFu) - r0;
-        const uint32_t pos = s_off[lr] + (i - s_start[lr]);
-        ids[pos] = v.y;
+        ids[s_off[lr] + (i - s_start[lr])] = v.y;
+      }
+      __syncthreads();
+      // pair lists: the entries with partners
+#pragma unroll
+      for (int u = 0; u < kFinPer; ++u)
+        if (rk[u] != kSentinel && ((rk[u] >> 13) & 0x1FFFu) != 0x1FFFu)
+          s_ent[s_startp[rk[u] >> 26] + ((rk[u] >> 13) & 0x1FFFu)] = e[u];
+      __syncthreads();
+      const uint32_t m_pairs = s_startp[kBinRows - 1] + s_cntp[kBinRows - 1];
+      for (uint32_t i = tid; i < m_pairs; i += kFinThreads) {
+        const uint4 v = s_ent[i];
+        const uint32_t lr = (v.x & 0xFFFFFFu) - r0;
+        const uint32_t pos = s_offp[lr] + (i - s_startp[lr]);
         suf[pos] = make_uint2(v.z, v.w);
         if (sufss) sufss[pos] = (uint8_t)(v.x >> 24);
       }
       __syncthreads();
       if (tid < kBinRows) {
         s_off[tid] += s_cnt[tid];
-        s_cnt[tid] = 0;
+        s_offp[tid] += s_cntp[tid];
+        s_cnt[tid] = s_cntp[tid] = 0;
       }
       __syncthreads();
     }
@@ -448,11 +514,13 @@ __global__ void __launch_bounds__(kFinThreads)
       const uint32_t r = r0 + tid;
       const unsigned long long w = ((unsigned long long)s_whi[tid] << 32) | s_wlo[tid];
       rowlen[r] = s_off[tid] - rowcap_prefix[r];
+      rowlen_pair[r] = s_offp[tid] - rowcap_prefix[r];
       rowwork64[r] = w;
       rowwork[r] = w > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)w;
       rowinl[r] = s_inl[tid];
       rowmaxlen[r] = s_max[tid];
     }
+    if (tid == 0) run_cnt[bin] = s_nruns;
     __syncthreads();
   }
 }

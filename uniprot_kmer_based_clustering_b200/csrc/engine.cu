@@ -122,7 +122,9 @@ struct kc_engine {
   uint64_t v_local = 0;    // ids handed out by this build (= n_repeated when not sharded)
   uint64_t kept_hint = 0;  // records the last sharded build kept (sizes the bucket count of the next one)
   uint32_t hint_shards = 0;
-  DBuf d_filter, d_binowner;
+  DBuf d_filter, d_binowner, d_runs, d_run_cnt, d_rowlen_p;
+  // rows of the pair lists (entries with partners): shorter than the id rows once bin-local pairs go to the tiles
+  const uint32_t* pair_rowlen() const { return (bucketed ? d_rowlen_p : d_rowlen).as<uint32_t>(); }
   RowOwner owner() const {
     return RowOwner{ishards > 1 ? d_binowner.as<uint8_t>() : nullptr, ishard};
   }
@@ -407,7 +409,7 @@ int launch_hash(kc_engine* e, uint8_t bin, const EdgeSink& sink) {
   KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CTA_WARPS * 32, smem));
   if (per_sm < 1) per_sm = 1;
   const uint32_t grid = (uint32_t)(e->num_sm * per_sm);
-  KC_LAUNCH(e, kern, grid, CTA_WARPS * 32, smem, e->pair_rowptr(), e->d_rowlen.as<uint32_t>(),
+  KC_LAUNCH(e, kern, grid, CTA_WARPS * 32, smem, e->pair_rowptr(), e->pair_rowlen(),
             e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), e->d_rowbin.as<uint8_t>(), bin, (uint32_t)e->n,
             &e->ds->row_cursor[bin], e->ds->bin_counts, sink, &e->ds->pc);
   return KC_OK;
@@ -423,7 +425,7 @@ int launch_packed(kc_engine* e, uint8_t bin, uint32_t count_bits, const EdgeSink
   KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CTA_WARPS * 32, smem));
   if (per_sm < 1) per_sm = 1;
   const uint32_t grid = (uint32_t)(e->num_sm * per_sm);
-  KC_LAUNCH(e, kern, grid, CTA_WARPS * 32, smem, e->pair_rowptr(), e->d_rowlen.as<uint32_t>(),
+  KC_LAUNCH(e, kern, grid, CTA_WARPS * 32, smem, e->pair_rowptr(), e->pair_rowlen(),
             e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), e->d_rowbin.as<uint8_t>(), bin, (uint32_t)e->n,
             count_bits, &e->ds->row_cursor[bin], e->ds->bin_counts, sink, &e->ds->pc);
   return KC_OK;
@@ -550,7 +552,10 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
   KC_CUDA(e, e->d_rowlen.ensure(((uint64_t)n + 1) * 4));
   KC_CUDA(e, e->d_recA.ensure((uint64_t)NB * kBkCap * 8));
   KC_CUDA(e, e->d_bucketoff.ensure(((uint64_t)NB_full + 2) * 4));
-  KC_CUDA(e, e->d_recB.ensure((E + 64) * 16));
+  KC_CUDA(e, e->d_recB.ensure((E + E / 2 + 64) * 16));  // entries + run records (bin_region)
+  KC_CUDA(e, e->d_runs.ensure((E / 2 + 64) * 16));
+  KC_CUDA(e, e->d_run_cnt.ensure(((uint64_t)n_bins + 2) * 4));
+  KC_CUDA(e, e->d_rowlen_p.ensure(((uint64_t)n + 1) * 4));
   KC_CUDA(e, e->d_bucketoff.ensure(((uint64_t)NB + 2) * 4));                // bucket cursors
   KC_CUDA(e, e->d_segoff.ensure(((uint64_t)n + 2) * 4));                    // rowcap prefix
   KC_CUDA(e, e->d_histA.ensure(((uint64_t)n_bins + 2) * 4));                // bin cursors
@@ -639,7 +644,8 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
   const uint32_t bin_lo = 0, bin_hi = n_bins;  // foreign rows keep (short) id lists too: see bucket_build_kernel
   if (bin_hi > bin_lo)
     KC_LAUNCH(e, rows_finalize_kernel, std::min<uint32_t>(bin_hi - bin_lo, (uint32_t)e->num_sm * 3), kFinThreads,
-              kFinSmemBytes, ent, rowcap, bin_cnt, n, bin_lo, bin_hi, e->d_rowlen.as<uint32_t>(), e->d_ids.as<uint32_t>(), e->d_suf.as<uint2>(),
+              kFinSmemBytes, ent, rowcap, bin_cnt, n, bin_lo, bin_hi, e->d_runs.as<uint4>(),
+              e->d_run_cnt.as<uint32_t>(), e->d_rowlen.as<uint32_t>(), e->d_rowlen_p.as<uint32_t>(), e->d_ids.as<uint32_t>(), e->d_suf.as<uint2>(),
             e->cfg.want_blosum ? e->d_sufss.as<uint8_t>() : nullptr, e->d_rowwork64.as<unsigned long long>(),
             e->d_rowwork.as<uint32_t>(), e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>());
   if (n_shards > 1)  // distinct k-mers of the own rows (ds->multi_total is free in this build: bg holds the totals)
@@ -817,7 +823,7 @@ void kc_destroy(kc_engine* e) {
                  &e->d_self, &e->d_colptr, &e->d_cursor, &e->d_col, &e->d_suf, &e->d_sufss, &e->d_rowwork, &e->d_lists,
                  &e->d_colscratch, &e->d_workprefix, &e->d_ksplit, &e->d_isplit, &e->d_rowwork64, &e->d_rowinl, &e->d_rowmaxlen, &e->d_psplit, &e->d_rowbase, &e->d_plist, &e->d_pss,
                  &e->d_recA, &e->d_recB, &e->d_histA, &e->d_histB, &e->d_segoff, &e->d_bucketoff, &e->d_rowptr, &e->d_ids,
-                 &e->d_vocab_h, &e->d_freq_h, &e->d_self_h, &e->d_zero, &e->d_rowlen_c, &e->d_islo_c, &e->d_filter, &e->d_binowner, &e->d_rowbin, &e->d_rowsafe, &e->d_rowlogh, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
+                 &e->d_vocab_h, &e->d_freq_h, &e->d_self_h, &e->d_zero, &e->d_rowlen_c, &e->d_islo_c, &e->d_filter, &e->d_binowner, &e->d_runs, &e->d_run_cnt, &e->d_rowlen_p, &e->d_rowbin, &e->d_rowsafe, &e->d_rowlogh, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
                  &e->d_vals_a, &e->d_vals_b, &e->d_hist, &e->d_edges_sorted, &e->d_scalars, &e->d_scan_tiles,
                  &e->d_tmp};
   for (DBuf* b : all) b->release();
@@ -1418,7 +1424,7 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
       KC_LAUNCH(e, shard_bounds_kernel, 1, 32, 0, e->d_workprefix.as<unsigned long long>(), n, shard, n_shards,
                 ds->shard_rows);
     KC_LAUNCH(e, classify_rows_kernel, (n + 255) / 256, 256, 0, e->d_rowwork.as<uint32_t>(),
-              e->d_rowlen.as<uint32_t>(), e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>(),
+              e->pair_rowlen(), e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>(),
               e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr, n,
               ds->shard_rows, dense_cols, count_bits, e->d_rowbin.as<uint8_t>(), e->d_rowsafe.as<uint8_t>(),
               e->d_rowlogh.as<uint8_t>(), ds->bin_counts, e->owner());
@@ -1426,6 +1432,26 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
                   e->cfg.want_blosum ? kUnscored : 0u};
     mark(e, EV_PK0);
     int rc;
+    if (e->bucketed) {  // the pairs inside one 64-row bin: dense shared-memory tiles over the run records
+      const uint32_t n_bins = (n + kBinRows - 1) >> kBinRowsLog;
+      const uint32_t tgrid = std::min<uint32_t>(n_bins, (uint32_t)e->num_sm * 4);
+      const uint32_t* fa = e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr;
+      const uint32_t* bounds = e->ishards > 1 ? nullptr : ds->shard_rows;
+#define KC_TILES(SC, CR)                                                                                        \
+  do {                                                                                                          \
+    KC_CUDA(e, cudaFuncSetAttribute((pairs_tile_kernel<SC, CR>), cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                    (int)kTileSmemBytes));                                                      \
+    KC_LAUNCH(e, (pairs_tile_kernel<SC, CR>), tgrid, kTileThreads, kTileSmemBytes, e->d_runs.as<uint4>(),       \
+              e->d_segoff.as<uint32_t>(), e->d_run_cnt.as<uint32_t>(), n, n_bins, fa, bounds, e->owner(), sink, \
+              &ds->pc);                                                                                         \
+  } while (0)
+      if (e->cfg.want_blosum) {
+        if (fa) KC_TILES(true, true); else KC_TILES(true, false);
+      } else {
+        if (fa) KC_TILES(false, true); else KC_TILES(false, false);
+      }
+#undef KC_TILES
+    }
     if (e->have_plist) {
 #define KC_STREAM(SC)                                                                                         \
   do {                                                                                                        \
@@ -1448,7 +1474,7 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
       KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairs_main_scored_kernel, kScoredWarps * 32, smem));
       if (per_sm < 1) per_sm = 1;
       KC_LAUNCH(e, pairs_main_scored_kernel, (uint32_t)(e->num_sm * per_sm), kScoredWarps * 32, smem,
-                e->pair_rowptr(), e->d_rowlen.as<uint32_t>(), e->d_suf.as<uint2>(),
+                e->pair_rowptr(), e->pair_rowlen(), e->d_suf.as<uint2>(),
                 e->d_sufss.as<uint8_t>(), e->d_col.as<uint32_t>(), e->d_rowbin.as<uint8_t>(),
                 e->d_rowsafe.as<uint8_t>(), n, &ds->row_cursor[kBinMain], &ds->n_overflow, ds->bin_counts, sink,
                 &ds->pc);
@@ -1459,7 +1485,7 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
       KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairs_main_kernel, kMainWarps * 32, smem));
       if (per_sm < 1) per_sm = 1;
       KC_LAUNCH(e, pairs_main_kernel, (uint32_t)(e->num_sm * per_sm), kMainWarps * 32, smem,
-                e->pair_rowptr(), e->d_rowlen.as<uint32_t>(), e->d_suf.as<uint2>(),
+                e->pair_rowptr(), e->pair_rowlen(), e->d_suf.as<uint2>(),
                 e->d_col.as<uint32_t>(), e->d_rowbin.as<uint8_t>(), e->d_rowsafe.as<uint8_t>(),
                 e->d_rowlogh.as<uint8_t>(), n, count_bits, &ds->row_cursor[kBinMain], &ds->n_overflow,
                 ds->bin_counts, sink, &ds->pc);
@@ -1488,11 +1514,11 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
       const uint32_t* fa = e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr;
       if (wide)
         KC_LAUNCH(e, pairs_dense_kernel<true>, grid, 256, dense_smem, e->pair_rowptr(),
-                  e->d_rowlen.as<uint32_t>(), e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), fa,
+                  e->pair_rowlen(), e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), fa,
                   e->d_rowbin.as<uint8_t>(), n, dense_cols, &ds->row_cursor[kBinDense], ds->bin_counts, sink, &ds->pc);
       else
         KC_LAUNCH(e, pairs_dense_kernel<false>, grid, 256, dense_smem, e->pair_rowptr(),
-                  e->d_rowlen.as<uint32_t>(), e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), fa,
+                  e->pair_rowlen(), e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), fa,
                   e->d_rowbin.as<uint8_t>(), n, dense_cols, &ds->row_cursor[kBinDense], ds->bin_counts, sink, &ds->pc);
     }
     mark(e, EV_PK1);

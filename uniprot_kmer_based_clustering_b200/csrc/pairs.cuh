@@ -1140,6 +1140,103 @@ __global__ void __launch_bounds__(kStreamWarps * 32)
 }
 
 // ---------------------------------------------------------------------------------------
+// Bin-local pairs (partitioned index, bucket.cuh): both rows in the same 64-row bin.  The index
+// stage leaves, per bin, the "run records" of its k-mers: the holders of a k-mer inside the bin
+// as a 64-bit mask plus the k-mer's BLOSUM self-score.  One CTA per bin accumulates every pair
+// of set bits on a dense 64 x 64 tile of shared-memory counters (count and score), then reads the
+// tile out: no hashing, no postings.  The hash kernels never see these partners (the suffix of an
+// entry starts behind the row's bin).
+// ---------------------------------------------------------------------------------------
+constexpr int kTileThreads = 256;
+constexpr size_t kTileSmemBytes = (size_t)(2 * kBinRows * kBinRows + (kTileThreads / 32) * kStageWords) * 4;
+
+template <bool SCORED, bool CROSS>
+__global__ void __launch_bounds__(kTileThreads)
+    pairs_tile_kernel(const uint4* __restrict__ runs, const uint32_t* __restrict__ rowcap_prefix,
+                      const uint32_t* __restrict__ run_cnt, uint32_t n, uint32_t n_bins,
+                      const uint32_t* __restrict__ first_after, const uint32_t* __restrict__ bounds, RowOwner owner,
+                      EdgeSink sink, PairCounters* __restrict__ counters) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(dyn_smem);  // [64][64] shared k-mers of (i, j), i < j
+  uint32_t* s_score = s_cnt + kBinRows * kBinRows;          // [64][64] sum of their self-scores
+  __shared__ uint32_t s_fa[kBinRows];
+  const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+  EdgeStage stage{s_score + kBinRows * kBinRows + warp * kStageWords, 0u};
+  const uint32_t row_lo = bounds ? bounds[0] : 0u, row_hi = bounds ? bounds[1] : n;
+  unsigned long long n_pairs = 0, n_edges = 0, sum_count = 0, n_multi = 0;
+  for (uint32_t i = tid; i < kBinRows * kBinRows; i += kTileThreads) {
+    s_cnt[i] = 0;
+    s_score[i] = 0;
+  }
+  __syncthreads();
+  for (uint32_t bin = blockIdx.x; bin < n_bins; bin += gridDim.x) {
+    const uint32_t r0 = bin << kBinRowsLog;
+    const uint32_t nr = run_cnt[bin];
+    if (nr == 0 || !owner.mine(r0) || r0 >= row_hi || r0 + kBinRows <= row_lo) continue;  // uniform per CTA
+    if (CROSS && tid < kBinRows) s_fa[tid] = r0 + tid < n ? first_after[r0 + tid] : n;
+    if (CROSS) __syncthreads();
+    const uint4* src = runs + (rowcap_prefix[r0] >> 1);
+    for (uint32_t t = tid; t < nr; t += kTileThreads) {
+      const uint4 rec = ld_stream_u32x4(src + t);
+      const uint32_t ss = rec.x & 0xFFu;
+      unsigned long long m = ((unsigned long long)rec.w << 32) | rec.z;
+      while (m) {
+        const uint32_t i = (uint32_t)__ffsll((long long)m) - 1u;
+        m &= m - 1ull;
+        if (r0 + i < row_lo || r0 + i >= row_hi) continue;  // row i is scored by another shard
+        unsigned long long rest = m;  // the holders after row i
+        if (CROSS) {  // only the rows of later class blocks pair with row i
+          const uint32_t fa = s_fa[i];
+          rest = fa >= r0 + kBinRows ? 0ull : rest & ~((1ull << (fa - r0)) - 1ull);
+        }
+        while (rest) {
+          const uint32_t j = (uint32_t)__ffsll((long long)rest) - 1u;
+          rest &= rest - 1ull;
+          atomicAdd(&s_cnt[i * kBinRows + j], 1u);
+          if (SCORED) atomicAdd(&s_score[i * kBinRows + j], ss);
+        }
+      }
+    }
+    __syncthreads();
+    for (uint32_t c0 = 0; c0 < kBinRows * kBinRows; c0 += kTileThreads) {  // read out and clear
+      const uint32_t cell = c0 + tid;
+      const uint32_t cq = s_cnt[cell];
+      if (__any_sync(kFullMask, cq != 0)) {
+        const uint32_t score = SCORED ? s_score[cell] : 0u;
+        if (cq) {
+          s_cnt[cell] = 0;
+          if (SCORED) s_score[cell] = 0;
+        }
+        const bool out = cq > sink.threshold;
+        n_pairs += cq != 0;
+        n_multi += cq;
+        n_edges += out;
+        sum_count += out ? cq : 0u;
+        if (SCORED) {
+          if (stage.cnt + 32u > kStageEdges4) stage4_flush(stage, sink);
+          stage4_push(stage, out, r0 + cell / kBinRows, r0 + cell % kBinRows, cq, score);
+        } else {
+          if (stage.cnt + 32u > kStageEdges) stage_flush(stage, sink);
+          stage_push(stage, out, r0 + cell / kBinRows, r0 + cell % kBinRows, cq);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (SCORED) stage4_flush(stage, sink); else stage_flush(stage, sink);
+  n_pairs = warp_sum64(n_pairs);
+  n_edges = warp_sum64(n_edges);
+  sum_count = warp_sum64(sum_count);
+  n_multi = warp_sum64(n_multi);
+  if (lane == 0) {
+    if (n_multi) atomicAdd(&counters->n_multi, n_multi);
+    if (n_pairs) atomicAdd(&counters->n_pairs, n_pairs);
+    if (n_edges) atomicAdd(&counters->n_edges, n_edges);
+    if (sum_count) atomicAdd(&counters->sum_count, sum_count);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // dense accumulators: one CTA per row, one counter per candidate partner, in column blocks of
 // `block_cols` partners.  WIDE = u32 counters (rows with >= 65535 ids), else two u16 per word.
 // ---------------------------------------------------------------------------------------
