@@ -137,6 +137,9 @@ int kc_build_index_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_ind
 /* What the engine's current index covers: info[0..3] = {shard, n_shards, n_blocks, rows owned};
  * n_shards == 1 means a whole index (stats are whole-set numbers). */
 int kc_index_shard_info(kc_engine* e, uint32_t info[4]);
+/* Which build produced the current index: 0 = universe-table build (index.cuh), else the bucket slot
+ * size of the partitioned build (bucket.cuh): 4096, or 8192 after a bucket overflow. */
+int kc_index_flavour(kc_engine* e);
 /* bounds[n_blocks + 1]: the row blocks of the pair order (block b is owned by rank b if b < n_shards,
  * else by rank n_blocks - 1 - b); a whole index has the one block {0, n}. */
 int kc_index_shard_blocks(kc_engine* e, uint32_t* bounds, uint32_t capacity);

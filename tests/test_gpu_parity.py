@@ -560,19 +560,32 @@ def test_pair_index_is_a_perfect_hash_of_the_canonical_one(k, cross, arg_set, ar
     assert np.array_equal(np.sort(key) - row_of * np.int64(v.size + 1), ix.ids)
 
 
-def test_bucket_overflow_falls_back_to_the_table_build(index_flavour):
-    """one k-mer held by more proteins than a shared-memory bucket takes (kBkCap = 8192): the
-    partitioned build reports it and the engine builds the universe-table index instead"""
-    n = 9000
-    seq = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
-    res = np.tile(seq[:9], n)
-    off = (np.arange(n + 1) * 9).astype(np.uint64)
+@pytest.mark.parametrize("n_hot,expect", [(2500, 8192), (9000, 0)])
+def test_bucket_overflow_retries_with_larger_buckets_then_the_table_build(n_hot, expect, index_flavour):
+    """one k-mer held by more proteins than a shared-memory bucket takes: 2 500 holders overflow the
+    4 096-record buckets and fit the 8 192-record ones, 9 000 holders fit neither and the engine
+    builds the universe-table index instead"""
+    rng = np.random.default_rng(11)
+    letters = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+    hot = letters[:7]
+    tail = 0 if n_hot == 9000 else 120
+    seqs = [np.concatenate([hot, letters[rng.integers(0, 20, size=tail)]]) for _ in range(n_hot)]
+    n = len(seqs)
+    res = np.concatenate(seqs).astype(np.uint8)
+    off = np.zeros(n + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([x.size for x in seqs])
     cls = (np.arange(n) % 3).astype(np.uint32)
     ps = kc.ProteinSet(res, off, cls, [], ["a", "b", "c"])
     km, ix, pr = run_oracle(ps, 7, 3, True)
     with kc.Engine(7, threshold=3, cross_class_only=True, want_blosum=True) as e:
         e.set_protein_set(ps)
         e.build_index()
+        if index_flavour == "bucket":
+            assert e.index_flavour() == expect
+            e.build_index()  # the slot size that worked is remembered for this protein set
+            assert e.index_flavour() == expect
+        else:
+            assert e.index_flavour() == 0
         check_index(e, ix)
         check_pairs(e.score_pairs(), e.get_edges(), pr)
 

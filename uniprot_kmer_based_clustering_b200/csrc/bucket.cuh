@@ -27,10 +27,13 @@
 
 namespace kc {
 
-constexpr uint32_t kBkSlots = 4096;   // hash slots per bucket (>= kBkCap: distinct <= incidences)
-constexpr int kBkThreads = 512;
-constexpr int kBkPerThread = kBkCap / kBkThreads;
-constexpr uint32_t kBkTargetFill = 2560;  // mean records per bucket (62 % of a slot)
+// Bucket geometry: CAP records per slot = CAP hash slots (distinct <= incidences), CAP / 8 threads,
+// mean fill 62 % of a slot.  4096 (two CTAs per SM) by default; 8192 (one CTA per SM) when a bucket
+// of 4096 overflowed (a k-mer with thousands of holders).
+constexpr uint32_t bk_target_fill(uint32_t cap) { return cap / 8u * 5u; }
+constexpr size_t bk_smem_bytes(uint32_t cap) {
+  return (size_t)cap * (4 + 4 + 4 + 2) + (size_t)cap * (4 + 2 + 4 + 2) + (size_t)(cap / 2) * 2;
+}
 
 // Entry bin of the rows [r0, r0 + 64): room for one entry per distinct k-mer of its rows plus one run
 // record per two entries (1.5 x the capacity prefix)
@@ -56,17 +59,16 @@ struct BucketGlobals {
 // sorted holders.  The next bucket's records are prefetched into registers while the current
 // one is processed.
 // ---------------------------------------------------------------------------------------
-constexpr size_t kBkSmemBytes = (size_t)kBkSlots * (4 + 4 + 4 + 2) + (size_t)kBkCap * (4 + 2 + 4 + 2) + (size_t)(kBkCap / 2) * 2;
 
 __device__ __forceinline__ uint32_t bucket_slot_hash(uint32_t kmer) {
   uint32_t h = kmer ^ (kmer >> 15);
   h *= 0x2C1B3C6Du;
   h ^= h >> 12;
-  return h & (kBkSlots - 1u);
+  return h;
 }
 
-template <bool CROSS>
-__global__ void __launch_bounds__(kBkThreads, 2)
+template <bool CROSS, uint32_t kBkCap>
+__global__ void __launch_bounds__(kBkCap / 8, kBkCap == 4096 ? 2 : 1)
     bucket_build_kernel(const uint2* __restrict__ rec, const uint32_t* __restrict__ bucket_cnt, uint32_t n_buckets,
                         const uint32_t* __restrict__ first_after, int k, uint32_t* __restrict__ col,
                         uint4* __restrict__ entries, const uint32_t* __restrict__ rowcap_prefix,
@@ -78,6 +80,9 @@ __global__ void __launch_bounds__(kBkThreads, 2)
   // suffix of an entry then starts behind the row's bin, so the hash kernels only see the partners
   // of other bins.  Related proteins are usually neighbours in the input: most multi-edges are
   // bin-local and never touch a hash table or the postings.
+  constexpr uint32_t kBkSlots = kBkCap;
+  constexpr int kBkThreads = kBkCap / 8;
+  constexpr int kBkPerThread = 8;
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   uint32_t* s_key = reinterpret_cast<uint32_t*>(dyn_smem);      // [slots] k-mer
   uint32_t* s_val = s_key + kBkSlots;                           // [slots] holders -> cursor -> group end
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(kBkThreads, 2)
         const uint32_t i = tid + j * kBkThreads;
         if (i < nrec) {
           const uint32_t km = nxt[j].x;
-          uint32_t h = bucket_slot_hash(km);
+          uint32_t h = bucket_slot_hash(km) & (kBkSlots - 1u);
           for (;;) {
             const uint32_t cur = s_key[h];
             if (cur == km) break;

@@ -99,6 +99,11 @@ struct kc_engine {
   unsigned long long n_pos_unsampled = 0;
   uint32_t max_plen = 0;
   bool retry_full_buckets = false;
+  uint32_t try_cap = 0;  // bucket slot size of the running attempt (0: choose)
+  // the slot size that worked for the protein set with this signature (a k-mer with thousands of
+  // holders overflows 4096-record buckets: start with 8192 next time)
+  uint32_t cap_hint = 4096;
+  uint64_t cap_hint_n = 0, cap_hint_R = 0;
   DBuf d_res, d_off, d_kpos, d_pstart, d_plen, d_orig, d_rank, d_first_after, d_long, d_huge, d_huge_off,
       d_huge_scratch;
   // index
@@ -331,7 +336,7 @@ int stage_layout(kc_engine* e) {
 size_t padded_res_bytes(uint64_t R) { return (size_t)((R + kTileRes - 1) / kTileRes + 1) * kTileRes; }
 
 template <int K>
-int run_extract_census(kc_engine* e, BucketScatter scatter = BucketScatter{nullptr, nullptr, 0u, nullptr, 0u, RowOwner{nullptr, 0u}}) {
+int run_extract_census(kc_engine* e, BucketScatter scatter = BucketScatter{nullptr, nullptr, 0u, 0u, nullptr, 0u, RowOwner{nullptr, 0u}}) {
   const uint32_t n = (uint32_t)e->n;
   DeviceScalars* ds = e->ds;
   const uint8_t* res = e->d_res.as<uint8_t>();
@@ -531,6 +536,10 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
   // The records this build keeps: all of its own rows' plus what passes the filter.  Bucket count
   // from what the last build of this shape kept, else from a guess (a bucket overflow retries with
   // the whole-set count).
+  const uint32_t cap = e->try_cap ? e->try_cap
+                                  : (e->cap_hint_n == e->n && e->cap_hint_R == e->R && e->cap_hint ? e->cap_hint : 4096u);
+  const uint32_t kBkTargetFill = bk_target_fill(cap);
+  const size_t kBkSmemBytes = bk_smem_bytes(cap);
   const uint32_t NB_full = (uint32_t)((E + kBkTargetFill - 1) / kBkTargetFill);
   uint32_t NB = NB_full;
   if (n_shards > 1) {
@@ -550,7 +559,7 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
   KC_CUDA(e, e->d_pk.ensure((R + 64) * 4));
   KC_CUDA(e, e->d_ndist.ensure(((uint64_t)n + 1) * 4));
   KC_CUDA(e, e->d_rowlen.ensure(((uint64_t)n + 1) * 4));
-  KC_CUDA(e, e->d_recA.ensure((uint64_t)NB * kBkCap * 8));
+  KC_CUDA(e, e->d_recA.ensure((uint64_t)NB * cap * 8));
   KC_CUDA(e, e->d_bucketoff.ensure(((uint64_t)NB_full + 2) * 4));
   KC_CUDA(e, e->d_recB.ensure((E + E / 2 + 64) * 16));  // entries + run records (bin_region)
   KC_CUDA(e, e->d_runs.ensure((E / 2 + 64) * 16));
@@ -612,7 +621,7 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
   {
     DBuf none;
     std::swap(none, e->d_ksplit);  // the rows are not sliced: run_extract_census passes ksplit = null
-    const BucketScatter scatter{rec, bucket_cnt, NB, n_shards > 1 ? e->d_filter.as<uint32_t>() : nullptr,
+    const BucketScatter scatter{rec, bucket_cnt, NB, cap, n_shards > 1 ? e->d_filter.as<uint32_t>() : nullptr,
                                 filter_bits - 1u, owner};
     rc = e->cfg.k == 5 ? run_extract_census<5>(e, scatter) : run_extract_census<7>(e, scatter);
     std::swap(none, e->d_ksplit);
@@ -624,19 +633,23 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
   // buckets: census, ids, postings, entries
   {
     const uint32_t* fa = e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr;
-#define KC_BUCKETS(CROSS)                                                                                       \
+#define KC_BUCKETS(CROSS, CAP)                                                                                  \
   do {                                                                                                          \
-    KC_CUDA(e, cudaFuncSetAttribute(bucket_build_kernel<CROSS>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+    KC_CUDA(e, cudaFuncSetAttribute((bucket_build_kernel<CROSS, CAP>), cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     (int)kBkSmemBytes));                                                        \
     int per_sm = 1;                                                                                             \
-    KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bucket_build_kernel<CROSS>, kBkThreads,   \
+    KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (bucket_build_kernel<CROSS, CAP>), CAP / 8, \
                                                              kBkSmemBytes));                                    \
     const uint32_t grid = std::min<uint32_t>(NB, (uint32_t)(e->num_sm * std::max(per_sm, 1)));                   \
-    KC_LAUNCH(e, bucket_build_kernel<CROSS>, grid, kBkThreads, kBkSmemBytes, rec, bucket_cnt, NB, fa, e->cfg.k, \
+    KC_LAUNCH(e, (bucket_build_kernel<CROSS, CAP>), grid, CAP / 8, kBkSmemBytes, rec, bucket_cnt, NB, fa, e->cfg.k, \
               e->d_col.as<uint32_t>(), ent, rowcap, bin_cnt, e->d_vocab_h.as<uint32_t>(),                       \
               e->d_freq_h.as<uint32_t>(), e->d_self_h.as<uint8_t>(), owner, &ds->bg);                           \
   } while (0)
-    if (fa) KC_BUCKETS(true); else KC_BUCKETS(false);
+    if (cap == 4096u) {
+      if (fa) KC_BUCKETS(true, 4096u); else KC_BUCKETS(false, 4096u);
+    } else {
+      if (fa) KC_BUCKETS(true, 8192u); else KC_BUCKETS(false, 8192u);
+    }
 #undef KC_BUCKETS
   }
   // entry bins -> rows (laid out by capacity: row r starts at rowcap[r])
@@ -661,15 +674,24 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
   KC_CUDA(e, cudaStreamSynchronize(e->stream));
   KC_CUDA(e, cudaGetLastError());
   if (hs.bg.overflow) {
-    if (NB < NB_full) {  // the guess of what a sharded build keeps was too small: whole-set bucket count
+    if (NB < NB_full && !e->retry_full_buckets) {  // the guess of what a sharded build keeps was too small
       e->retry_full_buckets = true;
       int rc2 = build_index_bucketed(e, shard, n_shards, stats, overflow);
       e->retry_full_buckets = false;
       return rc2;
     }
+    if (cap == 4096u) {  // a k-mer (or a clump) with thousands of holders: twice the slot size
+      e->try_cap = 8192u;
+      int rc2 = build_index_bucketed(e, shard, n_shards, stats, overflow);
+      e->try_cap = 0;
+      return rc2;
+    }
     *overflow = true;
     return KC_OK;
   }
+  e->cap_hint = cap;
+  e->cap_hint_n = e->n;
+  e->cap_hint_R = e->R;
   e->kept_hint = hs.bg.n_records;
   e->hint_shards = n_shards;
   // totals over the k-mers this build owns: the whole-set numbers when summed over the shards
@@ -980,6 +1002,11 @@ int kc_index_shard_info(kc_engine* e, uint32_t info[4]) {
   return KC_OK;
 }
 
+int kc_index_flavour(kc_engine* e) {
+  if (!e || !e->have_index) return -1;
+  return e->bucketed ? (int)e->cap_hint : 0;
+}
+
 int kc_index_shard_blocks(kc_engine* e, uint32_t* bounds, uint32_t capacity) {
   if (!e || !bounds) return KC_EINVAL;
   if (!e->have_index) return fail(e, KC_EINVAL, "kc_build_index first");
@@ -1013,11 +1040,17 @@ int kc_build_index_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_ind
     bool want = e->cfg.k == 7;
     if (env && !std::strcmp(env, "bucket")) want = true;
     if (env && !std::strcmp(env, "table")) want = false;
+    // (remembered per protein-set signature: buckets that overflowed once are not tried again)
+    if (want && e->cap_hint == 0 && e->cap_hint_n == e->n && e->cap_hint_R == e->R && !(env && !std::strcmp(env, "bucket")))
+      want = false;
     if (want && n > 0 && n <= (1u << 24)) {
       bool overflow = false;
       int rc = build_index_bucketed(e, shard, n_shards, stats, &overflow);
       if (rc != KC_OK || !overflow) return rc;
-      // a k-mer (or a clump of them) with more holders than a shared-memory bucket takes: table build
+      // k-mers (or clumps of them) with more holders than a shared-memory bucket takes: table build
+      e->cap_hint = 0;
+      e->cap_hint_n = e->n;
+      e->cap_hint_R = e->R;
     }
   }
   KC_CUDA(e, e->d_pk.ensure((R + 64) * 4));

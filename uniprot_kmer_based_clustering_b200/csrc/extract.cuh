@@ -16,7 +16,7 @@ __constant__ uint8_t c_residue_lut[256];
 
 // ---- partitioned index (bucket.cuh): the extract kernels append every (distinct k-mer, row)
 // incidence to the bucket its k-mer hashes to
-constexpr uint32_t kBkCap = 4096;  // records per bucket slot
+// (the slot size is a run-time choice: 4096 records, or 8192 when a bucket overflowed; bucket.cuh)
 __host__ __device__ __forceinline__ uint32_t kmer_bucket_hash(uint32_t kmer) { return kmer * 0x9E3779B1u; }
 
 // where the extract kernels append the incidences (rec == nullptr: the universe-table build).
@@ -25,9 +25,10 @@ __host__ __device__ __forceinline__ uint32_t kmer_bucket_hash(uint32_t kmer) { r
 // hash of the k-mers of the rank's own rows (kmer_filter_build_kernel); the incidences of the
 // other rows are appended only when their k-mer passes it (false positives only cost work).
 struct BucketScatter {
-  uint2* rec;          // n_buckets slots of kBkCap {k-mer, row} records
-  uint32_t* cursor;    // records appended per bucket (may pass kBkCap: overflow, the build falls back)
+  uint2* rec;          // n_buckets slots of `cap` {k-mer, row} records
+  uint32_t* cursor;    // records appended per bucket (may pass cap: overflow, the build retries / falls back)
   uint32_t n_buckets;
+  uint32_t cap;
   const uint32_t* filter;  // null: every incidence is kept
   uint32_t filter_mask;    // filter bits - 1 (power of two)
   RowOwner owner;
@@ -43,7 +44,7 @@ struct BucketScatter {
     }
     const uint32_t b = __umulhi(kmer_bucket_hash(kmer), n_buckets);
     const uint32_t pos = atomicAdd(&cursor[b], 1u);
-    return pos < kBkCap ? (unsigned long long)b * kBkCap + pos : ~0ull;
+    return pos < cap ? (unsigned long long)b * cap + pos : ~0ull;
   }
   __device__ __forceinline__ void store(unsigned long long at, uint32_t kmer, uint32_t row) const {
     if (at != ~0ull) rec[at] = make_uint2(kmer, row);

@@ -193,6 +193,10 @@ class Engine:
         return {"shard": int(info[0]), "n_shards": int(info[1]), "n_blocks": int(info[2]),
                 "n_own_rows": int(info[3]), "block_bounds": bounds}
 
+    def index_flavour(self) -> int:
+        """0: universe-table build; 4096 / 8192: partitioned build with that bucket slot size"""
+        return int(self._L.kc_index_flavour(self._h))
+
     def get_distinct_kmers(self) -> np.ndarray:
         out = np.empty(self.index_stats["n_distinct"], dtype=np.uint32)
         self._check(self._L.kc_get_distinct_kmers(self._h, _ptr(out), out.size))
