@@ -1033,11 +1033,12 @@ int kc_build_index_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_ind
   e->ishard = 0;
   e->ishards = 1;
   {
-    // Index flavour: the partitioned build (bucket.cuh) for sparse universes (k = 7: 21^7 k-mers,
-    // random access into universe-sized tables misses L2), the universe-table build (index.cuh)
-    // for k = 5.  KC_B200_INDEX=bucket|table overrides (tests run both).
+    // Index flavour: the partitioned build (bucket.cuh) unless the set is small and k = 5 (a 4 M
+    // universe: the universe tables sit in L2 and a redundant set like the ARG one overflows the
+    // buckets anyway); a bucket overflow falls back to the universe-table build (index.cuh).
+    // KC_B200_INDEX=bucket|table overrides (tests run both).
     const char* env = std::getenv("KC_B200_INDEX");
-    bool want = e->cfg.k == 7;
+    bool want = e->cfg.k == 7 || e->h_pospref[n] >= (16ull << 20);
     if (env && !std::strcmp(env, "bucket")) want = true;
     if (env && !std::strcmp(env, "table")) want = false;
     // (remembered per protein-set signature: buckets that overflowed once are not tried again)
@@ -1460,7 +1461,7 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
               e->pair_rowlen(), e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>(),
               e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr, n,
               ds->shard_rows, dense_cols, count_bits, e->d_rowbin.as<uint8_t>(), e->d_rowsafe.as<uint8_t>(),
-              e->d_rowlogh.as<uint8_t>(), ds->bin_counts, e->owner());
+              e->d_rowlogh.as<uint8_t>(), ds->bin_counts, e->owner(), e->bucketed);
     EdgeSink sink{e->d_edges.as<uint4>(), &ds->edge_cursor, e->edge_cap, e->cfg.threshold,
                   e->cfg.want_blosum ? kUnscored : 0u};
     mark(e, EV_PK0);

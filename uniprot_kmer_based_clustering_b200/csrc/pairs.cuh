@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256)
                          const uint32_t* __restrict__ first_after, uint32_t n, const uint32_t* __restrict__ bounds,
                          uint32_t dense_single_pass_cols, uint32_t count_bits, uint8_t* __restrict__ rowbin,
                          uint8_t* __restrict__ rowsafe, uint8_t* __restrict__ rowlogh,
-                         uint32_t* __restrict__ bin_counts, RowOwner owner) {
+                         uint32_t* __restrict__ bin_counts, RowOwner owner, bool exact_main) {
   __shared__ uint32_t s_cnt[16];
   if (threadIdx.x < 16) s_cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -172,8 +172,12 @@ __global__ void __launch_bounds__(256)
         // a row up when they pass kMainCap (a bounded loss: at most kMainCap insertions), so a row
         // is tried there unless a lower bound on its partners (inline partners are distinct; the
         // longest suffix holds distinct partners) already comes close to the cap.
+        // exact_main (partitioned index): the bin-local partners, the ones that repeat, are scored on
+        // the tiles; what is left are mostly distinct partners, so U is a good estimate and a row
+        // beyond the cap goes straight to its safely sized kernel instead of failing here first.
         const uint32_t lower = max(rowinl[r], rowmaxlen[r]);
-        if ((U <= kMainCap || lower <= kMainCap / 2) && rowlen[r] < (1u << kScoreShift) && P != 0xFFFFFFFFu) {
+        if ((U <= kMainCap || (!exact_main && lower <= kMainCap / 2)) && rowlen[r] < (1u << kScoreShift) &&
+            P != 0xFFFFFFFFu) {
           bin = kBinMain;
           rowlogh[r] = (uint8_t)kMainLogHMax;
         }
