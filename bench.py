@@ -40,10 +40,11 @@ WORKLOADS = {
     "synth_1m_k7": (1_000_000, "A", 7, 0xB2000004, False),    # BASELINE.json configs[3]
     "synth_100k_k5": (100_000, "A", 5, 0xB2000003, False),    # configs[2]
     "synth_20k_k5": (20_000, "A", 5, 0xB2000003, False),      # quick check
+    "synth_1m_skew_k7": (1_000_000, "B", 7, 0xB2000005, False),  # one GPU's quarter of configs[4] (skewed lengths 50-2000)
 }
 THRESHOLD = 10
-CPU_SAMPLE = {"synth_1m_k7": 250_000, "synth_100k_k5": 50_000, "synth_20k_k5": 20_000}
-REF_SAMPLE = {"synth_1m_k7": 250_000, "synth_100k_k5": 50_000, "synth_20k_k5": 20_000}
+CPU_SAMPLE = {"synth_1m_k7": 250_000, "synth_100k_k5": 50_000, "synth_20k_k5": 20_000, "synth_1m_skew_k7": 200_000}
+REF_SAMPLE = {"synth_1m_k7": 250_000, "synth_100k_k5": 50_000, "synth_20k_k5": 20_000, "synth_1m_skew_k7": 200_000}
 
 
 def measured_traffic(workload: str, kernel: str):

@@ -92,6 +92,7 @@ struct kc_engine {
   std::vector<uint64_t> h_off;
   std::vector<uint32_t> h_cls, h_orig, h_rank, h_first_after, h_pstart, h_plen;
   std::vector<uint32_t> h_long, h_huge;
+  std::vector<uint32_t> h_cta, h_vlong;  // partitioned build: CTA-hashed rows (717..2800 positions), sorted rows beyond
   std::vector<unsigned long long> h_huge_off;
   uint32_t max_block_np2 = 0, max_block_len = 0;
   uint32_t n_mid_rows = 0;  // proteins of kHashMaxPos+1 .. kWarpMaxPos positions
@@ -105,7 +106,7 @@ struct kc_engine {
   uint32_t cap_hint = 4096;
   uint64_t cap_hint_n = 0, cap_hint_R = 0;
   DBuf d_res, d_off, d_kpos, d_pstart, d_plen, d_orig, d_rank, d_first_after, d_long, d_huge, d_huge_off,
-      d_huge_scratch;
+      d_huge_scratch, d_cta, d_vlong;
   // index
   uint32_t universe = 0;
   uint64_t n_words = 0;
@@ -262,6 +263,8 @@ int stage_layout(kc_engine* e) {
   e->h_long.clear();
   e->h_huge.clear();
   e->h_huge_off.clear();
+  e->h_cta.clear();
+  e->h_vlong.clear();
   e->max_block_np2 = 0;
   e->max_block_len = 0;
   e->n_mid_rows = 0;
@@ -295,8 +298,10 @@ int stage_layout(kc_engine* e) {
           e->h_long.push_back((uint32_t)r);
           e->max_block_np2 = std::max(e->max_block_np2, next_pow2_u32(npos));
           e->max_block_len = std::max(e->max_block_len, (uint32_t)len);
+          (npos > kCtaHashMaxPos ? e->h_vlong : e->h_cta).push_back((uint32_t)r);
         } else {
           ++e->n_mid_rows;
+          e->h_cta.push_back((uint32_t)r);
         }
       }
     }
@@ -325,6 +330,8 @@ int stage_layout(kc_engine* e) {
     KC_CUDA(e, up(e->d_first_after, e->h_first_after.data(), n * 4));
   }
   KC_CUDA(e, up(e->d_long, e->h_long.data(), e->h_long.size() * 4));
+  KC_CUDA(e, up(e->d_cta, e->h_cta.data(), e->h_cta.size() * 4));
+  KC_CUDA(e, up(e->d_vlong, e->h_vlong.data(), e->h_vlong.size() * 4));
   KC_CUDA(e, up(e->d_huge, e->h_huge.data(), e->h_huge.size() * 4));
   KC_CUDA(e, up(e->d_huge_off, e->h_huge_off.data(), e->h_huge_off.size() * 8));
   if (huge_total) KC_CUDA(e, e->d_huge_scratch.ensure(huge_total * 4));
@@ -364,18 +371,27 @@ int run_extract_census(kc_engine* e, BucketScatter scatter = BucketScatter{nullp
     int rcw = wait_upload(e);
     if (rcw) return rcw;
   }
-  if (n && (!scatter.rec || e->n_mid_rows)) {
+  if (scatter.rec && !e->h_cta.empty()) {  // 717 .. 2800 positions: one CTA per protein, shared-memory hash set
+    KC_LAUNCH(e, extract_scatter_cta_kernel<K>, (uint32_t)std::min<size_t>(e->h_cta.size(), (size_t)e->num_sm * 16),
+              kXcThreads, 0, res, e->d_pstart.as<uint32_t>(), e->d_plen.as<uint32_t>(), e->d_cta.as<uint32_t>(),
+              (uint32_t)e->h_cta.size(), ndist, e->cfg.sample_every, e->cfg.sample_seed, e->d_orig.as<uint32_t>(),
+              &ds->n_incid, scatter);
+  }
+  if (n && !scatter.rec) {
     const uint32_t grid = blocks_for(n, kExtractWarps, e->num_sm * 5);
     KC_LAUNCH(e, extract_dedup_warp_kernel<K>, grid, kExtractWarps * 32, 0, res, e->d_pstart.as<uint32_t>(),
               e->d_plen.as<uint32_t>(), n, pk, ndist, e->slice_shift, e->n_slices, ksplit, e->cfg.sample_every,
               e->cfg.sample_seed, e->d_orig.as<uint32_t>(), &ds->n_incid, scatter, min_pos);
   }
-  if (!e->h_long.empty()) {
+  // sorted in shared memory: every protein of more than 1 024 positions, or (partitioned build) more than 2 800
+  const std::vector<uint32_t>& blk = scatter.rec ? e->h_vlong : e->h_long;
+  if (!blk.empty()) {
     const size_t smem = (size_t)e->max_block_np2 * 4 + e->max_block_len + 16;
     KC_CUDA(e, cudaFuncSetAttribute(extract_dedup_block_kernel<K, false>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KC_LAUNCH(e, (extract_dedup_block_kernel<K, false>), (uint32_t)e->h_long.size(), 512, smem, res,
-              e->d_pstart.as<uint32_t>(), e->d_plen.as<uint32_t>(), e->d_long.as<uint32_t>(), nullptr, nullptr,
+    KC_LAUNCH(e, (extract_dedup_block_kernel<K, false>), (uint32_t)blk.size(), 512, smem, res,
+              e->d_pstart.as<uint32_t>(), e->d_plen.as<uint32_t>(), (scatter.rec ? e->d_vlong : e->d_long).as<uint32_t>(),
+              nullptr, nullptr,
               pk, ndist, n, e->slice_shift, e->n_slices, ksplit, e->cfg.sample_every, e->cfg.sample_seed,
               e->d_orig.as<uint32_t>(), &ds->n_incid, scatter);
   }
@@ -840,7 +856,7 @@ void kc_destroy(kc_engine* e) {
   cudaSetDevice(e->dev);
   cudaDeviceSynchronize();
   DBuf* all[] = {&e->d_res, &e->d_off, &e->d_kpos, &e->d_pstart, &e->d_plen, &e->d_orig, &e->d_rank,
-                 &e->d_first_after, &e->d_long, &e->d_huge, &e->d_huge_off, &e->d_huge_scratch, &e->d_pk,
+                 &e->d_first_after, &e->d_long, &e->d_huge, &e->d_cta, &e->d_vlong, &e->d_huge_off, &e->d_huge_scratch, &e->d_pk,
                  &e->d_ndist, &e->d_rowlen, &e->d_seen, &e->d_dict, &e->d_vocab, &e->d_freq,
                  &e->d_self, &e->d_colptr, &e->d_cursor, &e->d_col, &e->d_suf, &e->d_sufss, &e->d_rowwork, &e->d_lists,
                  &e->d_colscratch, &e->d_workprefix, &e->d_ksplit, &e->d_isplit, &e->d_rowwork64, &e->d_rowinl, &e->d_rowmaxlen, &e->d_psplit, &e->d_rowbase, &e->d_plist, &e->d_pss,

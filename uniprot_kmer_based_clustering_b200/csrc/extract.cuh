@@ -470,6 +470,86 @@ __global__ void __launch_bounds__(kXsWarps * 32)
   if (lane == 0 && incid) atomicAdd(n_incid, incid);
 }
 
+// The same for proteins of kHashMaxPos+1 .. kCtaHashMaxPos positions: one CTA (4 warps) per listed
+// protein, a 4096-slot hash set in shared memory.  (Longer ones go through the sorting block
+// kernels: with skewed lengths up to 2 000 residues those were 24 % of the step, profiles/.)
+constexpr uint32_t kCtaHashSlots = 4096;
+constexpr uint32_t kCtaHashMaxPos = 2800;  // load factor <= 0.7
+constexpr int kXcThreads = 128;
+
+template <int K>
+__global__ void __launch_bounds__(kXcThreads)
+    extract_scatter_cta_kernel(const uint8_t* __restrict__ res, const uint32_t* __restrict__ pstart,
+                               const uint32_t* __restrict__ plen, const uint32_t* __restrict__ list, uint32_t n_list,
+                               uint32_t* __restrict__ ndist, uint32_t sample_every, unsigned long long sample_seed,
+                               const uint32_t* __restrict__ orig_of, unsigned long long* __restrict__ n_incid,
+                               BucketScatter scatter) {
+  __shared__ uint8_t s_lut[256];
+  __shared__ __align__(16) uint32_t s_tab[kCtaHashSlots];
+  __shared__ __align__(4) uint8_t s_codes[kCtaHashMaxPos + K + 8];
+  __shared__ uint32_t s_fresh;
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t i = tid; i < 256; i += kXcThreads) s_lut[i] = c_residue_lut[i];
+  unsigned long long incid = 0;
+  for (uint32_t li = blockIdx.x; li < n_list; li += gridDim.x) {
+    const uint32_t r = list[li];
+    const uint32_t len = plen[r], ps = pstart[r];
+    const uint32_t npos_all = len - K + 1;
+    const uint32_t npos = sample_every > 1 ? npos_all / sample_every : npos_all;
+    __syncthreads();  // the previous row is done with the table and the codes
+    for (uint32_t i = tid * 4; i < kCtaHashSlots; i += kXcThreads * 4)
+      *reinterpret_cast<uint4*>(s_tab + i) = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+    if (tid == 0) s_fresh = 0;
+    stage_codes(res, ps, len, s_codes, s_lut, tid, kXcThreads);
+    __syncthreads();
+    const uint32_t skey = sample_every > 1 ? sample_key(sample_seed, orig_of ? orig_of[r] : r) : 0u;
+    uint32_t fresh = 0;
+    for (uint32_t c = 0; c < npos; c += 4 * kXcThreads) {  // four k-mers per thread: four reservations in flight
+      uint32_t v[4];
+      bool first[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = c + u * kXcThreads + tid;
+        first[u] = false;
+        v[u] = 0;
+        if (i < npos) {
+          v[u] = pack_kmer<K>(s_codes + (sample_every > 1 ? sample_perm(skey, npos_all, i) : i));
+          uint32_t h = (v[u] * 2654435761u) >> 20;
+          for (;;) {
+            const uint32_t cur = s_tab[h];
+            if (cur == v[u]) break;
+            if (cur == kSentinel) {
+              const uint32_t old = atomicCAS(&s_tab[h], kSentinel, v[u]);
+              if (old == kSentinel) {
+                first[u] = true;
+                break;
+              }
+              if (old == v[u]) break;
+            }
+            h = (h + 1u) & (kCtaHashSlots - 1u);
+          }
+        }
+      }
+      unsigned long long at[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) at[u] = first[u] ? scatter.reserve(v[u], r) : ~0ull;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        scatter.store(at[u], v[u], r);
+        fresh += first[u];
+      }
+    }
+    fresh = warp_sum(fresh);
+    if (lane_id() == 0 && fresh) atomicAdd(&s_fresh, fresh);
+    __syncthreads();
+    if (tid == 0) {
+      ndist[r] = s_fresh;
+      incid += s_fresh;
+    }
+  }
+  if (tid == 0 && incid) atomicAdd(n_incid, incid);
+}
+
 // Sharded build: mark (a hash of) every k-mer of this rank's rows in the filter bitmap.
 // One warp per row, any length; duplicates are harmless.
 template <int K>

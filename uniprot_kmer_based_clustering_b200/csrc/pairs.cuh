@@ -353,6 +353,33 @@ __device__ __forceinline__ void scored_bump_dirty(uint32_t* key, uint32_t* val, 
   }
 }
 
+// scored main kernel: bump, and return the slot when the partner is NEW (else the sentinel); the
+// caller appends new slots to the dirty list with one ballot per round (the list length is a
+// warp-uniform register: no shared-memory atomic on a single hot counter)
+__device__ __forceinline__ uint32_t scored_bump_new(uint32_t* key, uint32_t* val, uint32_t mask, uint32_t log_h,
+                                                    uint32_t b, uint32_t inc) {
+  uint32_t h = (b * 2654435761u) >> (32u - log_h);
+  for (;;) {
+    const uint32_t k = key[h];
+    if (k == b) {
+      atomicAdd(&val[h], inc);
+      return kSentinel;
+    }
+    if (k == kSentinel) {
+      const uint32_t old = atomicCAS(&key[h], kSentinel, b);
+      if (old == kSentinel) {
+        atomicAdd(&val[h], inc);
+        return h;
+      }
+      if (old == b) {
+        atomicAdd(&val[h], inc);
+        return kSentinel;
+      }
+    }
+    h = (h + 1u) & mask;
+  }
+}
+
 // main-kernel variant: every new key's slot is appended to the warp's dirty list (so the read-out
 // touches only occupied slots and the distinct-partner count is exact); gives up beyond `cap`
 __device__ __forceinline__ void packed_bump_dirty(uint32_t* tab, uint32_t mask, uint32_t log_h, uint32_t cb,
@@ -853,8 +880,20 @@ __global__ void __launch_bounds__(kScoredWarps * 32)
       const uint32_t r = base + l;
       const uint32_t nl = __shfl_sync(kFullMask, m_len, l), ps = __shfl_sync(kFullMask, m_ps, l);
       bool full = false, overflow = false;
-      auto bump = [&](uint32_t b, uint32_t ss) {
-        scored_bump_dirty(key, val, HMAX - 1u, log_h, b, (ss << kScoreShift) | 1u, dirty_cnt, dirty, kMainCap, full);
+      uint32_t n_new = 0;  // distinct partners so far = length of the dirty list (warp-uniform)
+      // all 32 lanes call it: bump the lane's partner (if any) and append the new slots to the dirty list
+      auto bump = [&](bool valid, uint32_t b, uint32_t ss) {
+        const uint32_t slot =
+            valid && !full ? scored_bump_new(key, val, HMAX - 1u, log_h, b, (ss << kScoreShift) | 1u) : kSentinel;
+        const uint32_t m = __ballot_sync(kFullMask, slot != kSentinel);
+        if (m) {
+          if (slot != kSentinel) {
+            const uint32_t pos = n_new + __popc(m & lanemask_lt());
+            if (pos < kMainCap) dirty[pos] = (uint16_t)slot;
+          }
+          n_new += __popc(m);
+          full = n_new > kMainCap;  // at most 32 slots beyond the cap: the table (1024 slots) never fills up
+        }
       };
       uint2 e_cur = lane < nl ? ld_stream_u32x2(suf + ps + lane) : make_uint2(0, 0);
       uint32_t s_cur = lane < nl ? sufss[ps + lane] : 0u;
@@ -875,10 +914,9 @@ __global__ void __launch_bounds__(kScoredWarps * 32)
           tot_nxt = chunk_prepare_scored(col, e_nxt, s_nxt, idx0 + (k ^ 1u) * kIdxPerWarp,
                                          idxs0 + (k ^ 1u) * kIdxPerWarp, w, sw);
         }
-        if (e_cur.y == kSentinel) bump(e_cur.x, s_cur);  // inline single partner
+        bump(e_cur.y == kSentinel, e_cur.x, s_cur);  // inline single partner
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (v[u] != kSentinel) bump(v[u], sv[u]);
+        for (int u = 0; u < 4; ++u) bump(v[u] != kSentinel, v[u], sv[u]);
         for (uint32_t t00 = 128; t00 < tot_cur; t00 += 128) {  // rare: more than 128 short postings
           const uint32_t t0 = t00 + lane;
           uint32_t x[4], sx[4];
@@ -889,8 +927,7 @@ __global__ void __launch_bounds__(kScoredWarps * 32)
             sx[u] = t < tot_cur ? idxs0[k * kIdxPerWarp + t] : 0u;
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (x[u] != kSentinel) bump(x[u], sx[u]);
+          for (int u = 0; u < 4; ++u) bump(x[u] != kSentinel, x[u], sx[u]);
         }
         {  // long suffixes: the whole warp reads 32 consecutive postings at a time
           const uint32_t len = e_cur.y == kSentinel ? 0u : e_cur.y - e_cur.x;
@@ -906,13 +943,12 @@ __global__ void __launch_bounds__(kScoredWarps * 32)
 #pragma unroll
               for (int u = 0; u < 4; ++u) x[u] = j + 32 * u < t1 ? col[j + 32 * u] : kSentinel;
 #pragma unroll
-              for (int u = 0; u < 4; ++u)
-                if (x[u] != kSentinel) bump(x[u], ssl);
-              if (__any_sync(kFullMask, full)) break;
+              for (int u = 0; u < 4; ++u) bump(x[u] != kSentinel, x[u], ssl);
+              if (full) break;
             }
           }
         }
-        if (__any_sync(kFullMask, full)) {
+        if (full) {
           overflow = true;
           break;
         }
@@ -942,7 +978,7 @@ __global__ void __launch_bounds__(kScoredWarps * 32)
         __syncwarp();
         continue;
       }
-      const uint32_t n_dirty = *dirty_cnt;
+      const uint32_t n_dirty = n_new;
       __syncwarp();
       for (uint32_t i0 = 0; i0 < n_dirty; i0 += 32) {
         const uint32_t i = i0 + lane;
