@@ -230,7 +230,11 @@ def main():
     def step_e2e():
         t0 = time.perf_counter()
         # no sync here: the engine uploads the residue stream in chunks on its own copy stream and
-        # the extract kernels of build_index start on the first chunk while the rest is in flight
+        # the extract kernels of build_index start on the first chunk while the rest is in flight.
+        # (N > 1: every rank uploads the whole stream over its own PCIe link.  Uploading 1/N per rank
+        # and all-gathering over NVLink, sharded.stage_residues_allgather, was measured at N = 2 only
+        # (slower there: nothing overlaps the copy) and hung at N = 8 next to the unbatched send/recv
+        # of the edge gather: not used.)
         eng.set_proteins_ptr(h_res.data_ptr(), h_off.data_ptr(), h_cls.data_ptr(), n, on_device=False)
         t1 = time.perf_counter()
         ist = eng.build_index(rank, world)
@@ -326,7 +330,8 @@ def main():
         achieved = algo_bytes / (stage_ms["pair_kernel_ms"] * 1e-3) / 1e9 if stage_ms["pair_kernel_ms"] > 0 else 0.0
         idx_bytes = 9 * (ist_rank["n_positions"] if sharded_index else ist["n_positions"])
         idx_achieved = idx_bytes / (stage_ms["index_ms"] * 1e-3) / 1e9 if stage_ms["index_ms"] > 0 else 0.0
-        h2d = int(h_res.numel() + h_off.numel() * 8 + h_cls.numel() * 4 + 16 * n)
+        # whole job: every rank uploads the residue stream, the offsets and (cross-class mode) the row layout
+        h2d = int(world * (h_res.numel() + h_off.numel() * 8 + (16 * n if cross else 0)))
         d2h = int(pst_e["n_edges_out"] * 16 + 12 * n + 512)
         line = {
             "metric": "protein_pairs_scored_per_s", "value": pairs_total / (dev_ms * 1e-3), "unit": "pairs/s",

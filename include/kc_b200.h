@@ -116,6 +116,12 @@ int kc_set_proteins(kc_engine* e, const uint8_t* residues, const uint64_t* offse
 int kc_set_proteins_device(kc_engine* e, const uint8_t* d_residues, const uint64_t* d_offsets,
                            const uint32_t* d_class_id, uint64_t n_proteins);
 
+/* Same, residue stream resident in HBM (e.g. all-gathered over NVLink from per-rank slices: every
+ * rank of a multi-GPU job needs the whole stream, but only 1/world of it has to cross its PCIe link),
+ * offsets and classes on the host. */
+int kc_set_proteins_device_residues(kc_engine* e, const uint8_t* d_residues, const uint64_t* offsets,
+                                    const uint32_t* class_id, uint64_t n_proteins);
+
 /* Protein::new + get_five_mers (src/protein.rs:107-132,141): one packed k-mer per start
  * position, proteins back to back, duplicates kept.  kmers_out may be NULL (compute only);
  * otherwise it receives n_positions u32 values (capacity checked). */

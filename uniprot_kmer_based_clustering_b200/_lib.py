@@ -55,7 +55,7 @@ def stats_dict(s: C.Structure) -> dict:
 # every symbol the two headers declare; tests check the library exports all of them
 EXPORTED = [
     "kc_sample_position", "kc_abi_version", "kc_device_count", "kc_create", "kc_destroy", "kc_last_error", "kc_set_stream",
-    "kc_set_proteins", "kc_set_proteins_device", "kc_extract_kmers", "kc_build_index", "kc_build_index_shard", "kc_index_shard_info", "kc_index_shard_blocks", "kc_index_flavour",
+    "kc_set_proteins", "kc_set_proteins_device", "kc_set_proteins_device_residues", "kc_extract_kmers", "kc_build_index", "kc_build_index_shard", "kc_index_shard_info", "kc_index_shard_blocks", "kc_index_flavour",
     "kc_get_distinct_kmers", "kc_get_vocab", "kc_get_protein_ids", "kc_lookup_kmers", "kc_get_pair_index", "kc_score_pairs",
     "kc_score_pairs_shard", "kc_get_edges", "kc_get_edges_device", "kc_get_edge_kmers", "kc_get_timings", "kc_reset_timings",
     "kc_bitset_pair_counts",
@@ -99,6 +99,7 @@ def lib():
         "kc_set_stream": (i32, [vp, vp]),
         "kc_set_proteins": (i32, [vp, vp, vp, vp, u64]),
         "kc_set_proteins_device": (i32, [vp, vp, vp, vp, u64]),
+        "kc_set_proteins_device_residues": (i32, [vp, vp, vp, vp, u64]),
         "kc_extract_kmers": (i32, [vp, vp, u64, P(u64)]),
         "kc_build_index": (i32, [vp, P(IndexStats)]),
         "kc_get_distinct_kmers": (i32, [vp, vp, u64]),

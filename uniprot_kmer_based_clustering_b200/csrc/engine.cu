@@ -976,6 +976,29 @@ int kc_set_proteins_device(kc_engine* e, const uint8_t* d_residues, const uint64
   return rc;
 }
 
+int kc_set_proteins_device_residues(kc_engine* e, const uint8_t* d_residues, const uint64_t* offsets,
+                                    const uint32_t* class_id, uint64_t n) {
+  if (!e || !offsets || (n && !class_id)) return KC_EINVAL;
+  KC_CUDA(e, cudaSetDevice(e->dev));
+  if (int rcw = wait_upload(e)) return rcw;
+  e->n = n;
+  e->h_off.assign(offsets, offsets + n + 1);
+  e->h_cls.assign(class_id, class_id + n);
+  const uint64_t R = offsets[n];
+  if (R && !d_residues) return fail(e, KC_EINVAL, "null residues");
+  if (R >= 0xFFFF0000ull) return fail(e, KC_ETOOLARGE, "more than 2^32-65536 residues");
+  mark(e, EV_H2D0);
+  const size_t padded = padded_res_bytes(R);
+  KC_CUDA(e, e->d_res.ensure(padded));
+  KC_CUDA(e, e->d_off.ensure((n + 1) * 8));
+  KC_CUDA(e, cudaMemcpyAsync(e->d_off.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+  if (R) KC_CUDA(e, cudaMemcpyAsync(e->d_res.p, d_residues, R, cudaMemcpyDeviceToDevice, e->stream));
+  KC_CUDA(e, cudaMemsetAsync(e->d_res.as<uint8_t>() + R, 0, padded - R, e->stream));
+  int rc = stage_layout(e);
+  mark(e, EV_H2D1);
+  return rc;
+}
+
 int kc_extract_kmers(kc_engine* e, uint32_t* kmers_out, uint64_t capacity, uint64_t* n_positions) {
   if (!e) return KC_EINVAL;
   if (!e->have_proteins) return fail(e, KC_EINVAL, "kc_set_proteins first");

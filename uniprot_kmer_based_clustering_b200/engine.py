@@ -159,6 +159,12 @@ class Engine:
         fn = self._L.kc_set_proteins_device if on_device else self._L.kc_set_proteins
         self._check(fn(self._h, C.c_void_p(residues_ptr), C.c_void_p(offsets_ptr), C.c_void_p(class_ptr), n))
 
+    def set_proteins_device_residues(self, d_residues_ptr: int, offsets_ptr: int, class_ptr: int, n: int):
+        """residue stream in HBM (device pointer), offsets / classes on the host (pointers)"""
+        self.n = int(n)
+        self._check(self._L.kc_set_proteins_device_residues(self._h, C.c_void_p(d_residues_ptr), C.c_void_p(offsets_ptr),
+                                                            C.c_void_p(class_ptr), n))
+
     def set_protein_set(self, ps: ProteinSet):
         self.set_proteins(ps.residues, ps.offsets, ps.class_id)
 

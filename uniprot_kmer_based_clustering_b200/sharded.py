@@ -159,6 +159,23 @@ def reduce_index_stats(stats: dict, dist, world: int, device=None, sharded_index
     return out
 
 
+def stage_residues_allgather(engine, dist, rank: int, world: int, h_res, h_off, h_cls, n: int, d_full):
+    """Multi-GPU staging: every rank needs the whole residue stream, but only its 1/world slice crosses
+    its PCIe link; the slices are all-gathered in place over NVLink (NCCL) into `d_full` (a uint8 CUDA
+    tensor of world * ceil(R / world) bytes, kept by the caller), then handed to the engine together
+    with the host offsets / classes (pinned torch tensors).
+    EXPERIMENTAL: verified on 2 GPUs only (slower there than the engine's chunked whole-stream upload,
+    which overlaps the first index kernel); bench.py does not use it."""
+    R = h_res.numel()
+    per = d_full.numel() // world
+    lo = rank * per
+    hi = min(R, lo + per)
+    if hi > lo:
+        d_full[lo:hi].copy_(h_res[lo:hi], non_blocking=True)
+    dist.all_gather_into_tensor(d_full, d_full[lo:lo + per])
+    engine.set_proteins_device_residues(d_full.data_ptr(), h_off.data_ptr(), h_cls.data_ptr(), n)
+
+
 def reduce_pair_stats(stats: dict, dist, world: int, device=None, sharded_index: bool = False) -> dict:
     """Whole-job counters from per-shard counters (n_multi_edges is a whole-set constant when every
     rank holds the whole index, a per-rank share when the index is sharded)."""
