@@ -116,11 +116,11 @@ struct kc_engine {
       d_suf, d_sufss, d_rowwork, d_lists, d_colscratch, d_workprefix, d_ksplit, d_isplit, d_rowwork64, d_rowinl, d_rowmaxlen, d_psplit, d_rowbase, d_plist, d_pss;
   bool have_plist = false;
   uint32_t slice_shift = 31, n_slices = 1;
-  // partitioned index (bucket.cuh): the pair stage reads d_rowptr / d_ids / d_self_h instead of
+  // partitioned index (bucket.cuh): the pair stage reads d_rowcap / d_ids / d_self_h instead of
   // d_pstart / d_pk / d_self; the canonical view (legacy arrays) is derived on demand
   bool bucketed = false, canonical_ready = false;
-  // sharded build (kc_build_index_shard with n_shards > 1): this engine holds the index of the row
-  // block [row_bounds[0], row_bounds[1]) of the pair order only
+  // sharded build (kc_build_index_shard with n_shards > 1): this engine holds the index of the rows
+  // of rank `ishard` only (two row blocks of the pair order, see block_bounds)
   uint32_t ishard = 0, ishards = 1;
   std::vector<uint32_t> block_bounds;  // n_blocks + 1 rows of the pair order (2 blocks per rank, zig-zag)
   std::vector<uint8_t> h_binowner;
@@ -134,9 +134,9 @@ struct kc_engine {
   RowOwner owner() const {
     return RowOwner{ishards > 1 ? d_binowner.as<uint8_t>() : nullptr, ishard};
   }
-  DBuf d_recA, d_recB, d_histA, d_histB, d_segoff, d_bucketoff, d_rowptr, d_ids, d_vocab_h, d_freq_h, d_self_h,
+  DBuf d_rec, d_entries, d_bin_cnt, d_rowcap, d_bucket_cnt, d_ids, d_vocab_h, d_freq_h, d_self_h,
       d_zero, d_rowlen_c, d_islo_c;
-  const uint32_t* pair_rowptr() const { return (bucketed ? d_segoff : d_pstart).as<uint32_t>(); }  // d_segoff: capacity prefix
+  const uint32_t* pair_rowptr() const { return (bucketed ? d_rowcap : d_pstart).as<uint32_t>(); }  // d_rowcap: capacity prefix
   const uint32_t* pair_ids() const { return (bucketed ? d_ids : d_pk).as<uint32_t>(); }
   const uint8_t* pair_self() const { return (bucketed ? d_self_h : d_self).as<uint8_t>(); }
   const uint32_t* canon_rowlen() const { return (bucketed ? d_rowlen_c : d_rowlen).as<uint32_t>(); }
@@ -575,15 +575,15 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
   KC_CUDA(e, e->d_pk.ensure((R + 64) * 4));
   KC_CUDA(e, e->d_ndist.ensure(((uint64_t)n + 1) * 4));
   KC_CUDA(e, e->d_rowlen.ensure(((uint64_t)n + 1) * 4));
-  KC_CUDA(e, e->d_recA.ensure((uint64_t)NB * cap * 8));
-  KC_CUDA(e, e->d_bucketoff.ensure(((uint64_t)NB_full + 2) * 4));
-  KC_CUDA(e, e->d_recB.ensure((E + E / 2 + 64) * 16));  // entries + run records (bin_region)
+  KC_CUDA(e, e->d_rec.ensure((uint64_t)NB * cap * 8));
+  KC_CUDA(e, e->d_bucket_cnt.ensure(((uint64_t)NB_full + 2) * 4));
+  KC_CUDA(e, e->d_entries.ensure((E + E / 2 + 64) * 16));  // entries + run records (bin_region)
   KC_CUDA(e, e->d_runs.ensure((E / 2 + 64) * 16));
   KC_CUDA(e, e->d_run_cnt.ensure(((uint64_t)n_bins + 2) * 4));
   KC_CUDA(e, e->d_rowlen_p.ensure(((uint64_t)n + 1) * 4));
-  KC_CUDA(e, e->d_bucketoff.ensure(((uint64_t)NB + 2) * 4));                // bucket cursors
-  KC_CUDA(e, e->d_segoff.ensure(((uint64_t)n + 2) * 4));                    // rowcap prefix
-  KC_CUDA(e, e->d_histA.ensure(((uint64_t)n_bins + 2) * 4));                // bin cursors
+  KC_CUDA(e, e->d_bucket_cnt.ensure(((uint64_t)NB + 2) * 4));                // bucket cursors
+  KC_CUDA(e, e->d_rowcap.ensure(((uint64_t)n + 2) * 4));                    // rowcap prefix
+  KC_CUDA(e, e->d_bin_cnt.ensure(((uint64_t)n_bins + 2) * 4));                // bin cursors
   KC_CUDA(e, e->d_ids.ensure((E + 64) * 4));
   KC_CUDA(e, e->d_col.ensure((E + 64) * 4));
   KC_CUDA(e, e->d_suf.ensure((E + 64) * 8));
@@ -600,11 +600,11 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
   if (rc) return rc;
   e->have_plist = false;
   e->n_slices = 0;
-  uint32_t* bucket_cnt = e->d_bucketoff.as<uint32_t>();
-  uint32_t* rowcap = e->d_segoff.as<uint32_t>();
-  uint32_t* bin_cnt = e->d_histA.as<uint32_t>();
-  uint2* rec = e->d_recA.as<uint2>();
-  uint4* ent = e->d_recB.as<uint4>();
+  uint32_t* bucket_cnt = e->d_bucket_cnt.as<uint32_t>();
+  uint32_t* rowcap = e->d_rowcap.as<uint32_t>();
+  uint32_t* bin_cnt = e->d_bin_cnt.as<uint32_t>();
+  uint2* rec = e->d_rec.as<uint2>();
+  uint4* ent = e->d_entries.as<uint4>();
 
   mark(e, EV_I0);
   KC_CUDA(e, cudaMemsetAsync(ds, 0, sizeof(DeviceScalars), e->stream));
@@ -860,7 +860,7 @@ void kc_destroy(kc_engine* e) {
                  &e->d_ndist, &e->d_rowlen, &e->d_seen, &e->d_dict, &e->d_vocab, &e->d_freq,
                  &e->d_self, &e->d_colptr, &e->d_cursor, &e->d_col, &e->d_suf, &e->d_sufss, &e->d_rowwork, &e->d_lists,
                  &e->d_colscratch, &e->d_workprefix, &e->d_ksplit, &e->d_isplit, &e->d_rowwork64, &e->d_rowinl, &e->d_rowmaxlen, &e->d_psplit, &e->d_rowbase, &e->d_plist, &e->d_pss,
-                 &e->d_recA, &e->d_recB, &e->d_histA, &e->d_histB, &e->d_segoff, &e->d_bucketoff, &e->d_rowptr, &e->d_ids,
+                 &e->d_rec, &e->d_entries, &e->d_bin_cnt, &e->d_rowcap, &e->d_bucket_cnt, &e->d_ids,
                  &e->d_vocab_h, &e->d_freq_h, &e->d_self_h, &e->d_zero, &e->d_rowlen_c, &e->d_islo_c, &e->d_filter, &e->d_binowner, &e->d_runs, &e->d_run_cnt, &e->d_rowlen_p, &e->d_rowbin, &e->d_rowsafe, &e->d_rowlogh, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
                  &e->d_vals_a, &e->d_vals_b, &e->d_hist, &e->d_edges_sorted, &e->d_scalars, &e->d_scan_tiles,
                  &e->d_tmp};
@@ -1515,7 +1515,7 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
     KC_CUDA(e, cudaFuncSetAttribute((pairs_tile_kernel<SC, CR>), cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                     (int)kTileSmemBytes));                                                      \
     KC_LAUNCH(e, (pairs_tile_kernel<SC, CR>), tgrid, kTileThreads, kTileSmemBytes, e->d_runs.as<uint4>(),       \
-              e->d_segoff.as<uint32_t>(), e->d_run_cnt.as<uint32_t>(), n, n_bins, fa, bounds, e->owner(), sink, \
+              e->d_rowcap.as<uint32_t>(), e->d_run_cnt.as<uint32_t>(), n, n_bins, fa, bounds, e->owner(), sink, \
               &ds->pc);                                                                                         \
   } while (0)
       if (e->cfg.want_blosum) {
