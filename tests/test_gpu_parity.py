@@ -620,6 +620,11 @@ def test_sharded_index_build_adds_up_to_the_whole(n_shards, k, cross, index_flav
             if sharded:
                 assert info["shard"] == s and info["n_blocks"] == 2 * n_shards
                 assert info["block_bounds"][0] == 0 and info["block_bounds"][-1] == ps.n
+                if not cross:  # pair order = input order: the host mirror of the block cut applies as is
+                    from uniprot_kmer_based_clustering_b200 import sharded as sh
+                    lens = np.diff(ps.offsets.astype(np.int64))
+                    exp_bounds, _ = sh.zigzag_blocks(np.maximum(lens - k + 1, 0), n_shards)
+                    assert np.array_equal(info["block_bounds"].astype(np.int64), exp_bounds)
                 with pytest.raises(kc.KcError):
                     e.get_vocab()
                 with pytest.raises(kc.KcError):

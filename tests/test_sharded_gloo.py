@@ -106,3 +106,86 @@ def test_shard_bounds_cover_all_rows():
         assert max(loads) <= sum(loads) / s + 1000
     assert sharded.shard_bounds(np.zeros(1, dtype=np.int64), 4).tolist() == [0, 0, 0, 0, 0]
     assert sharded.merge_edge_lists([None, np.zeros(0, dtype=sharded_dtype())]).size == 0
+
+
+def _worker_owner_computes(rank, world, port, seed, q):
+    """The sharded-index scheme on the host side: zig-zag row blocks, per-rank scoring of the owned
+    blocks, index / pair counters owned by the rank of a k-mer's first holder, summed over gloo."""
+    import torch.distributed as dist
+    from oracle.oracle import Oracle
+    from uniprot_kmer_based_clustering_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ps = random_protein_set(seed, 700, min_len=20, max_len=120, n_classes=4, family=8, mutate=0.03,
+                                alphabet="ACDEFGHIKLMNPQRSTVWY")
+        k = 5
+        o = Oracle(k, 1)
+        o.set_proteins(ps.residues, ps.offsets, ps.class_id)
+        o.extract_kmers()
+        ix = o.build_index()
+        lens = np.diff(ps.offsets.astype(np.int64))
+        bounds, owner = sharded.zigzag_blocks(np.maximum(lens - k + 1, 0), world)
+        row_owner = np.zeros(ps.n, dtype=np.int64)
+        for b in range(owner.size):
+            row_owner[bounds[b]:bounds[b + 1]] = owner[b]
+        # index counters: a k-mer belongs to the rank of its first holder
+        rowlen = np.diff(ix.row_offsets.astype(np.int64))
+        rows = np.repeat(np.arange(ps.n), rowlen)
+        first = np.full(ix.vocab.size, ps.n, dtype=np.int64)
+        np.minimum.at(first, ix.ids, rows)
+        mine_k = row_owner[first] == rank
+        f = ix.freq.astype(np.int64)
+        ist = {"n_positions": int(np.maximum(lens - k + 1, 0)[row_owner == rank].sum()), "n_incidences": 0,
+               "n_distinct": 0, "n_singleton": 0, "n_repeated": int(mine_k.sum()), "nnz": int(f[mine_k].sum())}
+        pst = {"n_multi_edges": int((f[mine_k] * (f[mine_k] - 1) // 2).sum()), "n_multi_edges_kept": 0,
+               "n_pairs_kept": 0, "n_edges_out": 0, "sum_count_out": 0, "n_rows": int((row_owner == rank).sum())}
+        parts = []
+        for b in range(owner.size):
+            if owner[b] != rank or bounds[b + 1] <= bounds[b]:
+                continue
+            r = o.score_pairs(3, False, True, mode=1, row_lo=int(bounds[b]), row_hi=int(bounds[b + 1]))
+            for name in ("n_multi_edges_kept", "n_pairs_kept", "n_edges_out", "sum_count_out"):
+                pst[name] += r.stats[name]
+            parts.append(r.edges)
+        tot_i = sharded.reduce_index_stats(ist, dist, world, sharded_index=True)
+        tot_p = sharded.reduce_pair_stats(pst, dist, world, sharded_index=True)
+        merged = sharded.gather_edges(sharded.merge_edge_lists(parts), dist, rank, world)
+        if rank == 0:
+            full = o.score_pairs(3, False, True, mode=1)
+            ok = (np.array_equal(merged, full.edges)
+                  and tot_i["n_repeated"] == ix.stats["n_repeated"] and tot_i["nnz"] == ix.stats["nnz"]
+                  and tot_i["n_positions"] == ix.stats["n_positions"]
+                  and tot_p["n_multi_edges"] == full.stats["n_multi_edges"]
+                  and tot_p["n_pairs_kept"] == full.stats["n_pairs_kept"] and tot_p["n_rows"] == ps.n
+                  and bounds[0] == 0 and bounds[-1] == ps.n and np.all(bounds[1:-1] % 64 == 0))
+            q.put((ok, bounds.tolist(), int(full.edges.size)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_owner_computes_sharding_over_gloo(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_owner_computes, args=(r, world, port, 13, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ok, bounds, n_edges = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ok, (bounds, n_edges)
+
+
+def test_zigzag_blocks_pair_early_with_late():
+    from uniprot_kmer_based_clustering_b200 import sharded
+    pos = np.full(64 * 40, 100)
+    bounds, owner = sharded.zigzag_blocks(pos, 4)
+    assert owner.tolist() == [0, 1, 2, 3, 3, 2, 1, 0]
+    assert bounds[0] == 0 and bounds[-1] == pos.size and np.all(np.diff(bounds) == 64 * 5)
+    b1, o1 = sharded.zigzag_blocks(pos, 1)
+    assert b1.tolist() == [0, pos.size] and o1.tolist() == [0]

@@ -28,6 +28,30 @@ def shard_bounds(work_prefix: np.ndarray, n_shards: int) -> np.ndarray:
     return out
 
 
+BIN_ROWS = 64  # row blocks are cut at 64-row borders (kBinRows, csrc/common.cuh)
+
+
+def zigzag_blocks(positions_per_row: np.ndarray, n_shards: int):
+    """Row blocks of a sharded index build (mirror of build_index_bucketed, csrc/engine.cu): the pair
+    order is cut into 2 * n_shards blocks of equal k-mer positions at 64-row borders; block b belongs
+    to rank b if b < n_shards, else to rank 2 * n_shards - 1 - b.  Returns (bounds[n_blocks + 1],
+    owner[n_blocks])."""
+    n = int(positions_per_row.size)
+    if n_shards <= 1:
+        return np.array([0, n], dtype=np.int64), np.array([0], dtype=np.int64)
+    n_blocks = 2 * n_shards
+    prefix = np.concatenate([[0], np.cumsum(positions_per_row.astype(np.int64))])
+    total = int(prefix[n])
+    bounds = np.full(n_blocks + 1, n, dtype=np.int64)
+    bounds[0] = 0
+    for b in range(1, n_blocks):
+        target = total // n_blocks * b + (total % n_blocks) * b // n_blocks
+        r = int(np.searchsorted(prefix, target, side="left"))
+        bounds[b] = max(bounds[b - 1], min(n, (r + BIN_ROWS - 1) // BIN_ROWS * BIN_ROWS))
+    owner = np.array([b if b < n_shards else n_blocks - 1 - b for b in range(n_blocks)], dtype=np.int64)
+    return bounds, owner
+
+
 def merge_edge_lists(parts) -> np.ndarray:
     """Concatenate per-rank edge arrays and restore the canonical (a, b) order."""
     parts = [p for p in parts if p is not None and p.size]
