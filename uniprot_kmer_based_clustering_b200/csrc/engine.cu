@@ -1062,6 +1062,7 @@ int kc_index_shard_blocks(kc_engine* e, uint32_t* bounds, uint32_t capacity) {
 
 int kc_build_index_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_index_stats* stats) {
   if (!e || n_shards == 0 || shard >= n_shards) return KC_EINVAL;
+  if (n_shards > 255) return fail(e, KC_EINVAL, "at most 255 shards (the row blocks' owner is one byte)");
   if (!e->have_proteins) return fail(e, KC_EINVAL, "kc_set_proteins first");
   KC_CUDA(e, cudaSetDevice(e->dev));
   const uint32_t n = (uint32_t)e->n;
