@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """one row per BASELINE.json config that fits one GPU (stage timings from the
-engine's CUDA events, inputs resident in HBM; bit-exactness against the CPU oracle on the spot).
+engine's CUDA events, inputs resident in HBM).  The CPU column is bench.py's cpu_baseline leg
+(`bench.oracle_run`, the one sanctioned place outside tests/ that executes oracle/); bit-exactness
+is the business of tests/ (`-m gpu`), not of this script.
 
     python scripts/config_table.py [--skip-oracle-above N]
 """
@@ -11,10 +13,9 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np  # noqa: E402
 
+import bench  # noqa: E402
 import uniprot_kmer_based_clustering_b200 as kc  # noqa: E402
-from oracle.oracle import Oracle  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--skip-oracle-above", type=int, default=300_000)
@@ -29,8 +30,8 @@ configs = [
 ]
 threads = os.cpu_count() or 1
 print("| Config | GPUs | step ms (index + pairs + edges) | k-mers indexed/s | pairs scored/s | multi-edges/s | CPU restatement "
-      f"({threads} threads) | bit-exact vs oracle |")
-print("|---|---|---|---|---|---|---|---|")
+      f"({threads} threads) |")
+print("|---|---|---|---|---|---|---|")
 for name, ps, k, cross, blosum in configs:
     with kc.Engine(k, threshold=10, cross_class_only=cross, want_blosum=blosum) as e:
         e.set_protein_set(ps)
@@ -49,20 +50,12 @@ for name, ps, k, cross, blosum in configs:
     n = ps.n
     pairs = n * (n - 1) // 2
     step = tot["index_ms"] + tot["pairs_ms"] + tot["edges_ms"]
-    cpu, exact = "not run (sample in bench.py)", "counters + properties (tests)"
+    cpu = "not run (sample in bench.py)"
     if n <= args.skip_oracle_above:
-        o = Oracle(k, threads)
-        o.set_proteins(ps.residues, ps.offsets, ps.class_id)
-        t0 = time.perf_counter()
-        o.extract_kmers()
-        ix = o.build_index()
-        t1 = time.perf_counter()
-        pr = o.score_pairs(10, cross, blosum, mode=1)
-        t2 = time.perf_counter()
-        ok = (np.array_equal(edges, pr.edges) and all(ist[x] == ix.stats[x] for x in ("n_distinct", "n_repeated", "nnz"))
-              and pst["n_pairs_kept"] == pr.stats["n_pairs_kept"])
-        exact = "yes (index stats, counters, edge list)" if ok else "NO"
-        cpu = f"{(t2 - t0) * 1e3:.0f} ms ({ist['n_positions'] / (t1 - t0):.3g} k-mers/s, {pairs / (t2 - t1):.3g} pairs/s)"
+        bench.THRESHOLD = 10
+        r = bench.oracle_run(ps, k, cross, n, threads)
+        cpu = (f"{r['total_s'] * 1e3:.0f} ms ({r['positions'] / r['index_s']:.3g} k-mers/s, "
+               f"{r['pairs'] / r['pairs_s']:.3g} pairs/s)")
     print(f"| {name} | 1 | {step:.2f} ({tot['index_ms']:.2f} + {tot['pairs_ms']:.2f} + {tot['edges_ms']:.2f}) | "
           f"{ist['n_positions'] / (tot['index_ms'] * 1e-3):.3g} | {pairs / ((tot['pairs_ms'] + tot['edges_ms']) * 1e-3):.3g} | "
-          f"{pst['n_multi_edges_kept'] / (tot['pair_kernel_ms'] * 1e-3):.3g} | {cpu} | {exact} |", flush=True)
+          f"{pst['n_multi_edges_kept'] / (tot['pair_kernel_ms'] * 1e-3):.3g} | {cpu} |", flush=True)
