@@ -354,10 +354,14 @@ def main():
                          "pair_kernels": pair_kernel_ms, "edges_sort_blosum": edges_ms},
             "counts": {"n_positions": ist["n_positions"], "n_repeated": ist["n_repeated"], "nnz": nnz,
                        "n_multi_edges": pst_all["n_multi_edges"], "n_pairs_nonzero": p_kept, "n_edges_out": e_out},
-            "roofline": {"bound": "hbm", "kernel": "pairs_main_scored_kernel + packed/dense retries (K7-K9)",
+            "roofline": {"bound": "hbm",
+                         "kernel": "pairs_tile_kernel + pairs_main_scored_kernel + packed/dense kernels (K7-K9)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(args.workload, "pairs_main_scored_kernel")
-                         if world == 1 and not args.n_proteins else None,
+                         "traffic": (measured_traffic(args.workload, "pairs_main_scored_kernel") +
+                                     measured_traffic(args.workload, "pairs_tile_kernel"))
+                         if world == 1 and not args.n_proteins and
+                         measured_traffic(args.workload, "pairs_main_scored_kernel") is not None and
+                         measured_traffic(args.workload, "pairs_tile_kernel") is not None else None,
                          "peak_source": peak_src,
                          "algorithmic_bytes": algo_bytes},
             "roofline_index": {"bound": "hbm",
