@@ -51,6 +51,7 @@ int main(int argc, char** argv) {
     else if (a == "--tree") want_tree = true;
     else if (a == "--sample-every" && i + 1 < argc) cfg.sample_every = (uint32_t)std::atoi(argv[++i]);
     else if (a == "--seed" && i + 1 < argc) cfg.sample_seed = std::strtoull(argv[++i], nullptr, 0);
+    else if (a == "--index" && i + 1 < argc) setenv("KC_B200_INDEX", argv[++i], 1);  // bucket | table (engine.cu)
     else {
       std::fprintf(stderr, "unknown option %s\n", a.c_str());
       return 101;
