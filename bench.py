@@ -340,7 +340,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.workload, "n_proteins": n, "mean_len": round(ps.residues.size / n, 1),
                        "k": k, "threshold": THRESHOLD, "cross_class_only": cross, "blosum": True,
-                       "generator": "G1 (include/kc_host.h)", "seed": hex(WORKLOADS[args.workload][3]),
+                       "generator": "G1 (include/kc_synth.h)", "seed": hex(WORKLOADS[args.workload][3]),
                        "l2_policy": f"inputs larger than L2 ({ps.residues.size / 1e6:.0f} MB residues, "
                                     f"{4 * nnz / 1e6:.0f} MB postings); no flush needed",
                        "parallelism": ("1 GPU" if world == 1 else

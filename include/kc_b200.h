@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KC_ABI_VERSION 1
+#define KC_ABI_VERSION 2
 
 enum {
   KC_OK = 0,
@@ -51,7 +51,23 @@ typedef struct kc_config {
                              * replacement (Protein::new_with_rand_fivemers, d = 10, src/protein.rs:77-104) */
   uint64_t max_edges;       /* device edge-buffer capacity; 0 = automatic (grows and retries) */
   uint64_t sample_seed;     /* seed of the counter-based position sampler (kc_sample_position) */
+  /* Tuning knobs (ABI 2; all 0 = the engine's own choice).  They are per engine: nothing on the product
+   * path reads the process environment. */
+  uint32_t index_build;     /* KC_INDEX_*: which build kc_build_index runs */
+  uint32_t bucket_cap;      /* streaming build: records a shared-memory bucket takes, 4096 (default) or 512
+                             * (tests: pushes ordinary buckets through the global-memory path) */
+  uint32_t index_slices;    /* table build: number of L2 slices of the k-mer universe (0 = from the footprint) */
+  uint32_t census_merge;    /* table build: slices merged per census launch (0/1 = none) */
+  uint32_t pair_lists;      /* table build: 1 = materialise the multi-edge lists for the stream pair kernel */
+  uint32_t no_upload_overlap; /* 1 = one residue upload on the main stream instead of the chunked overlap */
 } kc_config;
+
+enum {
+  KC_INDEX_AUTO = 0,   /* the streaming partitioned build, unless subsampling is on (then the table build) */
+  KC_INDEX_STREAM = 1, /* stream_index.cuh: stable two-level partition + one shared-memory pass per bucket */
+  KC_INDEX_BUCKET = 2, /* bucket.cuh: round 1's append-by-cursor partitioned build (kept for comparison) */
+  KC_INDEX_TABLE = 3   /* index.cuh: universe-sized tables, L2-sliced */
+};
 
 /* src/main.rs:84-147 census + split; nnz = sum over proteins of |get_five_hash()| */
 typedef struct kc_index_stats {
@@ -143,8 +159,9 @@ int kc_build_index_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_ind
 /* What the engine's current index covers: info[0..3] = {shard, n_shards, n_blocks, rows owned};
  * n_shards == 1 means a whole index (stats are whole-set numbers). */
 int kc_index_shard_info(kc_engine* e, uint32_t info[4]);
-/* Which build produced the current index: 0 = universe-table build (index.cuh), else the bucket slot
- * size of the partitioned build (bucket.cuh): 4096, or 8192 after a bucket overflow. */
+/* Which build produced the current index: 0 = universe-table build (index.cuh), 1 = streaming partitioned
+ * build (stream_index.cuh), else the bucket slot size of round 1's partitioned build (bucket.cuh): 4096, or
+ * 8192 after a bucket overflow. */
 int kc_index_flavour(kc_engine* e);
 /* bounds[n_blocks + 1]: the row blocks of the pair order (block b is owned by rank b if b < n_shards,
  * else by rank n_blocks - 1 - b); a whole index has the one block {0, n}. */

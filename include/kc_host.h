@@ -1,5 +1,5 @@
-/* kc_host.h — host-side helpers around the engine: FASTA staging and the synthetic
- * protein-set generator used by the benchmarks.  Plain C ABI, no CUDA types.
+/* kc_host.h — host-side helpers around the engine: FASTA staging and the host tree.  Plain C ABI, no
+ * CUDA types.  (The synthetic protein-set generator of the benchmarks lives in kc_synth.h / libkc_synth.so.)
  *
  * kc_fasta_* restates what the reference gets from seq_io (src/main.rs:62-72) and from
  * Protein::new / get_amr_class (src/protein.rs:107-110,135-138):
@@ -34,18 +34,6 @@ uint32_t kc_fasta_n_classes(const kc_fasta* f);
 uint64_t kc_fasta_n_missing_class(const kc_fasta* f);
 const char* kc_fasta_class_name(const kc_fasta* f, uint32_t class_id);
 const char* kc_fasta_id(const kc_fasta* f, uint64_t protein);
-
-/* Synthetic generator "G1" (frozen; BASELINE.md / DESIGN.md give the law).  All-integer and
- * counter-based, so any subset of proteins can be generated independently and in parallel.
- *   length_law 0 ("A"): 50 + sum of four uniform ints in [0,150]   (mean 350)
- *   length_law 1 ("B"): 50 + 1950 * (t / 2^16)^4, t uniform in [0, 65535] (50..2000, skewed)
- * Families of 16 consecutive proteins share a base sequence; member j re-draws each residue
- * with probability j * 1311 / 65536.  class = family % 15, except every 8th family where
- * class = (family + j) % 15.
- * Step 1 fills offsets[n+1] and class_id[n]; step 2 fills residues[offsets[n]]. */
-int kc_synth_layout(uint64_t n, int length_law, uint64_t seed, uint64_t* offsets, uint32_t* class_id);
-int kc_synth_residues(uint64_t n, int length_law, uint64_t seed, int threads, const uint64_t* offsets,
-                      uint8_t* residues);
 
 /* Host tree clustering: the reference's src/tree.rs (Tree::new + add_protein for every protein in
  * input order, src/tree.rs:519-536) over the engine's per-protein id lists

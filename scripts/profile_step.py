@@ -18,10 +18,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="synth_1m_k7")
 ap.add_argument("--n-proteins", type=int, default=None)
 ap.add_argument("--cross", action="store_true")
+ap.add_argument("--index", default="auto", choices=["auto", "stream", "bucket", "table"])
 args = ap.parse_args()
 ps, k, cross = make_set(args.workload, args.n_proteins)
 cross = cross or args.cross
-with kc.Engine(k, threshold=THRESHOLD, cross_class_only=cross, want_blosum=True) as e:
+with kc.Engine(k, threshold=THRESHOLD, cross_class_only=cross, want_blosum=True, index_build=args.index) as e:
     e.set_protein_set(ps)
     e.build_index()
     e.score_pairs()

@@ -20,13 +20,15 @@ ap.add_argument("--workload", default="synth_1m_k7")
 ap.add_argument("--n-proteins", type=int, default=None)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--cross", action="store_true")
+ap.add_argument("--ballots", action="store_true")
+ap.add_argument("--index", default="auto", choices=["auto", "stream", "bucket", "table"])
 ap.add_argument("--no-blosum", action="store_true")
 ap.add_argument("--shard", type=int, default=0)
 ap.add_argument("--n-shards", type=int, default=1)
 args = ap.parse_args()
 ps, k, cross = make_set(args.workload, args.n_proteins)
 cross = cross or args.cross
-with kc.Engine(k, threshold=THRESHOLD, cross_class_only=cross, want_blosum=not args.no_blosum) as e:
+with kc.Engine(k, threshold=THRESHOLD, cross_class_only=cross, want_blosum=not args.no_blosum, index_build=args.index, census_merge=77 if args.ballots else 0) as e:
     e.set_protein_set(ps)
     for _ in range(2):
         ist = e.build_index(args.shard, args.n_shards)
@@ -43,6 +45,6 @@ with kc.Engine(k, threshold=THRESHOLD, cross_class_only=cross, want_blosum=not a
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / args.steps * 1e3
     avg = {key: round(v / args.steps, 3) for key, v in tot.items()}
-    print(args.workload, f"shard {args.shard}/{args.n_shards}", os.environ.get("KC_B200_INDEX", "default"), f"wall {wall:.2f} ms/step", avg)
+    print(args.workload, f"shard {args.shard}/{args.n_shards}", args.index, f"wall {wall:.2f} ms/step", avg)
     print("  index", ist)
     print("  pairs", pst)

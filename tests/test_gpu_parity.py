@@ -10,11 +10,15 @@ from oracle.oracle import Oracle
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["bucket", "table"])
+@pytest.fixture(autouse=True, params=["stream", "stream512", "bucket", "table"])
 def index_flavour(request, monkeypatch):
-    """every test runs against both index builds: the partitioned one (csrc/bucket.cuh) and the
-    universe-table one (csrc/index.cuh); KC_B200_INDEX overrides the engine's own choice"""
-    monkeypatch.setenv("KC_B200_INDEX", request.param)
+    """every test runs against every index build (kc_config.index_build): the streaming partitioned one
+    (csrc/stream_index.cuh; "stream512" = with 512-record shared-memory buckets, so that ordinary buckets
+    take the global-memory path of oversized ones), round 1's partitioned one (csrc/bucket.cuh) and the
+    universe-table one (csrc/index.cuh)"""
+    from uniprot_kmer_based_clustering_b200 import engine as eng
+    monkeypatch.setitem(eng.DEFAULTS, "index_build", "stream" if request.param == "stream512" else request.param)
+    monkeypatch.setitem(eng.DEFAULTS, "bucket_cap", 512 if request.param == "stream512" else 0)
     return request.param
 
 
@@ -278,7 +282,9 @@ def test_skewed_lengths_against_oracle():
 def test_l2_blocking_slices_do_not_change_results(slices, monkeypatch, arg_set, arg_oracle):
     """the index is built slice by slice over the k-mer universe (L2 blocking); any slicing must
     give the same index and edges"""
-    monkeypatch.setenv("KC_B200_SLICES", slices)
+    from uniprot_kmer_based_clustering_b200 import engine as eng
+    monkeypatch.setitem(eng.DEFAULTS, "index_slices", int(slices))
+    monkeypatch.setitem(eng.DEFAULTS, "index_build", "table")
     ps = random_protein_set(4, 300, min_len=0, max_len=400, n_classes=3, family=6)
     for k in (5, 7):
         km, ix, pr = run_oracle(ps, k, 2, True)
@@ -514,9 +520,10 @@ def test_cli_tree_and_sampling(tmp_path, arg_fasta_bytes):
 
 @pytest.mark.parametrize("blosum", [True, False])
 def test_stream_pair_kernel_over_materialised_lists(blosum, monkeypatch, arg_set, arg_oracle):
-    """KC_B200_PLIST=1 materialises the multi-edge lists and scores them with the stream kernel
-    (opt-in: the fill costs more than the stream kernel saves); both paths must give identical results"""
-    monkeypatch.setenv("KC_B200_PLIST", "1")
+    """kc_config.pair_lists materialises the multi-edge lists (table build) and scores them with the stream
+    kernel (opt-in: the fill costs more than the stream kernel saves); both paths must give identical results"""
+    from uniprot_kmer_based_clustering_b200 import engine as eng
+    monkeypatch.setitem(eng.DEFAULTS, "pair_lists", True)
     for k, cross, thr in ((5, True, 10), (7, False, 10)):
         pr = arg_oracle[k][0].score_pairs(thr, cross, blosum, mode=1)
         with kc.Engine(k, threshold=thr, cross_class_only=cross, want_blosum=blosum) as e:
@@ -561,10 +568,11 @@ def test_pair_index_is_a_perfect_hash_of_the_canonical_one(k, cross, arg_set, ar
 
 
 @pytest.mark.parametrize("n_hot,expect", [(2500, 8192), (9000, 0)])
-def test_bucket_overflow_retries_with_larger_buckets_then_the_table_build(n_hot, expect, index_flavour):
-    """one k-mer held by more proteins than a shared-memory bucket takes: 2 500 holders overflow the
-    4 096-record buckets and fit the 8 192-record ones, 9 000 holders fit neither and the engine
-    builds the universe-table index instead"""
+def test_kmers_with_more_holders_than_a_shared_memory_bucket(n_hot, expect, index_flavour):
+    """one k-mer held by more proteins than a shared-memory bucket takes.  The streaming build sends such a
+    bucket through its global-memory path (no fallback, no retry: 9 000 holders, src/graph/mod.rs:44-48 sizes
+    f(f-1)/2 edges for them).  Round 1's partitioned build: 2 500 holders overflow the 4 096-record buckets and
+    fit the 8 192-record ones, 9 000 holders fit neither and it builds the universe-table index instead"""
     rng = np.random.default_rng(11)
     letters = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
     hot = letters[:7]
@@ -584,6 +592,8 @@ def test_bucket_overflow_retries_with_larger_buckets_then_the_table_build(n_hot,
             assert e.index_flavour() == expect
             e.build_index()  # the slot size that worked is remembered for this protein set
             assert e.index_flavour() == expect
+        elif index_flavour.startswith("stream"):
+            assert e.index_flavour() == 1
         else:
             assert e.index_flavour() == 0
         check_index(e, ix)
@@ -610,7 +620,7 @@ def test_sharded_index_build_adds_up_to_the_whole(n_shards, k, cross, index_flav
             ist = e.build_index(s, n_shards)
             info = e.index_shard_info()
             sharded = info["n_shards"] > 1
-            assert sharded == (index_flavour == "bucket")
+            assert sharded == (index_flavour != "table")  # (the streaming build shards through round 1's build)
             pst = e.score_pairs(s, n_shards)
             parts.append(e.get_edges())
             for name in tot_i:
@@ -638,3 +648,33 @@ def test_sharded_index_build_adds_up_to_the_whole(n_shards, k, cross, index_flav
         assert tot_p[name] == pr.stats[name], name
     from uniprot_kmer_based_clustering_b200.sharded import merge_edge_lists
     assert np.array_equal(merge_edge_lists(parts), pr.edges)
+
+
+# ---------------------------------------------------------------- full-size benchmark configurations
+@pytest.mark.parametrize("name", ["synth_20k_k5", "synth_100k_k5", "synth_250k_skew_k7", "synth_1m_k7"])
+def test_full_size_synthetic_goldens(name, index_flavour):
+    """BASELINE.json's synthetic configurations at FULL size against the oracle's committed golden values
+    (tests/golden/synth_golden.json, written by tests/golden/make_synth_golden.py): the index counters, the
+    counters the reference prints (src/graph/mod.rs:50-51,545,695) and the SHA-256 of the whole sorted
+    (a, b, count, blosum) edge list.  bench.py asserts the same SHA at every GPU count."""
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    if index_flavour in ("stream512", "bucket") or (index_flavour == "table" and name in ("synth_1m_k7", "synth_250k_skew_k7")):
+        pytest.skip("full size: the default build (and the table build on the k = 5 sets)")
+    with open(os.path.join(GOLDEN_DIR, "synth_golden.json")) as fh:
+        g = json.load(fh)[name]
+    ps = kc.ProteinSet.synthetic(g["n"], g["law"], int(g["seed"], 16), threads=os.cpu_count() or 8)
+    assert hashlib.sha256(ps.residues.tobytes()).hexdigest() == g["residues_sha256"]
+    with kc.Engine(g["k"], threshold=g["threshold"], cross_class_only=g["cross_class_only"], want_blosum=True) as e:
+        e.set_protein_set(ps)
+        ist = e.build_index()
+        pst = e.score_pairs()
+        edges = e.get_edges()
+    for key, val in g["index"].items():
+        assert ist[key] == val, key
+    for key, val in g["pairs"].items():
+        assert pst[key] == val, key
+    assert hashlib.sha256(np.ascontiguousarray(edges).tobytes()).hexdigest() == g["edges_sha256"]
+    assert int(edges["blosum"].astype(np.int64).sum()) == g["sum_blosum"]

@@ -148,7 +148,7 @@ def _py_stream(seed, index, tag):
 
 
 def _py_generate(n, law, seed):
-    """Pure-Python restatement of generator G1 (include/kc_host.h)."""
+    """Pure-Python restatement of generator G1 (include/kc_synth.h)."""
     letters = "LAGVISTFREKDPQNYMHWC"
     counts = [377380, 336508, 269059, 258845, 257326, 206108, 194902, 176903, 163437, 158642,
               158511, 153089, 143715, 124590, 118853, 101563, 92047, 64642, 54450, 26176]
@@ -224,7 +224,13 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(EXPORTED)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.kc_abi_version() == 1
+    assert L.kc_abi_version() == 2
+    # the benchmark generator is its own host-only library
+    from uniprot_kmer_based_clustering_b200._lib import SYNTH_EXPORTED, synth_lib
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "kc_synth.h")).read(), flags=re.S)
+    assert set(re.findall(r"\b(kc_[a-z0-9_]+)\s*\(", text)) == set(SYNTH_EXPORTED)
+    for name in SYNTH_EXPORTED:
+        assert hasattr(synth_lib(), name), name
 
 
 def test_reference_api_mirror_names():

@@ -27,7 +27,12 @@ class KcError(RuntimeError):
 class Config(C.Structure):
     _fields_ = [("k", C.c_int32), ("device", C.c_int32), ("threshold", C.c_uint32),
                 ("cross_class_only", C.c_int32), ("want_blosum", C.c_int32), ("sample_every", C.c_uint32),
-                ("max_edges", C.c_uint64), ("sample_seed", C.c_uint64)]
+                ("max_edges", C.c_uint64), ("sample_seed", C.c_uint64),
+                ("index_build", C.c_uint32), ("bucket_cap", C.c_uint32), ("index_slices", C.c_uint32),
+                ("census_merge", C.c_uint32), ("pair_lists", C.c_uint32), ("no_upload_overlap", C.c_uint32)]
+
+
+INDEX_BUILDS = {"auto": 0, "stream": 1, "bucket": 2, "table": 3}
 
 
 class IndexStats(C.Structure):
@@ -62,7 +67,6 @@ EXPORTED = [
     "kc_fasta_parse_file", "kc_fasta_parse_buffer", "kc_fasta_free", "kc_fasta_n_proteins",
     "kc_fasta_n_residues", "kc_fasta_residues", "kc_fasta_offsets", "kc_fasta_class_ids",
     "kc_fasta_n_classes", "kc_fasta_n_missing_class", "kc_fasta_class_name", "kc_fasta_id",
-    "kc_synth_layout", "kc_synth_residues",
     "kc_tree_build", "kc_tree_free", "kc_tree_n_merges", "kc_tree_n_no_common", "kc_tree_serialize",
     "kc_tree_clusters",
 ]
@@ -73,6 +77,27 @@ def build(verbose: bool = False) -> str:
     out = None if verbose else subprocess.DEVNULL
     subprocess.check_call(["make", "-C", CSRC, "all"], stdout=out)
     return LIB_PATH
+
+
+SYNTH_LIB_PATH = os.path.join(_PKG, "lib", "libkc_synth.so")
+SYNTH_EXPORTED = ["kc_synth_layout", "kc_synth_residues"]
+_synth = None
+
+
+def synth_lib():
+    """libkc_synth.so (include/kc_synth.h): the benchmark generator, host only.  Loading it does not
+    load the engine."""
+    global _synth
+    if _synth is None:
+        if not os.path.exists(SYNTH_LIB_PATH):
+            raise ImportError(f"{SYNTH_LIB_PATH} is missing: build it with `make -C {CSRC}`")
+        L = C.CDLL(SYNTH_LIB_PATH)
+        L.kc_synth_layout.restype = C.c_int
+        L.kc_synth_layout.argtypes = [C.c_uint64, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.kc_synth_residues.restype = C.c_int
+        L.kc_synth_residues.argtypes = [C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+        _synth = L
+    return _synth
 
 
 _lib = None
@@ -131,8 +156,6 @@ def lib():
         "kc_fasta_n_missing_class": (u64, [vp]),
         "kc_fasta_class_name": (cp, [vp, u32]),
         "kc_fasta_id": (cp, [vp, u64]),
-        "kc_synth_layout": (i32, [u64, i32, u64, vp, vp]),
-        "kc_synth_residues": (i32, [u64, i32, u64, i32, vp, vp]),
         "kc_tree_build": (i32, [vp, vp, u64, u32, P(vp)]),
         "kc_tree_free": (None, [vp]),
         "kc_tree_n_merges": (u64, [vp]),

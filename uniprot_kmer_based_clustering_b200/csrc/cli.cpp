@@ -51,7 +51,14 @@ int main(int argc, char** argv) {
     else if (a == "--tree") want_tree = true;
     else if (a == "--sample-every" && i + 1 < argc) cfg.sample_every = (uint32_t)std::atoi(argv[++i]);
     else if (a == "--seed" && i + 1 < argc) cfg.sample_seed = std::strtoull(argv[++i], nullptr, 0);
-    else if (a == "--index" && i + 1 < argc) setenv("KC_B200_INDEX", argv[++i], 1);  // bucket | table (engine.cu)
+    else if (a == "--index" && i + 1 < argc) {  // stream | bucket | table (kc_config.index_build)
+      const std::string v = argv[++i];
+      cfg.index_build = v == "stream" ? KC_INDEX_STREAM : v == "bucket" ? KC_INDEX_BUCKET : v == "table" ? KC_INDEX_TABLE : 99u;
+      if (cfg.index_build == 99u) {
+        std::fprintf(stderr, "--index takes stream, bucket or table\n");
+        return 101;
+      }
+    }
     else {
       std::fprintf(stderr, "unknown option %s\n", a.c_str());
       return 101;

@@ -14,6 +14,7 @@
 #include "extract.cuh"
 #include "index.cuh"
 #include "bucket.cuh"
+#include "stream_index.cuh"
 #include "pairs.cuh"
 #include "primitives.cuh"
 
@@ -59,7 +60,7 @@ struct DeviceScalars {  // one small block of u64 counters, zeroed per stage
   uint32_t pad;
   BucketGlobals bg;
   uint32_t ent_seg[2];  // {0, nnz}: the one segment of the first entry-partition pass
-  uint32_t pad3[2];
+  uint32_t sx_mid_cnt, sx_huge_cnt;  // streaming build: buckets beyond a warp's / a CTA's shared memory
 };
 
 enum Ev { EV_H2D0, EV_H2D1, EV_X0, EV_X1, EV_I0, EV_IC0, EV_IC1, EV_I1, EV_P0, EV_PK0, EV_PK1, EV_P1, EV_E1, EV_D0, EV_D1, EV_COUNT };
@@ -136,6 +137,13 @@ struct kc_engine {
   }
   DBuf d_rec, d_entries, d_bin_cnt, d_rowcap, d_bucket_cnt, d_ids, d_vocab_h, d_freq_h, d_self_h,
       d_zero, d_rowlen_c, d_islo_c;
+  // streaming partitioned build (stream_index.cuh): the residue stream in the pair order (an alias of d_res
+  // unless the pair order is class-major), its row starts, the two record arrays and the scanned histograms
+  bool streamed = false;
+  DBuf d_sres_own, d_soff, d_rec_a, d_rec_b, d_h1, d_h2, d_huge_list, d_mid_list, d_tile_row, d_ss3;
+  std::vector<uint32_t> h_soff;
+  uint32_t sx_huge_last = 0, sx_mid_last = 0, sx_max_bucket = 0;
+  const uint8_t* sres() const { return cfg.cross_class_only ? d_sres_own.as<uint8_t>() : d_res.as<uint8_t>(); }
   const uint32_t* pair_rowptr() const { return (bucketed ? d_rowcap : d_pstart).as<uint32_t>(); }  // d_rowcap: capacity prefix
   const uint32_t* pair_ids() const { return (bucketed ? d_ids : d_pk).as<uint32_t>(); }
   const uint8_t* pair_self() const { return (bucketed ? d_self_h : d_self).as<uint8_t>(); }
@@ -216,15 +224,22 @@ uint32_t blocks_for(uint64_t items, uint32_t per_block, uint32_t cap) {
 // pair order = input order (all-classes mode): the row layout straight from the offsets on the device
 __global__ void layout_identity_kernel(const unsigned long long* __restrict__ off, uint32_t n,
                                        uint32_t* __restrict__ pstart, uint32_t* __restrict__ plen,
-                                       uint32_t* __restrict__ orig, uint32_t* __restrict__ rank) {
+                                       uint32_t* __restrict__ orig, uint32_t* __restrict__ rank,
+                                       uint32_t* __restrict__ soff) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const unsigned long long a = off[r], b = off[r + 1];
+  soff[r] = (uint32_t)a;
+  if (r + 1 == n) soff[n] = (uint32_t)b;
   pstart[r] = (uint32_t)a;
   plen[r] = (uint32_t)(b - a);
   orig[r] = r;
   rank[r] = r;
 }
+
+// residue buffers are padded with zeros to whole tiles of the streaming kernels plus one tile (their 16-byte
+// loads and the k-mer halo never need a bounds check)
+size_t padded_res_bytes(uint64_t R) { return (size_t)((R + kSxTile - 1) / kSxTile + 1) * kSxTile; }
 
 // ---- host-side staging shared by both kc_set_proteins flavours ---------------------------
 // (this runs while the residue stream is crossing PCIe: one pass over the offsets)
@@ -259,6 +274,7 @@ int stage_layout(kc_engine* e) {
     for (uint64_t r = 0; r < n; ++r) e->h_rank[e->h_orig[r]] = (uint32_t)r;
     e->h_pstart.resize(n);
     e->h_plen.resize(n);
+    e->h_soff.assign(n + 1, 0u);
   }
   e->h_long.clear();
   e->h_huge.clear();
@@ -281,6 +297,7 @@ int stage_layout(kc_engine* e) {
     if (cross) {
       e->h_pstart[r] = (uint32_t)off[p];
       e->h_plen[r] = (uint32_t)len;
+      e->h_soff[r + 1] = e->h_soff[r] + (uint32_t)len;
     } else {
       e->h_orig[r] = e->h_rank[r] = (uint32_t)r;
     }
@@ -318,16 +335,26 @@ int stage_layout(kc_engine* e) {
     KC_CUDA(e, e->d_plen.ensure(std::max<size_t>(n * 4, 16)));
     KC_CUDA(e, e->d_orig.ensure(std::max<size_t>(n * 4, 16)));
     KC_CUDA(e, e->d_rank.ensure(std::max<size_t>(n * 4, 16)));
+    KC_CUDA(e, e->d_soff.ensure((n + 1) * 4 + 16));
     if (n)
       KC_LAUNCH(e, layout_identity_kernel, (uint32_t)((n + 255) / 256), 256, 0, e->d_off.as<unsigned long long>(),
                 (uint32_t)n, e->d_pstart.as<uint32_t>(), e->d_plen.as<uint32_t>(), e->d_orig.as<uint32_t>(),
-                e->d_rank.as<uint32_t>());
+                e->d_rank.as<uint32_t>(), e->d_soff.as<uint32_t>());
   } else {
+    // the residue stream in the pair (class-major) order for the streaming index build
+    KC_CUDA(e, up(e->d_soff, e->h_soff.data(), (n + 1) * 4));
+    const size_t padded = padded_res_bytes(e->R);
+    KC_CUDA(e, e->d_sres_own.ensure(padded));
+    KC_CUDA(e, cudaMemsetAsync(e->d_sres_own.as<uint8_t>() + e->R, 0, padded - e->R, e->stream));
     KC_CUDA(e, up(e->d_pstart, e->h_pstart.data(), n * 4));
     KC_CUDA(e, up(e->d_plen, e->h_plen.data(), n * 4));
     KC_CUDA(e, up(e->d_orig, e->h_orig.data(), n * 4));
     KC_CUDA(e, up(e->d_rank, e->h_rank.data(), n * 4));
     KC_CUDA(e, up(e->d_first_after, e->h_first_after.data(), n * 4));
+    if (n && e->R)
+      KC_LAUNCH(e, sx_permute_residues_kernel, (uint32_t)std::min<uint64_t>((n + 7) / 8, (uint64_t)e->num_sm * 16), 256, 0,
+                e->d_res.as<uint8_t>(), e->d_pstart.as<uint32_t>(), e->d_soff.as<uint32_t>(), (uint32_t)n,
+                e->d_sres_own.as<uint8_t>());
   }
   KC_CUDA(e, up(e->d_long, e->h_long.data(), e->h_long.size() * 4));
   KC_CUDA(e, up(e->d_cta, e->h_cta.data(), e->h_cta.size() * 4));
@@ -340,7 +367,6 @@ int stage_layout(kc_engine* e) {
   return KC_OK;
 }
 
-size_t padded_res_bytes(uint64_t R) { return (size_t)((R + kTileRes - 1) / kTileRes + 1) * kTileRes; }
 
 template <int K>
 int run_extract_census(kc_engine* e, BucketScatter scatter = BucketScatter{nullptr, nullptr, 0u, 0u, nullptr, 0u, RowOwner{nullptr, 0u}}) {
@@ -732,6 +758,225 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
   return KC_OK;
 }
 
+// ---- the streaming partitioned index build (stream_index.cuh): the default -------------------
+static SxPlan sx_make_plan(uint64_t E, uint64_t R, int num_sm) {
+  SxPlan p{};
+  // ~330 records per bucket: one warp sorts a bucket in its own slice of shared memory (512 records).
+  // b >= 12: the CTA kernel's sort key (32 - b bits) must fit a u32 beside a 12-bit record index;
+  // b <= 20: 1 024 digits per level.
+  uint32_t b = 12;
+  while (b < 20 && (E >> b) > 330) ++b;
+  p.b1 = (b + 1) / 2;
+  p.b2 = b - p.b1;
+  p.r = 32 - b;
+  const uint32_t tiles = (uint32_t)std::max<uint64_t>(1, (R + kSxTile - 1) / kSxTile);
+  uint32_t g1 = std::min<uint32_t>(tiles, (uint32_t)num_sm * 2u);
+  p.tiles_per_chunk = (tiles + g1 - 1) / g1;
+  p.g1 = (tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+  p.c2 = std::min<uint32_t>(16u, std::max<uint32_t>(1u, ((uint32_t)num_sm * 16u) >> p.b1));
+  p.ballots = 1;  // level 1 / 2 (9-10 digit bits): one ballot per bit measured faster than match.any
+  return p;
+}
+
+static int build_index_stream(kc_engine* e, kc_index_stats* stats) {
+  const uint32_t n = (uint32_t)e->n;
+  const uint64_t R = e->R;
+  DeviceScalars* ds = e->ds;
+  const unsigned long long n_positions = e->h_pospref[n];
+  const uint64_t E = std::max<unsigned long long>(n_positions, 1);
+  const uint32_t n_bins = (n + kBinRows - 1) >> kBinRowsLog;
+  SxPlan plan = sx_make_plan(E, R, e->num_sm);
+  if (e->cfg.census_merge == 77u) plan.ballots = 0;  // (A/B switch while tuning; see profiles/r2_history.md)
+  const uint32_t n_tiles = (uint32_t)((R + kSxTile - 1) / kSxTile);
+  const uint32_t D1 = plan.d1(), D2 = plan.d2(), NB = plan.n_buckets();
+  const uint64_t n_h1 = (uint64_t)D1 * plan.g1, n_h2 = (uint64_t)NB * plan.c2;
+  KC_CUDA(e, wait_upload(e) == KC_OK ? cudaSuccess : cudaErrorUnknown);
+  KC_CUDA(e, e->d_rec_a.ensure((E + 64) * 8));
+  KC_CUDA(e, e->d_rec_b.ensure((E + 64) * 8));
+  KC_CUDA(e, e->d_h1.ensure((n_h1 + 2) * 4));
+  KC_CUDA(e, e->d_h2.ensure((n_h2 + 2) * 4));
+  KC_CUDA(e, e->d_huge_list.ensure(((uint64_t)NB + 2) * 4));
+  KC_CUDA(e, e->d_mid_list.ensure(((uint64_t)NB + 2) * 4));
+  KC_CUDA(e, e->d_tile_row.ensure(((uint64_t)n_tiles + 2) * 4));
+  KC_CUDA(e, e->d_rowlen.ensure(((uint64_t)n + 1) * 4));
+  KC_CUDA(e, e->d_entries.ensure((E + E / 2 + 64) * 16));
+  KC_CUDA(e, e->d_runs.ensure((E / 2 + 64) * 16));
+  KC_CUDA(e, e->d_run_cnt.ensure(((uint64_t)n_bins + 2) * 4));
+  KC_CUDA(e, e->d_rowlen_p.ensure(((uint64_t)n + 1) * 4));
+  KC_CUDA(e, e->d_rowcap.ensure(((uint64_t)n + 2) * 4));
+  KC_CUDA(e, e->d_bin_cnt.ensure(((uint64_t)n_bins + 2) * 4));
+  KC_CUDA(e, e->d_ids.ensure((E + 64) * 4));
+  KC_CUDA(e, e->d_col.ensure((E + 64) * 4));
+  KC_CUDA(e, e->d_suf.ensure((E + 64) * 8));
+  if (e->cfg.want_blosum) KC_CUDA(e, e->d_sufss.ensure(E + 64));
+  KC_CUDA(e, e->d_vocab_h.ensure((E / 2 + 2) * 4));
+  KC_CUDA(e, e->d_freq_h.ensure((E / 2 + 2) * 4));
+  KC_CUDA(e, e->d_self_h.ensure(E / 2 + 16));
+  KC_CUDA(e, e->d_rowwork.ensure(((uint64_t)n + 1) * 4));
+  KC_CUDA(e, e->d_rowwork64.ensure(((uint64_t)n + 1) * 8));
+  KC_CUDA(e, e->d_rowinl.ensure(((uint64_t)n + 1) * 4));
+  KC_CUDA(e, e->d_rowmaxlen.ensure(((uint64_t)n + 1) * 4));
+  KC_CUDA(e, e->d_workprefix.ensure(((uint64_t)n + 2) * 8));
+  int rc = ensure_scan(e, std::max<uint64_t>(std::max<uint64_t>(n_h1, n_h2), (uint64_t)n) + 1);
+  if (rc) return rc;
+  e->have_plist = false;
+  e->n_slices = 0;
+  const uint8_t* res = e->sres();
+  const uint32_t* soff = e->d_soff.as<uint32_t>();
+  uint32_t* h1 = e->d_h1.as<uint32_t>();
+  uint32_t* h2 = e->d_h2.as<uint32_t>();
+  uint2* rec_a = e->d_rec_a.as<uint2>();
+  uint2* rec_b = e->d_rec_b.as<uint2>();
+  uint32_t* rowcap = e->d_rowcap.as<uint32_t>();
+  uint32_t* bin_cnt = e->d_bin_cnt.as<uint32_t>();
+  uint4* ent = e->d_entries.as<uint4>();
+  const bool k5 = e->cfg.k == 5;
+
+  mark(e, EV_I0);
+  KC_CUDA(e, cudaMemsetAsync(ds, 0, sizeof(DeviceScalars), e->stream));
+  KC_CUDA(e, cudaMemsetAsync(bin_cnt, 0, ((uint64_t)n_bins + 1) * 4, e->stream));
+  mark(e, EV_IC0);
+  // entry capacity of every row: its k-mer positions
+  e->launches += exclusive_scan(SxPosIn{soff, (uint32_t)e->cfg.k}, SxExclOutTail{rowcap, n}, n, e->scan, e->stream);
+  KC_LAUNCH(e, sx_tile_rows_kernel, (n_tiles + 256) / 256, 256, 0, soff, n, (uint32_t)R, n_tiles,
+            e->d_tile_row.as<uint32_t>());
+  // level 1: count, scan, scatter (residue stream -> rec_a, partitioned by the top b1 hash bits)
+  {
+    const uint32_t* trow = e->d_tile_row.as<uint32_t>();
+    const size_t smem_c = (size_t)D1 * 4 + kSxTile + 64 + 256;
+    const size_t smem_s = sx_scatter_smem(D1);
+    if (k5) {
+      KC_CUDA(e, cudaFuncSetAttribute(sx_l1_count_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+      KC_CUDA(e, cudaFuncSetAttribute(sx_l1_scatter_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+      KC_LAUNCH(e, sx_l1_count_kernel<5>, plan.g1, kSxThreads, smem_c, res, (uint32_t)R, soff, trow, plan, h1);
+    } else {
+      KC_CUDA(e, cudaFuncSetAttribute(sx_l1_count_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+      KC_CUDA(e, cudaFuncSetAttribute(sx_l1_scatter_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+      KC_LAUNCH(e, sx_l1_count_kernel<7>, plan.g1, kSxThreads, smem_c, res, (uint32_t)R, soff, trow, plan, h1);
+    }
+    e->launches += exclusive_scan(U32In{h1}, SxExclOutTail{h1, n_h1}, n_h1, e->scan, e->stream);
+    if (k5)
+      KC_LAUNCH(e, sx_l1_scatter_kernel<5>, plan.g1, kSxThreads, smem_s, res, (uint32_t)R, soff, trow, plan, h1, rec_a);
+    else
+      KC_LAUNCH(e, sx_l1_scatter_kernel<7>, plan.g1, kSxThreads, smem_s, res, (uint32_t)R, soff, trow, plan, h1, rec_a);
+  }
+  // level 2: rec_a -> rec_b, every level-1 partition by the next b2 hash bits
+  {
+    const size_t smem_c = (size_t)D2 * 4;
+    const size_t smem_s = sx_scatter_smem(D2);
+    KC_CUDA(e, cudaFuncSetAttribute(sx_l2_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+    KC_LAUNCH(e, sx_l2_count_kernel, D1 * plan.c2, kSxThreads, smem_c, rec_a, h1, plan, h2);
+    e->launches += exclusive_scan(U32In{h2}, SxExclOutTail{h2, n_h2}, n_h2, e->scan, e->stream);
+    KC_LAUNCH(e, sx_l2_scatter_kernel, D1 * plan.c2, kSxThreads, smem_s, rec_a, h1, plan, h2, rec_b);
+  }
+  mark(e, EV_IC1);
+  // buckets: sort, census, ids, postings, entries
+  {
+    SxBucketArgs A{};
+    A.rec = rec_b;
+    A.scratch = rec_a;
+    A.h2 = h2;
+    A.plan = plan;
+    A.first_after = e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr;
+    A.k = e->cfg.k;
+    A.col = e->d_col.as<uint32_t>();
+    A.entries = ent;
+    A.rowcap_prefix = rowcap;
+    A.bin_cursor = bin_cnt;
+    A.vocab = e->d_vocab_h.as<uint32_t>();
+    A.freq = e->d_freq_h.as<uint32_t>();
+    A.selfscore = e->d_self_h.as<uint8_t>();
+    A.ss3 = e->d_ss3.as<uint8_t>();
+    A.g = &ds->bg;
+    A.n_incid = &ds->n_incid;
+    A.mid_list = e->d_mid_list.as<uint32_t>();
+    A.mid_cnt = &ds->sx_mid_cnt;
+    A.huge_list = e->d_huge_list.as<uint32_t>();
+    A.huge_cnt = &ds->sx_huge_cnt;
+    const bool small = e->cfg.bucket_cap == 512u;  // tests: tiny capacities push ordinary buckets down every path
+    A.mid_cap = small ? 512u : 4096u;
+    // one warp per bucket
+#define KC_SXW(CROSS, WCAP)                                                                                      \
+  do {                                                                                                           \
+    constexpr size_t smem = sx_wb_warp_bytes<WCAP>() * kWbWarps;                                                 \
+    KC_CUDA(e, cudaFuncSetAttribute((sx_warp_bucket_kernel<CROSS, WCAP>), cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)smem));                                                                 \
+    int per_sm = 1;                                                                                              \
+    KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (sx_warp_bucket_kernel<CROSS, WCAP>),      \
+                                                             kWbWarps * 32, smem));                              \
+    const uint32_t grid = std::max<uint32_t>(1u, std::min<uint32_t>((NB + kWbWarps - 1) / kWbWarps,               \
+                                                                     (uint32_t)(e->num_sm * std::max(per_sm, 1)))); \
+    KC_LAUNCH(e, (sx_warp_bucket_kernel<CROSS, WCAP>), grid, kWbWarps * 32, smem, A);                            \
+  } while (0)
+    if (small) {
+      if (A.first_after) KC_SXW(true, 64u); else KC_SXW(false, 64u);
+    } else {
+      if (A.first_after) KC_SXW(true, 512u); else KC_SXW(false, 512u);
+    }
+#undef KC_SXW
+    // buckets beyond a warp's slice: one CTA each (the list is short on ordinary sets)
+#define KC_SXB(CROSS, CAP)                                                                                       \
+  do {                                                                                                           \
+    constexpr size_t smem = sx_bucket_smem<CAP>();                                                               \
+    KC_CUDA(e, cudaFuncSetAttribute((sx_bucket_kernel<CROSS, CAP>), cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)smem));                                                                 \
+    int per_sm = 1;                                                                                              \
+    KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (sx_bucket_kernel<CROSS, CAP>), CAP / 8, smem)); \
+    const uint32_t grid = std::min<uint32_t>(NB, (uint32_t)(e->num_sm * std::max(per_sm, 1)));                    \
+    KC_LAUNCH(e, (sx_bucket_kernel<CROSS, CAP>), grid, CAP / 8, smem, A);                                        \
+  } while (0)
+    if (small) {
+      if (A.first_after) KC_SXB(true, 512u); else KC_SXB(false, 512u);
+    } else {
+      if (A.first_after) KC_SXB(true, 4096u); else KC_SXB(false, 4096u);
+    }
+#undef KC_SXB
+    // buckets beyond a CTA's shared memory (k-mers with thousands of holders); the list is usually empty
+    const uint32_t hgrid = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)e->num_sm, std::max<uint32_t>(e->sx_huge_last, 8u)));
+    if (A.first_after)
+      KC_LAUNCH(e, sx_huge_kernel<true>, hgrid, kHugeThreads, 0, A);
+    else
+      KC_LAUNCH(e, sx_huge_kernel<false>, hgrid, kHugeThreads, 0, A);
+  }
+  // entry bins -> rows (laid out by capacity: row r starts at rowcap[r])
+  KC_CUDA(e, cudaFuncSetAttribute(rows_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmemBytes));
+  if (n_bins)
+    KC_LAUNCH(e, rows_finalize_kernel, std::min<uint32_t>(n_bins, (uint32_t)e->num_sm * 3), kFinThreads, kFinSmemBytes, ent,
+              rowcap, bin_cnt, n, 0u, n_bins, e->d_runs.as<uint4>(), e->d_run_cnt.as<uint32_t>(),
+              e->d_rowlen.as<uint32_t>(), e->d_rowlen_p.as<uint32_t>(), e->d_ids.as<uint32_t>(), e->d_suf.as<uint2>(),
+              e->cfg.want_blosum ? e->d_sufss.as<uint8_t>() : nullptr, e->d_rowwork64.as<unsigned long long>(),
+              e->d_rowwork.as<uint32_t>(), e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>());
+  e->launches += exclusive_scan(WorkIn{e->d_rowwork.as<uint32_t>(), e->d_rowlen.as<uint32_t>()},
+                                U64ExclOutWithTail{e->d_workprefix.as<unsigned long long>(), n}, n, e->scan, e->stream);
+  mark(e, EV_I1);
+  DeviceScalars hs{};
+  KC_CUDA(e, cudaMemcpyAsync(&hs, ds, sizeof(hs), cudaMemcpyDeviceToHost, e->stream));
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  KC_CUDA(e, cudaGetLastError());
+  e->sx_huge_last = hs.sx_huge_cnt;
+  e->sx_mid_last = hs.sx_mid_cnt;
+  e->sx_max_bucket = hs.bg.max_bucket;
+  e->istats.n_positions = n_positions;
+  e->istats.n_incidences = hs.n_incid;
+  e->istats.n_distinct = hs.bg.n_distinct;
+  e->istats.n_repeated = hs.bg.n_repeated;
+  e->istats.n_singleton = hs.bg.n_distinct - hs.bg.n_repeated;
+  e->istats.nnz = hs.bg.nnz;
+  e->v_local = E / 2 + 1;  // ids are placed by capacity (stream_index.cuh): the id SPACE, with holes
+  e->multi_total = hs.bg.multi_total;
+  e->work_total = hs.bg.work_total;
+  e->ishard = 0;
+  e->ishards = 1;
+  e->block_bounds.clear();
+  e->n_own_rows = n;
+  if (stats) *stats = e->istats;
+  e->bucketed = true;
+  e->streamed = true;
+  e->canonical_ready = false;
+  e->have_index = true;
+  return KC_OK;
+}
+
 // The canonical view of a partitioned index: ascending-k-mer ids, sorted id rows, kmer_freq by
 // canonical id — the universe-table stages of index.cuh, unsliced, run on demand for the readback
 // / lookup entry points (never on the hot path).  d_pk still holds every row's sorted distinct
@@ -751,6 +996,8 @@ static int ensure_canonical(kc_engine* e) {
   KC_CUDA(e, e->d_vocab.ensure((V + 1) * 4));
   KC_CUDA(e, e->d_freq.ensure((V + 1) * 4));
   KC_CUDA(e, e->d_self.ensure(V + 16));
+  KC_CUDA(e, e->d_pk.ensure((e->R + 64) * 4));
+  KC_CUDA(e, e->d_ndist.ensure(((uint64_t)n + 1) * 4));
   int rc = ensure_scan(e, std::max<uint64_t>(W, (uint64_t)n + 1));
   if (rc) return rc;
   {  // the rows' sorted distinct k-mers (the partitioned build does not write them)
@@ -845,6 +1092,11 @@ int kc_create(const kc_config* cfg, kc_engine** out) {
   }
   e->ds = e->d_scalars.as<DeviceScalars>();
   cudaMemset(e->ds, 0, sizeof(DeviceScalars));
+  if (e->d_ss3.ensure(9261 + 64) != cudaSuccess) {
+    kc_destroy(e);
+    return KC_ENOMEM;
+  }
+  sx_ss3_kernel<<<(9261 + 255) / 256, 256, 0, e->stream>>>(e->d_ss3.as<uint8_t>());
   e->universe = pow21(cfg->k);
   e->n_words = ((uint64_t)e->universe + 31) / 32;
   *out = e;
@@ -863,7 +1115,8 @@ void kc_destroy(kc_engine* e) {
                  &e->d_rec, &e->d_entries, &e->d_bin_cnt, &e->d_rowcap, &e->d_bucket_cnt, &e->d_ids,
                  &e->d_vocab_h, &e->d_freq_h, &e->d_self_h, &e->d_zero, &e->d_rowlen_c, &e->d_islo_c, &e->d_filter, &e->d_binowner, &e->d_runs, &e->d_run_cnt, &e->d_rowlen_p, &e->d_rowbin, &e->d_rowsafe, &e->d_rowlogh, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
                  &e->d_vals_a, &e->d_vals_b, &e->d_hist, &e->d_edges_sorted, &e->d_scalars, &e->d_scan_tiles,
-                 &e->d_tmp};
+                 &e->d_tmp, &e->d_sres_own, &e->d_soff, &e->d_rec_a, &e->d_rec_b, &e->d_h1, &e->d_h2,
+                 &e->d_huge_list, &e->d_mid_list, &e->d_tile_row, &e->d_ss3};
   for (DBuf* b : all) b->release();
   for (int i = 0; i < EV_COUNT; ++i)
     if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -913,8 +1166,7 @@ int kc_set_proteins(kc_engine* e, const uint8_t* residues, const uint64_t* offse
   KC_CUDA(e, cudaMemcpyAsync(e->d_off.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, e->stream));
   e->n_chunks = 0;
   constexpr int C = kc_engine::kUploadChunks;
-  if (!e->cfg.cross_class_only && R >= (32u << 20) && n >= 64 * C && e->copy_stream &&
-      !std::getenv("KC_B200_NO_UPLOAD_OVERLAP")) {
+  if (!e->cfg.cross_class_only && R >= (32u << 20) && n >= 64 * C && e->copy_stream && !e->cfg.no_upload_overlap) {
     // pair order = input order: chunk c of the stream is the rows [chunk_row[c], chunk_row[c+1]).
     // The copy stream waits for what the main stream still does with the old residues.
     KC_CUDA(e, cudaEventRecord(e->main_ev, e->stream));
@@ -1043,7 +1295,7 @@ int kc_index_shard_info(kc_engine* e, uint32_t info[4]) {
 
 int kc_index_flavour(kc_engine* e) {
   if (!e || !e->have_index) return -1;
-  return e->bucketed ? (int)e->cap_hint : 0;
+  return e->streamed ? 1 : (e->bucketed ? (int)e->cap_hint : 0);
 }
 
 int kc_index_shard_blocks(kc_engine* e, uint32_t* bounds, uint32_t capacity) {
@@ -1072,19 +1324,21 @@ int kc_build_index_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_ind
   e->bucketed = e->canonical_ready = false;
   e->ishard = 0;
   e->ishards = 1;
+  e->streamed = false;
   {
-    // Index flavour: the partitioned build (bucket.cuh) unless the set is small and k = 5 (a 4 M
-    // universe: the universe tables sit in L2 and a redundant set like the ARG one overflows the
-    // buckets anyway); a bucket overflow falls back to the universe-table build (index.cuh).
-    // KC_B200_INDEX=bucket|table overrides (tests run both).
-    const char* env = std::getenv("KC_B200_INDEX");
-    bool want = e->cfg.k == 7 || e->h_pospref[n] >= (16ull << 20);
-    if (env && !std::strcmp(env, "bucket")) want = true;
-    if (env && !std::strcmp(env, "table")) want = false;
-    // (remembered per protein-set signature: buckets that overflowed once are not tried again)
-    if (want && e->cap_hint == 0 && e->cap_hint_n == e->n && e->cap_hint_R == e->R && !(env && !std::strcmp(env, "bucket")))
-      want = false;
-    if (want && n > 0 && n <= (1u << 24)) {
+    // Which build (kc_config.index_build): the streaming partitioned build (stream_index.cuh) by default.
+    // It has no subsampling mode (Protein::new_with_rand_fivemers is dead code in the reference) and no
+    // owner-computes sharding: those run the table build / round 1's bucket build.
+    uint32_t want = e->cfg.index_build;
+    if (want == KC_INDEX_AUTO) want = e->cfg.sample_every > 1 ? KC_INDEX_TABLE : (n_shards > 1 ? KC_INDEX_BUCKET : KC_INDEX_STREAM);
+    if (want == KC_INDEX_STREAM && (e->cfg.sample_every > 1 || n_shards > 1 || n >= (1u << 24)))
+      want = e->cfg.sample_every > 1 ? KC_INDEX_TABLE : KC_INDEX_BUCKET;
+    if (want == KC_INDEX_STREAM && n > 0) return build_index_stream(e, stats);
+    // (round 1's bucket build remembers per protein-set signature that its buckets overflowed)
+    if (want == KC_INDEX_BUCKET && e->cap_hint == 0 && e->cap_hint_n == e->n && e->cap_hint_R == e->R &&
+        e->cfg.index_build != KC_INDEX_BUCKET)
+      want = KC_INDEX_TABLE;
+    if (want == KC_INDEX_BUCKET && n > 0 && n <= (1u << 24)) {
       bool overflow = false;
       int rc = build_index_bucketed(e, shard, n_shards, stats, &overflow);
       if (rc != KC_OK || !overflow) return rc;
@@ -1104,7 +1358,7 @@ int kc_build_index_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_ind
     const unsigned long long n_positions_est = e->n_pos_unsampled;
     const double footprint = std::max((double)e->universe / 4.0 * 1.5, (double)n_positions_est * 5.0);
     uint32_t want = (uint32_t)std::min(64.0, std::ceil(footprint / (64.0 * 1024 * 1024)));
-    if (const char* env = std::getenv("KC_B200_SLICES")) want = (uint32_t)std::max(1, std::atoi(env));  // tests
+    if (e->cfg.index_slices) want = e->cfg.index_slices;
     uint32_t shift = 31;
     while (shift > 12 && ((((uint64_t)e->universe - 1) >> shift) + 1) < want) --shift;
     e->slice_shift = shift;
@@ -1140,7 +1394,7 @@ int kc_build_index_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_ind
   const uint32_t pass_grid = blocks_for(n, narrow ? 32 : 8, e->num_sm * 8);
   auto split = [&](DBuf& b, uint32_t q) { return b.as<uint32_t>() + (size_t)q * n; };
   // the census state is only 2 bits per k-mer: it can take coarser slices (longer row runs)
-  const uint32_t cmerge = std::getenv("KC_B200_CENSUS_MERGE") ? std::max(1, std::atoi(std::getenv("KC_B200_CENSUS_MERGE"))) : 1;
+  const uint32_t cmerge = std::max<uint32_t>(1u, e->cfg.census_merge);
   for (uint32_t q = 0; q < P && n; q += cmerge) {
     const uint32_t q1 = std::min(P, q + cmerge);
     const bool preread = e->universe <= (1u << 24);  // hot k-mers (k=5): skip marks that are no-ops
@@ -1272,10 +1526,10 @@ int kc_build_index_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_ind
   KC_CUDA(e, cudaMemcpyAsync(&hs, ds, sizeof(hs), cudaMemcpyDeviceToHost, e->stream));
   KC_CUDA(e, cudaStreamSynchronize(e->stream));
   KC_CUDA(e, cudaGetLastError());
-  // Materialised multi-edge lists for the stream pair kernel (opt-in, KC_B200_PLIST=1): 4 bytes
+  // Materialised multi-edge lists for the stream pair kernel (opt-in, kc_config.pair_lists): 4 bytes
   // (+1 with BLOSUM) per multi-edge.  Measured on synth_1m_k7: the fill costs 12 ms, the stream
   // kernel saves 3 ms over the gather kernels, so the default is the gather kernels.
-  if (n && V && hs.work_total && std::getenv("KC_B200_PLIST")) {
+  if (n && V && hs.work_total && e->cfg.pair_lists) {
     // budget: a quarter of the device memory (no cudaMemGetInfo here: it stalls for milliseconds)
     const unsigned long long need = hs.work_total * (4ull + (e->cfg.want_blosum ? 1ull : 0ull)) + (1ull << 20);
     if (need <= (unsigned long long)e->total_mem / 4) {
@@ -1412,36 +1666,89 @@ int kc_get_pair_index(kc_engine* e, uint32_t* kmers_out, uint32_t* freq_out, uin
   const uint64_t V = e->istats.n_repeated;
   const uint32_t n = (uint32_t)e->n;
   if ((kmers_out || freq_out || self_out) && capacity_vocab < V) return fail(e, KC_EINVAL, "capacity too small");
-  const DBuf& vb = e->bucketed ? e->d_vocab_h : e->d_vocab;
-  const DBuf& fb = e->bucketed ? e->d_freq_h : e->d_freq;
-  if (kmers_out && V) KC_CUDA(e, cudaMemcpyAsync(kmers_out, vb.p, V * 4, cudaMemcpyDeviceToHost, e->stream));
-  if (freq_out && V) KC_CUDA(e, cudaMemcpyAsync(freq_out, fb.p, V * 4, cudaMemcpyDeviceToHost, e->stream));
-  if (self_out && V) KC_CUDA(e, cudaMemcpyAsync(self_out, e->pair_self(), V, cudaMemcpyDeviceToHost, e->stream));
-  KC_CUDA(e, cudaStreamSynchronize(e->stream));
-  if (!row_offsets) return KC_OK;
+  // The streaming build places ids by capacity (holes in the id space): this entry point presents them
+  // densely, as a bijection onto [0, n_repeated) like boomphf's (src/main.rs:139-147).  map = rank among the used ids.
+  DBuf d_map, d_vd, d_fd, d_sd;
+  const bool sparse = e->streamed;
+  auto free_tmp = [&]() {
+    d_map.release();
+    d_vd.release();
+    d_fd.release();
+    d_sd.release();
+  };
+  if (sparse) {
+    const uint64_t slots = e->v_local;
+    cudaError_t a = d_map.ensure((slots + 2) * 4), b2 = d_vd.ensure((V + 1) * 4), c = d_fd.ensure((V + 1) * 4),
+                d = d_sd.ensure(V + 16);
+    if (a != cudaSuccess || b2 != cudaSuccess || c != cudaSuccess || d != cudaSuccess) {
+      free_tmp();
+      return fail(e, KC_ENOMEM, "out of device memory");
+    }
+    if (int rc = ensure_scan(e, slots + 1)) {
+      free_tmp();
+      return rc;
+    }
+    cudaMemsetAsync(d_map.p, 0, (slots + 2) * 4, e->stream);
+    if (n)
+      KC_LAUNCH(e, sx_mark_ids_kernel, blocks_for(n, 8, e->num_sm * 8), 256, 0, e->pair_rowptr(),
+                e->d_rowlen.as<uint32_t>(), n, e->pair_ids(), d_map.as<uint32_t>());
+    e->launches += exclusive_scan(U32In{d_map.as<uint32_t>()}, SxExclOutTail{d_map.as<uint32_t>(), slots + 1}, slots + 1,
+                                  e->scan, e->stream);
+    KC_LAUNCH(e, sx_gather_vocab_kernel, blocks_for(slots, 256, e->num_sm * 8), 256, 0, d_map.as<uint32_t>(), slots,
+              e->d_vocab_h.as<uint32_t>(), e->d_freq_h.as<uint32_t>(), e->d_self_h.as<uint8_t>(), d_vd.as<uint32_t>(),
+              d_fd.as<uint32_t>(), d_sd.as<uint8_t>());
+  }
+  const void* vb = sparse ? d_vd.p : (e->bucketed ? e->d_vocab_h.p : e->d_vocab.p);
+  const void* fb = sparse ? d_fd.p : (e->bucketed ? e->d_freq_h.p : e->d_freq.p);
+  const void* sb = sparse ? d_sd.p : (const void*)e->pair_self();
+  cudaError_t crc = cudaSuccess;
+  if (kmers_out && V) crc = cudaMemcpyAsync(kmers_out, vb, V * 4, cudaMemcpyDeviceToHost, e->stream);
+  if (crc == cudaSuccess && freq_out && V) crc = cudaMemcpyAsync(freq_out, fb, V * 4, cudaMemcpyDeviceToHost, e->stream);
+  if (crc == cudaSuccess && self_out && V) crc = cudaMemcpyAsync(self_out, sb, V, cudaMemcpyDeviceToHost, e->stream);
+  if (crc == cudaSuccess) crc = cudaStreamSynchronize(e->stream);
+  if (crc != cudaSuccess || !row_offsets) {
+    free_tmp();
+    KC_CUDA(e, crc);
+    return KC_OK;
+  }
   std::vector<uint32_t> rowlen(n);
-  if (n) KC_CUDA(e, cudaMemcpyAsync(rowlen.data(), e->d_rowlen.p, (uint64_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
-  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (n) crc = cudaMemcpyAsync(rowlen.data(), e->d_rowlen.p, (uint64_t)n * 4, cudaMemcpyDeviceToHost, e->stream);
+  if (crc == cudaSuccess) crc = cudaStreamSynchronize(e->stream);
+  if (crc != cudaSuccess) {
+    free_tmp();
+    KC_CUDA(e, crc);
+  }
   row_offsets[0] = 0;
   for (uint32_t p = 0; p < n; ++p) row_offsets[p + 1] = row_offsets[p] + rowlen[e->h_rank[p]];
   const uint64_t nnz = row_offsets[n];
-  if (!ids_out || !nnz) return KC_OK;
-  if (capacity_ids < nnz) return fail(e, KC_EINVAL, "capacity too small");
+  if (!ids_out || !nnz) {
+    free_tmp();
+    return KC_OK;
+  }
+  if (capacity_ids < nnz) {
+    free_tmp();
+    return fail(e, KC_EINVAL, "capacity too small");
+  }
   DBuf d_ro, d_out;
   cudaError_t a = d_ro.ensure(((uint64_t)n + 1) * 8), b = d_out.ensure(nnz * 4);
   if (a != cudaSuccess || b != cudaSuccess) {
     d_ro.release();
     d_out.release();
+    free_tmp();
     return fail(e, KC_ENOMEM, "out of device memory");
   }
   cudaMemcpyAsync(d_ro.p, row_offsets, ((uint64_t)n + 1) * 8, cudaMemcpyHostToDevice, e->stream);
   KC_LAUNCH(e, compact_rows_kernel, blocks_for(n, 8, e->num_sm * 8), 256, 0, e->pair_rowptr(),
             e->d_rowlen.as<uint32_t>(), d_ro.as<unsigned long long>(), e->d_rank.as<uint32_t>(), n, e->pair_ids(),
             d_out.as<uint32_t>());
+  if (sparse)
+    KC_LAUNCH(e, sx_remap_ids_kernel, blocks_for(nnz, 256, e->num_sm * 8), 256, 0, d_map.as<uint32_t>(),
+              d_out.as<uint32_t>(), nnz);
   cudaError_t rc = cudaMemcpyAsync(ids_out, d_out.p, nnz * 4, cudaMemcpyDeviceToHost, e->stream);
   if (rc == cudaSuccess) rc = cudaStreamSynchronize(e->stream);
   d_ro.release();
   d_out.release();
+  free_tmp();
   KC_CUDA(e, rc);
   return KC_OK;
 }

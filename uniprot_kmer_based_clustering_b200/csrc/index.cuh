@@ -57,11 +57,16 @@ __global__ void popc_reduce_kernel(const uint32_t* __restrict__ bits, uint64_t n
 
 // B62[r][r] in the reference's residue order (src/blosum.rs:8-30 diagonal); code 20 -> 0
 __constant__ uint8_t c_blosum_diag[21] = {9, 4, 5, 4, 6, 7, 6, 5, 5, 6, 8, 5, 5, 5, 4, 4, 4, 11, 7, 6, 0};
+// (the same table as 4-bit fields of two registers: a constant-memory load with a per-lane index is
+// replayed once per distinct index)
 __device__ __forceinline__ int kmer_self_score(uint32_t kmer, int k) {
+  constexpr unsigned long long lo = 0x4455586556764549ull;  // codes 0..15
+  constexpr uint32_t hi = 0x67b4u;                        // codes 16..20
   int s = 0;
   for (int i = 0; i < k; ++i) {
-    s += c_blosum_diag[kmer % 21u];
-    kmer /= 21u;
+    const uint32_t q = kmer / 21u, c = kmer - q * 21u;
+    s += c < 16u ? (int)((lo >> (4u * c)) & 15ull) : (int)((hi >> (4u * (c - 16u))) & 15u);
+    kmer = q;
   }
   return s;
 }

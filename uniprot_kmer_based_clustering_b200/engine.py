@@ -19,6 +19,13 @@ EDGE_DTYPE = np.dtype([("a", "<u4"), ("b", "<u4"), ("count", "<u4"), ("blosum", 
 SYNTH_SEEDS = {"synth_100k_k5": 0xB2000003, "synth_1m_k7": 0xB2000004, "synth_4m_skew": 0xB2000005}
 
 
+# Defaults of the engine's tuning knobs for engines created without explicit arguments (kc_config fields;
+# the C library reads nothing from the environment).  The GPU test-suite swaps these to run every test
+# against every index build.
+DEFAULTS = {"index_build": "auto", "bucket_cap": 0, "index_slices": 0, "census_merge": 0, "pair_lists": False,
+            "no_upload_overlap": False}
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -81,8 +88,8 @@ class ProteinSet:
     @staticmethod
     def synthetic(n: int, length_law: str = "A", seed: int = 0xB2000003, threads: int = 8,
                   with_ids: bool = False) -> "ProteinSet":
-        """Generator G1 (include/kc_host.h)."""
-        L = _lib.lib()
+        """Generator G1 (include/kc_synth.h, libkc_synth.so: host only, the engine library is not loaded)."""
+        L = _lib.synth_lib()
         law = {"A": 0, "B": 1}[length_law]
         off = np.zeros(n + 1, dtype=np.uint64)
         cls = np.zeros(max(n, 1), dtype=np.uint32)[:n]
@@ -109,11 +116,23 @@ class Engine:
     """One engine per GPU.  Method names follow include/kc_b200.h."""
 
     def __init__(self, k: int = 5, device: int = 0, threshold: int = 10, cross_class_only: bool = True,
-                 want_blosum: bool = False, max_edges: int = 0, sample_every: int = 0, sample_seed: int = 0):
+                 want_blosum: bool = False, max_edges: int = 0, sample_every: int = 0, sample_seed: int = 0,
+                 index_build: str | None = None, bucket_cap: int | None = None, index_slices: int | None = None,
+                 census_merge: int | None = None, pair_lists: bool | None = None,
+                 no_upload_overlap: bool | None = None):
+        """index_build: "auto" | "stream" | "bucket" | "table" (kc_config.index_build); the rest are the
+        tuning knobs of include/kc_b200.h (0 = the engine's own choice; None = DEFAULTS)"""
         self._L = _lib.lib()
         self._h = C.c_void_p()
+        index_build = DEFAULTS["index_build"] if index_build is None else index_build
+        bucket_cap = DEFAULTS["bucket_cap"] if bucket_cap is None else bucket_cap
+        index_slices = DEFAULTS["index_slices"] if index_slices is None else index_slices
+        census_merge = DEFAULTS["census_merge"] if census_merge is None else census_merge
+        pair_lists = DEFAULTS["pair_lists"] if pair_lists is None else pair_lists
+        no_upload_overlap = DEFAULTS["no_upload_overlap"] if no_upload_overlap is None else no_upload_overlap
         cfg = Config(k, device, threshold, int(cross_class_only), int(want_blosum), sample_every, max_edges,
-                     sample_seed)
+                     sample_seed, _lib.INDEX_BUILDS[index_build], bucket_cap, index_slices, census_merge,
+                     int(pair_lists), int(no_upload_overlap))
         rc = self._L.kc_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             self._h = None
@@ -200,7 +219,8 @@ class Engine:
                 "n_own_rows": int(info[3]), "block_bounds": bounds}
 
     def index_flavour(self) -> int:
-        """0: universe-table build; 4096 / 8192: partitioned build with that bucket slot size"""
+        """0: universe-table build; 1: streaming partitioned build; 4096 / 8192: round 1's partitioned
+        build with that bucket slot size"""
         return int(self._L.kc_index_flavour(self._h))
 
     def get_distinct_kmers(self) -> np.ndarray:
