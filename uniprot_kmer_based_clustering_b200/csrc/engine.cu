@@ -898,7 +898,7 @@ static int build_index_stream(kc_engine* e, kc_index_stats* stats) {
     // one warp per bucket
 #define KC_SXW(CROSS, WCAP)                                                                                      \
   do {                                                                                                           \
-    constexpr size_t smem = sx_wb_warp_bytes<WCAP>() * kWbWarps;                                                 \
+    constexpr size_t smem = sx_wb_warp_bytes<WCAP>() * kWbWarps + kWbTableBytes;                                 \
     KC_CUDA(e, cudaFuncSetAttribute((sx_warp_bucket_kernel<CROSS, WCAP>), cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     (int)smem));                                                                 \
     int per_sm = 1;                                                                                              \

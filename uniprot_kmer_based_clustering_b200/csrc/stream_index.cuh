@@ -130,13 +130,16 @@ __device__ __forceinline__ void sx_tile_rank(const uint32_t (&digit)[V], uint32_
                      : 0u;
   }
   __syncthreads();
-  uint16_t* cw = cnt + (size_t)warp * D;
+  uint16_t* cw = cnt + warp * D;
+  // (one shared-memory atomic per distinct digit and round + a shuffle, which lets the rounds pipeline, was
+  // measured slower than this load / store / __syncwarp chain: profiles/r2_history.md)
+  const uint32_t lt_mask = lanemask_lt();
 #pragma unroll
   for (int j = 0; j < V; ++j) {
     if ((uint32_t)j < rounds) {  // uniform
       const uint32_t d = digit[j];
       const bool valid = d != kNoDigit;
-      const uint32_t rin = __popc(peers[j] & lanemask_lt());
+      const uint32_t rin = __popc(peers[j] & lt_mask);
       const uint32_t before = valid ? cw[d] : 0u;
       __syncwarp();
       if (valid && rin == 0) cw[d] = (uint16_t)(before + __popc(peers[j]));
@@ -150,8 +153,8 @@ __device__ __forceinline__ void sx_tile_rank(const uint32_t (&digit)[V], uint32_
     uint32_t run = 0;
 #pragma unroll 4
     for (int w = 0; w < WARPS; ++w) {
-      const uint32_t t = cnt[(size_t)w * D + d];
-      cnt[(size_t)w * D + d] = (uint16_t)run;
+      const uint32_t t = cnt[(uint32_t)w * D + d];
+      cnt[(uint32_t)w * D + d] = (uint16_t)run;
       run += t;
     }
     dstart[d] = run;
@@ -507,13 +510,27 @@ __device__ __forceinline__ SxEmit sx_emit(const Rows& rows, uint32_t c, uint32_t
 constexpr int kWbWarps = 8;
 template <uint32_t WCAP>
 __host__ __device__ constexpr size_t sx_wb_warp_bytes() { return (size_t)WCAP * 16 + 128 * 2 + 16; }
+constexpr size_t kWbTableBytes = 448;  // BLOSUM62 self-score of every residue pair (441 entries)
+
+// self-score of a k-mer from the CTA's table of residue pairs: k = 7 -> 2 + 2 + 2 + 1 digits, k = 5 -> 2 + 2 + 1
+// (a lone digit d is looked up as the pair (0, d) = 9 + score(d): residue C pads it)
+__device__ __forceinline__ uint32_t sx_self_score2(const uint8_t* __restrict__ ss2, uint32_t kmer, int k) {
+  const uint32_t q1 = kmer / 441u, r1 = kmer - q1 * 441u;
+  const uint32_t q2 = q1 / 441u, r2 = q1 - q2 * 441u;
+  if (k == 5) return (uint32_t)ss2[r1] + ss2[r2] + ss2[q2] - 9u;
+  const uint32_t q3 = q2 / 441u, r3 = q2 - q3 * 441u;
+  return (uint32_t)ss2[r1] + ss2[r2] + ss2[r3] + ss2[q3] - 9u;
+}
 
 template <bool CROSS, uint32_t WCAP>
 __global__ void __launch_bounds__(kWbWarps * 32) sx_warp_bucket_kernel(SxBucketArgs A) {
   constexpr int RMAX = WCAP / 32;  // rounds
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  uint8_t* base = dyn_smem + (size_t)warp * sx_wb_warp_bytes<WCAP>();
+  uint8_t* s_ss2 = dyn_smem;
+  for (uint32_t i = threadIdx.x; i < 441u; i += kWbWarps * 32) s_ss2[i] = (uint8_t)kmer_self_score(i, 2);
+  __syncthreads();
+  uint8_t* base = dyn_smem + kWbTableBytes + (size_t)warp * sx_wb_warp_bytes<WCAP>();
   uint2* X = reinterpret_cast<uint2*>(base);
   uint2* Y = X + WCAP;
   uint16_t* cnt = reinterpret_cast<uint16_t*>(Y + WCAP);  // [128]
@@ -544,6 +561,11 @@ __global__ void __launch_bounds__(kWbWarps * 32) sx_warp_bucket_kernel(SxBucketA
       const uint32_t i = u * 32u + lane;
       if (i < nrec) X[i] = ld_stream_u32x2(A.rec + beg + i);
     }
+    if (b + nw < n_buckets) {  // the warp's next bucket: pull it into L2 now (one 128-byte line per lane)
+      const uint32_t nbeg = __ldg(A.h2 + (size_t)(b + nw) * c2), nend = __ldg(A.h2 + (size_t)(b + nw + 1u) * c2);
+      const uint8_t* pf = reinterpret_cast<const uint8_t*>(A.rec + nbeg) + lane * 128u;
+      if (nbeg + lane * 16u < nend) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+    }
     // ---- stable LSD sort on the low r hash bits
     for (uint32_t p = 0; p < n_pass; ++p) {
       const uint32_t sh = p * pass_bits;
@@ -553,17 +575,27 @@ __global__ void __launch_bounds__(kWbWarps * 32) sx_warp_bucket_kernel(SxBucketA
       uint32_t rk[RMAX / 2 > 0 ? RMAX / 2 : 1];  // two 16-bit ranks per register
 #pragma unroll
       for (int q = 0; q < (RMAX / 2 > 0 ? RMAX / 2 : 1); ++q) rk[q] = 0;
+      // the matches of every round up front (independent: they pipeline), then the serial counter chain
+      uint32_t peers[RMAX];
 #pragma unroll
       for (int u = 0; u < RMAX; ++u) {
+        peers[u] = 0;
         if ((uint32_t)u < R) {  // uniform
+          const uint32_t i = (uint32_t)u * 32u + lane;
+          const uint32_t d = i < nrec ? (sx_hash(X[i].x) >> sh) & dmask : (0x80000000u | lane);
+          peers[u] = __match_any_sync(kFullMask, d);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < RMAX; ++u) {
+        if ((uint32_t)u < R) {
           const uint32_t i = (uint32_t)u * 32u + lane;
           const bool valid = i < nrec;
           const uint32_t d = valid ? (sx_hash(X[i].x) >> sh) & dmask : 0u;
-          const uint32_t peers = __match_any_sync(kFullMask, valid ? d : (0x80000000u | lane));
-          const uint32_t rin = __popc(peers & lt);
+          const uint32_t rin = __popc(peers[u] & lt);
           const uint32_t before = valid ? cnt[d] : 0u;
           __syncwarp();
-          if (valid && rin == 0) cnt[d] = (uint16_t)(before + __popc(peers));
+          if (valid && rin == 0) cnt[d] = (uint16_t)(before + __popc(peers[u]));
           __syncwarp();
           rk[u >> 1] |= (before + rin) << (16 * (u & 1));
         }
@@ -644,7 +676,7 @@ __global__ void __launch_bounds__(kWbWarps * 32) sx_warp_bucket_kernel(SxBucketA
     const uint32_t col_base = beg, id_base = beg >> 1;
     uint32_t carryP = 0, carryI = 0;
     for (uint32_t u = 0; u < G; ++u) {
-      const uint32_t c = u * 32u + lane;
+      const uint32_t c = u * 32u + lane, c0 = u * 32u;
       const bool in = c < nk;
       const uint2 v = in ? X[c] : make_uint2(kSentinel, kSentinel);
       uint2 pv;
@@ -661,8 +693,12 @@ __global__ void __launch_bounds__(kWbWarps * 32) sx_warp_bucket_kernel(SxBucketA
       const uint32_t P = carryP + __popc(mrep & lt), I = carryI + __popc(mreph & lt);
       carryP += __popc(mrep);
       carryI += __popc(mreph);
-      // the rows' bins: adjacent lanes of one bin share a reservation, issued first
+      // the rows' bins: adjacent lanes of one bin share a reservation, issued first (and the bin's region
+      // start is fetched now) so that both latencies hide behind the rest of the round
       const uint32_t bin = rep ? v.y >> kBinRowsLog : kSentinel;
+      const uint32_t r0 = v.y & ~(kBinRows - 1u);
+      size_t region = 0;
+      if (rep) region = bin_region(A.rowcap_prefix, r0);
       const bool leader = rep && rh && gr - c >= 2u;
       const uint32_t pbin = __shfl_up_sync(kFullMask, bin, 1);
       const bool seghead = rep && (lane == 0 || pbin != bin);
@@ -675,13 +711,38 @@ __global__ void __launch_bounds__(kWbWarps * 32) sx_warp_bucket_kernel(SxBucketA
       }
       uint32_t rbase = 0;
       if (rep && lane == s0) rbase = atomicAdd(&A.bin_cursor[bin], (uint32_t)(__popc(mrep & range) + __popc(mlead & range)));
-      uint4 ent = make_uint4(0, 0, 0, 0);
+      // run masks: OR of the row bits over the lanes [c, min(gr, end of the round)), by a suffix OR-scan that
+      // stops at run heads; the leader of a run that continues into the next round adds the rest itself
       unsigned long long rmask = 0;
+      if (mlead) {  // uniform
+        const uint32_t mrh = __ballot_sync(kFullMask, rh);
+        uint32_t lo = 0, hi = 0;
+        if (in) {
+          const uint32_t bit = v.y & (kBinRows - 1u);
+          lo = bit < 32u ? 1u << bit : 0u;
+          hi = bit < 32u ? 0u : 1u << (bit - 32u);
+        }
+        // lanes until my run's end inside the round: up to the next run head (exclusive)
+        const uint32_t next_rh = (mrh & gt) ? (uint32_t)__ffs(mrh & gt) - 1u : 32u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t tlo = __shfl_down_sync(kFullMask, lo, o), thi = __shfl_down_sync(kFullMask, hi, o);
+          if (lane + (uint32_t)o < next_rh) {
+            lo |= tlo;
+            hi |= thi;
+          }
+        }
+        if (leader) {
+          rmask = ((unsigned long long)hi << 32) | lo;
+          for (uint32_t x = c0 + 32u; x < gr; ++x) rmask |= 1ull << (X[x].y & (kBinRows - 1u));
+        }
+      }
+      uint4 ent = make_uint4(0, 0, 0, 0);
       if (rep) {
         const uint32_t row = v.y;
         const uint32_t post = col_base + P;
         const uint32_t lid = I - (head ? 0u : 1u);
-        const uint32_t ss = sx_self_score(A.ss3, v.x, A.k);
+        const uint32_t ss = sx_self_score2(s_ss2, v.x, A.k);
         A.col[post] = row;
         if (head) {
           const uint32_t f = ge - c;
@@ -706,15 +767,12 @@ __global__ void __launch_bounds__(kWbWarps * 32) sx_warp_bucket_kernel(SxBucketA
         work += len;
         const uint2 sf = len == 1u ? make_uint2(X[a].y, kSentinel) : make_uint2(post + (a - c), post + (ge - c));
         ent = make_uint4(row | (ss << 24), id_base + lid, sf.x, sf.y);
-        if (leader)
-          for (uint32_t x = c; x < gr; ++x) rmask |= 1ull << (X[x].y & (kBinRows - 1u));
       }
       rbase = __shfl_sync(kFullMask, rbase, s0);
       if (rep) {
         const uint32_t mine_before = range & lt;
         const uint32_t at = rbase + __popc(mrep & mine_before) + __popc(mlead & mine_before);
-        const uint32_t r0 = v.y & ~(kBinRows - 1u);
-        uint4* d = A.entries + bin_region(A.rowcap_prefix, r0) + at;
+        uint4* d = A.entries + region + at;
         d[0] = ent;
         if (leader)
           d[1] = make_uint4(0x80000000u | (ent.x >> 24), r0 >> kBinRowsLog, (uint32_t)rmask, (uint32_t)(rmask >> 32));
