@@ -770,7 +770,7 @@ static SxPlan sx_make_plan(uint64_t E, uint64_t R, int num_sm) {
   p.b2 = b - p.b1;
   p.r = 32 - b;
   const uint32_t tiles = (uint32_t)std::max<uint64_t>(1, (R + kSxTile - 1) / kSxTile);
-  uint32_t g1 = std::min<uint32_t>(tiles, (uint32_t)num_sm * 2u);
+  uint32_t g1 = std::min<uint32_t>(tiles, (uint32_t)num_sm * 2u);  // two persistent CTAs per SM
   p.tiles_per_chunk = (tiles + g1 - 1) / g1;
   p.g1 = (tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
   p.c2 = std::min<uint32_t>(16u, std::max<uint32_t>(1u, ((uint32_t)num_sm * 16u) >> p.b1));
@@ -844,30 +844,30 @@ static int build_index_stream(kc_engine* e, kc_index_stats* stats) {
   {
     const uint32_t* trow = e->d_tile_row.as<uint32_t>();
     const size_t smem_c = (size_t)D1 * 4 + kSxTile + 64 + 256;
-    const size_t smem_s = sx_scatter_smem(D1);
+    const size_t smem_s = sx_scatter_smem(D1, kL1Threads / 32);
     if (k5) {
       KC_CUDA(e, cudaFuncSetAttribute(sx_l1_count_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
       KC_CUDA(e, cudaFuncSetAttribute(sx_l1_scatter_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-      KC_LAUNCH(e, sx_l1_count_kernel<5>, plan.g1, kSxThreads, smem_c, res, (uint32_t)R, soff, trow, plan, h1);
+      KC_LAUNCH(e, sx_l1_count_kernel<5>, plan.g1, kL1Threads, smem_c, res, (uint32_t)R, soff, trow, plan, h1);
     } else {
       KC_CUDA(e, cudaFuncSetAttribute(sx_l1_count_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
       KC_CUDA(e, cudaFuncSetAttribute(sx_l1_scatter_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-      KC_LAUNCH(e, sx_l1_count_kernel<7>, plan.g1, kSxThreads, smem_c, res, (uint32_t)R, soff, trow, plan, h1);
+      KC_LAUNCH(e, sx_l1_count_kernel<7>, plan.g1, kL1Threads, smem_c, res, (uint32_t)R, soff, trow, plan, h1);
     }
     e->launches += exclusive_scan(U32In{h1}, SxExclOutTail{h1, n_h1}, n_h1, e->scan, e->stream);
     if (k5)
-      KC_LAUNCH(e, sx_l1_scatter_kernel<5>, plan.g1, kSxThreads, smem_s, res, (uint32_t)R, soff, trow, plan, h1, rec_a);
+      KC_LAUNCH(e, sx_l1_scatter_kernel<5>, plan.g1, kL1Threads, smem_s, res, (uint32_t)R, soff, trow, plan, h1, rec_a);
     else
-      KC_LAUNCH(e, sx_l1_scatter_kernel<7>, plan.g1, kSxThreads, smem_s, res, (uint32_t)R, soff, trow, plan, h1, rec_a);
+      KC_LAUNCH(e, sx_l1_scatter_kernel<7>, plan.g1, kL1Threads, smem_s, res, (uint32_t)R, soff, trow, plan, h1, rec_a);
   }
   // level 2: rec_a -> rec_b, every level-1 partition by the next b2 hash bits
   {
     const size_t smem_c = (size_t)D2 * 4;
-    const size_t smem_s = sx_scatter_smem(D2);
+    const size_t smem_s = sx_scatter_smem(D2, kL2Threads / 32);
     KC_CUDA(e, cudaFuncSetAttribute(sx_l2_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-    KC_LAUNCH(e, sx_l2_count_kernel, D1 * plan.c2, kSxThreads, smem_c, rec_a, h1, plan, h2);
+    KC_LAUNCH(e, sx_l2_count_kernel, D1 * plan.c2, kL2Threads, smem_c, rec_a, h1, plan, h2);
     e->launches += exclusive_scan(U32In{h2}, SxExclOutTail{h2, n_h2}, n_h2, e->scan, e->stream);
-    KC_LAUNCH(e, sx_l2_scatter_kernel, D1 * plan.c2, kSxThreads, smem_s, rec_a, h1, plan, h2, rec_b);
+    KC_LAUNCH(e, sx_l2_scatter_kernel, D1 * plan.c2, kL2Threads, smem_s, rec_a, h1, plan, h2, rec_b);
   }
   mark(e, EV_IC1);
   // buckets: sort, census, ids, postings, entries

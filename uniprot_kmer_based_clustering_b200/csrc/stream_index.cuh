@@ -38,11 +38,13 @@ namespace kc {
 __host__ __device__ __forceinline__ uint32_t sx_hash(uint32_t kmer) { return kmer * 0x9E3779B1u; }  // odd: a bijection of u32
 
 constexpr uint32_t kNoDigit = 0xFFFFFFFFu;
-constexpr int kSxThreads = 512;
-constexpr int kSxWarps = kSxThreads / 32;
-constexpr int kSxV = 16;
-constexpr uint32_t kSxTile = kSxThreads * kSxV;  // records per CTA step
-constexpr uint32_t kSxSeg = 32 * kSxV;           // records per warp per step
+// Tile = 8 192 records per CTA step in both levels.  Level 1: 512 threads x 16 positions, two CTAs per SM
+// (its phases are barrier-separated: a second CTA fills the gaps).  Level 2: 1 024 threads x 8 records, one
+// CTA per SM (16 records per thread do not fit 64 registers next to their digits, peers and ranks; measured:
+// level 1 3.9 vs 5.0 ms, level 2 4.2 vs 3.7 ms for the two shapes, profiles/r2_history.md).
+constexpr uint32_t kSxTile = 8192;
+constexpr int kL1Threads = 512, kL1V = 16;
+constexpr int kL2Threads = 1024, kL2V = 8;
 
 struct SxPlan {
   uint32_t b1, b2;           // digit bits of the two levels (<= 10 each)
@@ -59,11 +61,11 @@ struct SxPlan {
 // dynamic shared memory of the two scatter kernels for D digits:
 // staged records | warp counters (u16; the level-1 kernel first keeps the tile's residue codes there) |
 // dstart[D + 1] | goff[D] | lut[256] | scan scratch
-__host__ __device__ constexpr size_t sx_cnt_bytes(uint32_t D) {
-  return (size_t)kSxWarps * D * 2 > (size_t)kSxTile + 64 ? (size_t)kSxWarps * D * 2 : (size_t)kSxTile + 64;
+__host__ __device__ constexpr size_t sx_cnt_bytes(uint32_t D, uint32_t warps) {
+  return (size_t)warps * D * 2 > (size_t)kSxTile + 64 ? (size_t)warps * D * 2 : (size_t)kSxTile + 64;
 }
-__host__ __device__ constexpr size_t sx_scatter_smem(uint32_t D) {
-  return (size_t)kSxTile * 8 + sx_cnt_bytes(D) + ((size_t)D + 4) * 4 + (size_t)D * 4 + 256 + 64 * 4;
+__host__ __device__ constexpr size_t sx_scatter_smem(uint32_t D, uint32_t warps) {
+  return (size_t)kSxTile * 8 + sx_cnt_bytes(D, warps) + ((size_t)D + 4) * 4 + (size_t)D * 4 + 256 + 64 * 4;
 }
 
 // block-wide exclusive scan of one u32 per thread (THREADS <= 1024); returns the exclusive prefix,
@@ -149,15 +151,20 @@ __device__ __forceinline__ void sx_tile_rank(const uint32_t (&digit)[V], uint32_
   }
   __syncthreads();
   // per digit: exclusive prefix over the warps (in place) and the digit's total
-  for (uint32_t d = tid; d < D; d += THREADS) {
-    uint32_t run = 0;
+  {  // two digits (one 32-bit word of 16-bit counters) per step: the packed halves never carry (<= tile size)
+    uint32_t* c32 = reinterpret_cast<uint32_t*>(cnt);
+    const uint32_t W = D >> 1;
+    for (uint32_t wd = tid; wd < W; wd += THREADS) {
+      uint32_t run = 0;
 #pragma unroll 4
-    for (int w = 0; w < WARPS; ++w) {
-      const uint32_t t = cnt[(uint32_t)w * D + d];
-      cnt[(uint32_t)w * D + d] = (uint16_t)run;
-      run += t;
+      for (int w = 0; w < WARPS; ++w) {
+        const uint32_t t = c32[(uint32_t)w * W + wd];
+        c32[(uint32_t)w * W + wd] = run;
+        run += t;
+      }
+      dstart[2u * wd] = run & 0xFFFFu;
+      dstart[2u * wd + 1u] = run >> 16;
     }
-    dstart[d] = run;
   }
   __syncthreads();
   // exclusive scan of the totals: thread t owns the digits [t * dpt, (t + 1) * dpt)
@@ -205,46 +212,59 @@ __device__ __forceinline__ uint32_t sx_row_of(const uint32_t* __restrict__ soff,
   return lo;
 }
 
-template <int K, class Sink>
+template <int K, int P, class Sink>
 __device__ __forceinline__ void sx_tile_positions(const uint8_t* __restrict__ res, uint32_t R,
                                                   const uint32_t* __restrict__ soff, uint32_t t0,
                                                   uint32_t row_lo, uint32_t row_hi,
                                                   uint8_t* __restrict__ s_codes, const uint8_t* __restrict__ s_lut,
                                                   Sink sink) {
+  static_assert(P == 8 || P == 16, "8 or 16 positions per thread");
+  constexpr int NW = P / 4;  // 32-bit words of residues per thread
   const uint32_t tid = threadIdx.x;
-  // stage the tile's residue codes (+ halo): one 16-byte load per thread, `res` is padded with zeros
+  // stage the tile's residue codes (+ halo): one 8- or 16-byte load per thread, `res` is padded with zeros
   {
-    const uint4 x = *reinterpret_cast<const uint4*>(res + (size_t)t0 + tid * 16u);
-    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-    uint32_t o[4];
+    uint32_t w[NW];
+    if (P == 16) {
+      const uint4 x = *reinterpret_cast<const uint4*>(res + (size_t)t0 + tid * 16u);
+      w[0] = x.x, w[1] = x.y, w[NW - 2] = x.z, w[NW - 1] = x.w;
+    } else {
+      const uint2 x = *reinterpret_cast<const uint2*>(res + (size_t)t0 + tid * 8u);
+      w[0] = x.x, w[1] = x.y;
+    }
+    uint32_t o[NW];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < NW; ++q)
       o[q] = (uint32_t)s_lut[w[q] & 255u] | ((uint32_t)s_lut[(w[q] >> 8) & 255u] << 8) |
              ((uint32_t)s_lut[(w[q] >> 16) & 255u] << 16) | ((uint32_t)s_lut[w[q] >> 24] << 24);
-    *reinterpret_cast<uint4*>(s_codes + tid * 16u) = make_uint4(o[0], o[1], o[2], o[3]);
+    if (P == 16) *reinterpret_cast<uint4*>(s_codes + tid * 16u) = make_uint4(o[0], o[1], o[NW - 2], o[NW - 1]);
+    else *reinterpret_cast<uint2*>(s_codes + tid * 8u) = make_uint2(o[0], o[1]);
     if (tid < 16) s_codes[kSxTile + tid] = s_lut[res[(size_t)t0 + kSxTile + tid]];
   }
   __syncthreads();
-  const uint32_t i0 = t0 + tid * 16u;
+  const uint32_t i0 = t0 + tid * (uint32_t)P;
   uint32_t row = 0, next = 0;
   if (i0 < R) {
     row = sx_row_of(soff, row_lo, row_hi, i0);
     next = __ldg(soff + row + 1);
   }
-  uint32_t c[16 + K - 1];
+  uint32_t c[P + K - 1];
   {
-    const uint4 a = *reinterpret_cast<const uint4*>(s_codes + tid * 16u);
-    const uint2 b = *reinterpret_cast<const uint2*>(s_codes + tid * 16u + 16u);
-    const uint32_t w[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
+    uint32_t w[NW + 2];
 #pragma unroll
-    for (int q = 0; q < 16 + K - 1; ++q) c[q] = (w[q >> 2] >> (8 * (q & 3))) & 255u;
+    for (int q = 0; q < NW + 2; q += 2) {
+      const uint2 a = *reinterpret_cast<const uint2*>(s_codes + tid * (uint32_t)P + 4u * q);
+      w[q] = a.x;
+      w[q + 1] = a.y;
+    }
+#pragma unroll
+    for (int q = 0; q < P + K - 1; ++q) c[q] = (w[q >> 2] >> (8 * (q & 3))) & 255u;
   }
   const uint32_t top = sx_pow21(K - 1);
   uint32_t km = 0;
 #pragma unroll
   for (int q = 0; q < K; ++q) km = km * 21u + c[q];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
+  for (int j = 0; j < P; ++j) {
     const uint32_t i = i0 + (uint32_t)j;
     bool valid = i < R;
     if (valid) {
@@ -255,17 +275,18 @@ __device__ __forceinline__ void sx_tile_positions(const uint8_t* __restrict__ re
       valid = i + K <= next;
     }
     sink(j, valid ? km : kSentinel, row);
-    if (j < 15) km = (km - c[j] * top) * 21u + c[j + K];
+    if (j < P - 1) km = (km - c[j] * top) * 21u + c[j + K];
   }
 }
 
-// record slot inside a warp's 512-record segment of the staging buffer: position p = 16 * lane + j of the
-// blocked phase, read back as p = 32 * j' + lane' by the striped phase; the XOR keeps both conflict-free
-__device__ __forceinline__ uint32_t sx_swz(uint32_t p) { return (p & ~15u) | ((p ^ (p >> 4)) & 15u); }
+// record slot inside a warp's segment (32 * V records) of the staging buffer: position p = V * lane + j of the
+// blocked phase, read back as p = 32 * j' + lane' by the striped phase; the XOR keeps both free of bank
+// conflicts (8-byte slots: 16 per bank row; V = 8 or 16)
+__device__ __forceinline__ uint32_t sx_swz(uint32_t p) { return p ^ ((p >> 4) & 15u); }
 
 // level-1 count: digit histogram of every chunk.  hist[d * g1 + chunk]
 template <int K>
-__global__ void __launch_bounds__(kSxThreads, 2)
+__global__ void __launch_bounds__(kL1Threads, 2)
     sx_l1_count_kernel(const uint8_t* __restrict__ res, uint32_t R, const uint32_t* __restrict__ soff,
                        const uint32_t* __restrict__ tile_row, SxPlan plan, uint32_t* __restrict__ hist) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
@@ -273,7 +294,7 @@ __global__ void __launch_bounds__(kSxThreads, 2)
   uint8_t* s_codes = dyn_smem + (size_t)plan.d1() * 4;       // [tile + 64]
   uint8_t* s_lut = s_codes + kSxTile + 64;
   const uint32_t tid = threadIdx.x, D = plan.d1(), sh = 32u - plan.b1;
-  for (uint32_t d = tid; d < D; d += kSxThreads) s_hist[d] = 0;
+  for (uint32_t d = tid; d < D; d += kL1Threads) s_hist[d] = 0;
   if (tid < 256) s_lut[tid] = c_residue_lut[tid];
   __syncthreads();
   const uint32_t chunk = blockIdx.x;
@@ -281,18 +302,18 @@ __global__ void __launch_bounds__(kSxThreads, 2)
   for (uint32_t t = 0; t < plan.tiles_per_chunk; ++t) {
     const unsigned long long t0 = (unsigned long long)(tile_lo + t) * kSxTile;
     if (t0 >= R) break;
-    sx_tile_positions<K>(res, R, soff, (uint32_t)t0, tile_row[tile_lo + t], tile_row[tile_lo + t + 1u], s_codes, s_lut,
+    sx_tile_positions<K, kL1V>(res, R, soff, (uint32_t)t0, tile_row[tile_lo + t], tile_row[tile_lo + t + 1u], s_codes, s_lut,
                          [&](int, uint32_t km, uint32_t) {
                            if (km != kSentinel) atomicAdd(&s_hist[sx_hash(km) >> sh], 1u);
                          });
     __syncthreads();
   }
-  for (uint32_t d = tid; d < D; d += kSxThreads) hist[(size_t)d * plan.g1 + chunk] = s_hist[d];
+  for (uint32_t d = tid; d < D; d += kL1Threads) hist[(size_t)d * plan.g1 + chunk] = s_hist[d];
 }
 
 // level-1 scatter: hist_scanned[d * g1 + chunk] = where this chunk's records of digit d start in `out`
 template <int K>
-__global__ void __launch_bounds__(kSxThreads, 2)
+__global__ void __launch_bounds__(kL1Threads, 2)
     sx_l1_scatter_kernel(const uint8_t* __restrict__ res, uint32_t R, const uint32_t* __restrict__ soff,
                          const uint32_t* __restrict__ tile_row, SxPlan plan, const uint32_t* __restrict__ hist_scanned,
                          uint2* __restrict__ out) {
@@ -301,44 +322,44 @@ __global__ void __launch_bounds__(kSxThreads, 2)
   uint2* s_buf = reinterpret_cast<uint2*>(dyn_smem);                          // [tile]
   uint16_t* s_cnt = reinterpret_cast<uint16_t*>(dyn_smem + (size_t)kSxTile * 8);  // [warps][D]  (codes first)
   uint8_t* s_codes = reinterpret_cast<uint8_t*>(s_cnt);
-  uint32_t* s_dstart = reinterpret_cast<uint32_t*>(dyn_smem + (size_t)kSxTile * 8 + sx_cnt_bytes(D));  // [D + 1]
+  uint32_t* s_dstart = reinterpret_cast<uint32_t*>(dyn_smem + (size_t)kSxTile * 8 + sx_cnt_bytes(D, kL1Threads / 32));  // [D + 1]
   uint32_t* s_goff = s_dstart + D + 4;                                       // [D]
   uint8_t* s_lut = reinterpret_cast<uint8_t*>(s_goff + D);                   // [256]
   uint32_t* s_wsum = reinterpret_cast<uint32_t*>(s_lut + 256);               // [33]
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t chunk = blockIdx.x;
-  for (uint32_t d = tid; d < D; d += kSxThreads) s_goff[d] = hist_scanned[(size_t)d * plan.g1 + chunk];
+  for (uint32_t d = tid; d < D; d += kL1Threads) s_goff[d] = hist_scanned[(size_t)d * plan.g1 + chunk];
   if (tid < 256) s_lut[tid] = c_residue_lut[tid];
   __syncthreads();
   const uint32_t tile_lo = chunk * plan.tiles_per_chunk;
-  uint2* seg = s_buf + warp * kSxSeg;
+  uint2* seg = s_buf + warp * (32u * kL1V);
   for (uint32_t t = 0; t < plan.tiles_per_chunk; ++t) {
     const unsigned long long t0 = (unsigned long long)(tile_lo + t) * kSxTile;
     if (t0 >= R) break;
-    sx_tile_positions<K>(res, R, soff, (uint32_t)t0, tile_row[tile_lo + t], tile_row[tile_lo + t + 1u], s_codes, s_lut,
-                         [&](int j, uint32_t km, uint32_t row) { seg[sx_swz(lane * 16u + (uint32_t)j)] = make_uint2(km, row); });
+    sx_tile_positions<K, kL1V>(res, R, soff, (uint32_t)t0, tile_row[tile_lo + t], tile_row[tile_lo + t + 1u], s_codes, s_lut,
+                         [&](int j, uint32_t km, uint32_t row) { seg[sx_swz(lane * (uint32_t)kL1V + (uint32_t)j)] = make_uint2(km, row); });
     __syncthreads();  // the codes live where the rank counters are zeroed next
-    uint32_t km[kSxV], rw[kSxV], digit[kSxV], pos[kSxV];
+    uint32_t km[kL1V], rw[kL1V], digit[kL1V], pos[kL1V];
 #pragma unroll
-    for (int j = 0; j < kSxV; ++j) {
+    for (int j = 0; j < kL1V; ++j) {
       const uint2 v = seg[sx_swz((uint32_t)j * 32u + lane)];
       km[j] = v.x;
       rw[j] = v.y;
       digit[j] = v.x == kSentinel ? kNoDigit : sx_hash(v.x) >> sh;
     }
-    sx_tile_rank<kSxThreads, kSxV>(digit, pos, plan.b1, kSxV, plan.ballots != 0, s_cnt, s_dstart, s_wsum);
+    sx_tile_rank<kL1Threads, kL1V>(digit, pos, plan.b1, kL1V, plan.ballots != 0, s_cnt, s_dstart, s_wsum);
 #pragma unroll
-    for (int j = 0; j < kSxV; ++j)
+    for (int j = 0; j < kL1V; ++j)
       if (digit[j] != kNoDigit) s_buf[pos[j]] = make_uint2(km[j], rw[j]);
     __syncthreads();
     const uint32_t n_valid = s_dstart[D];
-    for (uint32_t i = tid; i < n_valid; i += kSxThreads) {
+    for (uint32_t i = tid; i < n_valid; i += kL1Threads) {
       const uint2 v = s_buf[i];
       const uint32_t d = sx_hash(v.x) >> sh;
       out[(size_t)s_goff[d] + (i - s_dstart[d])] = v;
     }
     __syncthreads();
-    for (uint32_t d = tid; d < D; d += kSxThreads) s_goff[d] += s_dstart[d + 1] - s_dstart[d];
+    for (uint32_t d = tid; d < D; d += kL1Threads) s_goff[d] += s_dstart[d + 1] - s_dstart[d];
     __syncthreads();
   }
 }
@@ -357,31 +378,31 @@ __device__ __forceinline__ void sx_l2_chunk(const uint32_t* __restrict__ h1, con
   end = min(hi, beg + per);
 }
 
-__global__ void __launch_bounds__(kSxThreads)
+__global__ void __launch_bounds__(kL2Threads)
     sx_l2_count_kernel(const uint2* __restrict__ in, const uint32_t* __restrict__ h1, SxPlan plan,
                        uint32_t* __restrict__ hist) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(dyn_smem);
   const uint32_t tid = threadIdx.x, D = plan.d2(), sh = 32u - plan.b1 - plan.b2, mask = D - 1u;
   const uint32_t p = blockIdx.x / plan.c2, c = blockIdx.x % plan.c2;
-  for (uint32_t d = tid; d < D; d += kSxThreads) s_hist[d] = 0;
+  for (uint32_t d = tid; d < D; d += kL2Threads) s_hist[d] = 0;
   __syncthreads();
   uint32_t beg, end;
   sx_l2_chunk(h1, plan, p, c, beg, end);
-  for (uint32_t i = beg + tid; i < end; i += kSxThreads)
+  for (uint32_t i = beg + tid; i < end; i += kL2Threads)
     atomicAdd(&s_hist[(sx_hash(ld_stream_u32(&in[i].x)) >> sh) & mask], 1u);
   __syncthreads();
-  for (uint32_t d = tid; d < D; d += kSxThreads) hist[((size_t)p * D + d) * plan.c2 + c] = s_hist[d];
+  for (uint32_t d = tid; d < D; d += kL2Threads) hist[((size_t)p * D + d) * plan.c2 + c] = s_hist[d];
 }
 
-__global__ void __launch_bounds__(kSxThreads, 2)
+__global__ void __launch_bounds__(kL2Threads, 1)
     sx_l2_scatter_kernel(const uint2* __restrict__ in, const uint32_t* __restrict__ h1, SxPlan plan,
                          const uint32_t* __restrict__ hist_scanned, uint2* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   const uint32_t D = plan.d2(), sh = 32u - plan.b1 - plan.b2, mask = D - 1u;
   uint2* s_buf = reinterpret_cast<uint2*>(dyn_smem);
   uint16_t* s_cnt = reinterpret_cast<uint16_t*>(dyn_smem + (size_t)kSxTile * 8);
-  uint32_t* s_dstart = reinterpret_cast<uint32_t*>(dyn_smem + (size_t)kSxTile * 8 + sx_cnt_bytes(D));
+  uint32_t* s_dstart = reinterpret_cast<uint32_t*>(dyn_smem + (size_t)kSxTile * 8 + sx_cnt_bytes(D, kL2Threads / 32));
   uint32_t* s_goff = s_dstart + D + 4;
   uint32_t* s_wsum = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s_goff + D) + 256);
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -389,32 +410,32 @@ __global__ void __launch_bounds__(kSxThreads, 2)
   uint32_t beg, end;
   sx_l2_chunk(h1, plan, p, c, beg, end);
   if (beg >= end) return;
-  for (uint32_t d = tid; d < D; d += kSxThreads) s_goff[d] = hist_scanned[((size_t)p * D + d) * plan.c2 + c];
+  for (uint32_t d = tid; d < D; d += kL2Threads) s_goff[d] = hist_scanned[((size_t)p * D + d) * plan.c2 + c];
   __syncthreads();
   for (uint32_t t0 = beg; t0 < end; t0 += kSxTile) {
-    uint32_t km[kSxV], rw[kSxV], digit[kSxV], pos[kSxV];
+    uint32_t km[kL2V], rw[kL2V], digit[kL2V], pos[kL2V];
 #pragma unroll
-    for (int j = 0; j < kSxV; ++j) {
-      const uint32_t i = t0 + warp * kSxSeg + (uint32_t)j * 32u + lane;
+    for (int j = 0; j < kL2V; ++j) {
+      const uint32_t i = t0 + warp * (32u * kL2V) + (uint32_t)j * 32u + lane;
       uint2 v = make_uint2(kSentinel, 0u);
       if (i < end) v = ld_stream_u32x2(in + i);
       km[j] = v.x;
       rw[j] = v.y;
       digit[j] = v.x == kSentinel ? kNoDigit : (sx_hash(v.x) >> sh) & mask;
     }
-    sx_tile_rank<kSxThreads, kSxV>(digit, pos, plan.b2, kSxV, plan.ballots != 0, s_cnt, s_dstart, s_wsum);
+    sx_tile_rank<kL2Threads, kL2V>(digit, pos, plan.b2, kL2V, plan.ballots != 0, s_cnt, s_dstart, s_wsum);
 #pragma unroll
-    for (int j = 0; j < kSxV; ++j)
+    for (int j = 0; j < kL2V; ++j)
       if (digit[j] != kNoDigit) s_buf[pos[j]] = make_uint2(km[j], rw[j]);
     __syncthreads();
     const uint32_t n_valid = s_dstart[D];
-    for (uint32_t i = tid; i < n_valid; i += kSxThreads) {
+    for (uint32_t i = tid; i < n_valid; i += kL2Threads) {
       const uint2 v = s_buf[i];
       const uint32_t d = (sx_hash(v.x) >> sh) & mask;
       out[(size_t)s_goff[d] + (i - s_dstart[d])] = v;
     }
     __syncthreads();
-    for (uint32_t d = tid; d < D; d += kSxThreads) s_goff[d] += s_dstart[d + 1] - s_dstart[d];
+    for (uint32_t d = tid; d < D; d += kL2Threads) s_goff[d] += s_dstart[d + 1] - s_dstart[d];
     __syncthreads();
   }
 }
