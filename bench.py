@@ -13,10 +13,13 @@ launching stream; `e2e` is the same step through the C ABI from pinned HOST buff
 H2D staging and the D2H edge readback inside the timed region (wall clock around a sync; the
 upload is chunked and overlaps the first index kernel, so `breakdown_ms.stage_h2d` is only the
 host side of the staging call and the rest of the copy shows up in `build_index`).
-At N > 1 the pair triangle is cut into N row blocks (an equal share of the k-mer positions each);
-every rank builds the index of its own block from the whole residue stream (kc_build_index_shard:
-owner computes, no exchange) and scores it; the sorted edge lists are gathered to rank 0 over NCCL
-inside the timed region.  Total work is fixed, so "scaling" is "strong".
+At N > 1 the pair triangle is cut into 2 N row blocks (rank g owns blocks g and 2 N - 1 - g) and every rank
+computes everything for its own rows (kc_build_index_shard / kc_score_pairs_shard: owner computes, no collective
+between the kernels).  The e2e leg goes through the library's multi-GPU entry points (NCCL below the C ABI):
+every rank uploads 1 / N of the residue stream and the slices are all-gathered over NVLink, the counters are
+all-reduced, and every rank copies its own sorted edge runs over its own PCIe link into ONE host buffer shared
+by all ranks (POSIX shared memory).  Total work is fixed, so "scaling" is "strong".  At every N the gathered
+edge list is checked against the oracle's committed SHA-256 (tests/golden/synth_golden.json).
 """
 from __future__ import annotations
 
@@ -43,14 +46,37 @@ WORKLOADS = {
     "synth_1m_skew_k7": (1_000_000, "B", 7, 0xB2000005, False),  # one GPU's quarter of configs[4] (skewed lengths 50-2000)
 }
 THRESHOLD = 10
+# cpu_baseline leg of the GPU arm: a bounded sample (the default run has to finish within minutes).
+# The reference arm (--impl reference) runs the FULL workload per step: same config as the GPU arm.
 CPU_SAMPLE = {"synth_1m_k7": 250_000, "synth_100k_k5": 50_000, "synth_20k_k5": 20_000, "synth_1m_skew_k7": 200_000}
-REF_SAMPLE = {"synth_1m_k7": 250_000, "synth_100k_k5": 50_000, "synth_20k_k5": 20_000, "synth_1m_skew_k7": 200_000}
+
+
+def golden_for(workload: str, n: int):
+    """the oracle's committed full-size values for this workload (tests/golden/synth_golden.json), or None"""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "synth_golden.json")) as fh:
+            g = json.load(fh).get(workload)
+        return g if g and g["n"] == n else None
+    except Exception:
+        return None
+
+
+def config_of(workload: str, ps, k: int, cross: bool, world: int, nnz: int | None) -> dict:
+    """the `config` object of the JSON line: identical for the GPU arm and the reference arm"""
+    n = ps.n
+    return {"workload": workload, "n_proteins": n, "mean_len": round(ps.residues.size / n, 1),
+            "k": k, "threshold": THRESHOLD, "cross_class_only": cross, "blosum": True,
+            "generator": "G1 (include/kc_synth.h)", "seed": hex(WORKLOADS[workload][3]),
+            "l2_policy": f"inputs larger than L2 ({ps.residues.size / 1e6:.0f} MB residues); no flush needed",
+            "parallelism": ("1 GPU" if world == 1 else
+                            f"row-block sharded index + pair triangle on {world} GPUs (owner computes; NCCL: residue "
+                            "all-gather, counter all-reduce, edge gather)")}
 
 
 def measured_traffic(workload: str, kernel: str):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None"""
     try:
-        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "traffic_r2.json")) as fh:
             return int(json.load(fh)[workload][kernel])
     except Exception:
         return None
@@ -145,31 +171,31 @@ def oracle_run(ps, k, cross, n_sample, threads):
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU algorithm (the oracle port; the Rust crate needs a
-    nightly toolchain + crates.io and cannot be built here) on all host threads, each step a
-    bounded sample of the same workload."""
+    """--impl reference: the reference's CPU algorithm (the oracle port; the Rust crate needs a nightly
+    toolchain + crates.io and cannot be built here) on all host threads, the FULL workload per step: the same
+    config as the GPU arm.  Warm-up steps run a small prefix (they only fault the code and the pages in)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     ps, k, cross = make_set(args.workload, args.n_proteins)
-    n_sample = min(REF_SAMPLE[args.workload], ps.n)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     for _ in range(args.warmup):
-        oracle_run(ps, k, cross, max(2000, n_sample // 20), threads)
-    runs = [oracle_run(ps, k, cross, n_sample, threads) for _ in range(args.steps)]
+        oracle_run(ps, k, cross, max(2000, ps.n // 50), threads)
+    runs = [oracle_run(ps, k, cross, ps.n, threads) for _ in range(args.steps)]
     t = sum(r["total_s"] for r in runs) / len(runs)
     r = runs[-1]
     value = r["pairs"] / t
-    sample = (f"first {r['n']} of {ps.n} proteins of {args.workload} (k={k}), whole hot path per step; "
-              f"oracle port, {threads} threads")
+    sample = (f"all {r['n']} proteins of {args.workload} (k={k}), whole hot path per step; oracle port "
+              f"(oracle/kc_oracle.cpp), {threads} threads")
     line = {
         "impl": "reference", "metric": "protein_pairs_scored_per_s", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": args.workload, "k": k, "threshold": THRESHOLD, "cross_class_only": cross,
-                   "n_proteins": ps.n, "sample_proteins": r["n"]},
+        "config": config_of(args.workload, ps, k, cross, world, None),
         "kmers_indexed_per_s": r["positions"] / (sum(x["index_s"] for x in runs) / len(runs)),
         "multi_edges_per_s": r["multi_edges"] / (sum(x["pairs_s"] for x in runs) / len(runs)),
+        "counts": {"n_positions": r["positions"], "n_multi_edges": r["multi_edges"], "n_edges_out": r["edges"]},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -219,43 +245,42 @@ def main():
 
     eng = kc.Engine(k, device=local_rank, threshold=THRESHOLD, cross_class_only=cross, want_blosum=True)
     eng.set_stream(stream.cuda_stream)
+    if world > 1:  # the library's own NCCL rank (csrc/dist.cuh); torch.distributed only hands the id around
+        box = [kc.Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        eng.comm_init(box[0], rank, world)
 
     def step_resident():
         ist = eng.build_index(rank, world)
         pst = eng.score_pairs(rank, world)
         return ist, pst
 
-    e2e_parts = {"stage_h2d": 0.0, "build_index": 0.0, "score_pairs": 0.0, "edges_d2h": 0.0, "gather": 0.0}
+    e2e_parts = {"stage_h2d": 0.0, "build_index": 0.0, "score_pairs": 0.0, "edges_d2h": 0.0}
 
     def step_e2e():
         t0 = time.perf_counter()
-        # no sync here: the engine uploads the residue stream in chunks on its own copy stream and
-        # the extract kernels of build_index start on the first chunk while the rest is in flight.
-        # (N > 1: every rank uploads the whole stream over its own PCIe link.  Uploading 1/N per rank
-        # and all-gathering over NVLink, sharded.stage_residues_allgather, was measured at N = 2 only
-        # (slower there: nothing overlaps the copy) and hung at N = 8 next to the unbatched send/recv
-        # of the edge gather: not used.)
-        eng.set_proteins_ptr(h_res.data_ptr(), h_off.data_ptr(), h_cls.data_ptr(), n, on_device=False)
-        t1 = time.perf_counter()
-        ist = eng.build_index(rank, world)
-        t2 = time.perf_counter()
-        pst = eng.score_pairs(rank, world)
-        t3 = time.perf_counter()
-        n_e = pst["n_edges_out"]
+        # no sync here: the copies are asynchronous (N = 1: chunked on the engine's copy stream, the first
+        # index kernel starts on the first chunk; N > 1: 1 / N uploaded per rank + NCCL all-gather)
         if world == 1:
-            if h_edges.numel() < n_e * 4:
-                raise RuntimeError("edge staging buffer too small")
-            eng.get_edges_into(h_edges.data_ptr(), h_edges.numel() // 4)
-            out = h_edges[:n_e * 4].numpy().view(kc.EDGE_DTYPE)
-            t4 = t5 = time.perf_counter()
+            eng.set_proteins_ptr(h_res.data_ptr(), h_off.data_ptr(), h_cls.data_ptr(), n, on_device=False)
         else:
-            t4 = time.perf_counter()
-            out = sharded.gather_edges_device(eng, dist, rank, world, pinned_out=h_edges,
-                                              rows_in_input_order=not cross)
-            t5 = time.perf_counter()
-        for key, dt in zip(e2e_parts, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+            eng.set_proteins_dist_ptr(h_res.data_ptr(), h_off.data_ptr(), h_cls.data_ptr(), n)
+        t1 = time.perf_counter()
+        ist = eng.build_index_dist() if world > 1 else eng.build_index()
+        t2 = time.perf_counter()
+        pst = eng.score_pairs_dist() if world > 1 else eng.score_pairs()
+        t3 = time.perf_counter()
+        if world == 1:
+            n_e = pst["n_edges_out"]
+            if edge_cap < n_e:
+                raise RuntimeError("edge staging buffer too small")
+            eng.get_edges_into(edge_ptr, edge_cap)
+        else:  # every rank copies its own runs into the buffer all ranks map
+            n_e = eng.gather_edges_into(edge_ptr, edge_cap, shared=True)
+        t4 = time.perf_counter()
+        for key, dt in zip(e2e_parts, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
             e2e_parts[key] += dt * 1e3
-        return ist, pst, out
+        return ist, pst, n_e
 
     def barrier():
         if world > 1:
@@ -287,11 +312,34 @@ def main():
     for key in stage_ms:
         stage_ms[key] /= args.steps
 
-    # ---- e2e: host buffers, H2D + D2H (+ NCCL gather) inside the timed region, wall clock ------
+    # ---- e2e: host buffers, H2D + D2H (+ NCCL) inside the timed region, wall clock -------------
     n_e_all = torch.tensor([pst["n_edges_out"]], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(n_e_all)
-    h_edges = torch.empty(max(int(n_e_all.item() * 1.25) + 1024, 1 << 16) * 4, dtype=torch.int32).pin_memory()
+    edge_cap = max(int(n_e_all.item() * 1.25) + 1024, 1 << 16)
+    shm = None
+    if world == 1:
+        h_edges = torch.empty(edge_cap * 4, dtype=torch.int32).pin_memory()
+        edge_ptr, edges_np = h_edges.data_ptr(), h_edges.numpy()
+    else:
+        # ONE host buffer for the gathered list, mapped by every rank (POSIX shared memory) and page-locked
+        # in every process: each rank's D2H copy goes over its own PCIe link
+        from multiprocessing import shared_memory
+        name = f"kc_b200_edges_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
+        if rank == 0:
+            try:
+                shared_memory.SharedMemory(name=name).unlink()
+            except FileNotFoundError:
+                pass
+            shm = shared_memory.SharedMemory(name=name, create=True, size=edge_cap * 16)
+        dist.barrier()
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=name)
+        edges_np = np.frombuffer(shm.buf, dtype=np.int32, count=edge_cap * 4)
+        edge_ptr = edges_np.ctypes.data
+        rc = torch.cuda.cudart().cudaHostRegister(edge_ptr, edge_cap * 16, 0)
+        if int(rc) != 0 and rank == 0:
+            print(f"cudaHostRegister of the shared edge buffer failed ({rc}): pageable copies", file=sys.stderr)
     for _ in range(2):
         step_e2e()
     for key in e2e_parts:
@@ -299,22 +347,25 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ist_e, pst_e, edges = step_e2e()
+        ist_e, pst_e, n_e_total = step_e2e()
     barrier()
     e2e_s = (time.perf_counter() - t0) / args.steps
 
     # max over ranks; sums over ranks for the sharded quantities
     red = torch.tensor([dev_ms, e2e_s, stage_ms["index_ms"], stage_ms["pairs_ms"], stage_ms["pair_kernel_ms"],
-                        stage_ms["census_kernel_ms"], stage_ms["edges_ms"]], dtype=torch.float64, device="cuda")
+                        stage_ms["census_kernel_ms"], stage_ms["edges_ms"]] + [e2e_parts[k2] / args.steps for k2 in e2e_parts],
+                       dtype=torch.float64, device="cuda")
     sums = torch.tensor([pst["n_multi_edges_kept"], pst["n_edges_out"], pst["n_pairs_kept"], launches],
                         dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_s, index_ms, pairs_ms, pair_kernel_ms, census_ms, edges_ms = red.tolist()
+    red = red.tolist()
+    dev_ms, e2e_s, index_ms, pairs_ms, pair_kernel_ms, census_ms, edges_ms = red[:7]
+    e2e_break = dict(zip(e2e_parts, red[7:]))
     m_kept, e_out, p_kept, launches_all = (int(x) for x in sums.tolist())
-    # a sharded index build reports per-rank shares that add up; a whole index per rank (k = 5: the
-    # universe-table build) reports the whole-set numbers on every rank
+    # a sharded index build reports per-rank shares that add up; a whole index per rank (the table build)
+    # reports the whole-set numbers on every rank
     sharded_index = eng.index_shard_info()["n_shards"] > 1
     ist_rank = dict(ist)
     ist = sharded.reduce_index_stats(ist, dist, world, torch.device("cuda"), sharded_index)
@@ -330,27 +381,21 @@ def main():
         achieved = algo_bytes / (stage_ms["pair_kernel_ms"] * 1e-3) / 1e9 if stage_ms["pair_kernel_ms"] > 0 else 0.0
         idx_bytes = 9 * (ist_rank["n_positions"] if sharded_index else ist["n_positions"])
         idx_achieved = idx_bytes / (stage_ms["index_ms"] * 1e-3) / 1e9 if stage_ms["index_ms"] > 0 else 0.0
-        # whole job: every rank uploads the residue stream, the offsets and (cross-class mode) the row layout
-        h2d = int(world * (h_res.numel() + h_off.numel() * 8 + (16 * n if cross else 0)))
-        d2h = int(pst_e["n_edges_out"] * 16 + 12 * n + 512)
+        # whole job: the residue stream crosses PCIe once (1 / N per rank), every rank uploads the offsets and
+        # (cross-class mode) the row layout; every edge crosses PCIe once
+        h2d = int(h_res.numel() + world * (h_off.numel() * 8 + (16 * n if cross else 0)))
+        d2h = int(n_e_total * 16 + world * 512)
+        stream_index = eng.index_flavour() == 1
         line = {
             "metric": "protein_pairs_scored_per_s", "value": pairs_total / (dev_ms * 1e-3), "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": dev_ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic",
-            "config": {"workload": args.workload, "n_proteins": n, "mean_len": round(ps.residues.size / n, 1),
-                       "k": k, "threshold": THRESHOLD, "cross_class_only": cross, "blosum": True,
-                       "generator": "G1 (include/kc_synth.h)", "seed": hex(WORKLOADS[args.workload][3]),
-                       "l2_policy": f"inputs larger than L2 ({ps.residues.size / 1e6:.0f} MB residues, "
-                                    f"{4 * nnz / 1e6:.0f} MB postings); no flush needed",
-                       "parallelism": ("1 GPU" if world == 1 else
-                                       "row-block sharded index + pair triangle (owner computes, no exchange)"
-                                       if sharded_index else
-                                       "replicated index, row-block sharded pair triangle")},
+            "config": config_of(args.workload, ps, k, cross, world, nnz),
             "kmers_indexed_per_s": ist["n_positions"] / (index_ms * 1e-3),
             "pair_stage_pairs_per_s": pairs_total / (pairs_ms * 1e-3) if pairs_ms > 0 else None,
             "multi_edges_per_s": m_kept / (pair_kernel_ms * 1e-3) if pair_kernel_ms > 0 else None,
-            "stage_ms": {"index": index_ms, "census_kernel": census_ms, "pairs": pairs_ms,
+            "stage_ms": {"index": index_ms, "partition_kernels": census_ms, "pairs": pairs_ms,
                          "pair_kernels": pair_kernel_ms, "edges_sort_blosum": edges_ms},
             "counts": {"n_positions": ist["n_positions"], "n_repeated": ist["n_repeated"], "nnz": nnz,
                        "n_multi_edges": pst_all["n_multi_edges"], "n_pairs_nonzero": p_kept, "n_edges_out": e_out},
@@ -365,19 +410,34 @@ def main():
                          "peak_source": peak_src,
                          "algorithmic_bytes": algo_bytes},
             "roofline_index": {"bound": "hbm",
-                               "kernel": "K1-K5 (extract_scatter, bucket_build, rows_finalize)" if k == 7
-                               else "K1-K5 (extract, census, ids, postings, suffix ranges)",
+                               "kernel": "K1-K5 (sx_l1/l2 partition kernels, sx_warp_bucket_kernel, rows_finalize_kernel)"
+                               if stream_index else "K1-K5 (extract, census, ids, postings, suffix ranges)",
                                "achieved": idx_achieved, "peak": peak, "unit": "GB/s", "frac": idx_achieved / peak,
                                "algorithmic_bytes": idx_bytes},
             "e2e": {"value": pairs_total / e2e_s, "unit": "pairs/s", "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "breakdown_ms": {key: v / args.steps for key, v in e2e_parts.items()}},
+                    "breakdown_ms": e2e_break},
             "gpu_launches": launches_all,
             "clocks": clocks,
         }
-        assert edges.size == e_out, (edges.size, e_out)
+        # the gathered list against the oracle: complete, sorted, and (full-size workloads) bit-identical to the
+        # committed golden SHA-256 at EVERY GPU count
+        assert n_e_total == e_out, (n_e_total, e_out)
+        edges = edges_np[:n_e_total * 4].view(kc.EDGE_DTYPE)
         ekey = (edges["a"].astype(np.uint64) << np.uint64(32)) | edges["b"].astype(np.uint64)
         assert bool(np.all(ekey[1:] > ekey[:-1])), "gathered edge list is not sorted by (a, b)"
+        gold = golden_for(args.workload, n)
+        if gold is not None:
+            import hashlib
+            sha = hashlib.sha256(np.ascontiguousarray(edges).tobytes()).hexdigest()
+            assert sha == gold["edges_sha256"], "edge list differs from the oracle's golden SHA-256"
+            for key, val in gold["index"].items():
+                assert ist_e[key] == val, (key, ist_e[key], val)
+            for key in ("n_multi_edges", "n_multi_edges_kept", "n_pairs_kept", "n_edges_out", "sum_count_out"):
+                assert pst_e[key] == gold["pairs"][key], (key, pst_e[key], gold["pairs"][key])
+            line["parity"] = {"edges_sha256": sha, "golden": "tests/golden/synth_golden.json", "checked": True}
+        else:
+            line["parity"] = {"checked": False, "why": "no golden for this workload / size"}
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             r = oracle_run(ps, k, cross, CPU_SAMPLE[args.workload], threads)
@@ -390,6 +450,26 @@ def main():
         print(json.dumps(line))
     eng.close()
     if world > 1:
+        dist.barrier()
+        try:
+            torch.cuda.cudart().cudaHostUnregister(edge_ptr)
+        except Exception:
+            pass
+        del edges_np
+        if rank == 0:
+            try:
+                del edges
+            except NameError:
+                pass
+        try:
+            shm.close()
+        except BufferError:
+            pass
+        if rank == 0:
+            try:
+                shm.unlink()
+            except FileNotFoundError:
+                pass
         dist.destroy_process_group()
 
 

@@ -103,7 +103,10 @@ typedef struct kc_timings {
   uint32_t kernel_launches; /* launches of this library's kernels since kc_reset_timings */
   uint32_t reserved;
   float pair_kernel_ms;     /* accumulation kernels only (the roofline kernel family) */
-  float census_kernel_ms;   /* extract+dedup+census kernel only */
+  float census_kernel_ms;   /* extract+dedup+census kernels only (streaming build: the partition kernels) */
+  uint64_t index_records;   /* streaming build: (k-mer, row) records partitioned (a sharded build: what it kept) */
+  uint32_t index_mid_buckets;  /* buckets that took the CTA path / the global-memory path */
+  uint32_t index_huge_buckets;
 } kc_timings;
 
 /* The sampler (host-callable, same integer arithmetic as the kernels): the x-th sampled start
@@ -199,6 +202,33 @@ int kc_get_edges_device(kc_engine* e, const kc_edge** d_edges_out, uint64_t* n_e
 /* KmerEdgeGroup.kmers (src/graph/edge.rs:49,74) for edge i of the last result, as k-mer
  * VALUES ascending; kmers_out holds edges[i].count entries */
 int kc_get_edge_kmers(kc_engine* e, uint64_t edge_index, uint32_t* kmers_out, uint64_t capacity);
+
+/* ---- Multi-GPU: one engine per GPU, one NCCL rank per engine (one process per GPU, or one host thread per
+ * GPU).  NCCL lives below this ABI (csrc/dist.cuh; libnccl.so.2 is loaded at run time), so a Rust / C++ host
+ * needs no collective library of its own.  The pair triangle is cut into 2 * world row blocks, rank g owns
+ * blocks g and 2 * world - 1 - g and computes everything for its rows (kc_build_index_shard /
+ * kc_score_pairs_shard); what crosses NVLink is the residue staging (1 / world uploaded per rank, all-gathered),
+ * two counter all-reduces and the edge gather.  The reference has no counterpart: it is one process
+ * (threads + mutexes, src/main.rs:84-122, src/graph/mod.rs:81-182). */
+#define KC_COMM_ID_BYTES 128
+/* rank 0 makes the id (ncclGetUniqueId); the host hands the same 128 bytes to every rank */
+int kc_comm_unique_id(uint8_t* id);
+int kc_comm_init(kc_engine* e, const uint8_t* id, int rank, int world);
+int kc_comm_info(kc_engine* e, int* rank, int* world);
+/* kc_set_proteins with every rank given the SAME host arrays: the rank uploads 1 / world of the residue
+ * stream over its own PCIe link, the slices are all-gathered over NVLink.  Collective. */
+int kc_set_proteins_dist(kc_engine* e, const uint8_t* residues, const uint64_t* offsets,
+                         const uint32_t* class_id, uint64_t n_proteins);
+/* kc_build_index_shard(rank, world) + all-reduce: `stats` are the whole-set numbers on every rank.  Collective. */
+int kc_build_index_dist(kc_engine* e, kc_index_stats* stats);
+/* kc_score_pairs_shard(rank, world) + all-reduce: whole-job counters on every rank.  Collective. */
+int kc_score_pairs_dist(kc_engine* e, kc_pair_stats* stats);
+/* The edge lists of all ranks as one list sorted by (a, b), n_total edges.  Collective.
+ * kc_gather_edges: device-to-device over NVLink to rank 0, one copy into rank 0's `out` (other ranks: NULL).
+ * kc_gather_edges_shared: `shared_out` is ONE host buffer mapped by every rank (threads of one process, or
+ * POSIX shared memory): every rank copies its own runs to their final place over its own PCIe link. */
+int kc_gather_edges(kc_engine* e, kc_edge* out, uint64_t capacity, uint64_t* n_total);
+int kc_gather_edges_shared(kc_engine* e, kc_edge* shared_out, uint64_t capacity, uint64_t* n_total);
 
 int kc_get_timings(kc_engine* e, kc_timings* out);
 int kc_reset_timings(kc_engine* e);

@@ -50,7 +50,8 @@ class Timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("extract_ms", C.c_float), ("index_ms", C.c_float),
                 ("pairs_ms", C.c_float), ("edges_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32),
-                ("pair_kernel_ms", C.c_float), ("census_kernel_ms", C.c_float)]
+                ("pair_kernel_ms", C.c_float), ("census_kernel_ms", C.c_float),
+                ("index_records", C.c_uint64), ("index_mid_buckets", C.c_uint32), ("index_huge_buckets", C.c_uint32)]
 
 
 def stats_dict(s: C.Structure) -> dict:
@@ -64,6 +65,8 @@ EXPORTED = [
     "kc_get_distinct_kmers", "kc_get_vocab", "kc_get_protein_ids", "kc_lookup_kmers", "kc_get_pair_index", "kc_score_pairs",
     "kc_score_pairs_shard", "kc_get_edges", "kc_get_edges_device", "kc_get_edge_kmers", "kc_get_timings", "kc_reset_timings",
     "kc_bitset_pair_counts",
+    "kc_comm_unique_id", "kc_comm_init", "kc_comm_info", "kc_set_proteins_dist", "kc_build_index_dist",
+    "kc_score_pairs_dist", "kc_gather_edges", "kc_gather_edges_shared",
     "kc_fasta_parse_file", "kc_fasta_parse_buffer", "kc_fasta_free", "kc_fasta_n_proteins",
     "kc_fasta_n_residues", "kc_fasta_residues", "kc_fasta_offsets", "kc_fasta_class_ids",
     "kc_fasta_n_classes", "kc_fasta_n_missing_class", "kc_fasta_class_name", "kc_fasta_id",
@@ -144,6 +147,14 @@ def lib():
         "kc_get_timings": (i32, [vp, P(Timings)]),
         "kc_reset_timings": (i32, [vp]),
         "kc_bitset_pair_counts": (i32, [vp, vp, u32, vp]),
+        "kc_comm_unique_id": (i32, [vp]),
+        "kc_comm_init": (i32, [vp, vp, i32, i32]),
+        "kc_comm_info": (i32, [vp, P(i32), P(i32)]),
+        "kc_set_proteins_dist": (i32, [vp, vp, vp, vp, u64]),
+        "kc_build_index_dist": (i32, [vp, P(IndexStats)]),
+        "kc_score_pairs_dist": (i32, [vp, P(PairStats)]),
+        "kc_gather_edges": (i32, [vp, vp, u64, P(u64)]),
+        "kc_gather_edges_shared": (i32, [vp, vp, u64, P(u64)]),
         "kc_fasta_parse_file": (i32, [cp, i32, P(vp)]),
         "kc_fasta_parse_buffer": (i32, [cp, u64, i32, P(vp)]),
         "kc_fasta_free": (None, [vp]),

@@ -7,6 +7,8 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/kc_b200.h"
@@ -16,6 +18,7 @@
 #include "bucket.cuh"
 #include "stream_index.cuh"
 #include "pairs.cuh"
+#include "dist.cuh"
 #include "primitives.cuh"
 
 using namespace kc;
@@ -140,9 +143,11 @@ struct kc_engine {
   // streaming partitioned build (stream_index.cuh): the residue stream in the pair order (an alias of d_res
   // unless the pair order is class-major), its row starts, the two record arrays and the scanned histograms
   bool streamed = false;
-  DBuf d_sres_own, d_soff, d_rec_a, d_rec_b, d_h1, d_h2, d_huge_list, d_mid_list, d_tile_row, d_ss3;
+  DBuf d_sres_own, d_soff, d_rec_a, d_rec_b, d_h1, d_h2, d_huge_list, d_mid_list, d_tile_row, d_ss3, d_keepmask;
   std::vector<uint32_t> h_soff;
   uint32_t sx_huge_last = 0, sx_mid_last = 0, sx_max_bucket = 0;
+  uint64_t index_records = 0;  // records the last streaming build partitioned (a sharded build: what it kept)
+  uint32_t rank_of(uint64_t p) const { return cfg.cross_class_only ? h_rank[p] : (uint32_t)p; }
   const uint8_t* sres() const { return cfg.cross_class_only ? d_sres_own.as<uint8_t>() : d_res.as<uint8_t>(); }
   const uint32_t* pair_rowptr() const { return (bucketed ? d_rowcap : d_pstart).as<uint32_t>(); }  // d_rowcap: capacity prefix
   const uint32_t* pair_ids() const { return (bucketed ? d_ids : d_pk).as<uint32_t>(); }
@@ -152,6 +157,10 @@ struct kc_engine {
   DBuf d_rowbin, d_rowsafe, d_rowlogh, d_edges, d_keys_a, d_keys_b, d_vals_a, d_vals_b, d_hist, d_edges_sorted;
   uint64_t edge_cap = 0, n_edges = 0;
   kc_pair_stats pstats{};
+  // multi-GPU (dist.cuh): this engine's NCCL rank
+  ncclComm_t comm = nullptr;
+  int crank = 0, cworld = 1;
+  DBuf d_comm, d_gather;
   // misc
   DBuf d_scalars, d_scan_tiles, d_tmp;
   ScanScratch scan;
@@ -254,12 +263,10 @@ int stage_layout(kc_engine* e) {
   // pair order: input order, or class-major (stable) when only cross-class pairs are wanted,
   // so that the same-class holders a row must skip are one contiguous run of every posting
   const bool cross = e->cfg.cross_class_only != 0;
-  e->h_orig.resize(n);
-  e->h_rank.resize(n);
   e->h_first_after.clear();
   if (cross) {
-    for (uint64_t p = 0; p < n; ++p)
-      if (off[p + 1] < off[p]) return fail(e, KC_EINVAL, "offsets must be non-decreasing");
+    e->h_orig.resize(n);
+    e->h_rank.resize(n);
     std::iota(e->h_orig.begin(), e->h_orig.end(), 0u);
     std::stable_sort(e->h_orig.begin(), e->h_orig.end(),
                      [&](uint32_t a, uint32_t b) { return e->h_cls[a] < e->h_cls[b]; });
@@ -289,40 +296,93 @@ int stage_layout(kc_engine* e) {
   e->n_pos_unsampled = 0;
   e->max_plen = 0;
   const uint64_t every = e->cfg.sample_every > 1 ? e->cfg.sample_every : 1;
-  unsigned long long huge_total = 0, pos_acc = 0;
-  for (uint64_t r = 0; r < n; ++r) {
-    const uint32_t p = cross ? e->h_orig[r] : (uint32_t)r;
-    if (off[p + 1] < off[p]) return fail(e, KC_EINVAL, "offsets must be non-decreasing");
-    const uint64_t len = off[p + 1] - off[p];
-    if (cross) {
-      e->h_pstart[r] = (uint32_t)off[p];
-      e->h_plen[r] = (uint32_t)len;
-      e->h_soff[r + 1] = e->h_soff[r] + (uint32_t)len;
-    } else {
-      e->h_orig[r] = e->h_rank[r] = (uint32_t)r;
-    }
-    e->max_plen = std::max(e->max_plen, (uint32_t)len);
-    if (len >= (uint64_t)k) {
-      const uint32_t npos = (uint32_t)(len - k + 1);
-      pos_acc += npos / every;
-      e->n_pos_unsampled += npos;
-      if (npos > kHashMaxPos) {
-        if (npos > kBlockMaxPos) {
-          e->h_huge.push_back((uint32_t)r);
-          e->h_huge_off.push_back(huge_total);
-          huge_total += next_pow2_u32(npos);
-        } else if (npos > kWarpMaxPos) {
-          e->h_long.push_back((uint32_t)r);
-          e->max_block_np2 = std::max(e->max_block_np2, next_pow2_u32(npos));
-          e->max_block_len = std::max(e->max_block_len, (uint32_t)len);
-          (npos > kCtaHashMaxPos ? e->h_vlong : e->h_cta).push_back((uint32_t)r);
-        } else {
-          ++e->n_mid_rows;
-          e->h_cta.push_back((uint32_t)r);
+  // One pass over the rows (pair order), in parallel slabs: k-mer positions per row (prefix in a second
+  // step), the longest row, and the rows the sorting kernels of the table / bucket builds take one by one.
+  // (This runs while the residue stream crosses PCIe; at 8 ranks per host it was the largest part of a step.)
+  struct Slab {
+    unsigned long long pos = 0, pos_all = 0;
+    uint32_t max_plen = 0, max_np2 = 0, max_len = 0, n_mid = 0;
+    std::vector<uint32_t> lng, cta, vlong, huge;
+  };
+  const unsigned n_slabs = n >= (1u << 16) ? 4u : 1u;
+  std::vector<Slab> slabs(n_slabs);
+  auto slab_rows = [&](unsigned t) { return std::pair<uint64_t, uint64_t>{n * t / n_slabs, n * (t + 1) / n_slabs}; };
+  auto pass1 = [&](unsigned t) {
+    Slab& sl = slabs[t];
+    const auto [lo, hi] = slab_rows(t);
+    for (uint64_t r = lo; r < hi; ++r) {
+      const uint32_t p = cross ? e->h_orig[r] : (uint32_t)r;
+      const uint64_t len = off[p + 1] - off[p];
+      if (cross) {
+        e->h_pstart[r] = (uint32_t)off[p];
+        e->h_plen[r] = (uint32_t)len;
+      }
+      sl.max_plen = std::max(sl.max_plen, (uint32_t)len);
+      uint32_t kept = 0;
+      if (len >= (uint64_t)k) {
+        const uint32_t npos = (uint32_t)(len - k + 1);
+        kept = (uint32_t)(npos / every);
+        sl.pos_all += npos;
+        if (npos > kHashMaxPos) {
+          if (npos > kBlockMaxPos) {
+            sl.huge.push_back((uint32_t)r);
+          } else if (npos > kWarpMaxPos) {
+            sl.lng.push_back((uint32_t)r);
+            sl.max_np2 = std::max(sl.max_np2, next_pow2_u32(npos));
+            sl.max_len = std::max(sl.max_len, (uint32_t)len);
+            (npos > kCtaHashMaxPos ? sl.vlong : sl.cta).push_back((uint32_t)r);
+          } else {
+            ++sl.n_mid;
+            sl.cta.push_back((uint32_t)r);
+          }
         }
       }
+      e->h_pospref[r + 1] = kept;  // (per row for now)
+      sl.pos += kept;
     }
-    e->h_pospref[r + 1] = pos_acc;
+  };
+  {
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < n_slabs; ++t) pool.emplace_back(pass1, t);
+    pass1(0);
+    for (auto& th : pool) th.join();
+  }
+  unsigned long long huge_total = 0;
+  {
+    std::vector<unsigned long long> base(n_slabs + 1, 0);
+    for (unsigned t = 0; t < n_slabs; ++t) base[t + 1] = base[t] + slabs[t].pos;
+    auto pass2 = [&](unsigned t) {
+      const auto [lo, hi] = slab_rows(t);
+      unsigned long long acc = base[t];
+      for (uint64_t r = lo; r < hi; ++r) {
+        acc += e->h_pospref[r + 1];
+        e->h_pospref[r + 1] = acc;
+      }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < n_slabs; ++t) pool.emplace_back(pass2, t);
+    pass2(0);
+    for (auto& th : pool) th.join();
+    for (unsigned t = 0; t < n_slabs; ++t) {
+      const Slab& sl = slabs[t];
+      e->n_pos_unsampled += sl.pos_all;
+      e->max_plen = std::max(e->max_plen, sl.max_plen);
+      e->max_block_np2 = std::max(e->max_block_np2, sl.max_np2);
+      e->max_block_len = std::max(e->max_block_len, sl.max_len);
+      e->n_mid_rows += sl.n_mid;
+      e->h_long.insert(e->h_long.end(), sl.lng.begin(), sl.lng.end());
+      e->h_cta.insert(e->h_cta.end(), sl.cta.begin(), sl.cta.end());
+      e->h_vlong.insert(e->h_vlong.end(), sl.vlong.begin(), sl.vlong.end());
+      for (uint32_t r : sl.huge) {
+        const uint32_t p = cross ? e->h_orig[r] : r;
+        const uint32_t npos = (uint32_t)(off[p + 1] - off[p] - k + 1);
+        e->h_huge.push_back(r);
+        e->h_huge_off.push_back(huge_total);
+        huge_total += next_pow2_u32(npos);
+      }
+    }
+    if (cross)
+      for (uint64_t r = 0; r < n; ++r) e->h_soff[r + 1] = e->h_soff[r] + e->h_plen[r];
   }
   auto up = [&](DBuf& b, const void* src, size_t bytes) -> cudaError_t {
     cudaError_t rc = b.ensure(std::max<size_t>(bytes, 16));
@@ -778,13 +838,59 @@ static SxPlan sx_make_plan(uint64_t E, uint64_t R, int num_sm) {
   return p;
 }
 
-static int build_index_stream(kc_engine* e, kc_index_stats* stats) {
+// Row blocks of a sharded build: the pair order is cut into 2 * n_shards blocks of equal k-mer positions (at bin
+// borders); rank g owns blocks g and 2 * n_shards - 1 - g (a row is scored against the rows after it, so its
+// work falls with its position: the zig-zag gives every rank one early and one late block).
+static void shard_blocks(const kc_engine* e, uint32_t shard, uint32_t n_shards, std::vector<uint32_t>& bounds,
+                         std::vector<uint8_t>& binowner, unsigned long long* own_positions, uint32_t* n_own_rows) {
+  const uint32_t n = (uint32_t)e->n;
+  const unsigned long long n_positions = e->h_pospref[n];
+  const uint32_t n_bins = (n + kBinRows - 1) >> kBinRowsLog;
+  const uint32_t n_blocks = 2 * n_shards;
+  bounds.assign(n_blocks + 1, n);
+  bounds[0] = 0;
+  for (uint32_t b = 1; b < n_blocks; ++b) {
+    const unsigned long long target = n_positions / n_blocks * b + (n_positions % n_blocks) * b / n_blocks;
+    const uint32_t r = (uint32_t)(std::lower_bound(e->h_pospref.begin(), e->h_pospref.end(), target) -
+                                  e->h_pospref.begin());  // first r with positions(rows < r) >= target
+    bounds[b] = std::max(bounds[b - 1], std::min<uint32_t>(n, (r + kBinRows - 1) & ~(kBinRows - 1u)));
+  }
+  binowner.assign(n_bins, 0);
+  *own_positions = 0;
+  *n_own_rows = 0;
+  for (uint32_t b = 0; b < n_blocks; ++b) {
+    const uint32_t who = b < n_shards ? b : n_blocks - 1 - b;
+    for (uint32_t bin = bounds[b] >> kBinRowsLog; bin < (bounds[b + 1] + kBinRows - 1) >> kBinRowsLog; ++bin)
+      binowner[bin] = (uint8_t)who;
+    if (who != shard) continue;
+    *n_own_rows += bounds[b + 1] - bounds[b];
+    *own_positions += e->h_pospref[bounds[b + 1]] - e->h_pospref[bounds[b]];
+  }
+}
+
+static int build_index_stream(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_index_stats* stats) {
   const uint32_t n = (uint32_t)e->n;
   const uint64_t R = e->R;
   DeviceScalars* ds = e->ds;
   const unsigned long long n_positions = e->h_pospref[n];
   const uint64_t E = std::max<unsigned long long>(n_positions, 1);
   const uint32_t n_bins = (n + kBinRows - 1) >> kBinRowsLog;
+  // sharded build (owner computes): this rank's row blocks, the filter of its rows' k-mers
+  unsigned long long own_positions = n_positions;
+  uint32_t n_own_rows = n, filter_bits = 0;
+  std::vector<uint32_t> bounds;
+  if (n_shards > 1) {
+    shard_blocks(e, shard, n_shards, bounds, e->h_binowner, &own_positions, &n_own_rows);
+    KC_CUDA(e, e->d_binowner.ensure((size_t)n_bins + 64));
+    KC_CUDA(e, cudaMemcpyAsync(e->d_binowner.p, e->h_binowner.data(), n_bins, cudaMemcpyHostToDevice, e->stream));
+    // 16 bits per own position, at most 2^29 bits = 64 MB: the probes (one per foreign position) must hit L2
+    filter_bits = 1u << 20;
+    while (filter_bits < (1u << 29) && (unsigned long long)filter_bits < 16ull * std::max<unsigned long long>(own_positions, 1))
+      filter_bits <<= 1;
+    KC_CUDA(e, e->d_filter.ensure((size_t)filter_bits / 8 + 64));
+    KC_CUDA(e, e->d_keepmask.ensure(((R + kSxTile - 1) / kSxTile + 1) * kL1Threads * 2));
+  }
+  const RowOwner owner{n_shards > 1 ? e->d_binowner.as<uint8_t>() : nullptr, shard};
   SxPlan plan = sx_make_plan(E, R, e->num_sm);
   if (e->cfg.census_merge == 77u) plan.ballots = 0;  // (A/B switch while tuning; see profiles/r2_history.md)
   const uint32_t n_tiles = (uint32_t)((R + kSxTile - 1) / kSxTile);
@@ -840,6 +946,27 @@ static int build_index_stream(kc_engine* e, kc_index_stats* stats) {
   e->launches += exclusive_scan(SxPosIn{soff, (uint32_t)e->cfg.k}, SxExclOutTail{rowcap, n}, n, e->scan, e->stream);
   KC_LAUNCH(e, sx_tile_rows_kernel, (n_tiles + 256) / 256, 256, 0, soff, n, (uint32_t)R, n_tiles,
             e->d_tile_row.as<uint32_t>());
+  const SxKeep keep{n_shards > 1 ? e->d_filter.as<uint32_t>() : nullptr, filter_bits / 32u - 1u, owner,
+                    n_shards > 1 ? e->d_keepmask.as<uint16_t>() : nullptr};
+  if (n_shards > 1) {  // the filter of the k-mers this rank's rows hold: its two row blocks, tile by tile
+    KC_CUDA(e, cudaMemsetAsync(e->d_filter.p, 0, (size_t)filter_bits / 8, e->stream));
+    for (int part = 0; part < 2; ++part) {
+      const uint32_t blk = part == 0 ? shard : 2 * n_shards - 1 - shard;
+      const uint32_t r_lo = bounds[blk], r_hi = bounds[blk + 1];
+      if (r_hi <= r_lo) continue;
+      const uint64_t b_lo = e->cfg.cross_class_only ? e->h_soff[r_lo] : e->h_off[r_lo];
+      const uint64_t b_hi = e->cfg.cross_class_only ? e->h_soff[r_hi] : e->h_off[r_hi];
+      if (b_hi <= b_lo) continue;
+      const uint32_t t_lo = (uint32_t)(b_lo / kSxTile), t_hi = (uint32_t)((b_hi + kSxTile - 1) / kSxTile);
+      const uint32_t fgrid = std::min<uint32_t>(t_hi - t_lo, (uint32_t)e->num_sm * 2u);
+      if (k5)
+        KC_LAUNCH(e, sx_filter_build_kernel<5>, fgrid, kL1Threads, 0, res, (uint32_t)R, soff, e->d_tile_row.as<uint32_t>(),
+                  t_lo, t_hi, keep);
+      else
+        KC_LAUNCH(e, sx_filter_build_kernel<7>, fgrid, kL1Threads, 0, res, (uint32_t)R, soff, e->d_tile_row.as<uint32_t>(),
+                  t_lo, t_hi, keep);
+    }
+  }
   // level 1: count, scan, scatter (residue stream -> rec_a, partitioned by the top b1 hash bits)
   {
     const uint32_t* trow = e->d_tile_row.as<uint32_t>();
@@ -848,17 +975,17 @@ static int build_index_stream(kc_engine* e, kc_index_stats* stats) {
     if (k5) {
       KC_CUDA(e, cudaFuncSetAttribute(sx_l1_count_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
       KC_CUDA(e, cudaFuncSetAttribute(sx_l1_scatter_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-      KC_LAUNCH(e, sx_l1_count_kernel<5>, plan.g1, kL1Threads, smem_c, res, (uint32_t)R, soff, trow, plan, h1);
+      KC_LAUNCH(e, sx_l1_count_kernel<5>, plan.g1, kL1Threads, smem_c, res, (uint32_t)R, soff, trow, plan, keep, h1);
     } else {
       KC_CUDA(e, cudaFuncSetAttribute(sx_l1_count_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
       KC_CUDA(e, cudaFuncSetAttribute(sx_l1_scatter_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-      KC_LAUNCH(e, sx_l1_count_kernel<7>, plan.g1, kL1Threads, smem_c, res, (uint32_t)R, soff, trow, plan, h1);
+      KC_LAUNCH(e, sx_l1_count_kernel<7>, plan.g1, kL1Threads, smem_c, res, (uint32_t)R, soff, trow, plan, keep, h1);
     }
     e->launches += exclusive_scan(U32In{h1}, SxExclOutTail{h1, n_h1}, n_h1, e->scan, e->stream);
     if (k5)
-      KC_LAUNCH(e, sx_l1_scatter_kernel<5>, plan.g1, kL1Threads, smem_s, res, (uint32_t)R, soff, trow, plan, h1, rec_a);
+      KC_LAUNCH(e, sx_l1_scatter_kernel<5>, plan.g1, kL1Threads, smem_s, res, (uint32_t)R, soff, trow, plan, keep, h1, rec_a);
     else
-      KC_LAUNCH(e, sx_l1_scatter_kernel<7>, plan.g1, kL1Threads, smem_s, res, (uint32_t)R, soff, trow, plan, h1, rec_a);
+      KC_LAUNCH(e, sx_l1_scatter_kernel<7>, plan.g1, kL1Threads, smem_s, res, (uint32_t)R, soff, trow, plan, keep, h1, rec_a);
   }
   // level 2: rec_a -> rec_b, every level-1 partition by the next b2 hash bits
   {
@@ -895,6 +1022,7 @@ static int build_index_stream(kc_engine* e, kc_index_stats* stats) {
     A.huge_cnt = &ds->sx_huge_cnt;
     const bool small = e->cfg.bucket_cap == 512u;  // tests: tiny capacities push ordinary buckets down every path
     A.mid_cap = small ? 512u : 4096u;
+    A.owner = owner;
     // one warp per bucket
 #define KC_SXW(CROSS, WCAP)                                                                                      \
   do {                                                                                                           \
@@ -946,17 +1074,22 @@ static int build_index_stream(kc_engine* e, kc_index_stats* stats) {
               e->d_rowlen.as<uint32_t>(), e->d_rowlen_p.as<uint32_t>(), e->d_ids.as<uint32_t>(), e->d_suf.as<uint2>(),
               e->cfg.want_blosum ? e->d_sufss.as<uint8_t>() : nullptr, e->d_rowwork64.as<unsigned long long>(),
               e->d_rowwork.as<uint32_t>(), e->d_rowinl.as<uint32_t>(), e->d_rowmaxlen.as<uint32_t>());
-  e->launches += exclusive_scan(WorkIn{e->d_rowwork.as<uint32_t>(), e->d_rowlen.as<uint32_t>()},
-                                U64ExclOutWithTail{e->d_workprefix.as<unsigned long long>(), n}, n, e->scan, e->stream);
+  if (n_shards <= 1)
+    e->launches += exclusive_scan(WorkIn{e->d_rowwork.as<uint32_t>(), e->d_rowlen.as<uint32_t>()},
+                                  U64ExclOutWithTail{e->d_workprefix.as<unsigned long long>(), n}, n, e->scan, e->stream);
   mark(e, EV_I1);
   DeviceScalars hs{};
+  uint32_t n_records = 0;
   KC_CUDA(e, cudaMemcpyAsync(&hs, ds, sizeof(hs), cudaMemcpyDeviceToHost, e->stream));
+  KC_CUDA(e, cudaMemcpyAsync(&n_records, h2 + n_h2, 4, cudaMemcpyDeviceToHost, e->stream));
   KC_CUDA(e, cudaStreamSynchronize(e->stream));
   KC_CUDA(e, cudaGetLastError());
+  e->index_records = n_records;
   e->sx_huge_last = hs.sx_huge_cnt;
   e->sx_mid_last = hs.sx_mid_cnt;
   e->sx_max_bucket = hs.bg.max_bucket;
-  e->istats.n_positions = n_positions;
+  // (sharded: totals over the k-mers whose first holder is one of this rank's rows; they add up over the ranks)
+  e->istats.n_positions = own_positions;
   e->istats.n_incidences = hs.n_incid;
   e->istats.n_distinct = hs.bg.n_distinct;
   e->istats.n_repeated = hs.bg.n_repeated;
@@ -965,10 +1098,10 @@ static int build_index_stream(kc_engine* e, kc_index_stats* stats) {
   e->v_local = E / 2 + 1;  // ids are placed by capacity (stream_index.cuh): the id SPACE, with holes
   e->multi_total = hs.bg.multi_total;
   e->work_total = hs.bg.work_total;
-  e->ishard = 0;
-  e->ishards = 1;
-  e->block_bounds.clear();
-  e->n_own_rows = n;
+  e->ishard = shard;
+  e->ishards = n_shards;
+  e->block_bounds = bounds;
+  e->n_own_rows = n_own_rows;
   if (stats) *stats = e->istats;
   e->bucketed = true;
   e->streamed = true;
@@ -1116,7 +1249,9 @@ void kc_destroy(kc_engine* e) {
                  &e->d_vocab_h, &e->d_freq_h, &e->d_self_h, &e->d_zero, &e->d_rowlen_c, &e->d_islo_c, &e->d_filter, &e->d_binowner, &e->d_runs, &e->d_run_cnt, &e->d_rowlen_p, &e->d_rowbin, &e->d_rowsafe, &e->d_rowlogh, &e->d_edges, &e->d_keys_a, &e->d_keys_b,
                  &e->d_vals_a, &e->d_vals_b, &e->d_hist, &e->d_edges_sorted, &e->d_scalars, &e->d_scan_tiles,
                  &e->d_tmp, &e->d_sres_own, &e->d_soff, &e->d_rec_a, &e->d_rec_b, &e->d_h1, &e->d_h2,
-                 &e->d_huge_list, &e->d_mid_list, &e->d_tile_row, &e->d_ss3};
+                 &e->d_huge_list, &e->d_mid_list, &e->d_tile_row, &e->d_ss3, &e->d_comm, &e->d_gather, &e->d_keepmask};
+  if (e->comm && nccl_api().ok()) nccl_api().CommDestroy(e->comm);
+  e->comm = nullptr;
   for (DBuf* b : all) b->release();
   for (int i = 0; i < EV_COUNT; ++i)
     if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -1147,18 +1282,31 @@ int kc_set_stream(kc_engine* e, void* cuda_stream) {
   return KC_OK;
 }
 
-int kc_set_proteins(kc_engine* e, const uint8_t* residues, const uint64_t* offsets, const uint32_t* class_id,
-                    uint64_t n) {
+// dist: every rank uploads 1 / world of the residue stream and the slices are all-gathered over NVLink
+static int set_proteins_host(kc_engine* e, const uint8_t* residues, const uint64_t* offsets, const uint32_t* class_id,
+                             uint64_t n, bool dist) {
   if (!e || !offsets || (n && !class_id)) return KC_EINVAL;
   KC_CUDA(e, cudaSetDevice(e->dev));
-  e->n = n;
-  e->h_off.assign(offsets, offsets + n + 1);
-  e->h_cls.assign(class_id, class_id + n);
+  // (a chunked upload of the previous call may still be in flight into d_res; the host buffers of THIS call
+  // must stay valid until the next kc_build_index* / kc_extract_kmers returns: the copies are asynchronous)
+  if (int rcw = wait_upload(e)) return rcw;
+  e->have_proteins = e->have_index = e->have_pairs = false;
+  // validate before any state is committed or any copy is queued
+  if (offsets[0] != 0) return fail(e, KC_EINVAL, "offsets[0] must be 0");
+  for (uint64_t p = 0; p < n; ++p)
+    if (offsets[p + 1] < offsets[p]) return fail(e, KC_EINVAL, "offsets must be non-decreasing");
   const uint64_t R = offsets[n];
   if (R && !residues) return fail(e, KC_EINVAL, "null residues");
   if (R >= 0xFFFF0000ull) return fail(e, KC_ETOOLARGE, "more than 2^32-65536 residues");
+  if (n >= 0xFFFFFFF0ull) return fail(e, KC_ETOOLARGE, "too many proteins");
+  e->n = n;
+  e->h_off.assign(offsets, offsets + n + 1);
+  e->h_cls.assign(class_id, class_id + n);
   mark(e, EV_H2D0);
-  const size_t padded = padded_res_bytes(R);
+  size_t padded = padded_res_bytes(R);
+  const uint64_t world = dist ? (uint64_t)e->cworld : 1;
+  const uint64_t per = ((R + world - 1) / world + 255) & ~255ull;  // slice of the all-gather
+  if (dist) padded = std::max<size_t>(padded, (size_t)(per * world) + kSxTile);
   KC_CUDA(e, e->d_res.ensure(padded));
   // the offsets first: the one H2D copy engine serves the copies in issue order, and the layout
   // kernel (main stream) must not wait behind the whole residue stream
@@ -1166,7 +1314,17 @@ int kc_set_proteins(kc_engine* e, const uint8_t* residues, const uint64_t* offse
   KC_CUDA(e, cudaMemcpyAsync(e->d_off.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, e->stream));
   e->n_chunks = 0;
   constexpr int C = kc_engine::kUploadChunks;
-  if (!e->cfg.cross_class_only && R >= (32u << 20) && n >= 64 * C && e->copy_stream && !e->cfg.no_upload_overlap) {
+  if (dist && world > 1) {
+    NcclApi& nc = nccl_api();
+    if (!e->comm || !nc.ok()) return fail(e, KC_EINVAL, "kc_comm_init first");
+    const uint64_t lo = std::min<uint64_t>(R, per * (uint64_t)e->crank), hi = std::min<uint64_t>(R, lo + per);
+    if (hi > lo)
+      KC_CUDA(e, cudaMemcpyAsync(e->d_res.as<uint8_t>() + lo, residues + lo, hi - lo, cudaMemcpyHostToDevice, e->stream));
+    const ncclResult_t nr = nc.AllGather(e->d_res.as<uint8_t>() + per * (uint64_t)e->crank, e->d_res.p, per, ncclUint8,
+                                         e->comm, e->stream);
+    if (nr != ncclSuccess) return fail(e, KC_ECUDA, std::string("ncclAllGather: ") + nc.GetErrorString(nr));
+    KC_CUDA(e, cudaMemsetAsync(e->d_res.as<uint8_t>() + R, 0, padded - R, e->stream));
+  } else if (!e->cfg.cross_class_only && R >= (32u << 20) && n >= 64 * C && e->copy_stream && !e->cfg.no_upload_overlap) {
     // pair order = input order: chunk c of the stream is the rows [chunk_row[c], chunk_row[c+1]).
     // The copy stream waits for what the main stream still does with the old residues.
     KC_CUDA(e, cudaEventRecord(e->main_ev, e->stream));
@@ -1201,11 +1359,17 @@ int kc_set_proteins(kc_engine* e, const uint8_t* residues, const uint64_t* offse
   return rc;
 }
 
+int kc_set_proteins(kc_engine* e, const uint8_t* residues, const uint64_t* offsets, const uint32_t* class_id,
+                    uint64_t n) {
+  return set_proteins_host(e, residues, offsets, class_id, n, false);
+}
+
 int kc_set_proteins_device(kc_engine* e, const uint8_t* d_residues, const uint64_t* d_offsets,
                            const uint32_t* d_class_id, uint64_t n) {
   if (!e || !d_offsets || (n && !d_class_id)) return KC_EINVAL;
   KC_CUDA(e, cudaSetDevice(e->dev));
   if (int rcw = wait_upload(e)) return rcw;
+  e->have_proteins = e->have_index = e->have_pairs = false;
   e->n = n;
   e->h_off.resize(n + 1);
   e->h_cls.resize(n);
@@ -1214,6 +1378,9 @@ int kc_set_proteins_device(kc_engine* e, const uint8_t* d_residues, const uint64
   KC_CUDA(e, cudaMemcpyAsync(e->h_off.data(), d_offsets, (n + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
   if (n) KC_CUDA(e, cudaMemcpyAsync(e->h_cls.data(), d_class_id, n * 4, cudaMemcpyDeviceToHost, e->stream));
   KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (e->h_off[0] != 0) return fail(e, KC_EINVAL, "offsets[0] must be 0");
+  for (uint64_t p = 0; p < n; ++p)
+    if (e->h_off[p + 1] < e->h_off[p]) return fail(e, KC_EINVAL, "offsets must be non-decreasing");
   const uint64_t R = e->h_off[n];
   if (R >= 0xFFFF0000ull) return fail(e, KC_ETOOLARGE, "more than 2^32-65536 residues");
   mark(e, EV_H2D0);
@@ -1233,6 +1400,10 @@ int kc_set_proteins_device_residues(kc_engine* e, const uint8_t* d_residues, con
   if (!e || !offsets || (n && !class_id)) return KC_EINVAL;
   KC_CUDA(e, cudaSetDevice(e->dev));
   if (int rcw = wait_upload(e)) return rcw;
+  e->have_proteins = e->have_index = e->have_pairs = false;
+  if (offsets[0] != 0) return fail(e, KC_EINVAL, "offsets[0] must be 0");
+  for (uint64_t p = 0; p < n; ++p)
+    if (offsets[p + 1] < offsets[p]) return fail(e, KC_EINVAL, "offsets must be non-decreasing");
   e->n = n;
   e->h_off.assign(offsets, offsets + n + 1);
   e->h_cls.assign(class_id, class_id + n);
@@ -1327,25 +1498,35 @@ int kc_build_index_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_ind
   e->streamed = false;
   {
     // Which build (kc_config.index_build): the streaming partitioned build (stream_index.cuh) by default.
-    // It has no subsampling mode (Protein::new_with_rand_fivemers is dead code in the reference) and no
-    // owner-computes sharding: those run the table build / round 1's bucket build.
+    // It has no subsampling mode (Protein::new_with_rand_fivemers is dead code in the reference): that runs
+    // the table build.
+    // Sharded (multi-GPU) builds: round 1's bucket build is the faster one there (its extract pass dedups per
+    // row while it scans the foreign rows; measured at 8 shards: index 8.3 ms against 12.2 ms), so it is tried
+    // first; when one of its buckets overflows (a k-mer with thousands of holders) the rank builds the SAME
+    // shard with the streaming build, which has no capacity to overflow.  Both cut the same row blocks and
+    // give the same per-rank results, so ranks may differ in which build they ran (a fallback to
+    // the replicated table build left ranks scoring incompatible row partitions).
     uint32_t want = e->cfg.index_build;
-    if (want == KC_INDEX_AUTO) want = e->cfg.sample_every > 1 ? KC_INDEX_TABLE : (n_shards > 1 ? KC_INDEX_BUCKET : KC_INDEX_STREAM);
-    if (want == KC_INDEX_STREAM && (e->cfg.sample_every > 1 || n_shards > 1 || n >= (1u << 24)))
-      want = e->cfg.sample_every > 1 ? KC_INDEX_TABLE : KC_INDEX_BUCKET;
-    if (want == KC_INDEX_STREAM && n > 0) return build_index_stream(e, stats);
-    // (round 1's bucket build remembers per protein-set signature that its buckets overflowed)
-    if (want == KC_INDEX_BUCKET && e->cap_hint == 0 && e->cap_hint_n == e->n && e->cap_hint_R == e->R &&
-        e->cfg.index_build != KC_INDEX_BUCKET)
-      want = KC_INDEX_TABLE;
+    const bool subsampled = e->cfg.sample_every > 1;
+    if (want == KC_INDEX_AUTO) want = subsampled ? KC_INDEX_TABLE : (n_shards > 1 ? KC_INDEX_BUCKET : KC_INDEX_STREAM);
+    if (want == KC_INDEX_STREAM && (subsampled || n >= (1u << 24))) want = subsampled ? KC_INDEX_TABLE : KC_INDEX_BUCKET;
+    if (want == KC_INDEX_STREAM && n > 0) return build_index_stream(e, shard, n_shards, stats);
+    // (the bucket build remembers per protein-set signature that its buckets overflowed)
+    const bool known_overflow = e->cap_hint == 0 && e->cap_hint_n == e->n && e->cap_hint_R == e->R;
+    if (want == KC_INDEX_BUCKET && known_overflow && !subsampled && n > 0 && n < (1u << 24) &&
+        (n_shards > 1 || e->cfg.index_build != KC_INDEX_BUCKET))
+      return build_index_stream(e, shard, n_shards, stats);
     if (want == KC_INDEX_BUCKET && n > 0 && n <= (1u << 24)) {
       bool overflow = false;
       int rc = build_index_bucketed(e, shard, n_shards, stats, &overflow);
       if (rc != KC_OK || !overflow) return rc;
-      // k-mers (or clumps of them) with more holders than a shared-memory bucket takes: table build
+      // k-mers (or clumps of them) with more holders than a shared-memory bucket takes
       e->cap_hint = 0;
       e->cap_hint_n = e->n;
       e->cap_hint_R = e->R;
+      if (!subsampled && n < (1u << 24) && (n_shards > 1 || e->cfg.index_build != KC_INDEX_BUCKET))
+        return build_index_stream(e, shard, n_shards, stats);
+      // (an explicit KC_INDEX_BUCKET on one GPU keeps round 1's behaviour: the table build)
     }
   }
   KC_CUDA(e, e->d_pk.ensure((R + 64) * 4));
@@ -1616,7 +1797,7 @@ int kc_get_protein_ids(kc_engine* e, uint64_t* row_offsets, uint32_t* ids_out, u
   if (n) KC_CUDA(e, cudaMemcpyAsync(rowlen.data(), e->canon_rowlen(), (uint64_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
   KC_CUDA(e, cudaStreamSynchronize(e->stream));
   row_offsets[0] = 0;
-  for (uint32_t p = 0; p < n; ++p) row_offsets[p + 1] = row_offsets[p] + rowlen[e->h_rank[p]];
+  for (uint32_t p = 0; p < n; ++p) row_offsets[p + 1] = row_offsets[p] + rowlen[e->rank_of(p)];
   const uint64_t nnz = row_offsets[n];
   if (!ids_out) return KC_OK;
   if (capacity < nnz) return fail(e, KC_EINVAL, "capacity too small");
@@ -1719,7 +1900,7 @@ int kc_get_pair_index(kc_engine* e, uint32_t* kmers_out, uint32_t* freq_out, uin
     KC_CUDA(e, crc);
   }
   row_offsets[0] = 0;
-  for (uint32_t p = 0; p < n; ++p) row_offsets[p + 1] = row_offsets[p] + rowlen[e->h_rank[p]];
+  for (uint32_t p = 0; p < n; ++p) row_offsets[p + 1] = row_offsets[p] + rowlen[e->rank_of(p)];
   const uint64_t nnz = row_offsets[n];
   if (!ids_out || !nnz) {
     free_tmp();
@@ -2022,7 +2203,7 @@ int kc_get_edge_kmers(kc_engine* e, uint64_t edge_index, uint32_t* kmers_out, ui
   KC_CUDA(e, cudaStreamSynchronize(e->stream));
   if (capacity < ed.z) return fail(e, KC_EINVAL, "capacity too small");
   KC_CUDA(e, e->d_tmp.ensure((uint64_t)ed.z * 4 + 16));
-  KC_LAUNCH(e, shared_kmers_kernel, 1, 32, 0, e->h_rank[ed.x], e->h_rank[ed.y], e->d_pstart.as<uint32_t>(),
+  KC_LAUNCH(e, shared_kmers_kernel, 1, 32, 0, e->rank_of(ed.x), e->rank_of(ed.y), e->d_pstart.as<uint32_t>(),
             e->canon_rowlen(), e->d_pk.as<uint32_t>(), e->d_vocab.as<uint32_t>(), e->d_tmp.as<uint32_t>(),
             ed.z, &e->ds->n_shared);
   KC_CUDA(e, cudaMemcpyAsync(kmers_out, e->d_tmp.p, (uint64_t)ed.z * 4, cudaMemcpyDeviceToHost, e->stream));
@@ -2044,6 +2225,9 @@ int kc_get_timings(kc_engine* e, kc_timings* out) {
   out->pair_kernel_ms = elapsed(e, EV_PK0, EV_PK1);
   out->census_kernel_ms = elapsed(e, EV_IC0, EV_IC1);
   out->kernel_launches = e->launches;
+  out->index_records = e->index_records;
+  out->index_mid_buckets = e->sx_mid_last;
+  out->index_huge_buckets = e->sx_huge_last;
   return KC_OK;
 }
 
@@ -2064,7 +2248,7 @@ int kc_bitset_pair_counts(kc_engine* e, const uint32_t* rows, uint32_t n_rows, u
   if (int rc = ensure_canonical(e)) return rc;
   const uint32_t words = (uint32_t)((e->istats.n_repeated + 31) / 32) + 1;
   std::vector<uint32_t> ranks(n_rows);
-  for (uint32_t i = 0; i < n_rows; ++i) ranks[i] = e->h_rank[rows[i]];
+  for (uint32_t i = 0; i < n_rows; ++i) ranks[i] = e->rank_of(rows[i]);
   DBuf d_rows, d_bits, d_counts;
   cudaError_t a = d_rows.ensure((size_t)n_rows * 4), b = d_bits.ensure((size_t)n_rows * words * 4),
               c = d_counts.ensure((size_t)n_rows * n_rows * 4);
@@ -2090,6 +2274,223 @@ int kc_bitset_pair_counts(kc_engine* e, const uint32_t* rows, uint32_t n_rows, u
   d_counts.release();
   KC_CUDA(e, rc);
   return KC_OK;
+}
+
+// ---- multi-GPU entry points (dist.cuh) ---------------------------------------------------------
+int kc_comm_unique_id(uint8_t* id) {
+  if (!id) return KC_EINVAL;
+  NcclApi& nc = nccl_api();
+  if (!nc.ok()) return KC_ENODEVICE;
+  ncclUniqueId u;
+  if (nc.GetUniqueId(&u) != ncclSuccess) return KC_ECUDA;
+  static_assert(sizeof(u) == KC_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+  std::memcpy(id, &u, sizeof(u));
+  return KC_OK;
+}
+
+int kc_comm_init(kc_engine* e, const uint8_t* id, int rank, int world) {
+  if (!e || !id || world < 1 || rank < 0 || rank >= world) return KC_EINVAL;
+  if (world > 255) return fail(e, KC_EINVAL, "at most 255 ranks (the row blocks' owner is one byte)");
+  KC_CUDA(e, cudaSetDevice(e->dev));
+  NcclApi& nc = nccl_api();
+  if (!nc.ok()) return fail(e, KC_ENODEVICE, "NCCL is not available: " + nc.err);
+  if (e->comm) {
+    nc.CommDestroy(e->comm);
+    e->comm = nullptr;
+  }
+  ncclUniqueId u;
+  std::memcpy(&u, id, sizeof(u));
+  const ncclResult_t nr = nc.CommInitRank(&e->comm, world, u, rank);
+  if (nr != ncclSuccess) {
+    e->comm = nullptr;
+    return fail(e, KC_ECUDA, std::string("ncclCommInitRank: ") + nc.GetErrorString(nr));
+  }
+  e->crank = rank;
+  e->cworld = world;
+  KC_CUDA(e, e->d_comm.ensure(4096));
+  return KC_OK;
+}
+
+int kc_comm_info(kc_engine* e, int* rank, int* world) {
+  if (!e) return KC_EINVAL;
+  if (rank) *rank = e->comm ? e->crank : 0;
+  if (world) *world = e->comm ? e->cworld : 1;
+  return KC_OK;
+}
+
+int kc_set_proteins_dist(kc_engine* e, const uint8_t* residues, const uint64_t* offsets, const uint32_t* class_id,
+                         uint64_t n) {
+  if (!e) return KC_EINVAL;
+  return set_proteins_host(e, residues, offsets, class_id, n, e->comm != nullptr && e->cworld > 1);
+}
+
+// sum of `count` u64 values over the ranks, through the engine's device scratch
+static int allreduce_u64(kc_engine* e, unsigned long long* vals, int count) {
+  if (!e->comm || e->cworld <= 1) return KC_OK;
+  NcclApi& nc = nccl_api();
+  unsigned long long* d = e->d_comm.as<unsigned long long>();
+  KC_CUDA(e, cudaMemcpyAsync(d, vals, (size_t)count * 8, cudaMemcpyHostToDevice, e->stream));
+  const ncclResult_t nr = nc.AllReduce(d, d, (size_t)count, ncclUint64, ncclSum, e->comm, e->stream);
+  if (nr != ncclSuccess) return fail(e, KC_ECUDA, std::string("ncclAllReduce: ") + nc.GetErrorString(nr));
+  KC_CUDA(e, cudaMemcpyAsync(vals, d, (size_t)count * 8, cudaMemcpyDeviceToHost, e->stream));
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  return KC_OK;
+}
+
+int kc_build_index_dist(kc_engine* e, kc_index_stats* stats) {
+  if (!e) return KC_EINVAL;
+  kc_index_stats st{};
+  int rc = kc_build_index_shard(e, (uint32_t)(e->comm ? e->crank : 0), (uint32_t)(e->comm ? e->cworld : 1), &st);
+  // Every rank must take the same branch below (a collective follows): whether the build sharded the index
+  // is a function of the configuration only (kc_config.index_build, subsampling), never of the data.
+  unsigned long long v[8] = {st.n_positions, st.n_incidences, st.n_distinct, st.n_singleton, st.n_repeated, st.nnz,
+                             (unsigned long long)(rc != KC_OK), (unsigned long long)(e->ishards > 1)};
+  if (e->comm && e->cworld > 1) {
+    const bool sharded = e->ishards > 1 || rc != KC_OK;
+    if (!sharded) {  // a whole index on every rank: only the error flag travels
+      for (int i = 0; i < 6; ++i) v[i] = 0;
+    }
+    const kc_index_stats mine = st;
+    const int rc2 = allreduce_u64(e, v, 8);
+    if (rc2) return rc2;
+    if (v[6]) return rc != KC_OK ? rc : fail(e, KC_ECUDA, "kc_build_index_dist failed on another rank");
+    if (sharded) {
+      st.n_positions = v[0], st.n_incidences = v[1], st.n_distinct = v[2];
+      st.n_singleton = v[3], st.n_repeated = v[4], st.nnz = v[5];
+    } else {
+      st = mine;
+    }
+  } else if (rc != KC_OK) {
+    return rc;
+  }
+  if (stats) *stats = st;
+  return KC_OK;
+}
+
+int kc_score_pairs_dist(kc_engine* e, kc_pair_stats* stats) {
+  if (!e) return KC_EINVAL;
+  kc_pair_stats ps{};
+  const int rc = kc_score_pairs_shard(e, (uint32_t)(e->comm ? e->crank : 0), (uint32_t)(e->comm ? e->cworld : 1), &ps);
+  if (e->comm && e->cworld > 1) {
+    unsigned long long v[8] = {ps.n_multi_edges_kept, ps.n_pairs_kept, ps.n_edges_out, ps.sum_count_out, ps.n_rows,
+                               e->ishards > 1 ? ps.n_multi_edges : 0ull, (unsigned long long)(rc != KC_OK),
+                               ps.n_rows_rescored};
+    const int rc2 = allreduce_u64(e, v, 8);
+    if (rc2) return rc2;
+    if (v[6]) return rc != KC_OK ? rc : fail(e, KC_ECUDA, "kc_score_pairs_dist failed on another rank");
+    // (the engine keeps the rank-local numbers: kc_get_edges / kc_gather_edges size by them)
+    ps.n_multi_edges_kept = v[0], ps.n_pairs_kept = v[1], ps.n_edges_out = v[2], ps.sum_count_out = v[3];
+    ps.n_rows = v[4];
+    if (e->ishards > 1) ps.n_multi_edges = v[5];
+    ps.n_rows_rescored = v[7];
+  } else if (rc != KC_OK) {
+    return rc;
+  }
+  if (stats) *stats = ps;
+  return KC_OK;
+}
+
+// The edge lists of all ranks as one list sorted by (a, b).  shared == 0: device-to-device over NVLink into a
+// buffer on rank 0, one D2H copy into rank 0's `out` (the other ranks pass out = NULL).  shared != 0: `out` is
+// ONE host buffer mapped by every rank (one process with a thread per GPU, or POSIX shared memory across
+// processes): every rank copies its own runs straight to their final place over its own PCIe link.
+static int gather_edges_impl(kc_engine* e, kc_edge* out, uint64_t capacity, uint64_t* n_total, int shared) {
+  if (!e) return KC_EINVAL;
+  if (!e->have_pairs) return fail(e, KC_EINVAL, "kc_score_pairs first");
+  KC_CUDA(e, cudaSetDevice(e->dev));
+  const int world = e->comm ? e->cworld : 1, rank = e->comm ? e->crank : 0;
+  const uint64_t ne = e->n_edges;
+  if (world == 1) {
+    if (n_total) *n_total = ne;
+    return kc_get_edges(e, out, capacity);
+  }
+  NcclApi& nc = nccl_api();
+  // every rank's list = the run of its early block, then the run of its late block (both sorted by a, b)
+  unsigned long long n_low = ne;
+  unsigned long long* d = e->d_comm.as<unsigned long long>();  // [0..1]: my runs, [16 .. 16 + 2 world): all
+  if (e->ishards > 1 && ne) {
+    const uint32_t hi_start = e->block_bounds[e->block_bounds.size() - 2 - (size_t)rank];
+    // (class-major pair order: rows are ranks of the pair order, the list is sorted by input index; one run)
+    if (!e->cfg.cross_class_only) {
+      KC_LAUNCH(e, edge_lower_bound_kernel, 1, 32, 0, e->d_edges_sorted.as<uint4>(), ne, hi_start, d);
+      KC_CUDA(e, cudaMemcpyAsync(&n_low, d, 8, cudaMemcpyDeviceToHost, e->stream));
+      KC_CUDA(e, cudaStreamSynchronize(e->stream));
+    }
+  }
+  unsigned long long mine[2] = {n_low, ne - n_low};
+  KC_CUDA(e, cudaMemcpyAsync(d, mine, 16, cudaMemcpyHostToDevice, e->stream));
+  ncclResult_t nr = nc.AllGather(d, d + 16, 2, ncclUint64, e->comm, e->stream);
+  if (nr != ncclSuccess) return fail(e, KC_ECUDA, std::string("ncclAllGather: ") + nc.GetErrorString(nr));
+  std::vector<unsigned long long> runs(2 * (size_t)world);
+  KC_CUDA(e, cudaMemcpyAsync(runs.data(), d + 16, 16 * (size_t)world, cudaMemcpyDeviceToHost, e->stream));
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  // block order: early runs of ranks 0 .. world-1, then late runs of ranks world-1 .. 0
+  std::vector<unsigned long long> place(2 * (size_t)world);
+  unsigned long long total = 0;
+  for (int r = 0; r < world; ++r) {
+    place[2 * r] = total;
+    total += runs[2 * r];
+  }
+  for (int r = world - 1; r >= 0; --r) {
+    place[2 * r + 1] = total;
+    total += runs[2 * r + 1];
+  }
+  if (n_total) *n_total = total;
+  const uint4* my = e->d_edges_sorted.as<uint4>();
+  if (shared) {
+    // (every rank passes the same buffer and sees the same total: they all return here together)
+    if (total > capacity || (total && !out)) return fail(e, KC_EINVAL, "capacity too small");
+    mark(e, EV_D0);
+    if (mine[0]) KC_CUDA(e, cudaMemcpyAsync(out + place[2 * rank], my, mine[0] * 16, cudaMemcpyDeviceToHost, e->stream));
+    if (mine[1])
+      KC_CUDA(e, cudaMemcpyAsync(out + place[2 * rank + 1], my + mine[0], mine[1] * 16, cudaMemcpyDeviceToHost, e->stream));
+    mark(e, EV_D1);
+    KC_CUDA(e, cudaStreamSynchronize(e->stream));
+    unsigned long long flag[1] = {0};  // barrier: every rank's copies have landed
+    if (int rc = allreduce_u64(e, flag, 1)) return rc;
+  } else {
+    if (rank == 0) KC_CUDA(e, e->d_gather.ensure(std::max<unsigned long long>(total, 1) * 16));
+    uint4* g = e->d_gather.as<uint4>();
+    nr = nc.GroupStart();
+    for (int part = 0; part < 2 && nr == ncclSuccess; ++part) {
+      if (rank != 0) {
+        if (mine[part]) nr = nc.Send(my + (part ? mine[0] : 0), mine[part] * 16, ncclUint8, 0, e->comm, e->stream);
+      } else {
+        for (int src = 1; src < world && nr == ncclSuccess; ++src)
+          if (runs[2 * src + part])
+            nr = nc.Recv(g + place[2 * src + part], runs[2 * src + part] * 16, ncclUint8, src, e->comm, e->stream);
+      }
+    }
+    const ncclResult_t nr2 = nc.GroupEnd();
+    if (nr == ncclSuccess) nr = nr2;
+    if (nr != ncclSuccess) return fail(e, KC_ECUDA, std::string("edge gather (ncclSend/ncclRecv): ") + nc.GetErrorString(nr));
+    if (rank == 0) {
+      if (mine[0]) KC_CUDA(e, cudaMemcpyAsync(g + place[0], my, mine[0] * 16, cudaMemcpyDeviceToDevice, e->stream));
+      if (mine[1]) KC_CUDA(e, cudaMemcpyAsync(g + place[1], my + mine[0], mine[1] * 16, cudaMemcpyDeviceToDevice, e->stream));
+      // (checked only now: rank 0 has to take part in the exchange whatever its buffer holds)
+      if (total > capacity || (total && !out)) {
+        cudaStreamSynchronize(e->stream);
+        return fail(e, KC_EINVAL, "capacity too small");
+      }
+      mark(e, EV_D0);
+      if (total) KC_CUDA(e, cudaMemcpyAsync(out, g, total * 16, cudaMemcpyDeviceToHost, e->stream));
+      mark(e, EV_D1);
+    }
+    KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  }
+  // a replicated index scored in contiguous shards is in block order as well; the class-major pair order is
+  // not (blocks of the pair order, list sorted by input index): restore (a, b) on the host
+  if (e->cfg.cross_class_only && (rank == 0) && total) {
+    std::sort(out, out + total, [](const kc_edge& x, const kc_edge& y) { return x.a != y.a ? x.a < y.a : x.b < y.b; });
+  }
+  return KC_OK;
+}
+
+int kc_gather_edges(kc_engine* e, kc_edge* out, uint64_t capacity, uint64_t* n_total) {
+  return gather_edges_impl(e, out, capacity, n_total, 0);
+}
+int kc_gather_edges_shared(kc_engine* e, kc_edge* shared_out, uint64_t capacity, uint64_t* n_total) {
+  return gather_edges_impl(e, shared_out, capacity, n_total, 1);
 }
 
 }  // extern "C"

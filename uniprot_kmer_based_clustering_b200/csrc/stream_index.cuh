@@ -279,16 +279,66 @@ __device__ __forceinline__ void sx_tile_positions(const uint8_t* __restrict__ re
   }
 }
 
+// Sharded build (multi-GPU, owner computes: every rank owns row blocks of the pair triangle and needs the
+// k-mers its own rows hold, with ALL their holders): the records of foreign rows are kept only when their
+// k-mer passes the filter of the rank's own k-mers (kmer_filter_build_kernel; false positives only cost work).
+struct SxKeep {
+  uint32_t* filter;        // null: keep everything.  A Bloom filter blocked to one 32-bit word: two bits per
+  uint32_t word_mask;      // k-mer, one probe (one 32-byte sector) per foreign position
+  RowOwner owner;
+  uint16_t* keepmask;      // 16 positions per entry: the count pass records its decisions, the scatter pass
+                           // reads them back instead of probing again
+  __device__ __forceinline__ static uint32_t word_of(uint32_t kmer, uint32_t word_mask, uint32_t* need) {
+    uint32_t h = kmer * 0x85EBCA6Bu;
+    h ^= h >> 15;
+    h *= 0xC2B2AE35u;
+    h ^= h >> 13;
+    *need = (1u << (h & 31u)) | (1u << ((h >> 5) & 31u));
+    return (h >> 10) & word_mask;
+  }
+  __device__ __forceinline__ bool operator()(uint32_t kmer, uint32_t row) const {
+    if (!filter || owner.mine(row)) return true;
+    uint32_t need;
+    const uint32_t w = word_of(kmer, word_mask, &need);
+    return (__ldg(filter + w) & need) == need;
+  }
+  __device__ __forceinline__ void add(uint32_t kmer) const {
+    uint32_t need;
+    const uint32_t w = word_of(kmer, word_mask, &need);
+    if ((filter[w] & need) != need) atomicOr(&filter[w], need);
+  }
+};
+
 // record slot inside a warp's segment (32 * V records) of the staging buffer: position p = V * lane + j of the
 // blocked phase, read back as p = 32 * j' + lane' by the striped phase; the XOR keeps both free of bank
 // conflicts (8-byte slots: 16 per bank row; V = 8 or 16)
 __device__ __forceinline__ uint32_t sx_swz(uint32_t p) { return p ^ ((p >> 4) & 15u); }
 
+// sharded build: the filter of the k-mers the rank's own rows hold.  Tiles [tile_lo, tile_hi) of the stream.
+template <int K>
+__global__ void __launch_bounds__(kL1Threads, 2)
+    sx_filter_build_kernel(const uint8_t* __restrict__ res, uint32_t R, const uint32_t* __restrict__ soff,
+                           const uint32_t* __restrict__ tile_row, uint32_t tile_lo, uint32_t tile_hi, SxKeep keep) {
+  __shared__ __align__(16) uint8_t s_codes[kSxTile + 64];
+  __shared__ uint8_t s_lut[256];
+  if (threadIdx.x < 256) s_lut[threadIdx.x] = c_residue_lut[threadIdx.x];
+  __syncthreads();
+  for (uint32_t t = tile_lo + blockIdx.x; t < tile_hi; t += gridDim.x) {
+    const unsigned long long t0 = (unsigned long long)t * kSxTile;
+    if (t0 >= R) break;
+    sx_tile_positions<K, kL1V>(res, R, soff, (uint32_t)t0, tile_row[t], tile_row[t + 1u], s_codes, s_lut,
+                               [&](int, uint32_t km, uint32_t row) {
+                                 if (km != kSentinel && keep.owner.mine(row)) keep.add(km);
+                               });
+    __syncthreads();
+  }
+}
+
 // level-1 count: digit histogram of every chunk.  hist[d * g1 + chunk]
 template <int K>
 __global__ void __launch_bounds__(kL1Threads, 2)
     sx_l1_count_kernel(const uint8_t* __restrict__ res, uint32_t R, const uint32_t* __restrict__ soff,
-                       const uint32_t* __restrict__ tile_row, SxPlan plan, uint32_t* __restrict__ hist) {
+                       const uint32_t* __restrict__ tile_row, SxPlan plan, SxKeep keep, uint32_t* __restrict__ hist) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(dyn_smem);  // [D1]
   uint8_t* s_codes = dyn_smem + (size_t)plan.d1() * 4;       // [tile + 64]
@@ -302,10 +352,15 @@ __global__ void __launch_bounds__(kL1Threads, 2)
   for (uint32_t t = 0; t < plan.tiles_per_chunk; ++t) {
     const unsigned long long t0 = (unsigned long long)(tile_lo + t) * kSxTile;
     if (t0 >= R) break;
+    uint32_t kept = 0;
     sx_tile_positions<K, kL1V>(res, R, soff, (uint32_t)t0, tile_row[tile_lo + t], tile_row[tile_lo + t + 1u], s_codes, s_lut,
-                         [&](int, uint32_t km, uint32_t) {
-                           if (km != kSentinel) atomicAdd(&s_hist[sx_hash(km) >> sh], 1u);
+                         [&](int j, uint32_t km, uint32_t row) {
+                           if (km != kSentinel && keep(km, row)) {
+                             atomicAdd(&s_hist[sx_hash(km) >> sh], 1u);
+                             kept |= 1u << j;
+                           }
                          });
+    if (keep.keepmask) keep.keepmask[(size_t)(tile_lo + t) * kL1Threads + tid] = (uint16_t)kept;
     __syncthreads();
   }
   for (uint32_t d = tid; d < D; d += kL1Threads) hist[(size_t)d * plan.g1 + chunk] = s_hist[d];
@@ -315,8 +370,8 @@ __global__ void __launch_bounds__(kL1Threads, 2)
 template <int K>
 __global__ void __launch_bounds__(kL1Threads, 2)
     sx_l1_scatter_kernel(const uint8_t* __restrict__ res, uint32_t R, const uint32_t* __restrict__ soff,
-                         const uint32_t* __restrict__ tile_row, SxPlan plan, const uint32_t* __restrict__ hist_scanned,
-                         uint2* __restrict__ out) {
+                         const uint32_t* __restrict__ tile_row, SxPlan plan, SxKeep keep,
+                         const uint32_t* __restrict__ hist_scanned, uint2* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   const uint32_t D = plan.d1(), sh = 32u - plan.b1;
   uint2* s_buf = reinterpret_cast<uint2*>(dyn_smem);                          // [tile]
@@ -336,18 +391,43 @@ __global__ void __launch_bounds__(kL1Threads, 2)
   for (uint32_t t = 0; t < plan.tiles_per_chunk; ++t) {
     const unsigned long long t0 = (unsigned long long)(tile_lo + t) * kSxTile;
     if (t0 >= R) break;
+    const uint32_t kept = keep.keepmask ? keep.keepmask[(size_t)(tile_lo + t) * kL1Threads + tid] : 0xFFFFu;
     sx_tile_positions<K, kL1V>(res, R, soff, (uint32_t)t0, tile_row[tile_lo + t], tile_row[tile_lo + t + 1u], s_codes, s_lut,
-                         [&](int j, uint32_t km, uint32_t row) { seg[sx_swz(lane * (uint32_t)kL1V + (uint32_t)j)] = make_uint2(km, row); });
+                         [&](int j, uint32_t km, uint32_t row) {
+                           if (!((kept >> j) & 1u)) km = kSentinel;
+                           seg[sx_swz(lane * (uint32_t)kL1V + (uint32_t)j)] = make_uint2(km, row);
+                         });
     __syncthreads();  // the codes live where the rank counters are zeroed next
+    // Sharded build: most records of a tile are dropped (foreign rows whose k-mer is not in the filter).
+    // Compact the warp's segment first (in place, order kept) so that the ranking below only runs the
+    // rounds that hold records; the other builds lose 2 % of the positions (row ends): not worth the pass.
+    uint32_t rounds = kL1V;
+    if (keep.keepmask) {
+      uint32_t cntw = 0;
+#pragma unroll
+      for (int j = 0; j < kL1V; ++j) {
+        const uint2 v = seg[sx_swz((uint32_t)j * 32u + lane)];
+        const uint32_t m = __ballot_sync(kFullMask, v.x != kSentinel);
+        __syncwarp();
+        if (v.x != kSentinel) seg[cntw + __popc(m & lanemask_lt())] = v;
+        cntw += __popc(m);
+        __syncwarp();
+      }
+      rounds = (cntw + 31u) >> 5;
+      // (records beyond cntw in the last round are stale copies: mark them)
+      if (rounds * 32u > cntw && cntw + lane < rounds * 32u) seg[cntw + lane] = make_uint2(kSentinel, 0u);
+      __syncwarp();
+    }
     uint32_t km[kL1V], rw[kL1V], digit[kL1V], pos[kL1V];
 #pragma unroll
     for (int j = 0; j < kL1V; ++j) {
-      const uint2 v = seg[sx_swz((uint32_t)j * 32u + lane)];
+      uint2 v = make_uint2(kSentinel, 0u);
+      if ((uint32_t)j < rounds) v = seg[keep.keepmask ? (uint32_t)j * 32u + lane : sx_swz((uint32_t)j * 32u + lane)];
       km[j] = v.x;
       rw[j] = v.y;
       digit[j] = v.x == kSentinel ? kNoDigit : sx_hash(v.x) >> sh;
     }
-    sx_tile_rank<kL1Threads, kL1V>(digit, pos, plan.b1, kL1V, plan.ballots != 0, s_cnt, s_dstart, s_wsum);
+    sx_tile_rank<kL1Threads, kL1V>(digit, pos, plan.b1, rounds, plan.ballots != 0, s_cnt, s_dstart, s_wsum);
 #pragma unroll
     for (int j = 0; j < kL1V; ++j)
       if (digit[j] != kNoDigit) s_buf[pos[j]] = make_uint2(km[j], rw[j]);
@@ -468,6 +548,8 @@ struct SxBucketArgs {
   uint32_t* huge_list;        // buckets beyond a CTA's shared memory: global-memory path (sx_huge_kernel)
   uint32_t* huge_cnt;
   uint32_t mid_cap;           // records the CTA kernel takes (4096; 512 in the tests)
+  RowOwner owner;             // sharded build: the counters are owned by the rank of a k-mer's FIRST holder,
+                              // the run records and the pair work by the rank of the row (null: all mine)
 };
 // Postings and ids are placed by CAPACITY, with no reservation: bucket b = records [beg, end) writes its
 // postings at col[beg ..) (it has at most end - beg of them) and numbers its repeated k-mers beg / 2 + local
@@ -664,10 +746,10 @@ __global__ void __launch_bounds__(kWbWarps * 32) sx_warp_bucket_kernel(SxBucketA
         __syncwarp();
         if (keep) X[nk + __popc(m & lt)] = v;
         nk += __popc(m);
+        n_kept += keep && A.owner.mine(v.y);
         __syncwarp();
       }
     }
-    n_kept += lane == 0 ? nk : 0u;
     // ---- backward: next k-mer head and next run head (new k-mer or new 64-row bin) behind every record
     uint32_t* meta = reinterpret_cast<uint32_t*>(Y);
     const uint32_t G = (nk + 31u) >> 5;
@@ -689,7 +771,7 @@ __global__ void __launch_bounds__(kWbWarps * 32) sx_warp_bucket_kernel(SxBucketA
         if (in) meta[c] = ge | (gr << 16);
         if (mh) carry_h = c0 + (__ffs(mh) - 1u);
         if (mrh) carry_rh = c0 + (__ffs(mrh) - 1u);
-        n_distinct += head;
+        n_distinct += head && A.owner.mine(v.y);
       }
     }
     __syncwarp();
@@ -720,7 +802,8 @@ __global__ void __launch_bounds__(kWbWarps * 32) sx_warp_bucket_kernel(SxBucketA
       const uint32_t r0 = v.y & ~(kBinRows - 1u);
       size_t region = 0;
       if (rep) region = bin_region(A.rowcap_prefix, r0);
-      const bool leader = rep && rh && gr - c >= 2u;
+      const bool mine = rep && A.owner.mine(v.y);
+      const bool leader = mine && rh && gr - c >= 2u;
       const uint32_t pbin = __shfl_up_sync(kFullMask, bin, 1);
       const bool seghead = rep && (lane == 0 || pbin != bin);
       const uint32_t mseg = __ballot_sync(kFullMask, seghead), mlead = __ballot_sync(kFullMask, leader);
@@ -770,9 +853,11 @@ __global__ void __launch_bounds__(kWbWarps * 32) sx_warp_bucket_kernel(SxBucketA
           A.vocab[id_base + lid] = v.x;
           A.freq[id_base + lid] = f;
           A.selfscore[id_base + lid] = (uint8_t)ss;
-          ++n_rep;
-          nnz_t += f;
-          multi += (unsigned long long)f * (f - 1u) / 2u;
+          if (mine) {  // the first holder's rank owns the k-mer's totals
+            ++n_rep;
+            nnz_t += f;
+            multi += (unsigned long long)f * (f - 1u) / 2u;
+          }
         }
         uint32_t a = gr;
         if (CROSS) {
@@ -785,7 +870,7 @@ __global__ void __launch_bounds__(kWbWarps * 32) sx_warp_bucket_kernel(SxBucketA
           a = lo;
         }
         const uint32_t len = ge - a;
-        work += len;
+        if (mine) work += len;
         const uint2 sf = len == 1u ? make_uint2(X[a].y, kSentinel) : make_uint2(post + (a - c), post + (ge - c));
         ent = make_uint4(row | (ss << 24), id_base + lid, sf.x, sf.y);
       }
@@ -987,6 +1072,7 @@ __global__ void __launch_bounds__(CAP / 8, CAP == 4096 ? 2 : 4) sx_bucket_kernel
       const uint32_t m = __ballot_sync(kFullMask, k1);
       if (lane == 0) s_bsum[(uint32_t)u * WARPS + warp] = __popc(m);
       if (k1) keep |= 1u << u;
+      n_kept += k1 && A.owner.mine(v.y);
       km[u] = v.x;
       rw[u] = __popc(m & lt);  // (the row moves to rw[] below; until then: the offset inside the block)
       pos[u] = v.y;
@@ -1000,7 +1086,6 @@ __global__ void __launch_bounds__(CAP / 8, CAP == 4096 ? 2 : 4) sx_bucket_kernel
       if ((uint32_t)u >= rounds) break;
       if ((keep >> u) & 1u) s_cmp[s_bsum[(uint32_t)u * WARPS + warp] + rw[u]] = make_uint2(km[u], pos[u]);
     }
-    n_kept += __popc(keep);
     __syncthreads();
     // ---- groups: heads, run heads (a new k-mer or a new 64-row bin), repeated k-mers; per block for the scans
     const uint32_t grounds = (nk + THREADS - 1u) / THREADS, gnb = grounds * WARPS;
@@ -1024,7 +1109,7 @@ __global__ void __launch_bounds__(CAP / 8, CAP == 4096 ? 2 : 4) sx_bucket_kernel
         s_bfrh[blk] = mrh ? c0 + (__ffs(mrh) - 1u) : kSentinel;
         s_blh[blk] = mh ? c0 + (31u - __clz(mh)) + 1u : 0u;
       }
-      n_distinct += head;
+      n_distinct += head && A.owner.mine(v.y);
     }
     __syncthreads();
     if (warp == 0) sx_scan_blocks(gnb, s_bsum, s_bfh, s_bfrh, s_blh, &s_total);
@@ -1055,7 +1140,8 @@ __global__ void __launch_bounds__(CAP / 8, CAP == 4096 ? 2 : 4) sx_bucket_kernel
       // the rows' bins: adjacent lanes of one bin share a reservation, issued first (its latency hides behind
       // the rest of the round)
       const uint32_t bin = rep ? v.y >> kBinRowsLog : kSentinel;
-      const bool leader = rep && rh && gr - c >= 2u;
+      const bool mine = rep && A.owner.mine(v.y);
+      const bool leader = mine && rh && gr - c >= 2u;
       const uint32_t pbin = __shfl_up_sync(kFullMask, bin, 1);
       const bool seghead = rep && (lane == 0 || pbin != bin);
       const uint32_t mseg = __ballot_sync(kFullMask, seghead), mlead = __ballot_sync(kFullMask, leader);
@@ -1080,9 +1166,11 @@ __global__ void __launch_bounds__(CAP / 8, CAP == 4096 ? 2 : 4) sx_bucket_kernel
           A.vocab[id_base + lid] = v.x;
           A.freq[id_base + lid] = f;
           A.selfscore[id_base + lid] = (uint8_t)ss;
-          ++n_rep;
-          nnz_t += f;
-          multi += (unsigned long long)f * (f - 1u) / 2u;
+          if (mine) {
+            ++n_rep;
+            nnz_t += f;
+            multi += (unsigned long long)f * (f - 1u) / 2u;
+          }
         }
         // the suffix starts behind the row's bin-run (its pairs go to the tiles); cross-class mode: and not
         // before the first holder of a later class block
@@ -1097,7 +1185,7 @@ __global__ void __launch_bounds__(CAP / 8, CAP == 4096 ? 2 : 4) sx_bucket_kernel
           a = lo;
         }
         const uint32_t len = ge - a;
-        work += len;
+        if (mine) work += len;
         const uint2 sf = len == 1u ? make_uint2(s_cmp[a].y, kSentinel) : make_uint2(post + (a - c), post + (ge - c));
         ent = make_uint4(row | (ss << 24), id_base + lid, sf.x, sf.y);
         if (leader)
@@ -1224,12 +1312,12 @@ __global__ void __launch_bounds__(kHugeThreads) sx_huge_kernel(SxBucketArgs A) {
       const uint32_t ex = sx_block_scan<kHugeThreads>(keep ? 1u : 0u, s_wsum, &total);
       const uint32_t carry = s_carry[0];
       if (keep) Y[carry + ex] = v;
+      n_kept += keep && A.owner.mine(v.y);
       __syncthreads();
       if (tid == 0) s_carry[0] = carry + total;
       __syncthreads();
     }
     const uint32_t nk = s_carry[0];
-    n_kept += tid == 0 ? nk : 0u;
     __threadfence_block();
     __syncthreads();
     // ---- 3. backward: next head after every compacted position -> NX[c]; totals of the repeated groups
@@ -1304,7 +1392,8 @@ __global__ void __launch_bounds__(kHugeThreads) sx_huge_kernel(SxBucketArgs A) {
       // (a tile holds at most 512 records: the packed halves cannot overflow)
       const uint32_t ex = sx_block_scan<kHugeThreads>(sv, s_wsum, &total);
       const uint32_t post0 = s_carry[2], id0 = s_carry[3];
-      if (c < nk && head) ++n_distinct;
+      const bool mine = c < nk && A.owner.mine(v.y);
+      if (c < nk && head && mine) ++n_distinct;
       if (rep) {
         const uint32_t post = col_base + post0 + (ex & 0xFFFFu);
         const uint32_t gid = id_base + id0 + (ex >> 16) - (head ? 0u : 1u);
@@ -1315,12 +1404,15 @@ __global__ void __launch_bounds__(kHugeThreads) sx_huge_kernel(SxBucketArgs A) {
           A.vocab[gid] = v.x;
           A.freq[gid] = f;
           A.selfscore[gid] = (uint8_t)ss;
-          ++n_rep;
-          nnz_t += f;
-          multi += (unsigned long long)f * (f - 1u) / 2u;
+          if (mine) {
+            ++n_rep;
+            nnz_t += f;
+            multi += (unsigned long long)f * (f - 1u) / 2u;
+          }
         }
-        const SxEmit em = sx_emit(rows, c, ge, head, v.y, ss, gid, post, CROSS ? A.first_after : nullptr);
-        work += em.len;
+        SxEmit em = sx_emit(rows, c, ge, head, v.y, ss, gid, post, CROSS ? A.first_after : nullptr);
+        if (!mine) em.rmask = 0;
+        if (mine) work += em.len;
         const uint32_t bin = v.y >> kBinRowsLog;
         const uint32_t at = atomicAdd(&A.bin_cursor[bin], 1u + (em.rmask ? 1u : 0u));
         uint4* d = A.entries + bin_region(A.rowcap_prefix, v.y & ~(kBinRows - 1u)) + at;

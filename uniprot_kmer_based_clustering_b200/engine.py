@@ -289,6 +289,46 @@ class Engine:
         self._check(self._L.kc_bitset_pair_counts(self._h, _ptr(rows), rows.size, _ptr(out)))
         return out
 
+    # ---- multi-GPU (NCCL below the C ABI, csrc/dist.cuh) --------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128 bytes made by rank 0 (ncclGetUniqueId); the host distributes them to every rank"""
+        buf = C.create_string_buffer(128)
+        rc = _lib.lib().kc_comm_unique_id(buf)
+        if rc != 0:
+            raise KcError(rc, "kc_comm_unique_id: NCCL is not available")
+        return buf.raw
+
+    def comm_init(self, comm_id: bytes, rank: int, world: int):
+        self._check(self._L.kc_comm_init(self._h, C.c_char_p(comm_id), rank, world))
+        self.rank, self.world = rank, world
+
+    def set_proteins_dist_ptr(self, residues_ptr: int, offsets_ptr: int, class_ptr: int, n: int):
+        """host pointers, the same arrays on every rank: 1 / world is uploaded, the rest all-gathered"""
+        self.n = int(n)
+        self._check(self._L.kc_set_proteins_dist(self._h, C.c_void_p(residues_ptr), C.c_void_p(offsets_ptr),
+                                                 C.c_void_p(class_ptr), n))
+
+    def build_index_dist(self) -> dict:
+        st = IndexStats()
+        self._check(self._L.kc_build_index_dist(self._h, C.byref(st)))
+        self.index_stats = stats_dict(st)
+        return self.index_stats
+
+    def score_pairs_dist(self) -> dict:
+        st = PairStats()
+        self._check(self._L.kc_score_pairs_dist(self._h, C.byref(st)))
+        self.pair_stats = stats_dict(st)  # whole-job counters
+        return self.pair_stats
+
+    def gather_edges_into(self, out_ptr: int, capacity: int, shared: bool = False) -> int:
+        """the edge lists of all ranks as one sorted list: into rank 0's buffer, or (shared) into one host
+        buffer every rank maps; returns the total number of edges"""
+        n = C.c_uint64()
+        fn = self._L.kc_gather_edges_shared if shared else self._L.kc_gather_edges
+        self._check(fn(self._h, C.c_void_p(out_ptr) if out_ptr else None, capacity, C.byref(n)))
+        return int(n.value)
+
     # ---- timing ---------------------------------------------------------------------
     def timings(self) -> dict:
         t = Timings()
