@@ -35,6 +35,19 @@ uint64_t kc_fasta_n_missing_class(const kc_fasta* f);
 const char* kc_fasta_class_name(const kc_fasta* f, uint32_t class_id);
 const char* kc_fasta_id(const kc_fasta* f, uint64_t protein);
 
+/* DIAMOND hand-off of align_and_output_pairs (src/graph/mod.rs:195-319) without the `diamond` subprocesses:
+ * creates <dir>/fasta_files and <dir>/db_files (:202-220), writes for edge i the two one-record files
+ * fasta_files/{i}_{accession}.fasta with ">{id}\n{sequence}" (:253-261 reference = edges[i].a, :273-280 query =
+ * edges[i].b; accession = id up to the first '|'), and starts <dir>/blastp_output.tsv with the reference's
+ * header line (:304).  A DIAMOND step (makedb on the first file, blastp --outfmt 6 qseqid qlen sseqid slen
+ * qstart qend sstart send length pident evalue bitscore on the second, :266-293) appends its rows to that
+ * file.  The edge key is the index in the emitted list (the reference's is the racy index in its edge vector).
+ * Needs kc_b200.h for kc_edge. */
+struct kc_edge;
+int kc_write_handoff(const kc_fasta* f, const struct kc_edge* edges, uint64_t n_edges, const char* dir,
+                     uint64_t* n_files_out);
+const char* kc_blastp_header(void);
+
 /* Host tree clustering: the reference's src/tree.rs (Tree::new + add_protein for every protein in
  * input order, src/tree.rs:519-536) over the engine's per-protein id lists
  * (kc_get_protein_ids: row_offsets[n+1], ids ascending within a row, ids < n_ids).

@@ -148,6 +148,10 @@ def test_arg_reference_api_flow(arg_set, golden, capsys):
         assert np.array_equal(kms, np.intersect1d(np.intersect1d(a, b), v))
         assert np.array_equal(ke.get_kmers(), np.searchsorted(v, kms))
         assert ke.get_proteins_ids_and_sequences()[1][0] == arg_set.ids[2838]
+        # `pub edges` after combine_edges (src/graph/mod.rs:32): every pair that shares a k-mer
+        allp = graph.all_pair_edges()
+        assert allp.size == 4350628 and int(allp["count"].sum()) == 5300233
+        assert np.array_equal(edges_abc(allp[allp["count"] > 10]), edges_abc(edges))
 
 
 # ---------------------------------------------------------------- randomised + edge cases

@@ -293,3 +293,20 @@ def test_position_sampler_is_a_permutation_and_matches_the_oracle():
     for p in range(ps.n):
         exp = [fk[fo[p] + L.kc_sample_position(0xB2005EED, p, int(npos[p]), x)] for x in range(int(npos[p]) // 10)]
         assert sk[so[p]:so[p + 1]].tolist() == exp
+
+
+def test_diamond_handoff_files(tmp_path):
+    """kc_write_handoff: the per-pair FASTA files and the blastp TSV header of align_and_output_pairs
+    (src/graph/mod.rs:253-261,273-280,304-317); host only"""
+    from uniprot_kmer_based_clustering_b200.engine import EDGE_DTYPE, write_handoff
+    ps = kc.ProteinSet.from_fasta_bytes(b">A1|F|U|beta_lactam|bla extra\nMKHKNQA\n>B2|F|U|polymyxin|arnA\nMKH\nKNQATT\n"
+                                        b">C3|F|U|beta_lactam|x\nAAAA\n")
+    edges = np.array([(0, 1, 11, 0), (1, 2, 12, 0)], dtype=EDGE_DTYPE)
+    assert write_handoff(ps, edges, str(tmp_path)) == 4
+    assert (tmp_path / "fasta_files" / "0_A1.fasta").read_text() == ">A1|F|U|beta_lactam|bla\nMKHKNQA"
+    assert (tmp_path / "fasta_files" / "0_B2.fasta").read_text() == ">B2|F|U|polymyxin|arnA\nMKHKNQATT"
+    assert (tmp_path / "fasta_files" / "1_C3.fasta").read_text() == ">C3|F|U|beta_lactam|x\nAAAA"
+    assert (tmp_path / "db_files").is_dir()
+    hdr = (tmp_path / "blastp_output.tsv").read_text()
+    assert hdr.startswith("query id\tquery length\tsubject id\t") and hdr.endswith("evalue\tbit score\n")
+    assert hdr.count("\t") == 11

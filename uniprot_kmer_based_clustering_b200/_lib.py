@@ -70,6 +70,7 @@ EXPORTED = [
     "kc_fasta_parse_file", "kc_fasta_parse_buffer", "kc_fasta_free", "kc_fasta_n_proteins",
     "kc_fasta_n_residues", "kc_fasta_residues", "kc_fasta_offsets", "kc_fasta_class_ids",
     "kc_fasta_n_classes", "kc_fasta_n_missing_class", "kc_fasta_class_name", "kc_fasta_id",
+    "kc_write_handoff", "kc_blastp_header",
     "kc_tree_build", "kc_tree_free", "kc_tree_n_merges", "kc_tree_n_no_common", "kc_tree_serialize",
     "kc_tree_clusters",
 ]
@@ -167,6 +168,8 @@ def lib():
         "kc_fasta_n_missing_class": (u64, [vp]),
         "kc_fasta_class_name": (cp, [vp, u32]),
         "kc_fasta_id": (cp, [vp, u64]),
+        "kc_write_handoff": (i32, [vp, vp, u64, cp, P(u64)]),
+        "kc_blastp_header": (cp, []),
         "kc_tree_build": (i32, [vp, vp, u64, u32, P(vp)]),
         "kc_tree_free": (None, [vp]),
         "kc_tree_n_merges": (u64, [vp]),

@@ -40,6 +40,7 @@ int main(int argc, char** argv) {
   cfg.cross_class_only = 1;
   cfg.want_blosum = 0;
   bool list_kmers = false, want_tree = false;
+  const char* handoff_dir = nullptr;
   for (int i = 3; i < argc; ++i) {
     const std::string a = argv[i];
     if (a == "--k" && i + 1 < argc) cfg.k = std::atoi(argv[++i]);
@@ -49,6 +50,7 @@ int main(int argc, char** argv) {
     else if (a == "--blosum") cfg.want_blosum = 1;
     else if (a == "--kmers") list_kmers = true;
     else if (a == "--tree") want_tree = true;
+    else if (a == "--handoff" && i + 1 < argc) handoff_dir = argv[++i];  // fasta_files/, db_files/, blastp_output.tsv
     else if (a == "--sample-every" && i + 1 < argc) cfg.sample_every = (uint32_t)std::atoi(argv[++i]);
     else if (a == "--seed" && i + 1 < argc) cfg.sample_seed = std::strtoull(argv[++i], nullptr, 0);
     else if (a == "--index" && i + 1 < argc) {  // stream | bucket | table (kc_config.index_build)
@@ -78,6 +80,11 @@ int main(int argc, char** argv) {
     return 101;
   }
   const uint64_t n = kc_fasta_n_proteins(fa);
+  if (kc_fasta_n_missing_class(fa)) {  // the reference panics on such a record (src/protein.rs:137)
+    std::fprintf(stderr, "%llu record ids have fewer than 4 '|'-separated fields: no AMR class (src/protein.rs:135-138)\n",
+                 (unsigned long long)kc_fasta_n_missing_class(fa));
+    return 101;
+  }
   rc = kc_set_proteins(e, kc_fasta_residues(fa), kc_fasta_offsets(fa), kc_fasta_class_ids(fa), n);
   if (rc) die("kc_set_proteins", e, rc);
   kc_index_stats is{};
@@ -119,6 +126,13 @@ int main(int argc, char** argv) {
       for (size_t j = 0; j < kms.size(); ++j) std::printf(j ? ",%u" : "%u", kms[j]);
     }
     std::printf("\n");
+  }
+  if (handoff_dir) {  // what align_and_output_pairs leaves for DIAMOND (src/graph/mod.rs:253-261,273-280,304-317)
+    uint64_t n_files = 0;
+    rc = kc_write_handoff(fa, edges.data(), edges.size(), handoff_dir, &n_files);
+    if (rc) die("kc_write_handoff", e, rc);
+    std::fprintf(stderr, "Wrote %llu fasta files and blastp_output.tsv (header) under %s\n",
+                 (unsigned long long)n_files, handoff_dir);
   }
   if (want_tree) {
     // src/tree.rs (host): Tree::new + add_protein in input order over the per-protein id lists

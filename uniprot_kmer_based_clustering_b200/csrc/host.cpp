@@ -7,6 +7,8 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cerrno>
+#include <cstdio>
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -211,5 +213,53 @@ const char* kc_fasta_class_name(const kc_fasta* f, uint32_t c) {
   return c < f->class_names.size() ? f->class_names[c].c_str() : "";
 }
 const char* kc_fasta_id(const kc_fasta* f, uint64_t p) { return p < f->n ? f->ids[p].c_str() : ""; }
+
+// ---- DIAMOND hand-off (src/graph/mod.rs:202-220 directories, :253-261 and :273-280 the two one-record
+// FASTA files of a kept pair, :304-317 blastp_output.tsv).  The `diamond` subprocesses themselves
+// (:266-270, :283-293) are out of scope; what is written here is exactly what they would be started on.
+static bool write_file(const std::string& path, const std::string& text) {
+  FILE* fh = std::fopen(path.c_str(), "wb");
+  if (!fh) return false;
+  const bool ok = std::fwrite(text.data(), 1, text.size(), fh) == text.size();
+  return std::fclose(fh) == 0 && ok;
+}
+
+const char* kc_blastp_header(void) {
+  return "query id\tquery length\tsubject id\tsubject length\tquery alignment start\tquery alignment end\t"
+         "subject alignment start\tsubject alignment end\talignment length\tpercent identity\tevalue\tbit score\n";
+}
+
+int kc_write_handoff(const kc_fasta* f, const kc_edge* edges, uint64_t n_edges, const char* dir,
+                     uint64_t* n_files_out) {
+  if (!f || (n_edges && !edges) || !dir) return KC_EINVAL;
+  const std::string base = std::string(dir);
+  // (the reference removes and re-creates both directories, src/graph/mod.rs:202-220)
+  for (const char* sub : {"/fasta_files", "/db_files"}) {
+    const std::string d = base + sub;
+    if (mkdir(d.c_str(), 0777) != 0 && errno != EEXIST) return KC_EINVAL;
+  }
+  uint64_t n_files = 0;
+  auto accession = [](const std::string& id) {  // split_once('|').0 (the reference panics without a '|')
+    const size_t bar = id.find('|');
+    return bar == std::string::npos ? id : id.substr(0, bar);
+  };
+  for (uint64_t i = 0; i < n_edges; ++i) {
+    const uint32_t ends[2] = {edges[i].a, edges[i].b};  // [reference, query] = vertices_key order
+    for (int side = 0; side < 2; ++side) {
+      const uint64_t p = ends[side];
+      if (p >= f->n) return KC_EINVAL;
+      const std::string id = f->ids[p];
+      const std::string seq(reinterpret_cast<const char*>(f->residues + f->offsets[p]),
+                            (size_t)(f->offsets[p + 1] - f->offsets[p]));
+      // format!("fasta_files/{}_{}.fasta", edge_key, accession); format!(">{}\n{}", id, seq)
+      const std::string name = base + "/fasta_files/" + std::to_string(i) + "_" + accession(id) + ".fasta";
+      if (!write_file(name, ">" + id + "\n" + seq)) return KC_EINVAL;
+      ++n_files;
+    }
+  }
+  if (!write_file(base + "/blastp_output.tsv", kc_blastp_header())) return KC_EINVAL;
+  if (n_files_out) *n_files_out = n_files;
+  return KC_OK;
+}
 
 }  // extern "C"

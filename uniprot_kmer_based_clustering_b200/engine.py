@@ -139,6 +139,7 @@ class Engine:
             raise KcError(rc, "kc_create: no usable CUDA device (there is no CPU fallback)"
                           if rc == _lib.KC_ENODEVICE else "kc_create")
         self.k, self.device = k, device
+        self.threshold, self.cross_class_only, self.want_blosum = threshold, bool(cross_class_only), bool(want_blosum)
         self.n = 0
         self.index_stats: dict = {}
         self.pair_stats: dict = {}
@@ -339,6 +340,26 @@ class Engine:
 
     def reset_timings(self):
         self._check(self._L.kc_reset_timings(self._h))
+
+
+def write_handoff(ps: ProteinSet, edges: np.ndarray, directory: str) -> int:
+    """The files align_and_output_pairs leaves for DIAMOND (kc_write_handoff, include/kc_host.h); returns the
+    number of FASTA files written.  Host only."""
+    L = _lib.lib()
+    data = ps.to_fasta_bytes()
+    h = C.c_void_p()
+    rc = L.kc_fasta_parse_buffer(data, len(data), 1, C.byref(h))
+    if rc != 0:
+        raise KcError(rc, "cannot re-stage the protein set")
+    try:
+        edges = np.ascontiguousarray(edges, dtype=EDGE_DTYPE)
+        n_files = C.c_uint64()
+        rc = L.kc_write_handoff(h, _ptr(edges), edges.size, directory.encode(), C.byref(n_files))
+        if rc != 0:
+            raise KcError(rc, f"kc_write_handoff({directory!r})")
+        return int(n_files.value)
+    finally:
+        L.kc_fasta_free(h)
 
 
 def cluster(ps: ProteinSet, k: int = 5, threshold: int = 10, cross_class_only: bool = True,

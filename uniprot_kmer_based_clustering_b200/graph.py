@@ -89,13 +89,33 @@ class Graph:
         """pairs over the threshold (the only edges align_and_output_pairs looks at)"""
         return [KmerEdge(self, i) for i in range(len(self._edges))]
 
-    def align_and_output_pairs(self, thread_count: int = 1):
-        """src/graph/mod.rs:195-251 without the DIAMOND subprocesses: logs every surviving
-        pair like :250-251 and returns the edge array."""
+    def all_pair_edges(self) -> np.ndarray:
+        """`pub edges` as the reference holds it after combine_edges (src/graph/mod.rs:32): EVERY pair that
+        shares at least one k-mer (4 350 628 on the ARG set), not only the pairs over the threshold, as an
+        (a, b, count, blosum) array sorted by (a, b).  Scored by a second engine with threshold 0 on the same
+        device (the threshold is fixed when an engine is created); the pairs over the threshold are the
+        subset `count > threshold`."""
+        from .engine import Engine
+        eng = self.protein_list.engine
+        cross = bool(eng.cross_class_only)
+        with Engine(eng.k, device=eng.device, threshold=0, cross_class_only=cross, want_blosum=eng.want_blosum) as e0:
+            e0.set_protein_set(self.protein_list.set)
+            e0.build_index()
+            e0.score_pairs()
+            return e0.get_edges()
+
+    def align_and_output_pairs(self, thread_count: int = 1, handoff_dir: str | None = None):
+        """src/graph/mod.rs:195-319 without the DIAMOND subprocesses: logs every surviving pair like :250-251
+        and returns the edge array; with `handoff_dir`, also writes what the reference leaves for DIAMOND
+        (fasta_files/{i}_{accession}.fasta per endpoint, db_files/, blastp_output.tsv with the header line,
+        :202-220,253-261,273-280,304-317: kc_write_handoff)."""
         ids = self.protein_list.set.ids
         for e in self._edges:
             print(f"Cross-checking:\n\treference protein:{ids[e['a']]}\n\tquery protein:{ids[e['b']]}"
                   f"\n\tkmers in common:{e['count']}", file=self._log)
+        if handoff_dir is not None:
+            from .engine import write_handoff
+            write_handoff(self.protein_list.set, self._edges, handoff_dir)
         return self._edges
 
     @property
