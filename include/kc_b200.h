@@ -233,10 +233,16 @@ int kc_gather_edges_shared(kc_engine* e, kc_edge* shared_out, uint64_t capacity,
 int kc_get_timings(kc_engine* e, kc_timings* out);
 int kc_reset_timings(kc_engine* e);
 
-/* Dense presence-bitset path (north star item 3; used by the host tree, src/tree.rs:185-216):
- * counts[i*n_rows+j] = |K_rows[i] ∩ K_rows[j]| over the repeated-k-mer vocabulary, computed
- * with AND+popcount on per-protein bitsets.  rows = protein indices (host), counts = host. */
+/* Dense presence-bitset path (north star item 3): counts[i*n_rows+j] = |K_rows[i] ∩ K_rows[j]| over the
+ * repeated-k-mer vocabulary, computed with AND + popcount on per-protein bitsets (the operation of
+ * intersect_bitarrays, src/tree.rs:21-45, and of the |c_i ∩ c_j| loop at src/tree.rs:185-216, as a dense
+ * all-pairs tile).  A secondary path: the sparse pair stage does ~10^3 times less work on these sets (DESIGN.md
+ * §6); the host tree (csrc/tree.cpp) keeps its own sorted-list intersections.  rows = protein indices (host),
+ * counts = host. */
 int kc_bitset_pair_counts(kc_engine* e, const uint32_t* rows, uint32_t n_rows, uint32_t* counts_out);
+/* AND + POPC + ADD issue rate of this GPU in 10^9 operations per second (register-only chains): the measured
+ * denominator of the bitset path's roofline (profiles/r2_bitset.md). */
+int kc_popc_microbench(kc_engine* e, uint32_t iters, double* gpopc_per_s);
 
 #ifdef __cplusplus
 }

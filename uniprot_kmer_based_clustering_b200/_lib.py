@@ -64,7 +64,7 @@ EXPORTED = [
     "kc_set_proteins", "kc_set_proteins_device", "kc_set_proteins_device_residues", "kc_extract_kmers", "kc_build_index", "kc_build_index_shard", "kc_index_shard_info", "kc_index_shard_blocks", "kc_index_flavour",
     "kc_get_distinct_kmers", "kc_get_vocab", "kc_get_protein_ids", "kc_lookup_kmers", "kc_get_pair_index", "kc_score_pairs",
     "kc_score_pairs_shard", "kc_get_edges", "kc_get_edges_device", "kc_get_edge_kmers", "kc_get_timings", "kc_reset_timings",
-    "kc_bitset_pair_counts",
+    "kc_bitset_pair_counts", "kc_popc_microbench",
     "kc_comm_unique_id", "kc_comm_init", "kc_comm_info", "kc_set_proteins_dist", "kc_build_index_dist",
     "kc_score_pairs_dist", "kc_gather_edges", "kc_gather_edges_shared",
     "kc_fasta_parse_file", "kc_fasta_parse_buffer", "kc_fasta_free", "kc_fasta_n_proteins",
@@ -148,6 +148,7 @@ def lib():
         "kc_get_timings": (i32, [vp, P(Timings)]),
         "kc_reset_timings": (i32, [vp]),
         "kc_bitset_pair_counts": (i32, [vp, vp, u32, vp]),
+        "kc_popc_microbench": (i32, [vp, u32, P(C.c_double)]),
         "kc_comm_unique_id": (i32, [vp]),
         "kc_comm_init": (i32, [vp, vp, i32, i32]),
         "kc_comm_info": (i32, [vp, P(i32), P(i32)]),

@@ -146,6 +146,7 @@ struct kc_engine {
   DBuf d_sres_own, d_soff, d_rec_a, d_rec_b, d_h1, d_h2, d_huge_list, d_mid_list, d_tile_row, d_ss3, d_keepmask;
   std::vector<uint32_t> h_soff;
   uint32_t sx_huge_last = 0, sx_mid_last = 0, sx_max_bucket = 0;
+  double bitset_word_ops = 0;  // AND+POPC+ADD word operations of the last kc_bitset_pair_counts
   uint64_t index_records = 0;  // records the last streaming build partitioned (a sharded build: what it kept)
   uint32_t rank_of(uint64_t p) const { return cfg.cross_class_only ? h_rank[p] : (uint32_t)p; }
   const uint8_t* sres() const { return cfg.cross_class_only ? d_sres_own.as<uint8_t>() : d_res.as<uint8_t>(); }
@@ -2263,9 +2264,9 @@ int kc_bitset_pair_counts(kc_engine* e, const uint32_t* rows, uint32_t n_rows, u
   KC_LAUNCH(e, bitset_fill_kernel, blocks_for(n_rows, 8, e->num_sm * 8), 256, 0, d_rows.as<uint32_t>(), n_rows,
             e->d_pstart.as<uint32_t>(), e->canon_rowlen(), e->d_pk.as<uint32_t>(), words,
             d_bits.as<uint32_t>());
-  const uint32_t tiles = (n_rows + kBitTile - 1) / kBitTile;
-  KC_LAUNCH(e, bitset_pairs_kernel, dim3(tiles, tiles), kBitTile * 32, 0, d_bits.as<uint32_t>(), n_rows, words,
-            d_counts.as<uint32_t>());
+  KC_LAUNCH(e, bitset_pairs_kernel, dim3((n_rows + kBitCols - 1) / kBitCols, (n_rows + kBitRows - 1) / kBitRows),
+            kBitWarps * 32, 0, d_bits.as<uint32_t>(), n_rows, words, d_counts.as<uint32_t>());
+  e->bitset_word_ops = (double)n_rows * n_rows * words;
   cudaError_t rc = cudaMemcpyAsync(counts_out, d_counts.p, (size_t)n_rows * n_rows * 4, cudaMemcpyDeviceToHost,
                                    e->stream);
   if (rc == cudaSuccess) rc = cudaStreamSynchronize(e->stream);
@@ -2273,6 +2274,28 @@ int kc_bitset_pair_counts(kc_engine* e, const uint32_t* rows, uint32_t n_rows, u
   d_bits.release();
   d_counts.release();
   KC_CUDA(e, rc);
+  return KC_OK;
+}
+
+// POPC issue-rate microbenchmark: the measured denominator of the bitset path's roofline.
+int kc_popc_microbench(kc_engine* e, uint32_t iters, double* gpopc_per_s) {
+  if (!e || !gpopc_per_s || iters == 0) return KC_EINVAL;
+  KC_CUDA(e, cudaSetDevice(e->dev));
+  KC_CUDA(e, e->d_tmp.ensure(64));
+  const uint32_t grid = (uint32_t)e->num_sm * 8u;
+  cudaEvent_t a, b;
+  KC_CUDA(e, cudaEventCreate(&a));
+  KC_CUDA(e, cudaEventCreate(&b));
+  KC_LAUNCH(e, popc_microbench_kernel, grid, 256, 0, iters / 8 + 1, 1u, e->d_tmp.as<uint32_t>());  // warm-up
+  cudaEventRecord(a, e->stream);
+  KC_LAUNCH(e, popc_microbench_kernel, grid, 256, 0, iters, 2u, e->d_tmp.as<uint32_t>());
+  cudaEventRecord(b, e->stream);
+  KC_CUDA(e, cudaStreamSynchronize(e->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *gpopc_per_s = ms > 0.f ? (double)grid * 256.0 * 8.0 * iters / (ms * 1e-3) / 1e9 : 0.0;
   return KC_OK;
 }
 

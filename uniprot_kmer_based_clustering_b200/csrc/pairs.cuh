@@ -1601,48 +1601,79 @@ __global__ void bitset_fill_kernel(const uint32_t* __restrict__ rows, uint32_t n
   }
 }
 
-constexpr int kBitTile = 8;  // 8x8 pairs per CTA, one warp per row of the tile
-__global__ void __launch_bounds__(kBitTile * 32)
+// Dense tile of the pair matrix from presence bitsets: counts[i][j] = popc(bits_i & bits_j) summed over the
+// vocabulary words.  INT / POPC-issue bound by construction: every warp keeps a 4 x 8 register tile of
+// accumulators (its 4 rows against the CTA's 8 columns), so one 32-word slab costs 4 global loads and
+// 8 shared-memory loads per lane against 32 x (LOP3.AND + POPC + IADD).  CTA = 8 warps = 32 rows x 8 columns.
+constexpr int kBitCols = 8;          // columns per CTA (staged in shared memory)
+constexpr int kBitRowsPerWarp = 4;   // rows per warp (registers)
+constexpr int kBitWarps = 8;
+constexpr int kBitRows = kBitWarps * kBitRowsPerWarp;  // rows per CTA
+__global__ void __launch_bounds__(kBitWarps * 32)
     bitset_pairs_kernel(const uint32_t* __restrict__ bits, uint32_t n_rows, uint32_t words,
                         uint32_t* __restrict__ counts) {
-  // tile (ti, tj): warp w owns row ti*8+w and accumulates against the 8 rows of tj, the
-  // 8 column bitsets being staged chunk by chunk in shared memory
-  __shared__ uint32_t s_col[kBitTile][256];
+  __shared__ uint32_t s_col[kBitCols][256];
   const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
-  const uint32_t ti = blockIdx.y, tj = blockIdx.x;
-  if (tj < ti) return;
-  const uint32_t i = ti * kBitTile + w;
-  uint32_t acc[kBitTile];
+  const uint32_t i0 = blockIdx.y * kBitRows + w * kBitRowsPerWarp, j0 = blockIdx.x * kBitCols;
+  uint32_t acc[kBitRowsPerWarp][kBitCols];
 #pragma unroll
-  for (int q = 0; q < kBitTile; ++q) acc[q] = 0;
+  for (int r = 0; r < kBitRowsPerWarp; ++r)
+#pragma unroll
+    for (int q = 0; q < kBitCols; ++q) acc[r][q] = 0;
   for (uint32_t w0 = 0; w0 < words; w0 += 256) {
     __syncthreads();
-    for (uint32_t x = threadIdx.x; x < kBitTile * 256; x += kBitTile * 32) {
-      const uint32_t q = x >> 8, ww = w0 + (x & 255u), j = tj * kBitTile + q;
+    for (uint32_t x = threadIdx.x; x < kBitCols * 256; x += kBitWarps * 32) {
+      const uint32_t q = x >> 8, ww = w0 + (x & 255u), j = j0 + q;
       s_col[q][x & 255u] = (j < n_rows && ww < words) ? bits[(size_t)j * words + ww] : 0u;
     }
     __syncthreads();
-    if (i < n_rows) {
+#pragma unroll 2
+    for (int s = 0; s < 8; ++s) {
+      const uint32_t ww = w0 + s * 32 + lane;
+      uint32_t a[kBitRowsPerWarp];
 #pragma unroll
-      for (int s = 0; s < 8; ++s) {
-        const uint32_t ww = w0 + s * 32 + lane;
-        const uint32_t a = ww < words ? bits[(size_t)i * words + ww] : 0u;
+      for (int r = 0; r < kBitRowsPerWarp; ++r)
+        a[r] = (i0 + r < n_rows && ww < words) ? __ldg(bits + (size_t)(i0 + r) * words + ww) : 0u;
 #pragma unroll
-        for (int q = 0; q < kBitTile; ++q) acc[q] += __popc(a & s_col[q][s * 32 + lane]);
+      for (int q = 0; q < kBitCols; ++q) {
+        const uint32_t bq = s_col[q][s * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < kBitRowsPerWarp; ++r) acc[r][q] += __popc(a[r] & bq);
       }
     }
   }
-  if (i < n_rows) {
 #pragma unroll
-    for (int q = 0; q < kBitTile; ++q) {
-      const uint32_t v = warp_sum(acc[q]);
-      const uint32_t j = tj * kBitTile + q;
-      if (lane == 0 && j < n_rows) {
-        counts[(size_t)i * n_rows + j] = v;
-        counts[(size_t)j * n_rows + i] = v;
-      }
+  for (int r = 0; r < kBitRowsPerWarp; ++r)
+#pragma unroll
+    for (int q = 0; q < kBitCols; ++q) {
+      const uint32_t v = warp_sum(acc[r][q]);
+      if (lane == 0 && i0 + r < n_rows && j0 + q < n_rows) counts[(size_t)(i0 + r) * n_rows + j0 + q] = v;
+    }
+}
+
+// POPC issue-rate microbenchmark (the roofline denominator of the bitset path): every thread runs
+// `iters` x 8 independent AND + POPC + ADD chains on registers; nothing touches memory until the end.
+__global__ void __launch_bounds__(256) popc_microbench_kernel(uint32_t iters, uint32_t seed, uint32_t* __restrict__ out) {
+  uint32_t x[8], acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    x[q] = seed * 2654435761u + threadIdx.x * 40503u + q * 0x9E3779B9u + blockIdx.x;
+    acc[q] = 0;
+  }
+  const uint32_t m = seed ^ 0x5A5A5A5Au;
+  for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint32_t p;
+      asm volatile("popc.b32 %0, %1;" : "=r"(p) : "r"(x[q] & (m + it)));
+      acc[q] += p;
+      x[q] += p;  // (keeps the chain data dependent: the compiler cannot hoist or fold it)
     }
   }
+  uint32_t s = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s += acc[q];
+  if (s == 0xFFFFFFFFu) out[0] = s;  // never true in practice: keeps the loop alive
 }
 
 }  // namespace kc

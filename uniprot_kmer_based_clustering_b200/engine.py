@@ -290,6 +290,12 @@ class Engine:
         self._check(self._L.kc_bitset_pair_counts(self._h, _ptr(rows), rows.size, _ptr(out)))
         return out
 
+    def popc_microbench(self, iters: int = 4096) -> float:
+        """AND + POPC + ADD issue rate, 10^9 operations per second (kc_popc_microbench)"""
+        v = C.c_double()
+        self._check(self._L.kc_popc_microbench(self._h, iters, C.byref(v)))
+        return float(v.value)
+
     # ---- multi-GPU (NCCL below the C ABI, csrc/dist.cuh) --------------------------------
     @staticmethod
     def comm_unique_id() -> bytes:
