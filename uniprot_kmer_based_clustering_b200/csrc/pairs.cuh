@@ -176,7 +176,12 @@ __global__ void __launch_bounds__(256)
         // the tiles; what is left are mostly distinct partners, so U is a good estimate and a row
         // beyond the cap goes straight to its safely sized kernel instead of failing here first.
         const uint32_t lower = max(rowinl[r], rowmaxlen[r]);
-        if ((U <= kMainCap || (!exact_main && lower <= kMainCap / 2)) && rowlen[r] < (1u << kScoreShift) &&
+        // exact_main is off when most multi-edges are left to the hash kernels (related proteins are NOT
+        // neighbours in the input, the bin-local tiles see little: the family partners come through here with
+        // their multiplicity and U overshoots); a row sent to the unscored packed kernels costs a list
+        // intersection per emitted edge afterwards (8.5 ms on the shuffled 1 M set, profiles/r2_history.md).
+        if ((U <= kMainCap || (!exact_main && lower <= kMainCap / 2)) &&
+            rowlen[r] < (1u << kScoreShift) &&
             P != 0xFFFFFFFFu) {
           bin = kBinMain;
           rowlogh[r] = (uint8_t)kMainLogHMax;
