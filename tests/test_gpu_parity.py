@@ -682,3 +682,33 @@ def test_full_size_synthetic_goldens(name, index_flavour):
         assert pst[key] == val, key
     assert hashlib.sha256(np.ascontiguousarray(edges).tobytes()).hexdigest() == g["edges_sha256"]
     assert int(edges["blosum"].astype(np.int64).sum()) == g["sum_blosum"]
+
+
+def test_cli_two_gpus_matches_one(tmp_path, arg_fasta_bytes, golden, index_flavour):
+    """`kmer_cluster <fasta> <threads> --gpus 2`: one engine and one NCCL rank per GPU inside the C library (host
+    threads, kc_comm_* / kc_*_dist / kc_gather_edges_shared); same counters and the same TSV as one GPU.  The ARG
+    set's hot k-mers overflow the sharded bucket build, so this also covers its streaming fallback."""
+    import os
+    import subprocess
+    if index_flavour != "stream":
+        pytest.skip("one flavour is enough: the CLI picks the build itself")
+    if kc.lib().kc_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from uniprot_kmer_based_clustering_b200._lib import _PKG
+    exe = os.path.join(_PKG, "bin", "kmer_cluster")
+    fa = tmp_path / "arg.fasta"
+    fa.write_bytes(arg_fasta_bytes)
+    outs = []
+    for gpus in ("1", "2"):
+        r = subprocess.run([exe, str(fa), "4", "--gpus", gpus], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r)
+    g = golden["k5"]
+    for r in outs:
+        assert "Number of 5mers found in at least two proteins: 231253" in r.stderr
+        assert "Number of total edges: 258621291" in r.stderr
+        assert "Number of edges now: 5300233" in r.stderr
+        assert "Number of edges now: 4350628" in r.stderr
+        assert r.stderr.count("Cross-checking:") == 465
+    tsv = ["\n".join(ln for ln in r.stdout.splitlines() if not ln.startswith("NCCL version")) for r in outs]
+    assert tsv[0] == tsv[1]  # (NCCL announces its version on stdout)

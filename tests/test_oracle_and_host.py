@@ -310,3 +310,24 @@ def test_diamond_handoff_files(tmp_path):
     hdr = (tmp_path / "blastp_output.tsv").read_text()
     assert hdr.startswith("query id\tquery length\tsubject id\t") and hdr.endswith("evalue\tbit score\n")
     assert hdr.count("\t") == 11
+
+
+def test_rust_ffi_crate_binds_declared_symbols():
+    """ffi/src/kc_sys.rs (shipped as source: no Rust toolchain in the image) must only bind entry points the
+    headers declare, with the ABI version the library reports"""
+    rs = open(os.path.join(ROOT, "ffi", "src", "kc_sys.rs")).read()
+    bound = set(re.findall(r"pub fn (kc_[a-z0-9_]+)\s*\(", rs))
+    declared = set()
+    for hdr in ("kc_b200.h", "kc_host.h"):
+        text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", hdr)).read(), flags=re.S)
+        declared |= set(re.findall(r"\b(kc_[a-z0-9_]+)\s*\(", text))
+    assert bound and bound <= declared, sorted(bound - declared)
+    for must in ("kc_create", "kc_set_proteins", "kc_build_index", "kc_score_pairs", "kc_get_edges", "kc_comm_init",
+                 "kc_build_index_dist", "kc_gather_edges", "kc_write_handoff"):
+        assert must in bound, must
+    assert f"KC_ABI_VERSION: c_int = {kc.lib().kc_abi_version()};" in rs
+    # the Rust kc_config mirrors the C struct field for field
+    c_fields = re.findall(r"^\s+(?:u?int\d+_t)\s+(\w+);", re.search(r"typedef struct kc_config \{(.*?)\} kc_config;", open(
+        os.path.join(ROOT, "include", "kc_b200.h")).read(), flags=re.S).group(1), flags=re.M)
+    r_fields = re.findall(r"pub (\w+): [iu]\d+,", re.search(r"pub struct kc_config \{(.*?)\n\}", rs, flags=re.S).group(1))
+    assert c_fields == r_fields, (c_fields, r_fields)

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/kc_b200.h"
@@ -40,6 +41,7 @@ int main(int argc, char** argv) {
   cfg.cross_class_only = 1;
   cfg.want_blosum = 0;
   bool list_kmers = false, want_tree = false;
+  int n_gpus = 1;
   const char* handoff_dir = nullptr;
   for (int i = 3; i < argc; ++i) {
     const std::string a = argv[i];
@@ -47,6 +49,7 @@ int main(int argc, char** argv) {
     else if (a == "--threshold" && i + 1 < argc) cfg.threshold = (uint32_t)std::atoi(argv[++i]);
     else if (a == "--device" && i + 1 < argc) cfg.device = std::atoi(argv[++i]);
     else if (a == "--all-classes") cfg.cross_class_only = 0;
+    else if (a == "--gpus" && i + 1 < argc) n_gpus = std::atoi(argv[++i]);  // one engine (one NCCL rank) per GPU
     else if (a == "--blosum") cfg.want_blosum = 1;
     else if (a == "--kmers") list_kmers = true;
     else if (a == "--tree") want_tree = true;
@@ -73,31 +76,69 @@ int main(int argc, char** argv) {
     return 101;
   }
   std::fprintf(stderr, "We created Protein structs\n");
-  kc_engine* e = nullptr;
-  rc = kc_create(&cfg, &e);
-  if (rc != KC_OK) {
-    std::fprintf(stderr, "kc_create failed (%d): no usable CUDA device or bad option\n", rc);
+  if (n_gpus < 1 || n_gpus > kc_device_count()) {
+    std::fprintf(stderr, "--gpus %d: %d CUDA devices are visible\n", n_gpus, kc_device_count());
     return 101;
   }
+  if (n_gpus > 1 && (list_kmers || want_tree)) {
+    std::fprintf(stderr, "--kmers and --tree need the whole index on one GPU (--gpus 1)\n");
+    return 101;
+  }
+  // one engine per GPU; with more than one, a host thread per engine and NCCL below the C ABI (kc_comm_*)
+  std::vector<kc_engine*> engines((size_t)n_gpus, nullptr);
+  for (int g = 0; g < n_gpus; ++g) {
+    kc_config c = cfg;
+    c.device = n_gpus > 1 ? g : cfg.device;
+    rc = kc_create(&c, &engines[(size_t)g]);
+    if (rc != KC_OK) {
+      std::fprintf(stderr, "kc_create failed (%d): no usable CUDA device or bad option\n", rc);
+      return 101;
+    }
+  }
+  kc_engine* e = engines[0];
   const uint64_t n = kc_fasta_n_proteins(fa);
   if (kc_fasta_n_missing_class(fa)) {  // the reference panics on such a record (src/protein.rs:137)
     std::fprintf(stderr, "%llu record ids have fewer than 4 '|'-separated fields: no AMR class (src/protein.rs:135-138)\n",
                  (unsigned long long)kc_fasta_n_missing_class(fa));
     return 101;
   }
-  rc = kc_set_proteins(e, kc_fasta_residues(fa), kc_fasta_offsets(fa), kc_fasta_class_ids(fa), n);
-  if (rc) die("kc_set_proteins", e, rc);
   kc_index_stats is{};
-  rc = kc_build_index(e, &is);
-  if (rc) die("kc_build_index", e, rc);
+  kc_pair_stats ps{};
+  double secs = 0.0;
+  std::vector<int> rcs((size_t)n_gpus, 0);
+  uint8_t comm_id[KC_COMM_ID_BYTES] = {0};
+  if (n_gpus > 1 && kc_comm_unique_id(comm_id) != KC_OK) {
+    std::fprintf(stderr, "NCCL is not available (libnccl.so.2)\n");
+    return 101;
+  }
+  auto per_rank = [&](int g) {
+    kc_engine* eg = engines[(size_t)g];
+    int r = KC_OK;
+    if (n_gpus > 1) r = kc_comm_init(eg, comm_id, g, n_gpus);
+    if (!r) r = kc_set_proteins_dist(eg, kc_fasta_residues(fa), kc_fasta_offsets(fa), kc_fasta_class_ids(fa), n);
+    kc_index_stats ig{};
+    if (!r) r = kc_build_index_dist(eg, &ig);
+    const auto t0 = std::chrono::steady_clock::now();
+    kc_pair_stats pg{};
+    if (!r) r = kc_score_pairs_dist(eg, &pg);
+    if (g == 0) {
+      is = ig;
+      ps = pg;
+      secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    rcs[(size_t)g] = r;
+  };
+  {
+    std::vector<std::thread> pool;
+    for (int g = 1; g < n_gpus; ++g) pool.emplace_back(per_rank, g);
+    per_rank(0);
+    for (auto& th : pool) th.join();
+  }
+  for (int g = 0; g < n_gpus; ++g)
+    if (rcs[(size_t)g]) die("index / pair stage", engines[(size_t)g], rcs[(size_t)g]);
   std::fprintf(stderr, "We combined k-mers\nWe found unique k-mers\nWe made unique hash\nWe can make a graph\n");
   std::fprintf(stderr, "Number of %dmers found in at least two proteins: %llu\n", cfg.k,
                (unsigned long long)is.n_repeated);
-  auto t0 = std::chrono::steady_clock::now();
-  kc_pair_stats ps{};
-  rc = kc_score_pairs(e, &ps);
-  if (rc) die("kc_score_pairs", e, rc);
-  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   std::fprintf(stderr, "Number of total edges: %llu\n", (unsigned long long)ps.n_multi_edges);
   if (cfg.cross_class_only) {
     std::fprintf(stderr, "Remove edges without diverging AMR labels\n");
@@ -107,8 +148,21 @@ int main(int argc, char** argv) {
   std::fprintf(stderr, "Number of edges now: %llu\n", (unsigned long long)ps.n_pairs_kept);
   std::fprintf(stderr, "Graph construction and refinement time: %g seconds\n", secs);
   std::vector<kc_edge> edges(ps.n_edges_out);
-  rc = kc_get_edges(e, edges.data(), edges.size());
-  if (rc) die("kc_get_edges", e, rc);
+  if (n_gpus == 1) {
+    rc = kc_get_edges(e, edges.data(), edges.size());
+    if (rc) die("kc_get_edges", e, rc);
+  } else {  // every rank copies its own sorted runs to their place in the one list
+    auto gather = [&](int g) {
+      uint64_t total = 0;
+      rcs[(size_t)g] = kc_gather_edges_shared(engines[(size_t)g], edges.data(), edges.size(), &total);
+    };
+    std::vector<std::thread> pool;
+    for (int g = 1; g < n_gpus; ++g) pool.emplace_back(gather, g);
+    gather(0);
+    for (auto& th : pool) th.join();
+    for (int g = 0; g < n_gpus; ++g)
+      if (rcs[(size_t)g]) die("kc_gather_edges_shared", engines[(size_t)g], rcs[(size_t)g]);
+  }
   std::printf("a\tb\tid_a\tid_b\tkmers_in_common%s%s\n", cfg.want_blosum ? "\tblosum" : "",
               list_kmers ? "\tkmers" : "");
   std::vector<uint32_t> kms;
@@ -153,7 +207,7 @@ int main(int argc, char** argv) {
     for (uint64_t p = 0; p < n; ++p) std::printf("#%s\t%u\n", kc_fasta_id(fa, p), cluster[p]);
     kc_tree_free(tree);
   }
-  kc_destroy(e);
+  for (kc_engine* eg : engines) kc_destroy(eg);
   kc_fasta_free(fa);
   return 0;
 }
