@@ -44,11 +44,17 @@ WORKLOADS = {
     "synth_100k_k5": (100_000, "A", 5, 0xB2000003, False),    # configs[2]
     "synth_20k_k5": (20_000, "A", 5, 0xB2000003, False),      # quick check
     "synth_1m_skew_k7": (1_000_000, "B", 7, 0xB2000005, False),  # one GPU's quarter of configs[4] (skewed lengths 50-2000)
+    "synth_250k_skew_k7": (250_000, "B", 7, 0xB2000005, False),  # the golden prefix of configs[4]
+    "synth_4m_skew_k7": (4_000_000, "B", 7, 0xB2000005, False),  # BASELINE.json configs[4], k = 7 (8 GPUs)
+    "synth_4m_skew_k5": (4_000_000, "B", 5, 0xB2000005, False),  # configs[4], k = 5: ~1.6e12 multi-edges
+    "synth_250k_skew_k5": (250_000, "B", 5, 0xB2000005, False),  # the k = 5 regime at a size that fits a short run
 }
 THRESHOLD = 10
 # cpu_baseline leg of the GPU arm: a bounded sample (the default run has to finish within minutes).
 # The reference arm (--impl reference) runs the FULL workload per step: same config as the GPU arm.
-CPU_SAMPLE = {"synth_1m_k7": 250_000, "synth_100k_k5": 50_000, "synth_20k_k5": 20_000, "synth_1m_skew_k7": 200_000}
+CPU_SAMPLE = {"synth_1m_k7": 250_000, "synth_100k_k5": 50_000, "synth_20k_k5": 20_000, "synth_1m_skew_k7": 200_000,
+              "synth_250k_skew_k7": 100_000, "synth_4m_skew_k7": 200_000, "synth_4m_skew_k5": 20_000,
+              "synth_250k_skew_k5": 20_000}
 
 
 def golden_for(workload: str, n: int):
@@ -385,7 +391,7 @@ def main():
         # (cross-class mode) the row layout; every edge crosses PCIe once
         h2d = int(h_res.numel() + world * (h_off.numel() * 8 + (16 * n if cross else 0)))
         d2h = int(n_e_total * 16 + world * 512)
-        stream_index = eng.index_flavour() == 1
+        flavour = eng.index_flavour()
         line = {
             "metric": "protein_pairs_scored_per_s", "value": pairs_total / (dev_ms * 1e-3), "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": dev_ms,
@@ -411,7 +417,8 @@ def main():
                          "algorithmic_bytes": algo_bytes},
             "roofline_index": {"bound": "hbm",
                                "kernel": "K1-K5 (sx_l1/l2 partition kernels, sx_warp_bucket_kernel, rows_finalize_kernel)"
-                               if stream_index else "K1-K5 (extract, census, ids, postings, suffix ranges)",
+                               if flavour == 1 else "K1-K5 (extract, census, ids, postings, suffix ranges)" if flavour == 0
+                               else "K1-K5 (extract_scatter, bucket_build, rows_finalize kernels: the sharded build)",
                                "achieved": idx_achieved, "peak": peak, "unit": "GB/s", "frac": idx_achieved / peak,
                                "algorithmic_bytes": idx_bytes},
             "e2e": {"value": pairs_total / e2e_s, "unit": "pairs/s", "ms_per_step": e2e_s * 1e3,

@@ -1992,7 +1992,7 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
               ds->shard_rows, dense_cols, count_bits, e->d_rowbin.as<uint8_t>(), e->d_rowsafe.as<uint8_t>(),
               e->d_rowlogh.as<uint8_t>(), ds->bin_counts, e->owner(),
               // trust the partner bound only when the tiles took most of the multi-edges (input with locality)
-              e->bucketed && (double)e->work_total <= 0.6 * (double)e->multi_total);
+              !e->bucketed ? 0 : ((double)e->work_total <= 0.6 * (double)e->multi_total ? 1 : 2));
     EdgeSink sink{e->d_edges.as<uint4>(), &ds->edge_cursor, e->edge_cap, e->cfg.threshold,
                   e->cfg.want_blosum ? kUnscored : 0u};
     mark(e, EV_PK0);

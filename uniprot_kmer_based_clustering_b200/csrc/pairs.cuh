@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256)
                          const uint32_t* __restrict__ first_after, uint32_t n, const uint32_t* __restrict__ bounds,
                          uint32_t dense_single_pass_cols, uint32_t count_bits, uint8_t* __restrict__ rowbin,
                          uint8_t* __restrict__ rowsafe, uint8_t* __restrict__ rowlogh,
-                         uint32_t* __restrict__ bin_counts, RowOwner owner, bool exact_main) {
+                         uint32_t* __restrict__ bin_counts, RowOwner owner, int exact_main) {
   __shared__ uint32_t s_cnt[16];
   if (threadIdx.x < 16) s_cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -180,7 +180,11 @@ __global__ void __launch_bounds__(256)
         // neighbours in the input, the bin-local tiles see little: the family partners come through here with
         // their multiplicity and U overshoots); a row sent to the unscored packed kernels costs a list
         // intersection per emitted edge afterwards (8.5 ms on the shuffled 1 M set, profiles/r2_history.md).
-        if ((U <= kMainCap || (!exact_main && lower <= kMainCap / 2)) &&
+        // exact_main: 0 = the table build (no tiles: always optimistic), 1 = trust U, 2 = little went to the
+        // tiles: optimistic for rows whose U is within a few times the cap (rows with thousands of multi-edges,
+        // the k = 5 regime, really have that many partners and go straight to their safely sized kernel).
+        const bool optimistic = exact_main == 0 || (exact_main == 2 && U <= 4u * kMainCap);
+        if ((U <= kMainCap || (optimistic && lower <= kMainCap / 2)) &&
             rowlen[r] < (1u << kScoreShift) &&
             P != 0xFFFFFFFFu) {
           bin = kBinMain;
