@@ -973,20 +973,21 @@ static int build_index_stream(kc_engine* e, uint32_t shard, uint32_t n_shards, k
     const uint32_t* trow = e->d_tile_row.as<uint32_t>();
     const size_t smem_c = (size_t)D1 * 4 + kSxTile + 64 + 256;
     const size_t smem_s = sx_scatter_smem(D1, kL1Threads / 32);
+#define KC_L1(KK, SH)                                                                                              \
+  do {                                                                                                            \
+    KC_CUDA(e, cudaFuncSetAttribute((sx_l1_count_kernel<KK, SH>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));   \
+    KC_CUDA(e, cudaFuncSetAttribute((sx_l1_scatter_kernel<KK, SH>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)); \
+    KC_LAUNCH(e, (sx_l1_count_kernel<KK, SH>), plan.g1, kL1Threads, smem_c, res, (uint32_t)R, soff, trow, plan, keep, h1);      \
+    e->launches += exclusive_scan(U32In{h1}, SxExclOutTail{h1, n_h1}, n_h1, e->scan, e->stream);                 \
+    KC_LAUNCH(e, (sx_l1_scatter_kernel<KK, SH>), plan.g1, kL1Threads, smem_s, res, (uint32_t)R, soff, trow, plan, keep, h1,     \
+              rec_a);                                                                                             \
+  } while (0)
     if (k5) {
-      KC_CUDA(e, cudaFuncSetAttribute(sx_l1_count_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-      KC_CUDA(e, cudaFuncSetAttribute(sx_l1_scatter_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-      KC_LAUNCH(e, sx_l1_count_kernel<5>, plan.g1, kL1Threads, smem_c, res, (uint32_t)R, soff, trow, plan, keep, h1);
+      if (n_shards > 1) KC_L1(5, true); else KC_L1(5, false);
     } else {
-      KC_CUDA(e, cudaFuncSetAttribute(sx_l1_count_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-      KC_CUDA(e, cudaFuncSetAttribute(sx_l1_scatter_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-      KC_LAUNCH(e, sx_l1_count_kernel<7>, plan.g1, kL1Threads, smem_c, res, (uint32_t)R, soff, trow, plan, keep, h1);
+      if (n_shards > 1) KC_L1(7, true); else KC_L1(7, false);
     }
-    e->launches += exclusive_scan(U32In{h1}, SxExclOutTail{h1, n_h1}, n_h1, e->scan, e->stream);
-    if (k5)
-      KC_LAUNCH(e, sx_l1_scatter_kernel<5>, plan.g1, kL1Threads, smem_s, res, (uint32_t)R, soff, trow, plan, keep, h1, rec_a);
-    else
-      KC_LAUNCH(e, sx_l1_scatter_kernel<7>, plan.g1, kL1Threads, smem_s, res, (uint32_t)R, soff, trow, plan, keep, h1, rec_a);
+#undef KC_L1
   }
   // level 2: rec_a -> rec_b, every level-1 partition by the next b2 hash bits
   {

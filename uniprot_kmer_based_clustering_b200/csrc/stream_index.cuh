@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kL1Threads, 2)
 }
 
 // level-1 count: digit histogram of every chunk.  hist[d * g1 + chunk]
-template <int K>
+template <int K, bool SHARDED>
 __global__ void __launch_bounds__(kL1Threads, 2)
     sx_l1_count_kernel(const uint8_t* __restrict__ res, uint32_t R, const uint32_t* __restrict__ soff,
                        const uint32_t* __restrict__ tile_row, SxPlan plan, SxKeep keep, uint32_t* __restrict__ hist) {
@@ -355,19 +355,19 @@ __global__ void __launch_bounds__(kL1Threads, 2)
     uint32_t kept = 0;
     sx_tile_positions<K, kL1V>(res, R, soff, (uint32_t)t0, tile_row[tile_lo + t], tile_row[tile_lo + t + 1u], s_codes, s_lut,
                          [&](int j, uint32_t km, uint32_t row) {
-                           if (km != kSentinel && keep(km, row)) {
+                           if (km != kSentinel && (!SHARDED || keep(km, row))) {
                              atomicAdd(&s_hist[sx_hash(km) >> sh], 1u);
-                             kept |= 1u << j;
+                             if (SHARDED) kept |= 1u << j;
                            }
                          });
-    if (keep.keepmask) keep.keepmask[(size_t)(tile_lo + t) * kL1Threads + tid] = (uint16_t)kept;
+    if (SHARDED) keep.keepmask[(size_t)(tile_lo + t) * kL1Threads + tid] = (uint16_t)kept;
     __syncthreads();
   }
   for (uint32_t d = tid; d < D; d += kL1Threads) hist[(size_t)d * plan.g1 + chunk] = s_hist[d];
 }
 
 // level-1 scatter: hist_scanned[d * g1 + chunk] = where this chunk's records of digit d start in `out`
-template <int K>
+template <int K, bool SHARDED>
 __global__ void __launch_bounds__(kL1Threads, 2)
     sx_l1_scatter_kernel(const uint8_t* __restrict__ res, uint32_t R, const uint32_t* __restrict__ soff,
                          const uint32_t* __restrict__ tile_row, SxPlan plan, SxKeep keep,
@@ -391,10 +391,10 @@ __global__ void __launch_bounds__(kL1Threads, 2)
   for (uint32_t t = 0; t < plan.tiles_per_chunk; ++t) {
     const unsigned long long t0 = (unsigned long long)(tile_lo + t) * kSxTile;
     if (t0 >= R) break;
-    const uint32_t kept = keep.keepmask ? keep.keepmask[(size_t)(tile_lo + t) * kL1Threads + tid] : 0xFFFFu;
+    const uint32_t kept = SHARDED ? keep.keepmask[(size_t)(tile_lo + t) * kL1Threads + tid] : 0xFFFFu;
     sx_tile_positions<K, kL1V>(res, R, soff, (uint32_t)t0, tile_row[tile_lo + t], tile_row[tile_lo + t + 1u], s_codes, s_lut,
                          [&](int j, uint32_t km, uint32_t row) {
-                           if (!((kept >> j) & 1u)) km = kSentinel;
+                           if (SHARDED && !((kept >> j) & 1u)) km = kSentinel;
                            seg[sx_swz(lane * (uint32_t)kL1V + (uint32_t)j)] = make_uint2(km, row);
                          });
     __syncthreads();  // the codes live where the rank counters are zeroed next
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kL1Threads, 2)
     // Compact the warp's segment first (in place, order kept) so that the ranking below only runs the
     // rounds that hold records; the other builds lose 2 % of the positions (row ends): not worth the pass.
     uint32_t rounds = kL1V;
-    if (keep.keepmask) {
+    if (SHARDED) {
       uint32_t cntw = 0;
 #pragma unroll
       for (int j = 0; j < kL1V; ++j) {
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(kL1Threads, 2)
 #pragma unroll
     for (int j = 0; j < kL1V; ++j) {
       uint2 v = make_uint2(kSentinel, 0u);
-      if ((uint32_t)j < rounds) v = seg[keep.keepmask ? (uint32_t)j * 32u + lane : sx_swz((uint32_t)j * 32u + lane)];
+      if (!SHARDED || (uint32_t)j < rounds) v = seg[SHARDED ? (uint32_t)j * 32u + lane : sx_swz((uint32_t)j * 32u + lane)];
       km[j] = v.x;
       rw[j] = v.y;
       digit[j] = v.x == kSentinel ? kNoDigit : sx_hash(v.x) >> sh;
