@@ -1293,17 +1293,16 @@ static int set_proteins_host(kc_engine* e, const uint8_t* residues, const uint64
   // must stay valid until the next kc_build_index* / kc_extract_kmers returns: the copies are asynchronous)
   if (int rcw = wait_upload(e)) return rcw;
   e->have_proteins = e->have_index = e->have_pairs = false;
-  // validate before any state is committed or any copy is queued
+  // What sizes the copies is checked first (they are queued at once and run while the host does the rest);
+  // the engine is only marked as holding proteins after the whole offsets array has been validated below.
   if (offsets[0] != 0) return fail(e, KC_EINVAL, "offsets[0] must be 0");
-  for (uint64_t p = 0; p < n; ++p)
-    if (offsets[p + 1] < offsets[p]) return fail(e, KC_EINVAL, "offsets must be non-decreasing");
   const uint64_t R = offsets[n];
   if (R && !residues) return fail(e, KC_EINVAL, "null residues");
   if (R >= 0xFFFF0000ull) return fail(e, KC_ETOOLARGE, "more than 2^32-65536 residues");
   if (n >= 0xFFFFFFF0ull) return fail(e, KC_ETOOLARGE, "too many proteins");
   e->n = n;
-  e->h_off.assign(offsets, offsets + n + 1);
-  e->h_cls.assign(class_id, class_id + n);
+  e->h_off.resize(n + 1);
+  e->h_cls.resize(n);
   mark(e, EV_H2D0);
   size_t padded = padded_res_bytes(R);
   const uint64_t world = dist ? (uint64_t)e->cworld : 1;
@@ -1339,7 +1338,7 @@ static int set_proteins_host(kc_engine* e, const uint8_t* residues, const uint64
       e->chunk_row[c] = std::max(e->chunk_row[c], e->chunk_row[c - 1]);
     }
     for (int c = 0; c < C; ++c) {
-      const uint64_t b0 = offsets[e->chunk_row[c]], b1 = offsets[e->chunk_row[c + 1]];
+      const uint64_t b0 = std::min<uint64_t>(R, offsets[e->chunk_row[c]]), b1 = std::min<uint64_t>(R, offsets[e->chunk_row[c + 1]]);
       if (b1 > b0)
         KC_CUDA(e, cudaMemcpyAsync(e->d_res.as<uint8_t>() + b0, residues + b0, b1 - b0, cudaMemcpyHostToDevice,
                                    e->copy_stream));
@@ -1350,6 +1349,23 @@ static int set_proteins_host(kc_engine* e, const uint8_t* residues, const uint64
   } else {
     if (R) KC_CUDA(e, cudaMemcpyAsync(e->d_res.p, residues, R, cudaMemcpyHostToDevice, e->stream));
     KC_CUDA(e, cudaMemsetAsync(e->d_res.as<uint8_t>() + R, 0, padded - R, e->stream));
+  }
+  {  // the host's own copy of offsets / classes + the monotonicity check, in parallel slabs (the upload is running)
+    const unsigned n_slabs = n >= (1u << 16) ? 4u : 1u;
+    std::vector<int> bad(n_slabs, 0);
+    auto slab = [&](unsigned t) {
+      const uint64_t lo = n * t / n_slabs, hi = n * (t + 1) / n_slabs;
+      std::memcpy(e->h_off.data() + lo, offsets + lo, (hi - lo + (t + 1 == n_slabs ? 1 : 0)) * 8);
+      if (hi > lo) std::memcpy(e->h_cls.data() + lo, class_id + lo, (hi - lo) * 4);
+      for (uint64_t p = lo; p < hi; ++p)
+        if (offsets[p + 1] < offsets[p]) bad[t] = 1;
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < n_slabs; ++t) pool.emplace_back(slab, t);
+    slab(0);
+    for (auto& th : pool) th.join();
+    for (int b : bad)
+      if (b) return fail(e, KC_EINVAL, "offsets must be non-decreasing");  // (have_proteins stays false)
   }
   int rc = stage_layout(e);
   if (e->n_chunks) {
