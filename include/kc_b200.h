@@ -127,11 +127,15 @@ int kc_set_stream(kc_engine* e, void* cuda_stream);
 /* Stage the residue stream: replaces the Vec<Protein> built at src/main.rs:62-72.
  * residues = ASCII bytes of all sequences back to back (no separators, no line breaks),
  * offsets[n+1] delimit proteins, class_id[n] = dictionary id of the AMR class string
- * (Protein::get_amr_class, src/protein.rs:135-138).  Host pointers; copied to HBM. */
+ * (Protein::get_amr_class, src/protein.rs:135-138).  Host pointers; copied to HBM ASYNCHRONOUSLY (the upload overlaps
+ * the host-side staging and, for page-locked buffers, the first kernels): the three buffers must stay valid and
+ * unchanged until the next kc_build_index* / kc_extract_kmers on this engine has returned.  offsets[0] must be 0 and
+ * the offsets non-decreasing (KC_EINVAL otherwise; a failed call leaves the engine without proteins). */
 int kc_set_proteins(kc_engine* e, const uint8_t* residues, const uint64_t* offsets,
                     const uint32_t* class_id, uint64_t n_proteins);
-/* Same, inputs already resident in HBM on the engine's device (borrowed until the next
- * kc_set_proteins* / kc_destroy; the engine does not modify them). */
+/* Same, inputs already resident in HBM on the engine's device.  The engine COPIES them (device to device, on its
+ * stream; the offsets and classes also come back to the host for the row layout): the caller's buffers may be reused
+ * once the next kc_build_index* / kc_extract_kmers has returned. */
 int kc_set_proteins_device(kc_engine* e, const uint8_t* d_residues, const uint64_t* d_offsets,
                            const uint32_t* d_class_id, uint64_t n_proteins);
 
@@ -156,8 +160,11 @@ int kc_build_index(kc_engine* e, kc_index_stats* stats);
  * their holders, so every rank builds its part from the whole residue stream with no exchange
  * (owner computes): the stats are totals over the k-mers whose first holder is in the block and
  * add up to kc_build_index's over the shards.  Follow with kc_score_pairs_shard(shard, n_shards).
- * The readback / lookup entry points need a whole index.  With the universe-table build (k = 5)
- * every rank builds the whole index and the stats are the whole-set numbers on every rank. */
+ * The readback / lookup entry points need a whole index.  Which build runs (kc_config.index_build = AUTO): round 1's
+ * bucket build, and the streaming build of the SAME shard when one of its buckets overflows; both cut the same row
+ * blocks, so ranks may differ in the build they ran.  Only the table build (KC_INDEX_TABLE, or subsampling) builds the
+ * whole index on every rank: its stats are the whole-set numbers everywhere and kc_index_shard_info reports
+ * n_shards = 1 (kc_score_pairs_shard then cuts work-balanced contiguous row blocks). */
 int kc_build_index_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_index_stats* stats);
 /* What the engine's current index covers: info[0..3] = {shard, n_shards, n_blocks, rows owned};
  * n_shards == 1 means a whole index (stats are whole-set numbers). */

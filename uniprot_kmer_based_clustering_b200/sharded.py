@@ -1,11 +1,12 @@
-"""Multi-GPU host logic: one process per GPU, `torch.distributed` (NCCL over NVLink on the
-GPU box, gloo in the CPU tests) for the plumbing.
+"""Multi-GPU host-side helpers in Python: the mirror of the engine's row-block cut (`zigzag_blocks`,
+`shard_bounds`), edge-list merging and `torch.distributed` reductions of the per-rank counters.
 
-The pair triangle S = A*A^T is cut into `world` contiguous row blocks of equal estimated work
-(`kc_score_pairs_shard`); every rank scores its own block with no data-path collective, then
-the sorted per-rank edge lists are gathered to rank 0 and merged.  The index
-is either built by every rank (replicated, no communication) or built by rank 0 and broadcast
-(`broadcast_index`, device buffers exposed by `kc_index_export`).
+The product path for several GPUs is BELOW the C ABI (csrc/dist.cuh: `kc_comm_init`, `kc_set_proteins_dist`,
+`kc_build_index_dist`, `kc_score_pairs_dist`, `kc_gather_edges[_shared]`; `Engine.comm_init` etc.), NCCL included;
+`bench.py` and the CLI use that.  What is left here serves the CPU tests (gloo, world size 2-3, a CPU checker standing
+in for the engine: `tests/test_sharded_gloo.py`), callers that already run `torch.distributed` and want the counters
+reduced there (`reduce_index_stats`, `reduce_pair_stats`), and `gather_edges*`, the torch-level edge gathers of
+round 1 (kept for comparison; the library's gather replaced them in `bench.py`).
 """
 from __future__ import annotations
 
