@@ -2009,7 +2009,8 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
               ds->shard_rows, dense_cols, count_bits, e->d_rowbin.as<uint8_t>(), e->d_rowsafe.as<uint8_t>(),
               e->d_rowlogh.as<uint8_t>(), ds->bin_counts, e->owner(),
               // trust the partner bound only when the tiles took most of the multi-edges (input with locality)
-              !e->bucketed ? 0 : ((double)e->work_total <= 0.6 * (double)e->multi_total ? 1 : 2));
+              !e->bucketed ? 0 : ((double)e->work_total <= 0.6 * (double)e->multi_total ? 1 : 2),
+              e->cfg.want_blosum != 0 && !e->have_plist);
     EdgeSink sink{e->d_edges.as<uint4>(), &ds->edge_cursor, e->edge_cap, e->cfg.threshold,
                   e->cfg.want_blosum ? kUnscored : 0u};
     mark(e, EV_PK0);
@@ -2050,16 +2051,21 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
       if (e->cfg.want_blosum) KC_STREAM(true); else KC_STREAM(false);
 #undef KC_STREAM
     } else     if (e->cfg.want_blosum) {
-      constexpr size_t smem = (size_t)kScoredWarps * kScoredWarpWords * 4;
-      KC_CUDA(e, cudaFuncSetAttribute(pairs_main_scored_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      int per_sm = 1;
-      KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairs_main_scored_kernel, kScoredWarps * 32, smem));
-      if (per_sm < 1) per_sm = 1;
-      KC_LAUNCH(e, pairs_main_scored_kernel, (uint32_t)(e->num_sm * per_sm), kScoredWarps * 32, smem,
-                e->pair_rowptr(), e->pair_rowlen(), e->d_suf.as<uint2>(),
-                e->d_sufss.as<uint8_t>(), e->d_col.as<uint32_t>(), e->d_rowbin.as<uint8_t>(),
-                e->d_rowsafe.as<uint8_t>(), n, &ds->row_cursor[kBinMain], &ds->n_overflow, ds->bin_counts, sink,
-                &ds->pc);
+#define KC_SCORED(LOGH, CAPV, BINV, WARPSV)                                                                       \
+  do {                                                                                                            \
+    auto kern = pairs_main_scored_kernel<LOGH, CAPV, BINV, WARPSV>;                                               \
+    constexpr size_t smem = (size_t)WARPSV * scored_warp_words<LOGH, CAPV>() * 4;                                 \
+    KC_CUDA(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+    int per_sm = 1;                                                                                               \
+    KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPSV * 32, smem));                  \
+    if (per_sm < 1) per_sm = 1;                                                                                   \
+    KC_LAUNCH(e, kern, (uint32_t)(e->num_sm * per_sm), WARPSV * 32, smem, e->pair_rowptr(), e->pair_rowlen(),     \
+              e->d_suf.as<uint2>(), e->d_sufss.as<uint8_t>(), e->d_col.as<uint32_t>(), e->d_rowbin.as<uint8_t>(), \
+              e->d_rowsafe.as<uint8_t>(), n, &ds->row_cursor[BINV], &ds->n_overflow, ds->bin_counts, sink, &ds->pc); \
+  } while (0)
+      KC_SCORED(kMainSLogH, kMainSCap, kBinMainS, 7);
+      KC_SCORED(kMainLogHMax, kMainCap, kBinMain, 5);
+#undef KC_SCORED
     } else {
       constexpr size_t smem = (size_t)kMainWarps * ((1u << kMainLogHMax) + 2 * kIdxPerWarp + kMainCap / 2 + 4) * 4;
       KC_CUDA(e, cudaFuncSetAttribute(pairs_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

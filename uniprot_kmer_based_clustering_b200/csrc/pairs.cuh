@@ -126,11 +126,14 @@ enum : uint8_t {
   kBinWide = 8,     // key/count in separate words (rows whose counts do not fit a packed slot)
   kBinDense = 9,
   kBinMain = 10,    // packed hash, one warp per row, table sized per row from an optimistic estimate
-  kNumBins = 11,
+  kBinMainS = 11,   // scored main kernel with half-size tables: rows whose partner bound fits them for sure
+  kNumBins = 12,
   kBinRetry = 16    // added to a safe bin: the optimistic table of the main kernel overflowed
 };
 constexpr uint32_t kMainLogHMax = 10;  // 1024 slots = 4 KB per warp
 constexpr uint32_t kMainCap = 640;     // distinct partners a row may collect in the main kernel (load 0.625)
+constexpr uint32_t kMainSLogH = 9;     // the small variant of the scored main kernel: 512 slots,
+constexpr uint32_t kMainSCap = 320;    // rows with an EXACT partner bound U <= 320 (they cannot overflow)
 
 // bounds[0..1] = the shard's row range (device memory: no host round trip).
 // count_bits = bits left for the counter in a packed slot (32 - bits of a protein rank).
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(256)
                          const uint32_t* __restrict__ first_after, uint32_t n, const uint32_t* __restrict__ bounds,
                          uint32_t dense_single_pass_cols, uint32_t count_bits, uint8_t* __restrict__ rowbin,
                          uint8_t* __restrict__ rowsafe, uint8_t* __restrict__ rowlogh,
-                         uint32_t* __restrict__ bin_counts, RowOwner owner, int exact_main) {
+                         uint32_t* __restrict__ bin_counts, RowOwner owner, int exact_main, bool small_main) {
   __shared__ uint32_t s_cnt[16];
   if (threadIdx.x < 16) s_cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(256)
         if ((U <= kMainCap || (optimistic && lower <= kMainCap / 2)) &&
             rowlen[r] < (1u << kScoreShift) &&
             P != 0xFFFFFFFFu) {
-          bin = kBinMain;
+          bin = small_main && U <= kMainSCap ? kBinMainS : kBinMain;
           rowlogh[r] = (uint8_t)kMainLogHMax;
         }
       }
@@ -815,8 +818,12 @@ __global__ void __launch_bounds__(kMainWarps * 32)
 // carries the BLOSUM62 self-score of its k-mer (sufss, one byte per row entry), accumulated in
 // the same atomic as the count.  K9 fused into K7: no per-edge list intersection afterwards.
 // ---------------------------------------------------------------------------------------
-constexpr int kScoredWarps = 5;
-constexpr uint32_t kScoredWarpWords = 2 * (1u << kMainLogHMax) + 2 * kIdxPerWarp + 2 * (kIdxPerWarp / 4) + kMainCap / 2 + 4;
+// two instances: <kMainLogHMax, kMainCap, kBinMain, 5 warps> and the half-size <kMainSLogH, kMainSCap, kBinMainS, 7 warps>
+// (9.9 KB instead of 14.6 KB of shared memory per warp: 21 instead of 15 rows in flight per SM)
+template <uint32_t LOG_H, uint32_t CAP>
+__host__ __device__ constexpr uint32_t scored_warp_words() {
+  return 2 * (1u << LOG_H) + 2 * kIdxPerWarp + 2 * (kIdxPerWarp / 4) + CAP / 2 + 4;
+}
 
 __device__ __forceinline__ uint32_t chunk_prepare_scored(const uint32_t* __restrict__ col, uint2 e, uint32_t ss,
                                                          uint32_t* idx, uint8_t* idxs, uint32_t (&v)[4],
@@ -841,27 +848,29 @@ __device__ __forceinline__ uint32_t chunk_prepare_scored(const uint32_t* __restr
   return total;
 }
 
-__global__ void __launch_bounds__(kScoredWarps * 32)
+template <uint32_t LOG_H, uint32_t CAP, uint8_t BIN, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
     pairs_main_scored_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen,
                              const uint2* __restrict__ suf, const uint8_t* __restrict__ sufss,
                              const uint32_t* __restrict__ col, uint8_t* __restrict__ rowbin,
                              const uint8_t* __restrict__ rowsafe, uint32_t n, uint32_t* __restrict__ row_cursor,
                              uint32_t* __restrict__ n_overflow, uint32_t* __restrict__ bin_counts, EdgeSink sink,
                              PairCounters* __restrict__ counters) {
-  constexpr uint32_t HMAX = 1u << kMainLogHMax;
-  constexpr uint32_t log_h = kMainLogHMax;
-  if (bin_counts[kBinMain] == 0) return;
+  constexpr uint32_t HMAX = 1u << LOG_H;
+  constexpr uint32_t log_h = LOG_H;
+  constexpr uint32_t kWords = scored_warp_words<LOG_H, CAP>();
+  if (bin_counts[BIN] == 0) return;
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   // per warp: keys | values | idx buffers 0,1 (buffer 1 doubles as the edge stage) | idx score
   // buffers 0,1 | dirty list | dirty count
-  uint32_t* wbase = reinterpret_cast<uint32_t*>(dyn_smem) + (size_t)warp * kScoredWarpWords;
+  uint32_t* wbase = reinterpret_cast<uint32_t*>(dyn_smem) + (size_t)warp * kWords;
   uint32_t* key = wbase;
   uint32_t* val = wbase + HMAX;
   uint32_t* idx0 = wbase + 2 * HMAX;
   uint8_t* idxs0 = reinterpret_cast<uint8_t*>(wbase + 2 * HMAX + 2 * kIdxPerWarp);
   uint16_t* dirty = reinterpret_cast<uint16_t*>(wbase + 2 * HMAX + 2 * kIdxPerWarp + 2 * (kIdxPerWarp / 4));
-  uint32_t* dirty_cnt = wbase + 2 * HMAX + 2 * kIdxPerWarp + 2 * (kIdxPerWarp / 4) + kMainCap / 2;
+  uint32_t* dirty_cnt = wbase + 2 * HMAX + 2 * kIdxPerWarp + 2 * (kIdxPerWarp / 4) + CAP / 2;
   if (lane == 0) *dirty_cnt = 0;
   EdgeStage stage{idx0 + kIdxPerWarp, 0u};
   unsigned long long n_pairs = 0, n_edges = 0, sum_count = 0, n_multi = 0;
@@ -877,7 +886,7 @@ __global__ void __launch_bounds__(kScoredWarps * 32)
     if (base >= n) break;
     uint32_t m_len = 0, m_ps = 0;
     bool mine = false;
-    if (lane < 4 && base + lane < n && rowbin[base + lane] == kBinMain) {
+    if (lane < 4 && base + lane < n && rowbin[base + lane] == BIN) {
       mine = true;
       m_len = rowlen[base + lane];
       m_ps = pstart[base + lane];
@@ -898,10 +907,10 @@ __global__ void __launch_bounds__(kScoredWarps * 32)
         if (m) {
           if (slot != kSentinel) {
             const uint32_t pos = n_new + __popc(m & lanemask_lt());
-            if (pos < kMainCap) dirty[pos] = (uint16_t)slot;
+            if (pos < CAP) dirty[pos] = (uint16_t)slot;
           }
           n_new += __popc(m);
-          full = n_new > kMainCap;  // at most 32 slots beyond the cap: the table (1024 slots) never fills up
+          full = n_new > CAP;  // at most 32 slots beyond the cap: the table (1024 slots) never fills up
         }
       };
       uint2 e_cur = lane < nl ? ld_stream_u32x2(suf + ps + lane) : make_uint2(0, 0);
