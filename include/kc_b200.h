@@ -59,7 +59,9 @@ typedef struct kc_config {
   uint32_t index_slices;    /* table build: number of L2 slices of the k-mer universe (0 = from the footprint) */
   uint32_t census_merge;    /* table build: slices merged per census launch (0/1 = none) */
   uint32_t pair_lists;      /* table build: 1 = materialise the multi-edge lists for the stream pair kernel */
-  uint32_t no_upload_overlap; /* 1 = one residue upload on the main stream instead of the chunked overlap */
+  uint32_t no_upload_overlap; /* 0 = a large residue stream is uploaded in chunks on a copy stream and the index
+                             * build starts on the first chunk; 1 = one upload on the main stream; 2 = chunked
+                             * at any size (tests) */
 } kc_config;
 
 enum {

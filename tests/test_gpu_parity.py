@@ -347,6 +347,31 @@ def test_device_resident_input_matches_host_input(arg_set):
         assert np.array_equal(e.get_edges(), h.get_edges())
 
 
+@pytest.mark.parametrize("k", [5, 7])
+def test_chunked_upload_builds_the_same_index(k, arg_set, arg_oracle):
+    """kc_set_proteins from host buffers uploads a large residue stream in chunks on a copy stream and the
+    streaming build runs one level-1 pass per chunk (level 2 reads every partition through a segment table).
+    no_upload_overlap = 2 forces the chunked path at this size; the result must not depend on it, and a rebuild
+    of the resident stream (one pass) must give the same index again."""
+    o, _, ix = arg_oracle[k]
+    pr = o.score_pairs(10, False, True, mode=1)
+    with kc.Engine(k, cross_class_only=False, want_blosum=True, no_upload_overlap=2) as e, \
+            kc.Engine(k, cross_class_only=False, want_blosum=True, no_upload_overlap=1) as h:
+        for _ in range(2):  # the second round uploads into buffers the first one still owns
+            e.set_protein_set(arg_set)
+            h.set_protein_set(arg_set)
+            ist = e.build_index()
+            assert ist == h.build_index()
+            check_index(e, ix)
+            pst = e.score_pairs()
+            assert pst == h.score_pairs()
+            check_pairs(pst, e.get_edges(), pr)
+            assert np.array_equal(e.get_edges(), h.get_edges())
+        assert e.build_index() == ist  # resident now: a single pass
+        assert e.score_pairs() == pst
+        check_pairs(pst, e.get_edges(), pr)
+
+
 def test_rerun_is_idempotent_and_edge_buffer_grows(arg_set):
     with kc.Engine(5, threshold=10, cross_class_only=False, max_edges=1000) as e:
         e.set_protein_set(arg_set)

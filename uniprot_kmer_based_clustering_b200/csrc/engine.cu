@@ -84,6 +84,7 @@ struct kc_engine {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t chunk_ev[kUploadChunks]{}, main_ev = nullptr;
   uint32_t chunk_row[kUploadChunks + 1]{};
+  uint64_t chunk_byte[kUploadChunks + 1]{};  // chunk c = bytes [chunk_byte[c], chunk_byte[c+1]) (tile-aligned cuts)
   int n_chunks = 0;  // > 0: an upload is (possibly) in flight; chunk c holds the rows [chunk_row[c], chunk_row[c+1])
   std::string err;
   uint32_t launches = 0;
@@ -103,6 +104,14 @@ struct kc_engine {
   std::vector<unsigned long long> h_pospref;  // k-mer positions (after subsampling) of the rows before row r
   unsigned long long n_pos_unsampled = 0;
   uint32_t max_plen = 0;
+  unsigned long long huge_total = 0;  // scratch words of the rows beyond a CTA's shared memory
+  // Deferred host staging (kc_set_proteins from host buffers, pair order = input order): the caller's arrays
+  // stay valid until the next kc_build_index* / kc_extract_kmers returns, so the host's own copies, the
+  // position prefix and the row lists are made by ensure_staged() - inside the build, after its kernels are
+  // queued - instead of on the critical path in front of them.
+  const uint64_t* pend_off = nullptr;
+  const uint32_t* pend_cls = nullptr;
+  unsigned long long n_pos_quick = 0;  // k-mer positions of the set (no subsampling), known before the staging
   bool retry_full_buckets = false;
   uint32_t try_cap = 0;  // bucket slot size of the running attempt (0: choose)
   // the slot size that worked for the protein set with this signature (a k-mer with thousands of
@@ -253,7 +262,8 @@ size_t padded_res_bytes(uint64_t R) { return (size_t)((R + kSxTile - 1) / kSxTil
 
 // ---- host-side staging shared by both kc_set_proteins flavours ---------------------------
 // (this runs while the residue stream is crossing PCIe: one pass over the offsets)
-int stage_layout(kc_engine* e) {
+// host part: pair order, position prefix, row lists (needs h_off / h_cls)
+int stage_layout_host(kc_engine* e) {
   const uint64_t n = e->n;
   const int k = e->cfg.k;
   const auto& off = e->h_off;
@@ -309,7 +319,7 @@ int stage_layout(kc_engine* e) {
   std::vector<Slab> slabs(n_slabs);
   auto slab_rows = [&](unsigned t) { return std::pair<uint64_t, uint64_t>{n * t / n_slabs, n * (t + 1) / n_slabs}; };
   auto pass1 = [&](unsigned t) {
-    Slab& sl = slabs[t];
+    Slab sl;  // (a local: the slabs' counters would share cache lines between the threads)
     const auto [lo, hi] = slab_rows(t);
     for (uint64_t r = lo; r < hi; ++r) {
       const uint32_t p = cross ? e->h_orig[r] : (uint32_t)r;
@@ -341,6 +351,7 @@ int stage_layout(kc_engine* e) {
       e->h_pospref[r + 1] = kept;  // (per row for now)
       sl.pos += kept;
     }
+    slabs[t] = std::move(sl);
   };
   {
     std::vector<std::thread> pool;
@@ -385,12 +396,22 @@ int stage_layout(kc_engine* e) {
     if (cross)
       for (uint64_t r = 0; r < n; ++r) e->h_soff[r + 1] = e->h_soff[r] + e->h_plen[r];
   }
-  auto up = [&](DBuf& b, const void* src, size_t bytes) -> cudaError_t {
-    cudaError_t rc = b.ensure(std::max<size_t>(bytes, 16));
-    if (rc != cudaSuccess) return rc;
-    if (bytes == 0) return cudaSuccess;
-    return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, e->stream);
-  };
+  e->huge_total = huge_total;
+  return KC_OK;
+}
+
+static cudaError_t stage_up(kc_engine* e, DBuf& b, const void* src, size_t bytes) {
+  cudaError_t rc = b.ensure(std::max<size_t>(bytes, 16));
+  if (rc != cudaSuccess) return rc;
+  if (bytes == 0) return cudaSuccess;
+  return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, e->stream);
+}
+
+// device part 1: the row layout in the pair order (input order: derived on the device from d_off alone)
+int stage_layout_device(kc_engine* e) {
+  const uint64_t n = e->n;
+  const bool cross = e->cfg.cross_class_only != 0;
+  auto up = [&](DBuf& b, const void* src, size_t bytes) { return stage_up(e, b, src, bytes); };
   if (!cross) {  // d_off is already on its way on the same stream
     KC_CUDA(e, e->d_pstart.ensure(std::max<size_t>(n * 4, 16)));
     KC_CUDA(e, e->d_plen.ensure(std::max<size_t>(n * 4, 16)));
@@ -417,15 +438,58 @@ int stage_layout(kc_engine* e) {
                 e->d_res.as<uint8_t>(), e->d_pstart.as<uint32_t>(), e->d_soff.as<uint32_t>(), (uint32_t)n,
                 e->d_sres_own.as<uint8_t>());
   }
+  return KC_OK;
+}
+
+// device part 2: the row lists of the sorting extract kernels (table / bucket builds, kc_extract_kmers)
+int stage_lists_device(kc_engine* e) {
+  auto up = [&](DBuf& b, const void* src, size_t bytes) { return stage_up(e, b, src, bytes); };
   KC_CUDA(e, up(e->d_long, e->h_long.data(), e->h_long.size() * 4));
   KC_CUDA(e, up(e->d_cta, e->h_cta.data(), e->h_cta.size() * 4));
   KC_CUDA(e, up(e->d_vlong, e->h_vlong.data(), e->h_vlong.size() * 4));
   KC_CUDA(e, up(e->d_huge, e->h_huge.data(), e->h_huge.size() * 4));
   KC_CUDA(e, up(e->d_huge_off, e->h_huge_off.data(), e->h_huge_off.size() * 8));
-  if (huge_total) KC_CUDA(e, e->d_huge_scratch.ensure(huge_total * 4));
+  if (e->huge_total) KC_CUDA(e, e->d_huge_scratch.ensure(e->huge_total * 4));
+  return KC_OK;
+}
+
+// everything at once (the callers that have h_off / h_cls in place)
+int stage_layout(kc_engine* e) {
+  int rc = stage_layout_host(e);
+  if (rc == KC_OK) rc = stage_layout_device(e);
+  if (rc == KC_OK) rc = stage_lists_device(e);
+  if (rc != KC_OK) return rc;
   e->have_proteins = true;
   e->have_index = e->have_pairs = false;
   return KC_OK;
+}
+
+// the host's own copy of the caller's offsets / classes, in parallel slabs
+static void copy_host_arrays(kc_engine* e, const uint64_t* offsets, const uint32_t* class_id) {
+  const uint64_t n = e->n;
+  e->h_off.resize(n + 1);
+  e->h_cls.resize(n);
+  const unsigned n_slabs = n >= (1u << 16) ? 4u : 1u;
+  auto slab = [&](unsigned t) {
+    const uint64_t lo = n * t / n_slabs, hi = n * (t + 1) / n_slabs;
+    std::memcpy(e->h_off.data() + lo, offsets + lo, (hi - lo + (t + 1 == n_slabs ? 1 : 0)) * 8);
+    if (hi > lo) std::memcpy(e->h_cls.data() + lo, class_id + lo, (hi - lo) * 4);
+  };
+  std::vector<std::thread> pool;
+  for (unsigned t = 1; t < n_slabs; ++t) pool.emplace_back(slab, t);
+  slab(0);
+  for (auto& th : pool) th.join();
+}
+
+// completes a deferred host staging (see kc_engine::pend_off); a no-op otherwise
+int ensure_staged(kc_engine* e) {
+  if (!e->pend_off) return KC_OK;
+  copy_host_arrays(e, e->pend_off, e->pend_cls);
+  e->pend_off = nullptr;
+  e->pend_cls = nullptr;
+  int rc = stage_layout_host(e);
+  if (rc == KC_OK) rc = stage_lists_device(e);
+  return rc;
 }
 
 
@@ -820,7 +884,9 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
 }
 
 // ---- the streaming partitioned index build (stream_index.cuh): the default -------------------
-static SxPlan sx_make_plan(uint64_t E, uint64_t R, int num_sm) {
+// pass_end_tile: null / n_pass <= 1 = one level-1 pass over the whole stream; else pass u ends before tile
+// pass_end_tile[u] (the upload chunks of an asynchronous kc_set_proteins)
+static SxPlan sx_make_plan(uint64_t E, uint64_t R, int num_sm, int n_pass = 1, const uint32_t* pass_end_tile = nullptr) {
   SxPlan p{};
   // ~330 records per bucket: one warp sorts a bucket in its own slice of shared memory (512 records).
   // b >= 12: the CTA kernel's sort key (32 - b bits) must fit a u32 beside a 12-bit record index;
@@ -831,9 +897,19 @@ static SxPlan sx_make_plan(uint64_t E, uint64_t R, int num_sm) {
   p.b2 = b - p.b1;
   p.r = 32 - b;
   const uint32_t tiles = (uint32_t)std::max<uint64_t>(1, (R + kSxTile - 1) / kSxTile);
-  uint32_t g1 = std::min<uint32_t>(tiles, (uint32_t)num_sm * 2u);  // two persistent CTAs per SM
-  p.tiles_per_chunk = (tiles + g1 - 1) / g1;
-  p.g1 = (tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+  p.n_pass = 1;
+  p.pass_tile[0] = 0;
+  p.pass_tile[1] = tiles;
+  if (n_pass > 1 && pass_end_tile) {
+    p.n_pass = (uint32_t)std::min(n_pass, kSxMaxPass);
+    for (uint32_t u = 0; u < p.n_pass; ++u)
+      p.pass_tile[u + 1] = u + 1 == p.n_pass ? tiles : std::max(p.pass_tile[u], std::min(tiles, pass_end_tile[u]));
+  }
+  uint32_t widest = 1;
+  for (uint32_t u = 0; u < p.n_pass; ++u) widest = std::max(widest, p.pass_tile[u + 1] - p.pass_tile[u]);
+  uint32_t g1 = std::min<uint32_t>(widest, (uint32_t)num_sm * 2u);  // two persistent CTAs per SM
+  const uint32_t tpc = (widest + g1 - 1) / g1;
+  p.g1 = (widest + tpc - 1) / tpc;
   p.c2 = std::min<uint32_t>(16u, std::max<uint32_t>(1u, ((uint32_t)num_sm * 16u) >> p.b1));
   p.ballots = 1;  // level 1 / 2 (9-10 digit bits): one ballot per bit measured faster than match.any
   return p;
@@ -873,7 +949,9 @@ static int build_index_stream(kc_engine* e, uint32_t shard, uint32_t n_shards, k
   const uint32_t n = (uint32_t)e->n;
   const uint64_t R = e->R;
   DeviceScalars* ds = e->ds;
-  const unsigned long long n_positions = e->h_pospref[n];
+  if (n_shards > 1)
+    if (int rcs = ensure_staged(e)) return rcs;
+  const unsigned long long n_positions = e->pend_off ? e->n_pos_quick : e->h_pospref[n];
   const uint64_t E = std::max<unsigned long long>(n_positions, 1);
   const uint32_t n_bins = (n + kBinRows - 1) >> kBinRowsLog;
   // sharded build (owner computes): this rank's row blocks, the filter of its rows' k-mers
@@ -892,12 +970,26 @@ static int build_index_stream(kc_engine* e, uint32_t shard, uint32_t n_shards, k
     KC_CUDA(e, e->d_keepmask.ensure(((R + kSxTile - 1) / kSxTile + 1) * kL1Threads * 2));
   }
   const RowOwner owner{n_shards > 1 ? e->d_binowner.as<uint8_t>() : nullptr, shard};
-  SxPlan plan = sx_make_plan(E, R, e->num_sm);
+  // An upload still in flight (kc_set_proteins from host buffers, pair order = input order): one level-1 pass per
+  // upload chunk, each waiting for its own chunk only; the level-1 sort of chunk u runs while chunk u + 1
+  // crosses PCIe.  A tile also reads the first bytes of the next one (the k-mer halo): pass u stops one tile
+  // short of its chunk's end, the last pass takes the rest.
+  int n_pass = 1;
+  uint32_t pass_end[kc_engine::kUploadChunks] = {};
+  if (e->n_chunks > 1 && n_shards <= 1 && !e->cfg.cross_class_only) {
+    n_pass = e->n_chunks;
+    for (int u = 0; u < n_pass; ++u) {
+      const uint64_t t = e->chunk_byte[u + 1] / kSxTile;
+      pass_end[u] = (uint32_t)(t ? t - 1 : 0);
+    }
+  } else {
+    KC_CUDA(e, wait_upload(e) == KC_OK ? cudaSuccess : cudaErrorUnknown);
+  }
+  SxPlan plan = sx_make_plan(E, R, e->num_sm, n_pass, pass_end);
   if (e->cfg.census_merge == 77u) plan.ballots = 0;  // (A/B switch while tuning; see profiles/r2_history.md)
   const uint32_t n_tiles = (uint32_t)((R + kSxTile - 1) / kSxTile);
   const uint32_t D1 = plan.d1(), D2 = plan.d2(), NB = plan.n_buckets();
-  const uint64_t n_h1 = (uint64_t)D1 * plan.g1, n_h2 = (uint64_t)NB * plan.c2;
-  KC_CUDA(e, wait_upload(e) == KC_OK ? cudaSuccess : cudaErrorUnknown);
+  const uint64_t n_h1 = (uint64_t)plan.h1_stride() * plan.n_pass, n_h2 = (uint64_t)NB * plan.c2;
   KC_CUDA(e, e->d_rec_a.ensure((E + 64) * 8));
   KC_CUDA(e, e->d_rec_b.ensure((E + 64) * 8));
   KC_CUDA(e, e->d_h1.ensure((n_h1 + 2) * 4));
@@ -973,14 +1065,20 @@ static int build_index_stream(kc_engine* e, uint32_t shard, uint32_t n_shards, k
     const uint32_t* trow = e->d_tile_row.as<uint32_t>();
     const size_t smem_c = (size_t)D1 * 4 + kSxTile + 64 + 256;
     const size_t smem_s = sx_scatter_smem(D1, kL1Threads / 32);
+    const uint64_t n_hp = (uint64_t)D1 * plan.g1;  // histogram entries of one pass (+ 1: the end of its region)
 #define KC_L1(KK, SH)                                                                                              \
   do {                                                                                                            \
     KC_CUDA(e, cudaFuncSetAttribute((sx_l1_count_kernel<KK, SH>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));   \
     KC_CUDA(e, cudaFuncSetAttribute((sx_l1_scatter_kernel<KK, SH>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)); \
-    KC_LAUNCH(e, (sx_l1_count_kernel<KK, SH>), plan.g1, kL1Threads, smem_c, res, (uint32_t)R, soff, trow, plan, keep, h1);      \
-    e->launches += exclusive_scan(U32In{h1}, SxExclOutTail{h1, n_h1}, n_h1, e->scan, e->stream);                 \
-    KC_LAUNCH(e, (sx_l1_scatter_kernel<KK, SH>), plan.g1, kL1Threads, smem_s, res, (uint32_t)R, soff, trow, plan, keep, h1,     \
-              rec_a);                                                                                             \
+    for (uint32_t u = 0; u < plan.n_pass; ++u) {                                                                  \
+      if (n_pass > 1) KC_CUDA(e, cudaStreamWaitEvent(e->stream, e->chunk_ev[u], 0));                              \
+      uint32_t* hp = h1 + (size_t)u * plan.h1_stride();                                                           \
+      KC_LAUNCH(e, (sx_l1_count_kernel<KK, SH>), plan.g1, kL1Threads, smem_c, res, (uint32_t)R, soff, trow, plan, u, keep, h1); \
+      e->launches += exclusive_scan(U32In{hp}, SxExclOutTailBase{hp, n_hp, u ? hp - 1 : nullptr}, n_hp, e->scan, e->stream);    \
+      KC_LAUNCH(e, (sx_l1_scatter_kernel<KK, SH>), plan.g1, kL1Threads, smem_s, res, (uint32_t)R, soff, trow, plan, u, keep,    \
+                h1, rec_a);                                                                                       \
+    }                                                                                                             \
+    if (n_pass > 1) e->n_chunks = 0;                                                                              \
   } while (0)
     if (k5) {
       if (n_shards > 1) KC_L1(5, true); else KC_L1(5, false);
@@ -1084,8 +1182,11 @@ static int build_index_stream(kc_engine* e, uint32_t shard, uint32_t n_shards, k
   uint32_t n_records = 0;
   KC_CUDA(e, cudaMemcpyAsync(&hs, ds, sizeof(hs), cudaMemcpyDeviceToHost, e->stream));
   KC_CUDA(e, cudaMemcpyAsync(&n_records, h2 + n_h2, 4, cudaMemcpyDeviceToHost, e->stream));
+  // the host's own row tables, while the kernels above run (a deferred staging: kc_engine::pend_off)
+  const int rc_staged = ensure_staged(e);
   KC_CUDA(e, cudaStreamSynchronize(e->stream));
   KC_CUDA(e, cudaGetLastError());
+  if (rc_staged) return rc_staged;
   e->index_records = n_records;
   e->sx_huge_last = hs.sx_huge_cnt;
   e->sx_mid_last = hs.sx_mid_cnt;
@@ -1301,8 +1402,8 @@ static int set_proteins_host(kc_engine* e, const uint8_t* residues, const uint64
   if (R >= 0xFFFF0000ull) return fail(e, KC_ETOOLARGE, "more than 2^32-65536 residues");
   if (n >= 0xFFFFFFF0ull) return fail(e, KC_ETOOLARGE, "too many proteins");
   e->n = n;
-  e->h_off.resize(n + 1);
-  e->h_cls.resize(n);
+  e->pend_off = nullptr;
+  e->pend_cls = nullptr;
   mark(e, EV_H2D0);
   size_t padded = padded_res_bytes(R);
   const uint64_t world = dist ? (uint64_t)e->cworld : 1;
@@ -1325,20 +1426,25 @@ static int set_proteins_host(kc_engine* e, const uint8_t* residues, const uint64
                                          e->comm, e->stream);
     if (nr != ncclSuccess) return fail(e, KC_ECUDA, std::string("ncclAllGather: ") + nc.GetErrorString(nr));
     KC_CUDA(e, cudaMemsetAsync(e->d_res.as<uint8_t>() + R, 0, padded - R, e->stream));
-  } else if (!e->cfg.cross_class_only && R >= (32u << 20) && n >= 64 * C && e->copy_stream && !e->cfg.no_upload_overlap) {
-    // pair order = input order: chunk c of the stream is the rows [chunk_row[c], chunk_row[c+1]).
+  } else if (!e->cfg.cross_class_only && e->copy_stream && e->cfg.no_upload_overlap != 1u &&
+             ((R >= (32u << 20) && n >= 64 * C) || (e->cfg.no_upload_overlap == 2u && R >= 4ull * C * kSxTile))) {
+    // pair order = input order.  The stream is cut at tile borders of the streaming build (chunk c = the bytes
+    // [chunk_byte[c], chunk_byte[c+1])); chunk_row[c] = the rows that lie entirely inside the chunks before c
+    // (what the row-chunked extract kernels of the other builds may read after event c - 1).
     // The copy stream waits for what the main stream still does with the old residues.
     KC_CUDA(e, cudaEventRecord(e->main_ev, e->stream));
     KC_CUDA(e, cudaStreamWaitEvent(e->copy_stream, e->main_ev, 0));
     e->chunk_row[0] = 0;
+    e->chunk_byte[0] = 0;
     for (int c = 1; c <= C; ++c) {
-      const uint64_t target = R / C * c;
-      e->chunk_row[c] = c == C ? (uint32_t)n
-                               : (uint32_t)(std::lower_bound(offsets, offsets + n + 1, target) - offsets);
-      e->chunk_row[c] = std::max(e->chunk_row[c], e->chunk_row[c - 1]);
+      const uint64_t cut = c == C ? R : std::min<uint64_t>(R, (R / C * c + kSxTile - 1) / kSxTile * kSxTile);
+      e->chunk_byte[c] = std::max(cut, e->chunk_byte[c - 1]);
+      // (the offsets are validated below; whatever they hold, the rows stay monotone and within [0, n])
+      const uint64_t r = c == C ? n : (uint64_t)(std::upper_bound(offsets, offsets + n + 1, e->chunk_byte[c]) - offsets);
+      e->chunk_row[c] = std::max(e->chunk_row[c - 1], (uint32_t)std::min<uint64_t>(n, c == C ? n : (r ? r - 1 : 0)));
     }
     for (int c = 0; c < C; ++c) {
-      const uint64_t b0 = std::min<uint64_t>(R, offsets[e->chunk_row[c]]), b1 = std::min<uint64_t>(R, offsets[e->chunk_row[c + 1]]);
+      const uint64_t b0 = e->chunk_byte[c], b1 = e->chunk_byte[c + 1];
       if (b1 > b0)
         KC_CUDA(e, cudaMemcpyAsync(e->d_res.as<uint8_t>() + b0, residues + b0, b1 - b0, cudaMemcpyHostToDevice,
                                    e->copy_stream));
@@ -1350,24 +1456,55 @@ static int set_proteins_host(kc_engine* e, const uint8_t* residues, const uint64
     if (R) KC_CUDA(e, cudaMemcpyAsync(e->d_res.p, residues, R, cudaMemcpyHostToDevice, e->stream));
     KC_CUDA(e, cudaMemsetAsync(e->d_res.as<uint8_t>() + R, 0, padded - R, e->stream));
   }
-  {  // the host's own copy of offsets / classes + the monotonicity check, in parallel slabs (the upload is running)
+  // One read-only pass over the caller's offsets, in parallel slabs while the upload runs: the monotonicity check
+  // and the totals the build sizes its buffers from.  (Nothing is stored: what else the host keeps per row is
+  // made by ensure_staged(), see kc_engine::pend_off.)
+  {
     const unsigned n_slabs = n >= (1u << 16) ? 4u : 1u;
-    std::vector<int> bad(n_slabs, 0);
+    struct Quick {
+      unsigned long long pos = 0;
+      uint32_t max_len = 0;
+      int bad = 0;
+    };
+    std::vector<Quick> quick(n_slabs);
+    const uint64_t k = (uint64_t)e->cfg.k;
     auto slab = [&](unsigned t) {
+      Quick q;
       const uint64_t lo = n * t / n_slabs, hi = n * (t + 1) / n_slabs;
-      std::memcpy(e->h_off.data() + lo, offsets + lo, (hi - lo + (t + 1 == n_slabs ? 1 : 0)) * 8);
-      if (hi > lo) std::memcpy(e->h_cls.data() + lo, class_id + lo, (hi - lo) * 4);
-      for (uint64_t p = lo; p < hi; ++p)
-        if (offsets[p + 1] < offsets[p]) bad[t] = 1;
+      for (uint64_t p = lo; p < hi; ++p) {
+        const uint64_t a = offsets[p], b = offsets[p + 1];
+        if (b < a) q.bad = 1;
+        const uint64_t len = b - a;
+        q.max_len = std::max<uint32_t>(q.max_len, (uint32_t)std::min<uint64_t>(len, 0xFFFFFFFFull));
+        if (len >= k) q.pos += len - k + 1;
+      }
+      quick[t] = q;
     };
     std::vector<std::thread> pool;
     for (unsigned t = 1; t < n_slabs; ++t) pool.emplace_back(slab, t);
     slab(0);
     for (auto& th : pool) th.join();
-    for (int b : bad)
-      if (b) return fail(e, KC_EINVAL, "offsets must be non-decreasing");  // (have_proteins stays false)
+    e->n_pos_quick = 0;
+    for (const Quick& q : quick) {
+      if (q.bad) return fail(e, KC_EINVAL, "offsets must be non-decreasing");  // (have_proteins stays false)
+      e->n_pos_quick += q.pos;
+    }
   }
-  int rc = stage_layout(e);
+  e->R = R;
+  int rc = KC_OK;
+  if (!e->cfg.cross_class_only && e->cfg.sample_every <= 1) {
+    // pair order = input order: the device derives the row layout from d_off; the host side is deferred
+    e->pend_off = offsets;
+    e->pend_cls = class_id;
+    rc = stage_layout_device(e);
+    if (rc == KC_OK) {
+      e->have_proteins = true;
+      e->have_index = e->have_pairs = false;
+    }
+  } else {
+    copy_host_arrays(e, offsets, class_id);
+    rc = stage_layout(e);
+  }
   if (e->n_chunks) {
     cudaEventRecord(e->ev[EV_H2D1], e->copy_stream);
     e->ev_set[EV_H2D1] = true;
@@ -1388,6 +1525,8 @@ int kc_set_proteins_device(kc_engine* e, const uint8_t* d_residues, const uint64
   KC_CUDA(e, cudaSetDevice(e->dev));
   if (int rcw = wait_upload(e)) return rcw;
   e->have_proteins = e->have_index = e->have_pairs = false;
+  e->pend_off = nullptr;
+  e->pend_cls = nullptr;
   e->n = n;
   e->h_off.resize(n + 1);
   e->h_cls.resize(n);
@@ -1419,6 +1558,8 @@ int kc_set_proteins_device_residues(kc_engine* e, const uint8_t* d_residues, con
   KC_CUDA(e, cudaSetDevice(e->dev));
   if (int rcw = wait_upload(e)) return rcw;
   e->have_proteins = e->have_index = e->have_pairs = false;
+  e->pend_off = nullptr;
+  e->pend_cls = nullptr;
   if (offsets[0] != 0) return fail(e, KC_EINVAL, "offsets[0] must be 0");
   for (uint64_t p = 0; p < n; ++p)
     if (offsets[p + 1] < offsets[p]) return fail(e, KC_EINVAL, "offsets must be non-decreasing");
@@ -1444,6 +1585,7 @@ int kc_extract_kmers(kc_engine* e, uint32_t* kmers_out, uint64_t capacity, uint6
   if (!e) return KC_EINVAL;
   if (!e->have_proteins) return fail(e, KC_EINVAL, "kc_set_proteins first");
   KC_CUDA(e, cudaSetDevice(e->dev));
+  if (int rcs = ensure_staged(e)) return rcs;
   const uint64_t n = e->n;
   const int k = e->cfg.k;
   std::vector<unsigned long long> kpos(n + 1, 0);
@@ -1528,6 +1670,10 @@ int kc_build_index_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_ind
     const bool subsampled = e->cfg.sample_every > 1;
     if (want == KC_INDEX_AUTO) want = subsampled ? KC_INDEX_TABLE : (n_shards > 1 ? KC_INDEX_BUCKET : KC_INDEX_STREAM);
     if (want == KC_INDEX_STREAM && (subsampled || n >= (1u << 24))) want = subsampled ? KC_INDEX_TABLE : KC_INDEX_BUCKET;
+    // (a deferred host staging, kc_engine::pend_off: the unsharded streaming build completes it behind its
+    // own kernels; everything else needs the host's row tables first)
+    if (!(want == KC_INDEX_STREAM && n > 0 && n_shards <= 1))
+      if (int rcs = ensure_staged(e)) return rcs;
     if (want == KC_INDEX_STREAM && n > 0) return build_index_stream(e, shard, n_shards, stats);
     // (the bucket build remembers per protein-set signature that its buckets overflowed)
     const bool known_overflow = e->cap_hint == 0 && e->cap_hint_n == e->n && e->cap_hint_R == e->R;

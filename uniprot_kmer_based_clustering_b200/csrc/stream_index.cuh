@@ -46,16 +46,29 @@ constexpr uint32_t kSxTile = 8192;
 constexpr int kL1Threads = 512, kL1V = 16;
 constexpr int kL2Threads = 1024, kL2V = 8;
 
+// Level 1 runs in PASSES over consecutive tile ranges of the residue stream (one pass when the stream is
+// resident; one per upload chunk when it is still crossing PCIe, so that the level-1 sort of chunk u runs
+// while chunk u + 1 arrives).  Every pass is a complete counting sort of its own records into its own region
+// of the level-1 output (pass-major, regions back to back); a level-1 partition is then the concatenation of
+// its segments over the passes, which is again the stream order: level 2 reads it through a segment table.
+constexpr int kSxMaxPass = 8;
 struct SxPlan {
   uint32_t b1, b2;           // digit bits of the two levels (<= 10 each)
   uint32_t r;                // remaining hash bits: the in-bucket sort key
-  uint32_t g1;               // level-1 chunks = CTAs of the level-1 kernels
-  uint32_t tiles_per_chunk;  // level 1
+  uint32_t g1;               // level-1 chunks = CTAs of the level-1 kernels (per pass)
   uint32_t c2;               // level-2 chunks per level-1 partition
   uint32_t ballots;          // 1: warp peers by one ballot per digit bit, 0: by match.any (A/B switch)
+  uint32_t n_pass;           // level-1 passes (1 .. kSxMaxPass)
+  uint32_t pass_tile[kSxMaxPass + 1];  // pass u = tiles [pass_tile[u], pass_tile[u + 1])
   __host__ __device__ uint32_t d1() const { return 1u << b1; }
   __host__ __device__ uint32_t d2() const { return 1u << b2; }
   __host__ __device__ uint32_t n_buckets() const { return 1u << (b1 + b2); }
+  // level-1 histogram of pass u: h1[u * h1_stride() + d * g1 + chunk]; the slot behind the last one holds the
+  // end of the pass's region (= the start of the next pass's)
+  __host__ __device__ uint32_t h1_stride() const { return d1() * g1 + 1u; }
+  __host__ __device__ uint32_t pass_tiles_per_chunk(uint32_t u) const {
+    return (pass_tile[u + 1] - pass_tile[u] + g1 - 1u) / g1;
+  }
 };
 
 // dynamic shared memory of the two scatter kernels for D digits:
@@ -334,11 +347,12 @@ __global__ void __launch_bounds__(kL1Threads, 2)
   }
 }
 
-// level-1 count: digit histogram of every chunk.  hist[d * g1 + chunk]
+// level-1 count of one pass: digit histogram of every chunk.  hist[pass * stride + d * g1 + chunk]
 template <int K, bool SHARDED>
 __global__ void __launch_bounds__(kL1Threads, 2)
     sx_l1_count_kernel(const uint8_t* __restrict__ res, uint32_t R, const uint32_t* __restrict__ soff,
-                       const uint32_t* __restrict__ tile_row, SxPlan plan, SxKeep keep, uint32_t* __restrict__ hist) {
+                       const uint32_t* __restrict__ tile_row, SxPlan plan, uint32_t pass, SxKeep keep,
+                       uint32_t* __restrict__ hist) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(dyn_smem);  // [D1]
   uint8_t* s_codes = dyn_smem + (size_t)plan.d1() * 4;       // [tile + 64]
@@ -348,8 +362,10 @@ __global__ void __launch_bounds__(kL1Threads, 2)
   if (tid < 256) s_lut[tid] = c_residue_lut[tid];
   __syncthreads();
   const uint32_t chunk = blockIdx.x;
-  const uint32_t tile_lo = chunk * plan.tiles_per_chunk;
-  for (uint32_t t = 0; t < plan.tiles_per_chunk; ++t) {
+  const uint32_t tpc = plan.pass_tiles_per_chunk(pass), tile_end = plan.pass_tile[pass + 1];
+  const uint32_t tile_lo = plan.pass_tile[pass] + chunk * tpc;
+  hist += (size_t)pass * plan.h1_stride();
+  for (uint32_t t = 0; t < tpc && tile_lo + t < tile_end; ++t) {
     const unsigned long long t0 = (unsigned long long)(tile_lo + t) * kSxTile;
     if (t0 >= R) break;
     uint32_t kept = 0;
@@ -366,11 +382,12 @@ __global__ void __launch_bounds__(kL1Threads, 2)
   for (uint32_t d = tid; d < D; d += kL1Threads) hist[(size_t)d * plan.g1 + chunk] = s_hist[d];
 }
 
-// level-1 scatter: hist_scanned[d * g1 + chunk] = where this chunk's records of digit d start in `out`
+// level-1 scatter of one pass: hist_scanned[pass * stride + d * g1 + chunk] = where this chunk's records of
+// digit d start in `out`
 template <int K, bool SHARDED>
 __global__ void __launch_bounds__(kL1Threads, 2)
     sx_l1_scatter_kernel(const uint8_t* __restrict__ res, uint32_t R, const uint32_t* __restrict__ soff,
-                         const uint32_t* __restrict__ tile_row, SxPlan plan, SxKeep keep,
+                         const uint32_t* __restrict__ tile_row, SxPlan plan, uint32_t pass, SxKeep keep,
                          const uint32_t* __restrict__ hist_scanned, uint2* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   const uint32_t D = plan.d1(), sh = 32u - plan.b1;
@@ -383,12 +400,14 @@ __global__ void __launch_bounds__(kL1Threads, 2)
   uint32_t* s_wsum = reinterpret_cast<uint32_t*>(s_lut + 256);               // [33]
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t chunk = blockIdx.x;
+  hist_scanned += (size_t)pass * plan.h1_stride();
   for (uint32_t d = tid; d < D; d += kL1Threads) s_goff[d] = hist_scanned[(size_t)d * plan.g1 + chunk];
   if (tid < 256) s_lut[tid] = c_residue_lut[tid];
   __syncthreads();
-  const uint32_t tile_lo = chunk * plan.tiles_per_chunk;
+  const uint32_t tpc = plan.pass_tiles_per_chunk(pass), tile_end = plan.pass_tile[pass + 1];
+  const uint32_t tile_lo = plan.pass_tile[pass] + chunk * tpc;
   uint2* seg = s_buf + warp * (32u * kL1V);
-  for (uint32_t t = 0; t < plan.tiles_per_chunk; ++t) {
+  for (uint32_t t = 0; t < tpc && tile_lo + t < tile_end; ++t) {
     const unsigned long long t0 = (unsigned long long)(tile_lo + t) * kSxTile;
     if (t0 >= R) break;
     const uint32_t kept = SHARDED ? keep.keepmask[(size_t)(tile_lo + t) * kL1Threads + tid] : 0xFFFFu;
@@ -445,32 +464,76 @@ __global__ void __launch_bounds__(kL1Threads, 2)
 }
 
 // ---------------------------------------------------------------------------------------
-// Level 2: every level-1 partition p (records [p1off(p), p1off(p + 1)) of `in`, p1off(p) =
-// h1[p * g1], h1[d1 * g1] = all records) is cut into c2 chunks; one CTA per chunk.
+// Level 2: level-1 partition p = the concatenation, over the level-1 passes u, of the segments
+// [h1[u * stride + p * g1], h1[u * stride + (p + 1) * g1]) of `in` (one segment when the stream was resident).
+// That VIRTUAL record range is cut into c2 chunks; one CTA per chunk.
 // hist[(p * d2 + d) * c2 + chunk]: the global exclusive scan of that array is the final position
 // of every (partition, digit, chunk) run, and its stride-c2 samples are the bucket starts.
 // ---------------------------------------------------------------------------------------
+// segment table of partition p in shared memory: s_vs[u] = virtual start of segment u (s_vs[n_pass] = the
+// partition's records), s_pb[u] = where segment u starts in `in`.  Returns this CTA's virtual range.
 __device__ __forceinline__ void sx_l2_chunk(const uint32_t* __restrict__ h1, const SxPlan& plan, uint32_t p,
-                                            uint32_t c, uint32_t& beg, uint32_t& end) {
-  const uint32_t lo = h1[(size_t)p * plan.g1], hi = h1[(size_t)(p + 1u) * plan.g1];
-  const uint32_t per = (hi - lo + plan.c2 - 1u) / plan.c2;
-  beg = min(hi, lo + c * per);
-  end = min(hi, beg + per);
+                                            uint32_t c, uint32_t* __restrict__ s_vs, uint32_t* __restrict__ s_pb,
+                                            uint32_t& beg, uint32_t& end) {
+  if (threadIdx.x == 0) {
+    uint32_t lo[kSxMaxPass], hi[kSxMaxPass];
+#pragma unroll
+    for (int u = 0; u < kSxMaxPass; ++u) {
+      if ((uint32_t)u < plan.n_pass) {
+        const uint32_t* h = h1 + (size_t)u * plan.h1_stride();
+        lo[u] = h[(size_t)p * plan.g1];
+        hi[u] = h[(size_t)(p + 1u) * plan.g1];
+      }
+    }
+    uint32_t run = 0;
+#pragma unroll
+    for (int u = 0; u < kSxMaxPass; ++u) {
+      if ((uint32_t)u < plan.n_pass) {
+        s_vs[u] = run;
+        s_pb[u] = lo[u];
+        run += hi[u] - lo[u];
+      }
+    }
+    s_vs[plan.n_pass] = run;
+  }
+  __syncthreads();
+  const uint32_t total = s_vs[plan.n_pass];
+  const uint32_t per = (total + plan.c2 - 1u) / plan.c2;
+  beg = min(total, c * per);
+  end = min(total, beg + per);
+}
+// segment of virtual record i
+__device__ __forceinline__ uint32_t sx_l2_seg_of(const uint32_t* __restrict__ s_vs, uint32_t n_pass, uint32_t i) {
+  uint32_t s = 0;
+#pragma unroll
+  for (int u = 1; u < kSxMaxPass; ++u) s += ((uint32_t)u < n_pass && i >= s_vs[u]) ? 1u : 0u;
+  return s;
 }
 
 __global__ void __launch_bounds__(kL2Threads)
     sx_l2_count_kernel(const uint2* __restrict__ in, const uint32_t* __restrict__ h1, SxPlan plan,
                        uint32_t* __restrict__ hist) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
+  __shared__ uint32_t s_vs[kSxMaxPass + 1], s_pb[kSxMaxPass];
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(dyn_smem);
   const uint32_t tid = threadIdx.x, D = plan.d2(), sh = 32u - plan.b1 - plan.b2, mask = D - 1u;
   const uint32_t p = blockIdx.x / plan.c2, c = blockIdx.x % plan.c2;
   for (uint32_t d = tid; d < D; d += kL2Threads) s_hist[d] = 0;
-  __syncthreads();
   uint32_t beg, end;
-  sx_l2_chunk(h1, plan, p, c, beg, end);
-  for (uint32_t i = beg + tid; i < end; i += kL2Threads)
-    atomicAdd(&s_hist[(sx_hash(ld_stream_u32(&in[i].x)) >> sh) & mask], 1u);
+  sx_l2_chunk(h1, plan, p, c, s_vs, s_pb, beg, end);  // (barrier inside)
+  if (plan.n_pass == 1) {  // one segment: the plain strided loop (its loads batch)
+    const uint2* seg = in + s_pb[0];
+    for (uint32_t i = beg + tid; i < end; i += kL2Threads)
+      atomicAdd(&s_hist[(sx_hash(ld_stream_u32(&seg[i].x)) >> sh) & mask], 1u);
+  } else {
+    for (uint32_t u = 0; u < plan.n_pass; ++u) {
+      const uint32_t a = max(beg, s_vs[u]), b = min(end, s_vs[u + 1]);
+      if (a >= b) continue;
+      const uint2* seg = in + s_pb[u];
+      for (uint32_t i = a - s_vs[u] + tid; i < b - s_vs[u]; i += kL2Threads)
+        atomicAdd(&s_hist[(sx_hash(ld_stream_u32(&seg[i].x)) >> sh) & mask], 1u);
+    }
+  }
   __syncthreads();
   for (uint32_t d = tid; d < D; d += kL2Threads) hist[((size_t)p * D + d) * plan.c2 + c] = s_hist[d];
 }
@@ -479,6 +542,7 @@ __global__ void __launch_bounds__(kL2Threads, 1)
     sx_l2_scatter_kernel(const uint2* __restrict__ in, const uint32_t* __restrict__ h1, SxPlan plan,
                          const uint32_t* __restrict__ hist_scanned, uint2* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
+  __shared__ uint32_t s_vs[kSxMaxPass + 1], s_pb[kSxMaxPass];
   const uint32_t D = plan.d2(), sh = 32u - plan.b1 - plan.b2, mask = D - 1u;
   uint2* s_buf = reinterpret_cast<uint2*>(dyn_smem);
   uint16_t* s_cnt = reinterpret_cast<uint16_t*>(dyn_smem + (size_t)kSxTile * 8);
@@ -488,17 +552,40 @@ __global__ void __launch_bounds__(kL2Threads, 1)
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t p = blockIdx.x / plan.c2, c = blockIdx.x % plan.c2;
   uint32_t beg, end;
-  sx_l2_chunk(h1, plan, p, c, beg, end);
+  sx_l2_chunk(h1, plan, p, c, s_vs, s_pb, beg, end);
   if (beg >= end) return;
   for (uint32_t d = tid; d < D; d += kL2Threads) s_goff[d] = hist_scanned[((size_t)p * D + d) * plan.c2 + c];
   __syncthreads();
   for (uint32_t t0 = beg; t0 < end; t0 += kSxTile) {
     uint32_t km[kL2V], rw[kL2V], digit[kL2V], pos[kL2V];
+    // the warp's 32 * kL2V virtual records usually lie in one segment: one offset for all of them
+    const uint32_t w0 = t0 + warp * (32u * kL2V);
+    uint32_t delta = s_pb[0];
+    bool one_seg = true;
+    if (plan.n_pass > 1 && w0 < end) {
+      const uint32_t sa = sx_l2_seg_of(s_vs, plan.n_pass, w0);
+      const uint32_t sb = sx_l2_seg_of(s_vs, plan.n_pass, min(end, w0 + 32u * kL2V) - 1u);
+      one_seg = sa == sb;
+      delta = s_pb[sa] - s_vs[sa];
+    }
+    uint32_t pi[kL2V];  // physical index (mod 2^32) of the thread's records
 #pragma unroll
-    for (int j = 0; j < kL2V; ++j) {
-      const uint32_t i = t0 + warp * (32u * kL2V) + (uint32_t)j * 32u + lane;
+    for (int j = 0; j < kL2V; ++j) pi[j] = w0 + (uint32_t)j * 32u + lane + delta;
+    if (!one_seg) {  // (rare, warp-uniform: the range straddles a segment border)
+#pragma unroll
+      for (int j = 0; j < kL2V; ++j) {
+        const uint32_t i = w0 + (uint32_t)j * 32u + lane;
+        if (i < end) {
+          const uint32_t sg = sx_l2_seg_of(s_vs, plan.n_pass, i);
+          pi[j] = s_pb[sg] + (i - s_vs[sg]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kL2V; ++j) {  // (no control flow between the loads: they are issued back to back)
+      const uint32_t i = w0 + (uint32_t)j * 32u + lane;
       uint2 v = make_uint2(kSentinel, 0u);
-      if (i < end) v = ld_stream_u32x2(in + i);
+      if (i < end) v = ld_stream_u32x2(in + pi[j]);
       km[j] = v.x;
       rw[j] = v.y;
       digit[j] = v.x == kSentinel ? kNoDigit : (sx_hash(v.x) >> sh) & mask;
@@ -1518,6 +1605,18 @@ struct SxExclOutTail {
   __device__ void operator()(uint64_t i, unsigned long long excl, unsigned long long v) const {
     p[i] = (uint32_t)excl;
     if (i + 1 == n) p[n] = (uint32_t)(excl + v);
+  }
+};
+
+// the same, shifted by a base the device holds (the end of the previous level-1 pass's region)
+struct SxExclOutTailBase {
+  uint32_t* p;
+  uint64_t n;
+  const uint32_t* base;  // null: 0
+  __device__ void operator()(uint64_t i, unsigned long long excl, unsigned long long v) const {
+    const uint32_t b = base ? *base : 0u;
+    p[i] = b + (uint32_t)excl;
+    if (i + 1 == n) p[n] = b + (uint32_t)(excl + v);
   }
 };
 
