@@ -130,8 +130,10 @@ int kc_set_stream(kc_engine* e, void* cuda_stream);
  * residues = ASCII bytes of all sequences back to back (no separators, no line breaks),
  * offsets[n+1] delimit proteins, class_id[n] = dictionary id of the AMR class string
  * (Protein::get_amr_class, src/protein.rs:135-138).  Host pointers; copied to HBM ASYNCHRONOUSLY (the upload overlaps
- * the host-side staging and, for page-locked buffers, the first kernels): the three buffers must stay valid and
- * unchanged until the next kc_build_index* / kc_extract_kmers on this engine has returned.  offsets[0] must be 0 and
+ * the host-side staging and, for page-locked buffers, the first kernels: the streaming index build sorts upload
+ * chunk u while chunk u + 1 crosses PCIe), and the engine takes its own host copies of offsets / classes inside the
+ * next build, behind that build's kernels: the three buffers must stay valid and unchanged until the next
+ * kc_build_index* / kc_extract_kmers on this engine has returned.  offsets[0] must be 0 and
  * the offsets non-decreasing (KC_EINVAL otherwise; a failed call leaves the engine without proteins). */
 int kc_set_proteins(kc_engine* e, const uint8_t* residues, const uint64_t* offsets,
                     const uint32_t* class_id, uint64_t n_proteins);

@@ -105,13 +105,13 @@ struct kc_engine {
   unsigned long long n_pos_unsampled = 0;
   uint32_t max_plen = 0;
   unsigned long long huge_total = 0;  // scratch words of the rows beyond a CTA's shared memory
-  // Deferred host staging (kc_set_proteins from host buffers, pair order = input order): the caller's arrays
-  // stay valid until the next kc_build_index* / kc_extract_kmers returns, so the host's own copies, the
-  // position prefix and the row lists are made by ensure_staged() - inside the build, after its kernels are
-  // queued - instead of on the critical path in front of them.
+  // Deferred host copies (kc_set_proteins from host buffers, pair order = input order): the caller's arrays
+  // stay valid until the next kc_build_index* / kc_extract_kmers returns, so the engine's own copies of the
+  // offsets and classes (h_off, h_cls: readbacks, kc_extract_kmers, shard filters) are made by ensure_staged()
+  // - inside the build, after its kernels are queued - instead of on the critical path in front of them.
+  // The row tables (h_pospref, the row lists) are derived from the caller's array directly.
   const uint64_t* pend_off = nullptr;
   const uint32_t* pend_cls = nullptr;
-  unsigned long long n_pos_quick = 0;  // k-mer positions of the set (no subsampling), known before the staging
   bool retry_full_buckets = false;
   uint32_t try_cap = 0;  // bucket slot size of the running attempt (0: choose)
   // the slot size that worked for the protein set with this signature (a k-mer with thousands of
@@ -263,10 +263,11 @@ size_t padded_res_bytes(uint64_t R) { return (size_t)((R + kSxTile - 1) / kSxTil
 // ---- host-side staging shared by both kc_set_proteins flavours ---------------------------
 // (this runs while the residue stream is crossing PCIe: one pass over the offsets)
 // host part: pair order, position prefix, row lists (needs h_off / h_cls)
-int stage_layout_host(kc_engine* e) {
+// `off`: the engine's own copy, or the caller's array while that copy is still deferred (kc_engine::pend_off);
+// cross-class mode reads the classes from h_cls.  Checks that the offsets do not decrease.
+int stage_layout_host(kc_engine* e, const uint64_t* off) {
   const uint64_t n = e->n;
   const int k = e->cfg.k;
-  const auto& off = e->h_off;
   if (off[0] != 0) return fail(e, KC_EINVAL, "offsets[0] must be 0");
   e->R = off[n];
   if (e->R >= 0xFFFF0000ull) return fail(e, KC_ETOOLARGE, "more than 2^32-65536 residues");
@@ -312,7 +313,7 @@ int stage_layout_host(kc_engine* e) {
   // (This runs while the residue stream crosses PCIe; at 8 ranks per host it was the largest part of a step.)
   struct Slab {
     unsigned long long pos = 0, pos_all = 0;
-    uint32_t max_plen = 0, max_np2 = 0, max_len = 0, n_mid = 0;
+    uint32_t max_plen = 0, max_np2 = 0, max_len = 0, n_mid = 0, bad = 0;
     std::vector<uint32_t> lng, cta, vlong, huge;
   };
   const unsigned n_slabs = n >= (1u << 16) ? 4u : 1u;
@@ -323,6 +324,10 @@ int stage_layout_host(kc_engine* e) {
     const auto [lo, hi] = slab_rows(t);
     for (uint64_t r = lo; r < hi; ++r) {
       const uint32_t p = cross ? e->h_orig[r] : (uint32_t)r;
+      if (off[p + 1] < off[p]) {
+        sl.bad = 1;
+        break;
+      }
       const uint64_t len = off[p + 1] - off[p];
       if (cross) {
         e->h_pstart[r] = (uint32_t)off[p];
@@ -359,6 +364,8 @@ int stage_layout_host(kc_engine* e) {
     pass1(0);
     for (auto& th : pool) th.join();
   }
+  for (const Slab& sl : slabs)
+    if (sl.bad) return fail(e, KC_EINVAL, "offsets must be non-decreasing");
   unsigned long long huge_total = 0;
   {
     std::vector<unsigned long long> base(n_slabs + 1, 0);
@@ -455,7 +462,7 @@ int stage_lists_device(kc_engine* e) {
 
 // everything at once (the callers that have h_off / h_cls in place)
 int stage_layout(kc_engine* e) {
-  int rc = stage_layout_host(e);
+  int rc = stage_layout_host(e, e->h_off.data());
   if (rc == KC_OK) rc = stage_layout_device(e);
   if (rc == KC_OK) rc = stage_lists_device(e);
   if (rc != KC_OK) return rc;
@@ -487,9 +494,7 @@ int ensure_staged(kc_engine* e) {
   copy_host_arrays(e, e->pend_off, e->pend_cls);
   e->pend_off = nullptr;
   e->pend_cls = nullptr;
-  int rc = stage_layout_host(e);
-  if (rc == KC_OK) rc = stage_lists_device(e);
-  return rc;
+  return KC_OK;
 }
 
 
@@ -838,6 +843,7 @@ static int build_index_bucketed(kc_engine* e, uint32_t shard, uint32_t n_shards,
   mark(e, EV_I1);
   DeviceScalars hs{};
   KC_CUDA(e, cudaMemcpyAsync(&hs, ds, sizeof(hs), cudaMemcpyDeviceToHost, e->stream));
+  ensure_staged(e);  // the engine's own copies of offsets / classes, while the kernels above run
   KC_CUDA(e, cudaStreamSynchronize(e->stream));
   KC_CUDA(e, cudaGetLastError());
   if (hs.bg.overflow) {
@@ -951,7 +957,7 @@ static int build_index_stream(kc_engine* e, uint32_t shard, uint32_t n_shards, k
   DeviceScalars* ds = e->ds;
   if (n_shards > 1)
     if (int rcs = ensure_staged(e)) return rcs;
-  const unsigned long long n_positions = e->pend_off ? e->n_pos_quick : e->h_pospref[n];
+  const unsigned long long n_positions = e->h_pospref[n];
   const uint64_t E = std::max<unsigned long long>(n_positions, 1);
   const uint32_t n_bins = (n + kBinRows - 1) >> kBinRowsLog;
   // sharded build (owner computes): this rank's row blocks, the filter of its rows' k-mers
@@ -1456,48 +1462,18 @@ static int set_proteins_host(kc_engine* e, const uint8_t* residues, const uint64
     if (R) KC_CUDA(e, cudaMemcpyAsync(e->d_res.p, residues, R, cudaMemcpyHostToDevice, e->stream));
     KC_CUDA(e, cudaMemsetAsync(e->d_res.as<uint8_t>() + R, 0, padded - R, e->stream));
   }
-  // One read-only pass over the caller's offsets, in parallel slabs while the upload runs: the monotonicity check
-  // and the totals the build sizes its buffers from.  (Nothing is stored: what else the host keeps per row is
-  // made by ensure_staged(), see kc_engine::pend_off.)
-  {
-    const unsigned n_slabs = n >= (1u << 16) ? 4u : 1u;
-    struct Quick {
-      unsigned long long pos = 0;
-      uint32_t max_len = 0;
-      int bad = 0;
-    };
-    std::vector<Quick> quick(n_slabs);
-    const uint64_t k = (uint64_t)e->cfg.k;
-    auto slab = [&](unsigned t) {
-      Quick q;
-      const uint64_t lo = n * t / n_slabs, hi = n * (t + 1) / n_slabs;
-      for (uint64_t p = lo; p < hi; ++p) {
-        const uint64_t a = offsets[p], b = offsets[p + 1];
-        if (b < a) q.bad = 1;
-        const uint64_t len = b - a;
-        q.max_len = std::max<uint32_t>(q.max_len, (uint32_t)std::min<uint64_t>(len, 0xFFFFFFFFull));
-        if (len >= k) q.pos += len - k + 1;
-      }
-      quick[t] = q;
-    };
-    std::vector<std::thread> pool;
-    for (unsigned t = 1; t < n_slabs; ++t) pool.emplace_back(slab, t);
-    slab(0);
-    for (auto& th : pool) th.join();
-    e->n_pos_quick = 0;
-    for (const Quick& q : quick) {
-      if (q.bad) return fail(e, KC_EINVAL, "offsets must be non-decreasing");  // (have_proteins stays false)
-      e->n_pos_quick += q.pos;
-    }
-  }
   e->R = R;
   int rc = KC_OK;
-  if (!e->cfg.cross_class_only && e->cfg.sample_every <= 1) {
-    // pair order = input order: the device derives the row layout from d_off; the host side is deferred
-    e->pend_off = offsets;
-    e->pend_cls = class_id;
-    rc = stage_layout_device(e);
+  if (!e->cfg.cross_class_only) {
+    // pair order = input order: the row tables come straight from the caller's offsets (one pass in parallel
+    // slabs while the upload runs; it also checks that they do not decrease), the device derives the row
+    // layout from d_off, and the engine's own copies of offsets / classes are deferred (kc_engine::pend_off)
+    rc = stage_layout_host(e, offsets);
+    if (rc == KC_OK) rc = stage_layout_device(e);
+    if (rc == KC_OK) rc = stage_lists_device(e);
     if (rc == KC_OK) {
+      e->pend_off = offsets;
+      e->pend_cls = class_id;
       e->have_proteins = true;
       e->have_index = e->have_pairs = false;
     }
@@ -1643,7 +1619,17 @@ int kc_index_shard_blocks(kc_engine* e, uint32_t* bounds, uint32_t capacity) {
   return KC_OK;
 }
 
+static int build_index_shard_impl(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_index_stats* stats);
+
 int kc_build_index_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_index_stats* stats) {
+  const int rc = build_index_shard_impl(e, shard, n_shards, stats);
+  // the caller's offsets / classes are only borrowed until this call returns (kc_engine::pend_off; the hot
+  // builds have made the copies behind their kernels already)
+  if (e) ensure_staged(e);
+  return rc;
+}
+
+static int build_index_shard_impl(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_index_stats* stats) {
   if (!e || n_shards == 0 || shard >= n_shards) return KC_EINVAL;
   if (n_shards > 255) return fail(e, KC_EINVAL, "at most 255 shards (the row blocks' owner is one byte)");
   if (!e->have_proteins) return fail(e, KC_EINVAL, "kc_set_proteins first");
@@ -1670,10 +1656,6 @@ int kc_build_index_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_ind
     const bool subsampled = e->cfg.sample_every > 1;
     if (want == KC_INDEX_AUTO) want = subsampled ? KC_INDEX_TABLE : (n_shards > 1 ? KC_INDEX_BUCKET : KC_INDEX_STREAM);
     if (want == KC_INDEX_STREAM && (subsampled || n >= (1u << 24))) want = subsampled ? KC_INDEX_TABLE : KC_INDEX_BUCKET;
-    // (a deferred host staging, kc_engine::pend_off: the unsharded streaming build completes it behind its
-    // own kernels; everything else needs the host's row tables first)
-    if (!(want == KC_INDEX_STREAM && n > 0 && n_shards <= 1))
-      if (int rcs = ensure_staged(e)) return rcs;
     if (want == KC_INDEX_STREAM && n > 0) return build_index_stream(e, shard, n_shards, stats);
     // (the bucket build remembers per protein-set signature that its buckets overflowed)
     const bool known_overflow = e->cap_hint == 0 && e->cap_hint_n == e->n && e->cap_hint_R == e->R;
