@@ -36,15 +36,20 @@ struct BucketScatter {
     uint32_t h = kmer * 0x85EBCA6Bu;
     return h ^ (h >> 13);
   }
+  // does the k-mer of a foreign row pass the filter of this rank's k-mers?
+  __device__ __forceinline__ bool passes(uint32_t kmer) const {
+    const uint32_t f = filter_hash(kmer) & filter_mask;
+    return (__ldg(filter + (f >> 5)) >> (f & 31u)) & 1u;
+  }
   // two steps so that a caller can keep several reservations (L2 atomics) in flight
-  __device__ __forceinline__ unsigned long long reserve(uint32_t kmer, uint32_t row) const {
-    if (filter && !owner.mine(row)) {
-      const uint32_t f = filter_hash(kmer) & filter_mask;
-      if (!((__ldg(filter + (f >> 5)) >> (f & 31u)) & 1u)) return ~0ull;
-    }
+  __device__ __forceinline__ unsigned long long reserve_kept(uint32_t kmer) const {  // (filter already applied)
     const uint32_t b = __umulhi(kmer_bucket_hash(kmer), n_buckets);
     const uint32_t pos = atomicAdd(&cursor[b], 1u);
     return pos < cap ? (unsigned long long)b * cap + pos : ~0ull;
+  }
+  __device__ __forceinline__ unsigned long long reserve(uint32_t kmer, uint32_t row) const {
+    if (filter && !owner.mine(row) && !passes(kmer)) return ~0ull;
+    return reserve_kept(kmer);
   }
   __device__ __forceinline__ void store(unsigned long long at, uint32_t kmer, uint32_t row) const {
     if (at != ~0ull) rec[at] = make_uint2(kmer, row);
@@ -427,16 +432,27 @@ __global__ void __launch_bounds__(kXsWarps * 32)
     __syncwarp();
     const uint32_t skey = sample_every > 1 ? sample_key(sample_seed, orig_of ? orig_of[r] : r) : 0u;
     uint32_t fresh = 0;
+    // Sharded build, a row of another rank: most of its k-mers fail the filter of this rank's k-mers (81 % at
+    // 8 ranks), so the filter is probed FIRST (four L2 loads in flight) and only the survivors enter the hash
+    // set; ndist of such a row counts its kept k-mers (it only sizes the row's entry capacity).
+    const bool foreign = scatter.rec && scatter.filter && !scatter.owner.mine(r);
     for (uint32_t c = 0; c < npos; c += 128) {  // four k-mers per lane: four bucket reservations in flight
       uint32_t v[4];
-      bool first[4];
+      bool first[4], act[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const uint32_t i = c + 32 * u + lane;
         first[u] = false;
-        v[u] = 0;
-        if (i < npos) {
-          v[u] = pack_kmer<K>(codes + (sample_every > 1 ? sample_perm(skey, npos_all, i) : i));
+        act[u] = i < npos;
+        v[u] = act[u] ? pack_kmer<K>(codes + (sample_every > 1 ? sample_perm(skey, npos_all, i) : i)) : 0u;
+      }
+      if (foreign) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) act[u] = act[u] && scatter.passes(v[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (act[u]) {
           uint32_t h = (v[u] * 2654435761u) >> 22;
           for (;;) {
             const uint32_t cur = tab[h];
@@ -455,7 +471,8 @@ __global__ void __launch_bounds__(kXsWarps * 32)
       }
       unsigned long long at[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) at[u] = first[u] ? scatter.reserve(v[u], r) : ~0ull;
+      for (int u = 0; u < 4; ++u)
+        at[u] = !first[u] ? ~0ull : foreign ? scatter.reserve_kept(v[u]) : scatter.reserve(v[u], r);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         scatter.store(at[u], v[u], r);
