@@ -218,6 +218,8 @@ def main():
     ap.add_argument("--workload", default="synth_1m_k7", choices=sorted(WORKLOADS))
     ap.add_argument("--n-proteins", type=int, default=None, help="override the workload's protein count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--index", default="auto", choices=["auto", "stream", "bucket", "table"],
+                    help="kc_config.index_build (auto: streaming build on one GPU, bucket build first on shards)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -249,7 +251,8 @@ def main():
     d_res, d_off, d_cls = h_res.cuda(), h_off.cuda(), h_cls.cuda()
     stream = torch.cuda.current_stream()
 
-    eng = kc.Engine(k, device=local_rank, threshold=THRESHOLD, cross_class_only=cross, want_blosum=True)
+    eng = kc.Engine(k, device=local_rank, threshold=THRESHOLD, cross_class_only=cross, want_blosum=True,
+                    index_build=args.index)
     eng.set_stream(stream.cuda_stream)
     if world > 1:  # the library's own NCCL rank (csrc/dist.cuh); torch.distributed only hands the id around
         box = [kc.Engine.comm_unique_id() if rank == 0 else None]
