@@ -2219,21 +2219,21 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
       if (wide) {
         KC_CUDA(e, cudaFuncSetAttribute(pairs_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)dense_smem));
-        KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairs_dense_kernel<true>, 256, dense_smem));
+        KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairs_dense_kernel<true>, kDenseThreads, dense_smem));
       } else {
         KC_CUDA(e, cudaFuncSetAttribute(pairs_dense_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)dense_smem));
-        KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairs_dense_kernel<false>, 256, dense_smem));
+        KC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pairs_dense_kernel<false>, kDenseThreads, dense_smem));
       }
       if (per_sm < 1) per_sm = 1;
       const uint32_t grid = (uint32_t)(e->num_sm * per_sm);
       const uint32_t* fa = e->cfg.cross_class_only ? e->d_first_after.as<uint32_t>() : nullptr;
       if (wide)
-        KC_LAUNCH(e, pairs_dense_kernel<true>, grid, 256, dense_smem, e->pair_rowptr(),
+        KC_LAUNCH(e, pairs_dense_kernel<true>, grid, kDenseThreads, dense_smem, e->pair_rowptr(),
                   e->pair_rowlen(), e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), fa,
                   e->d_rowbin.as<uint8_t>(), n, dense_cols, &ds->row_cursor[kBinDense], ds->bin_counts, sink, &ds->pc);
       else
-        KC_LAUNCH(e, pairs_dense_kernel<false>, grid, 256, dense_smem, e->pair_rowptr(),
+        KC_LAUNCH(e, pairs_dense_kernel<false>, grid, kDenseThreads, dense_smem, e->pair_rowptr(),
                   e->pair_rowlen(), e->d_suf.as<uint2>(), e->d_col.as<uint32_t>(), fa,
                   e->d_rowbin.as<uint8_t>(), n, dense_cols, &ds->row_cursor[kBinDense], ds->bin_counts, sink, &ds->pc);
     }

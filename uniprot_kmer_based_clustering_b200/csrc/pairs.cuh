@@ -49,7 +49,7 @@ __device__ __forceinline__ void emit_edge(bool pred, uint32_t ra, uint32_t rb, u
   if (lane_id() == leader) base = atomicAdd(sink.cursor, (unsigned long long)__popc(m));
   base = __shfl_sync(kFullMask, base, leader);
   const unsigned long long idx = base + __popc(m & lanemask_lt());
-  if (pred && idx < sink.cap) sink.buf[idx] = make_uint4(ra, rb, count, 0u);
+  if (pred && idx < sink.cap) sink.buf[idx] = make_uint4(ra, rb, count, sink.unscored);
 }
 
 // Per-warp staging of emitted edges in shared memory: one global atomic per flush instead of
@@ -1297,9 +1297,36 @@ __global__ void __launch_bounds__(kTileThreads)
 // ---------------------------------------------------------------------------------------
 // dense accumulators: one CTA per row, one counter per candidate partner, in column blocks of
 // `block_cols` partners.  WIDE = u32 counters (rows with >= 65535 ids), else two u16 per word.
+// The rows that land here hold thousands to hundreds of thousands of partners (the k = 5 sets; long
+// proteins of large k = 7 sets), far fewer than the columns they span, so what costs is the sweep over the
+// counters and the clipping of the postings suffixes to the block, not the increments:
+//   * 1 024 threads per CTA (one CTA per SM at 200 KB of counters: 32 warps instead of 8 to issue the sweep);
+//   * ONE sweep per block, 16-byte loads: read, count, emit, and store zeros back only where something was
+//     counted (the counters are zeroed once per CTA; the multi-edge total comes from the walk, not the sweep);
+//     a warp whose 128 words hold no counter over the threshold never enters the emission code;
+//   * blocks ascend, so every thread carries, for the entries it owns, where the previous block's clip
+//     ended (registers): one galloping search per entry and block instead of two binary searches.
 // ---------------------------------------------------------------------------------------
+constexpr int kDenseThreads = 1024;
+constexpr int kDenseCarry = 4;  // entries per thread with a carried cursor (rows of <= 4 096 entries; beyond: searched)
+
+// first posting >= x in col[lo, hi) (ascending), galloping from lo
+__device__ __forceinline__ uint32_t dense_clip_end(const uint32_t* __restrict__ col, uint32_t lo, uint32_t hi, uint32_t x) {
+  uint32_t step = 8;
+  while (lo + step < hi && col[lo + step - 1u] < x) {
+    lo += step;
+    step <<= 1;
+  }
+  hi = min(hi, lo + step);
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (col[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 template <bool WIDE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kDenseThreads)
     pairs_dense_kernel(const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen,
                        const uint2* __restrict__ suf, const uint32_t* __restrict__ col,
                        const uint32_t* __restrict__ first_after, const uint8_t* __restrict__ rowbin, uint32_t n,
@@ -1308,11 +1335,14 @@ __global__ void __launch_bounds__(256)
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   if (bin_counts[kBinDense] == 0) return;
   __shared__ uint32_t s_base;
-  __shared__ uint32_t s_stage[8][kStageWords];
   uint32_t* acc = reinterpret_cast<uint32_t*>(dyn_smem);
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   unsigned long long n_pairs = 0, n_edges = 0, sum_count = 0, n_multi = 0;
-  EdgeStage stage{s_stage[warp], 0u};
+  {  // the counters start (and every sweep leaves them) all zero
+    const uint32_t cap_words4 = ((WIDE ? block_cols : (block_cols + 1) / 2) + 3u) & ~3u;
+    for (uint32_t i = threadIdx.x * 4; i < cap_words4; i += kDenseThreads * 4)
+      *reinterpret_cast<uint4*>(acc + i) = make_uint4(0, 0, 0, 0);
+  }
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) s_base = atomicAdd(row_cursor, 32u);
@@ -1326,66 +1356,102 @@ __global__ void __launch_bounds__(256)
       const uint32_t nl = rowlen[r], ps = pstart[r];
       const uint32_t first = first_after ? first_after[r] : r + 1;
       const bool multipass = n - first > block_cols;
+      uint32_t cur[kDenseCarry];  // entry threadIdx.x + k * kDenseThreads: where the last block's clip ended
+#pragma unroll
+      for (int k = 0; k < kDenseCarry; ++k) cur[k] = kSentinel;
+      uint32_t bumps = 0;
       for (uint32_t blk_lo = first; blk_lo < n; blk_lo += block_cols) {
         const uint32_t blk_hi = min(n, blk_lo + block_cols);
         const uint32_t ncols = blk_hi - blk_lo;
         const uint32_t words = WIDE ? ncols : (ncols + 1) / 2;  // only what this block needs
         const uint32_t words4 = (words + 3u) & ~3u;
-        for (uint32_t i = threadIdx.x * 4; i < words4; i += 256 * 4)
-          *reinterpret_cast<uint4*>(acc + i) = make_uint4(0, 0, 0, 0);
-        __syncthreads();
-        for (uint32_t c = warp * 32; c < nl; c += 256) {
+        auto bump = [&](uint32_t b) {
+          const uint32_t idx = b - blk_lo;
+          ++bumps;
+          if (WIDE) atomicAdd(&acc[idx], 1u);
+          else atomicAdd(&acc[idx >> 1], 1u << ((idx & 1u) * 16u));
+        };
+#pragma unroll
+        for (int k = 0; k < kDenseCarry; ++k) {
+          const uint32_t c = warp * 32u + (uint32_t)k * kDenseThreads;
+          if (c >= nl) break;  // warp-uniform
           uint2 e = c + lane < nl ? ld_stream_u32x2(suf + ps + c + lane) : make_uint2(0, 0);
-          if (multipass && e.y == kSentinel) {
-            if (e.x < blk_lo || e.x >= blk_hi) e = make_uint2(0, 0);
-          } else if (multipass) {  // clip the suffix to holders in [blk_lo, blk_hi)
-            uint32_t lo = e.x, hi = e.y;
-            while (lo < hi) {
-              const uint32_t mid = (lo + hi) >> 1;
-              if (col[mid] < blk_lo) lo = mid + 1; else hi = mid;
+          if (multipass) {
+            if (e.y == kSentinel) {
+              if (e.x < blk_lo || e.x >= blk_hi) e = make_uint2(0, 0);
+            } else if (e.y > e.x) {  // the holders in [blk_lo, blk_hi): from where the previous block stopped
+              const uint32_t lo = cur[k] != kSentinel ? cur[k] : e.x;
+              const uint32_t hi = blk_hi >= n ? e.y : dense_clip_end(col, lo, e.y, blk_hi);
+              cur[k] = hi;
+              e = make_uint2(lo, hi);
             }
-            e.x = lo;
-            hi = e.y;
-            while (lo < hi) {
-              const uint32_t mid = (lo + hi) >> 1;
-              if (col[mid] < blk_hi) lo = mid + 1; else hi = mid;
-            }
-            e.y = lo;
           }
-          walk_chunk(col, e, [&](uint32_t b) {
-            const uint32_t idx = b - blk_lo;
-            if (WIDE) atomicAdd(&acc[idx], 1u);
-            else atomicAdd(&acc[idx >> 1], 1u << ((idx & 1u) * 16u));
-          });
+          walk_chunk(col, e, bump);
+        }
+        for (uint32_t c = warp * 32u + (uint32_t)kDenseCarry * kDenseThreads; c < nl; c += kDenseThreads) {
+          uint2 e = c + lane < nl ? ld_stream_u32x2(suf + ps + c + lane) : make_uint2(0, 0);
+          if (multipass) {  // (rows of more than 4 096 entries: both ends searched)
+            if (e.y == kSentinel) {
+              if (e.x < blk_lo || e.x >= blk_hi) e = make_uint2(0, 0);
+            } else if (e.y > e.x) {
+              uint32_t lo = e.x, hi = e.y;
+              while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (col[mid] < blk_lo) lo = mid + 1; else hi = mid;
+              }
+              e = make_uint2(lo, dense_clip_end(col, lo, e.y, blk_hi));
+            }
+          }
+          walk_chunk(col, e, bump);
         }
         __syncthreads();
-        for (uint32_t i0 = warp * 32; i0 < words; i0 += 256) {  // warp-uniform trip count
-          const uint32_t i = i0 + lane;
-          const uint32_t x = i < words ? acc[i] : 0u;
-          if (stage.cnt + 64u > kStageEdges) stage_flush(stage, sink);
-          if (WIDE) {
-            const bool out = x > sink.threshold;
-            n_pairs += x != 0;
-            n_multi += x;
-            n_edges += out;
-            sum_count += out ? x : 0u;
-            stage_push(stage, out, r, blk_lo + i, x);
-          } else {
-            const uint32_t c0 = x & 0xFFFFu, c1 = x >> 16;
-            const bool o0 = c0 > sink.threshold, o1 = c1 > sink.threshold && 2 * i + 1 < ncols;
-            n_pairs += (c0 != 0) + (c1 != 0);
-            n_multi += c0 + c1;
-            n_edges += (uint32_t)o0 + (uint32_t)o1;
-            sum_count += (o0 ? c0 : 0u) + (o1 ? c1 : 0u);
-            stage_push(stage, o0, r, blk_lo + 2 * i, c0);
-            stage_push(stage, o1, r, blk_lo + 2 * i + 1, c1);
+        // the sweep: read, count, emit, clear (warp-uniform trip count)
+        for (uint32_t i0 = warp * 128u; i0 < words4; i0 += kDenseThreads * 4u) {
+          const uint32_t i = i0 + lane * 4u;
+          uint4 x = make_uint4(0, 0, 0, 0);
+          if (i < words4) x = *reinterpret_cast<const uint4*>(acc + i);
+          const bool any = (x.x | x.y | x.z | x.w) != 0u;
+          if (!__any_sync(kFullMask, any)) continue;
+          if (any) *reinterpret_cast<uint4*>(acc + i) = make_uint4(0, 0, 0, 0);
+          const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+          const uint32_t thr = sink.threshold;
+          bool hot = false;
+          uint32_t nz = 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (WIDE) {
+              nz += w[q] != 0u;
+              hot |= w[q] > thr;
+            } else {
+              const uint32_t c0 = w[q] & 0xFFFFu, c1 = w[q] >> 16;
+              nz += (c0 != 0u) + (c1 != 0u);
+              hot |= c0 > thr || c1 > thr;
+            }
+          }
+          n_pairs += nz;
+          if (!__any_sync(kFullMask, hot)) continue;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (WIDE) {
+              const bool out = w[q] > thr;
+              n_edges += out;
+              sum_count += out ? w[q] : 0u;
+              emit_edge(out, r, blk_lo + i + q, w[q], sink);
+            } else {
+              const uint32_t c0 = w[q] & 0xFFFFu, c1 = w[q] >> 16;
+              const bool o0 = c0 > thr, o1 = c1 > thr;
+              n_edges += (uint32_t)o0 + (uint32_t)o1;
+              sum_count += (o0 ? c0 : 0u) + (o1 ? c1 : 0u);
+              emit_edge(o0, r, blk_lo + 2u * (i + q), c0, sink);
+              emit_edge(o1, r, blk_lo + 2u * (i + q) + 1u, c1, sink);
+            }
           }
         }
         __syncthreads();
       }
+      n_multi += bumps;
     }
   }
-  stage_flush(stage, sink);
   n_pairs = warp_sum64(n_pairs);
   n_edges = warp_sum64(n_edges);
   sum_count = warp_sum64(sum_count);
