@@ -2299,16 +2299,15 @@ int kc_score_pairs_shard(kc_engine* e, uint32_t shard, uint32_t n_shards, kc_pai
     if (e->cfg.want_blosum) {
       // hash size from the longest possible row (a row has at most plen - k + 1 ids)
       const bool small_rows = 10ull * max_rowlen <= 7ull * 1024;
-      const uint32_t bgrid = blocks_for((ne + 31) / 32, 4, e->num_sm * (small_rows ? 10 : 5));
       unsigned long long* skeys = (in_b ? e->d_keys_b : e->d_keys_a).as<unsigned long long>();
       unsigned long long* svals = (in_b ? e->d_vals_b : e->d_vals_a).as<unsigned long long>();
       if (small_rows)
-        KC_LAUNCH(e, (edge_blosum_kernel<1024, 22>), bgrid, 128, 0, skeys, svals, ne, e->d_rank.as<uint32_t>(),
-                  e->pair_rowptr(), e->d_rowlen.as<uint32_t>(), e->pair_ids(),
+        KC_LAUNCH(e, (edge_blosum_kernel<1024, 22, 4>), blocks_for((ne + 31) / 32, 4, e->num_sm * 10), 128, 0, skeys, svals,
+                  ne, e->d_rank.as<uint32_t>(), e->pair_rowptr(), e->d_rowlen.as<uint32_t>(), e->pair_ids(),
                   e->pair_self());
       else
-        KC_LAUNCH(e, (edge_blosum_kernel<2048, 21>), bgrid, 128, 0, skeys, svals, ne, e->d_rank.as<uint32_t>(),
-                  e->pair_rowptr(), e->d_rowlen.as<uint32_t>(), e->pair_ids(),
+        KC_LAUNCH(e, (edge_blosum_kernel<4096, 20, 2>), blocks_for((ne + 31) / 32, 2, e->num_sm * 5), 64, 0, skeys, svals,
+                  ne, e->d_rank.as<uint32_t>(), e->pair_rowptr(), e->d_rowlen.as<uint32_t>(), e->pair_ids(),
                   e->pair_self());
     }
     KC_LAUNCH(e, assemble_edges_kernel, blocks_for(ne, 256, e->num_sm * 8), 256, 0,

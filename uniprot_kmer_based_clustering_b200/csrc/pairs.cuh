@@ -1474,14 +1474,18 @@ __global__ void __launch_bounds__(kDenseThreads)
 // 32 consecutive edges; while `a` stays the same it keeps row a's ids in a shared-memory hash
 // set (id -> BLOSUM62 self-score), streams row b's ids with coalesced loads and probes.
 // vals = count | blosum << 32 (blosum filled in here).
-template <uint32_t SLOTS, uint32_t SHIFT>
-__global__ void __launch_bounds__(128)
+// <1024, 22, 4>: rows of up to 716 ids; <4096, 20, 2>: longer rows, load factor <= 0.5 (rows of up to 2 048 ids are hashed
+// once per run of edges with the same first row; at 2 048 slots and load 0.7 the unsuccessful probes of row b, most of
+// them, took ~6 steps each and rows beyond 1 433 ids were re-hashed in chunks for EVERY edge: 12 000 warp instructions
+// per edge at 5.5 active lanes on the k = 5 sets, profiles/r2_history.md)
+template <uint32_t SLOTS, uint32_t SHIFT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
     edge_blosum_kernel(const unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals,
                        unsigned long long n_edges, const uint32_t* __restrict__ rank_of,
                        const uint32_t* __restrict__ pstart, const uint32_t* __restrict__ rowlen,
                        const uint32_t* __restrict__ ids, const uint8_t* __restrict__ selfscore) {
-  __shared__ uint32_t s_key[4][SLOTS];
-  __shared__ uint8_t s_val[4][SLOTS];
+  __shared__ uint32_t s_key[WARPS][SLOTS];
+  __shared__ uint8_t s_val[WARPS][SLOTS];
   const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
   uint32_t* hk = s_key[w];
   uint8_t* hv = s_val[w];
@@ -1569,7 +1573,7 @@ __global__ void __launch_bounds__(128)
           h = (h + 1u) & (SLOTS - 1u);
         }
       };
-      constexpr uint32_t kChunk = 7u * SLOTS / 10u;
+      constexpr uint32_t kChunk = SLOTS >= 4096u ? SLOTS / 2u : 7u * SLOTS / 10u;
       if (a != cur_a) {
         cur_a = a;
         A = ids + pa;
