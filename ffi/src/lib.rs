@@ -47,6 +47,8 @@ impl Engine {
         if rc != KC_OK { panic!("kc_create failed ({rc}): no usable CUDA device (there is no CPU fallback)"); }
         Engine { h, k: cfg.k }
     }
+    /// The engine BORROWS the staged arrays of `fa` (asynchronous upload, host copies made inside the next build):
+    /// keep `fa` alive and unchanged until `build_index` has returned (include/kc_b200.h, kc_set_proteins).
     pub fn set_proteins(&mut self, fa: &Fasta) {
         let rc = unsafe { kc_set_proteins(self.h, kc_fasta_residues(fa.0), kc_fasta_offsets(fa.0), kc_fasta_class_ids(fa.0), fa.len() as u64) };
         check(self.h, rc, "kc_set_proteins");
