@@ -980,6 +980,7 @@ static int build_index_stream(kc_engine* e, uint32_t shard, uint32_t n_shards, k
   // upload chunk, each waiting for its own chunk only; the level-1 sort of chunk u runs while chunk u + 1
   // crosses PCIe.  A tile also reads the first bytes of the next one (the k-mer halo): pass u stops one tile
   // short of its chunk's end, the last pass takes the rest.
+  static_assert(kc_engine::kUploadChunks <= kSxMaxPass, "one level-1 pass per upload chunk");
   int n_pass = 1;
   uint32_t pass_end[kc_engine::kUploadChunks] = {};
   if (e->n_chunks > 1 && n_shards <= 1 && !e->cfg.cross_class_only) {

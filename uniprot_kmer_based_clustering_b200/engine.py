@@ -171,6 +171,9 @@ class Engine:
         if offsets.size != class_id.size + 1:
             raise ValueError("offsets must have n+1 entries")
         self.n = int(class_id.size)
+        # the engine borrows the three arrays until the next build_index / extract_kmers returns (asynchronous
+        # upload, host copies made inside the build): keep them (or the converted copies made above) alive
+        self._keep = [residues, offsets, class_id]
         self._check(self._L.kc_set_proteins(self._h, _ptr(residues), _ptr(offsets), _ptr(class_id), self.n))
 
     def set_proteins_ptr(self, residues_ptr: int, offsets_ptr: int, class_ptr: int, n: int, on_device: bool):
