@@ -17,12 +17,14 @@
 //      loads, rolling k-mer per thread).  Every position yields a record {k-mer, row}; the record's bucket is
 //      the top b1+b2 bits of a bijective hash of the k-mer.
 //   2. Level 1 and level 2 are STABLE counting-sort passes (count, scan, scatter) with the tile staged in
-//      shared memory and ranked with match.any (no shared-memory atomics in the scatter), written out as
-//      runs of consecutive records per digit.  Stability keeps every bucket sorted by row.
-//   3. One CTA per bucket: stable LSD radix sort of the bucket on the REMAINING hash bits in shared memory.
-//      Because the hash is a bijection, equal keys are equal k-mers; because the passes are stable, the
-//      holders of a k-mer come out ascending and the duplicates of a row are adjacent.  Census, ids,
-//      postings, suffixes and bin-local runs then fall out of three block scans; no hash table, no O(f^2).
+//      shared memory and ranked by warp ballots (no shared-memory atomics in the scatter), written out as
+//      runs of consecutive records per digit.  Stability keeps every bucket sorted by row.  Level 1 runs in
+//      PASSES (one per upload chunk while the stream is still crossing PCIe, else one): see SxPlan.
+//   3. One WARP per bucket (~330 records; one CTA for the few larger ones): stable LSD radix sort of the bucket
+//      on the REMAINING hash bits in shared memory.  Because the hash is a bijection, equal keys are equal
+//      k-mers; because the passes are stable, the holders of a k-mer come out ascending and the duplicates
+//      of a row are adjacent.  Census, ids, postings, suffixes and bin-local runs then fall out of ballots and
+//      carried counters; no hash table, no O(f^2).
 //   4. A bucket that does not fit shared memory (a k-mer with thousands of holders) takes the same steps
 //      through global scratch with one CTA (sx_huge_kernel): no fallback build, no retry.
 // The outputs (postings, vocabulary, entry bins, run records) are the ones bucket.cuh documents; the entry
